@@ -1,0 +1,452 @@
+// K3: persistent, warp-specialised tcgen05 GEMM for every Linear on the hot path.
+//
+//   D[M,N] = epilogue( A[M,K] . B[N,K]^T )            bf16 operands, fp32 accumulation in TMEM
+//
+// Replaces the cuBLASLt calls PyTorch makes for nn.Linear in the reference encoder/head
+// (qkv VT.pyc@L114,121; proj @L116,129; fc1/fc2 @L93-95; DINOHead mlp/last_layer @L303-318,327-329)
+// and their autograd dgrad / wgrad GEMMs.
+//
+// Operand layouts (runtime flags, so one kernel serves fprop, dgrad and wgrad):
+//   A K-major  : row-major [M,K]          A MN-major : row-major [K,M]  (A^T stored)
+//   B K-major  : row-major [N,K]          B MN-major : row-major [K,N]  (B^T stored)
+//   fprop  Y = X W^T        : A = X (K-major),  B = W  (K-major)
+//   dgrad  dX = dY W        : A = dY (K-major), B = W  (MN-major, reduction over W's rows)
+//   wgrad  dW = dY^T X      : A = dY (MN-major), B = X (MN-major), reduction over tokens, split-K
+//
+// Structure per CTA (one CTA per SM, persistent over output tiles of 128 x BN):
+//   warp 0      : TMA producer   (global -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1      : MMA issuer     (one elected lane issues tcgen05.mma; accumulators in TMEM,
+//                                 2 accumulator stages so tile i's epilogue overlaps tile i+1's MMAs)
+//   warps 4..11 : epilogue       (2 groups x 4 warps; tcgen05.ld -> bias/GELU/residual -> bf16 ->
+//                                 swizzled smem -> TMA store; or fp32 red.add for split-K wgrad)
+#include "common.cuh"
+
+namespace b200ssl {
+
+enum GemmEpilogue : int {
+  EPI_BIAS = 0,       // D = acc (+ bias)
+  EPI_BIAS_GELU = 1,  // D = acc + bias ; D2 = gelu(D)
+  EPI_BIAS_RES = 2,   // D = acc (+ bias) + aux
+  EPI_DGELU = 3,      // D = acc * gelu'(aux)
+  EPI_ATOMIC_F32 = 4, // D(fp32) += acc   (split-K)
+};
+
+struct GemmArgs {
+  int M, N, K;
+  int a_mn, b_mn;
+  int num_m_blocks, num_n_blocks, k_splits, k_blocks_per_split, k_blocks_total;
+  const float* bias;
+  const __nv_bfloat16* aux;
+  long long ldaux;
+  float* out_f32;
+  long long ldd;
+};
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int STAGING_BYTES = BLOCK_M * 128;           // 128 rows x 64 bf16
+constexpr int NUM_EPI_GROUPS = 2;
+constexpr int GEMM_THREADS = 128 + NUM_EPI_GROUPS * 128;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = BN == 256 ? 3 : BN == 192 ? 4 : BN == 128 ? 5 : 6;
+  static constexpr int kBStageBytes = BN * BLOCK_K * 2;
+  static constexpr int kStageBytes = A_STAGE_BYTES + kBStageBytes;
+  static constexpr int kTmemCols = BN * 2 <= 128 ? 128 : BN * 2 <= 256 ? 256 : 512;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + NUM_EPI_GROUPS * 2 * STAGING_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
+            const GemmArgs args) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* staging = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + NUM_EPI_GROUPS * 2 * STAGING_BYTES);
+  uint64_t* full_bar = bars;                 // [kStages]
+  uint64_t* empty_bar = bars + kStages;      // [kStages]
+  uint64_t* tmem_full = bars + 2 * kStages;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (EPI != EPI_ATOMIC_F32) tma_prefetch_desc(&tmD);
+    if (EPI == EPI_BIAS_GELU) tma_prefetch_desc(&tmD2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], NUM_EPI_GROUPS * 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_split = args.num_m_blocks * args.num_n_blocks;
+  const int total_tiles = tiles_per_split * args.k_splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n_blk = t % args.num_n_blocks;
+        const int m_blk = (t / args.num_n_blocks) % args.num_m_blocks;
+        const int ks = t / tiles_per_split;
+        const int kb0 = ks * args.k_blocks_per_split;
+        const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks_total);
+        const int m0 = m_blk * BLOCK_M, n0 = n_blk * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::kStageBytes;
+          uint8_t* sB = sA + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          const int k0 = kb * BLOCK_K;
+          if (!args.a_mn) {
+            tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)
+              tma_load_2d(sA + c * 8192, &tmA, &full_bar[stage], m0 + c * 64, k0);
+          }
+          if (!args.b_mn) {
+            tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sB + c * 8192, &tmB, &full_bar[stage], n0 + c * 64, k0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, args.a_mn != 0, args.b_mn != 0);
+      const uint32_t a_lbo = args.a_mn ? 8192u : 16u;
+      const uint32_t b_lbo = args.b_mn ? 8192u : 16u;
+      const uint32_t a_kstep = args.a_mn ? UMMA_K * 128u : UMMA_K * 2u;
+      const uint32_t b_kstep = args.b_mn ? UMMA_K * 128u : UMMA_K * 2u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int ks = t / tiles_per_split;
+        const int kb0 = ks * args.k_blocks_per_split;
+        const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks_total);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sB = sA + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(sA + k * a_kstep, a_lbo, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sB + k * b_kstep, b_lbo, 1024);
+            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int group = (warp - 4) >> 2;  // 0 or 1: which 64-column chunks this warp owns
+    const int gtid = threadIdx.x - 128 - group * 128;
+    uint8_t* stg = staging + group * 2 * STAGING_BYTES;
+    const int row_in_tile = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t slot = 0;  // staging buffer ring position (per group)
+    constexpr int kChunks = BN / 64;
+
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int n_blk = t % args.num_n_blocks;
+      const int m_blk = (t / args.num_n_blocks) % args.num_m_blocks;
+      const int m0 = m_blk * BLOCK_M, n0 = n_blk * BN;
+      const int row = m0 + row_in_tile;
+      const bool row_ok = row < args.M;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+
+      bool released = false;
+      for (int c = group; c < kChunks; c += NUM_EPI_GROUPS) {
+        uint32_t v[64];
+        {
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 static_cast<uint32_t>(acc * BN + c * 64);
+          uint32_t lo[32], hi[32];
+          tmem_ld_32x32b_x32(taddr, lo);
+          tmem_ld_32x32b_x32(taddr + 32, hi);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { v[j] = lo[j]; v[32 + j] = hi[j]; }
+        }
+        if (c + NUM_EPI_GROUPS >= kChunks) {
+          // last TMEM read of this tile by this thread: hand the accumulator stage back
+          tcgen05_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+          released = true;
+        }
+        const int col0 = n0 + c * 64;
+
+        if (EPI == EPI_ATOMIC_F32) {
+          if (row_ok) {
+            float* dst = args.out_f32 + static_cast<long long>(row) * args.ldd + col0;
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
+                           "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                           "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                           : "memory");
+            }
+          }
+          continue;
+        }
+
+        float f[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) f[j] = __uint_as_float(v[j]);
+        if (EPI != EPI_DGELU && args.bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(args.bias + col0);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 b = __ldg(bp + j);
+            f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+          }
+        }
+        if (EPI == EPI_BIAS_RES || EPI == EPI_DGELU) {
+          if (row_ok) {
+            const uint4* ap =
+                reinterpret_cast<const uint4*>(args.aux + static_cast<long long>(row) * args.ldaux + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 a = __ldg(ap + j);
+              const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 x = unpack_bf16x2(w[e]);
+                if (EPI == EPI_BIAS_RES) {
+                  f[8 * j + 2 * e] += x.x;
+                  f[8 * j + 2 * e + 1] += x.y;
+                } else {
+                  f[8 * j + 2 * e] *= dgelu_erf(x.x);
+                  f[8 * j + 2 * e + 1] *= dgelu_erf(x.y);
+                }
+              }
+            }
+          }
+        }
+
+        constexpr int kOutputs = EPI == EPI_BIAS_GELU ? 2 : 1;
+#pragma unroll
+        for (int o = 0; o < kOutputs; ++o) {
+          uint8_t* buf = stg + (slot & 1) * STAGING_BYTES;
+          if (gtid == 0) tma_store_wait_read<1>();  // the store that last used this buffer has drained
+          named_bar_sync(1 + group, 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 pk;
+            if (o == 0) {
+              pk.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              pk.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              pk.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              pk.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+            } else {
+              pk.x = pack_bf16x2(gelu_erf(f[8 * j + 0]), gelu_erf(f[8 * j + 1]));
+              pk.y = pack_bf16x2(gelu_erf(f[8 * j + 2]), gelu_erf(f[8 * j + 3]));
+              pk.z = pack_bf16x2(gelu_erf(f[8 * j + 4]), gelu_erf(f[8 * j + 5]));
+              pk.w = pack_bf16x2(gelu_erf(f[8 * j + 6]), gelu_erf(f[8 * j + 7]));
+            }
+            *reinterpret_cast<uint4*>(buf + sw128_offset(row_in_tile, j)) = pk;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1 + group, 128);
+          if (gtid == 0) {
+            tma_store_2d(o == 0 ? &tmD : &tmD2, buf, col0, m0);
+            tma_store_commit();
+          }
+          ++slot;
+        }
+      }
+      if (!released) {
+        tcgen05_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (gtid == 0) tma_store_wait_all<0>();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launcher
+// ------------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                       const CUtensorMap& tmD2, const GemmArgs& args, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    B200SSL_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int total = args.num_m_blocks * args.num_n_blocks * args.k_splits;
+  const int grid = total < sm_count() ? total : sm_count();
+  gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmD, tmD2, args);
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d,
+                        const CUtensorMap& d2, const GemmArgs& args, cudaStream_t s) {
+  switch (epi) {
+    case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(a, b, d, d2, args, s);
+    case EPI_BIAS_GELU: return launch_gemm<BN, EPI_BIAS_GELU>(a, b, d, d2, args, s);
+    case EPI_BIAS_RES: return launch_gemm<BN, EPI_BIAS_RES>(a, b, d, d2, args, s);
+    case EPI_DGELU: return launch_gemm<BN, EPI_DGELU>(a, b, d, d2, args, s);
+    case EPI_ATOMIC_F32: return launch_gemm<BN, EPI_ATOMIC_F32>(a, b, d, d2, args, s);
+  }
+  set_last_error("gemm: unknown epilogue %d", epi);
+  return -2;
+}
+
+static int pick_block_n(int N, int M, int k_splits) {
+  // largest tile that divides N; fall back to smaller tiles when the grid would not fill the SMs
+  const int cands[4] = {256, 192, 128, 64};
+  int best = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (N % cands[i]) continue;
+    if (!best) best = cands[i];
+    const long long tiles = static_cast<long long>((M + BLOCK_M - 1) / BLOCK_M) * (N / cands[i]) * k_splits;
+    if (tiles >= sm_count()) return cands[i];
+  }
+  // nothing fills the machine: use the smallest dividing tile for the most parallelism
+  for (int i = 3; i >= 0; --i)
+    if (N % cands[i] == 0) return cands[i];
+  return best;
+}
+
+}  // namespace b200ssl
+
+using namespace b200ssl;
+
+extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const void* B,
+                            long long ldb, int b_mn_major, void* D, long long ldd, void* D2,
+                            const float* bias, const void* aux, long long ldaux, int M, int N, int K,
+                            int epilogue, int split_k, int block_n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200SSL_CHECK(M > 0 && N > 0 && K > 0, -2, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  B200SSL_CHECK(N % 64 == 0, -2, "gemm: N=%d must be a multiple of 64", N);
+  B200SSL_CHECK(lda % 8 == 0 && ldb % 8 == 0, -2, "gemm: lda/ldb must be multiples of 8 elements");
+  B200SSL_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(D) & 15) == 0,
+                -2, "gemm: operands must be 16-byte aligned");
+  B200SSL_CHECK(epilogue >= 0 && epilogue <= 4, -2, "gemm: unknown epilogue %d", epilogue);
+  if (epilogue == EPI_BIAS_RES || epilogue == EPI_DGELU)
+    B200SSL_CHECK(aux != nullptr && ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0, -2,
+                  "gemm: epilogue %d needs a 16B-aligned aux operand", epilogue);
+  if (epilogue == EPI_BIAS_GELU) B200SSL_CHECK(D2 != nullptr, -2, "gemm: GELU epilogue needs D2");
+  if (epilogue == EPI_ATOMIC_F32) {
+    B200SSL_CHECK(ldd % 4 == 0, -2, "gemm: fp32 ldd must be a multiple of 4");
+  } else {
+    B200SSL_CHECK(ldd % 8 == 0, -2, "gemm: bf16 ldd must be a multiple of 8");
+    split_k = 1;
+  }
+  if (bias) B200SSL_CHECK((reinterpret_cast<uintptr_t>(bias) & 15) == 0, -2, "gemm: bias must be 16B aligned");
+
+  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  if (split_k < 1) split_k = 1;
+  if (split_k > k_blocks) split_k = k_blocks;
+  int kbps = (k_blocks + split_k - 1) / split_k;
+  split_k = (k_blocks + kbps - 1) / kbps;  // no empty splits
+
+  int bn = block_n;
+  if (bn == 0) bn = pick_block_n(N, M, split_k);
+  B200SSL_CHECK((bn == 64 || bn == 128 || bn == 192 || bn == 256) && N % bn == 0, -2,
+                "gemm: block_n=%d does not divide N=%d", bn, N);
+
+  GemmArgs args;
+  args.M = M; args.N = N; args.K = K;
+  args.a_mn = a_mn_major; args.b_mn = b_mn_major;
+  args.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  args.num_n_blocks = N / bn;
+  args.k_splits = split_k;
+  args.k_blocks_per_split = kbps;
+  args.k_blocks_total = k_blocks;
+  args.bias = bias;
+  args.aux = static_cast<const __nv_bfloat16*>(aux);
+  args.ldaux = ldaux;
+  args.out_f32 = static_cast<float*>(D);
+  args.ldd = ldd;
+
+  CUtensorMap tmA, tmB, tmD, tmD2;
+  {
+    // A: K-major -> dims (K, M), box (64, 128); MN-major -> dims (M, K), box (64, 64)
+    uint64_t dims[2], strides[2];
+    uint32_t box[2];
+    if (!a_mn_major) { dims[0] = K; dims[1] = M; box[0] = 64; box[1] = BLOCK_M; }
+    else             { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = 64; }
+    strides[0] = 2; strides[1] = static_cast<uint64_t>(lda) * 2;
+    if (int rc = make_tensor_map(&tmA, A, 2, 2, dims, strides, box, true)) return rc;
+    if (!b_mn_major) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = bn; }
+    else             { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = 64; }
+    strides[1] = static_cast<uint64_t>(ldb) * 2;
+    if (int rc = make_tensor_map(&tmB, B, 2, 2, dims, strides, box, true)) return rc;
+    if (epilogue != EPI_ATOMIC_F32) {
+      dims[0] = N; dims[1] = M; box[0] = 64; box[1] = BLOCK_M;
+      strides[1] = static_cast<uint64_t>(ldd) * 2;
+      if (int rc = make_tensor_map(&tmD, D, 2, 2, dims, strides, box, true)) return rc;
+      if (int rc = make_tensor_map(&tmD2, D2 ? D2 : D, 2, 2, dims, strides, box, true)) return rc;
+    } else {
+      tmD = tmA; tmD2 = tmA;  // unused
+    }
+  }
+
+  switch (bn) {
+    case 64: return dispatch_epi<64>(epilogue, tmA, tmB, tmD, tmD2, args, stream);
+    case 128: return dispatch_epi<128>(epilogue, tmA, tmB, tmD, tmD2, args, stream);
+    case 192: return dispatch_epi<192>(epilogue, tmA, tmB, tmD, tmD2, args, stream);
+    default: return dispatch_epi<256>(epilogue, tmA, tmB, tmD, tmD2, args, stream);
+  }
+}
