@@ -1,0 +1,242 @@
+// K2: LayerNorm forward / backward (+ residual-gradient add), HBM-bound.
+//
+// Replaces ATen layer_norm at every norm site of the reference encoder (Block.norm1/norm2
+// VT.pyc@L138,142,147,151; VisionTransformer.norm @L195,252; eps 1e-6 via the vit_* factories
+// @L278,285,292). bf16 activations, fp32 statistics, 128-bit accesses, LPR lanes per row with
+// CPL 16-byte chunks per lane (D = LPR * CPL * 8), warp-shuffle reductions inside the LPR group.
+#include "common.cuh"
+
+namespace b200ssl {
+
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int LPR, int CPL>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+              __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+              long long rows, float eps) {
+  constexpr int D = LPR * CPL * 8;
+  constexpr int RPW = 32 / LPR;  // rows per warp
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+
+  // per-lane slices of gamma / beta stay in registers across rows
+  float gw[CPL * 8], gb[CPL * 8];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    const int col = (c * LPR + sub) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      gw[c * 8 + e] = __ldg(w + col + e);
+      gb[c * 8 + e] = __ldg(b + col + e);
+    }
+  }
+  for (long long row = warp_global * RPW + lane / LPR; row < rows; row += nwarps * RPW) {
+    const uint4* px = reinterpret_cast<const uint4*>(x + row * D);
+    float v[CPL * 8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const uint4 u = __ldg(px + c * LPR + sub);
+      const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16x2(uw[e]);
+        v[c * 8 + 2 * e] = f.x;
+        v[c * 8 + 2 * e + 1] = f.y;
+        s += f.x + f.y;
+      }
+    }
+    const float mean = group_sum<LPR>(s) * (1.f / D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL * 8; ++i) {
+      const float d = v[i] - mean;
+      sq += d * d;
+    }
+    const float rstd = rsqrtf(group_sum<LPR>(sq) * (1.f / D) + eps);
+    uint4* py = reinterpret_cast<uint4*>(y + row * D);
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a0 = (v[c * 8 + 2 * e] - mean) * rstd * gw[c * 8 + 2 * e] + gb[c * 8 + 2 * e];
+        const float a1 = (v[c * 8 + 2 * e + 1] - mean) * rstd * gw[c * 8 + 2 * e + 1] + gb[c * 8 + 2 * e + 1];
+        o[e] = pack_bf16x2(a0, a1);
+      }
+      py[c * LPR + sub] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (sub == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) + dres, with g = dy * gamma;
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (fp32 atomics, one per column per CTA)
+template <int LPR, int CPL>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+              const float* __restrict__ w, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+              const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw,
+              float* __restrict__ db, long long rows) {
+  constexpr int D = LPR * CPL * 8;
+  constexpr int RPW = 32 / LPR;
+  __shared__ float s_dw[D];
+  __shared__ float s_db[D];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) { s_dw[i] = 0.f; s_db[i] = 0.f; }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+
+  float gw[CPL * 8], adw[CPL * 8], adb[CPL * 8];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    const int col = (c * LPR + sub) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      gw[c * 8 + e] = __ldg(w + col + e);
+      adw[c * 8 + e] = 0.f;
+      adb[c * 8 + e] = 0.f;
+    }
+  }
+  for (long long row = warp_global * RPW + lane / LPR; row < rows; row += nwarps * RPW) {
+    const uint4* px = reinterpret_cast<const uint4*>(x + row * D);
+    const uint4* pdy = reinterpret_cast<const uint4*>(dy + row * D);
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[CPL * 8], g[CPL * 8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const uint4 ux = __ldg(px + c * LPR + sub), ud = __ldg(pdy + c * LPR + sub);
+      const uint32_t xw[4] = {ux.x, ux.y, ux.z, ux.w}, dw4[4] = {ud.x, ud.y, ud.z, ud.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fx = unpack_bf16x2(xw[e]), fd = unpack_bf16x2(dw4[e]);
+        const int i = c * 8 + 2 * e;
+        xh[i] = (fx.x - mean) * rstd;
+        xh[i + 1] = (fx.y - mean) * rstd;
+        adw[i] += fd.x * xh[i];
+        adw[i + 1] += fd.y * xh[i + 1];
+        adb[i] += fd.x;
+        adb[i + 1] += fd.y;
+        g[i] = fd.x * gw[i];
+        g[i + 1] = fd.y * gw[i + 1];
+        s1 += g[i] + g[i + 1];
+        s2 += g[i] * xh[i] + g[i + 1] * xh[i + 1];
+      }
+    }
+    const float m1 = group_sum<LPR>(s1) * (1.f / D);
+    const float m2 = group_sum<LPR>(s2) * (1.f / D);
+    uint4* pdx = reinterpret_cast<uint4*>(dx + row * D);
+    const uint4* pr = dres ? reinterpret_cast<const uint4*>(dres + row * D) : nullptr;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      uint4 r4 = make_uint4(0, 0, 0, 0);
+      if (pr) r4 = __ldg(pr + c * LPR + sub);
+      const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = c * 8 + 2 * e;
+        const float2 fr = unpack_bf16x2(rw[e]);
+        const float a0 = rstd * (g[i] - m1 - xh[i] * m2) + fr.x;
+        const float a1 = rstd * (g[i + 1] - m1 - xh[i + 1] * m2) + fr.y;
+        o[e] = pack_bf16x2(a0, a1);
+      }
+      pdx[c * LPR + sub] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  // fold the per-thread column partials: smem atomics per CTA, then one global atomic per column
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    const int col = (c * LPR + sub) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&s_dw[col + e], adw[c * 8 + e]);
+      atomicAdd(&s_db[col + e], adb[c * 8 + e]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(dw + i, s_dw[i]);
+    atomicAdd(db + i, s_db[i]);
+  }
+}
+
+template <int LPR, int CPL>
+static int launch_ln_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd,
+                         long long rows, float eps, cudaStream_t s) {
+  constexpr int RPW = 32 / LPR;
+  const long long warps_needed = (rows + RPW - 1) / RPW;
+  long long blocks = (warps_needed + 7) / 8;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  ln_fwd_kernel<LPR, CPL><<<static_cast<int>(blocks), 256, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(x), w, b, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, eps);
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}
+template <int LPR, int CPL>
+static int launch_ln_bwd(const void* x, const void* dy, const float* w, const float* mean, const float* rstd,
+                         const void* dres, void* dx, float* dw, float* db, long long rows, cudaStream_t s) {
+  constexpr int RPW = 32 / LPR;
+  const long long warps_needed = (rows + RPW - 1) / RPW;
+  long long blocks = (warps_needed + 7) / 8;
+  const long long cap = static_cast<long long>(sm_count()) * 4;
+  if (blocks > cap) blocks = cap;
+  ln_bwd_kernel<LPR, CPL><<<static_cast<int>(blocks), 256, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), w, mean, rstd,
+      static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dw, db, rows);
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200ssl
+
+using namespace b200ssl;
+
+#define LN_DISPATCH(D, CALL)                                       \
+  switch (D) {                                                     \
+    case 192: return CALL(8, 3);                                   \
+    case 256: return CALL(32, 1);                                  \
+    case 384: return CALL(16, 3);                                  \
+    case 512: return CALL(32, 2);                                  \
+    case 768: return CALL(32, 3);                                  \
+    case 1024: return CALL(32, 4);                                 \
+    default:                                                       \
+      set_last_error("layernorm: width %d unsupported (192/256/384/512/768/1024)", D); \
+      return -2;                                                   \
+  }
+
+extern "C" int b200ssl_layernorm_fwd(const void* x, const float* w, const float* b, void* y, float* mean,
+                                     float* rstd, long long rows, int D, float eps, void* stream) {
+  B200SSL_CHECK(rows > 0, -2, "layernorm: no rows");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define CALL_FWD(L, C) launch_ln_fwd<L, C>(x, w, b, y, mean, rstd, rows, eps, s)
+  LN_DISPATCH(D, CALL_FWD)
+#undef CALL_FWD
+}
+
+// dw / db are ACCUMULATED into (fp32); the caller zeroes them when starting a fresh gradient.
+extern "C" int b200ssl_layernorm_bwd(const void* x, const void* dy, const float* w, const float* mean,
+                                     const float* rstd, const void* dres, void* dx, float* dw, float* db,
+                                     long long rows, int D, void* stream) {
+  B200SSL_CHECK(rows > 0, -2, "layernorm: no rows");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define CALL_BWD(L, C) launch_ln_bwd<L, C>(x, dy, w, mean, rstd, dres, dx, dw, db, rows, s)
+  LN_DISPATCH(D, CALL_BWD)
+#undef CALL_BWD
+}
