@@ -26,7 +26,7 @@ SIGNATURES = {
     "b200ssl_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "b200ssl_attention_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "b200ssl_patchify": [_P, _P, _I, _I, _I, _I, _I, _P],
-    "b200ssl_assemble_tokens": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "b200ssl_assemble_tokens": [_P, _P, _P, _P, _I, _I, _I, _P],
     "b200ssl_assemble_tokens_bwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "b200ssl_colsum": [_P, _L, _P, _L, _I, _I, _P],
     "b200ssl_cast_f32_to_bf16": [_P, _P, _L, _P],
@@ -35,10 +35,10 @@ SIGNATURES = {
     "b200ssl_weightnorm_fwd": [_P, _P, _P, _P, _L, _I, _P],
     "b200ssl_weightnorm_bwd": [_P, _P, _P, _P, _P, _P, _L, _I, _P],
     "b200ssl_dino_loss_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P],
-    "b200ssl_dino_loss_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P],
-    "b200ssl_center_update": [_P, _P, _I, _I, _F, _F, _P],
+    "b200ssl_dino_loss_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P],
+    "b200ssl_center_update": [_P, _P, _I, _L, _F, _P],
     "b200ssl_ema_multi_tensor": [_P, _I, _F, _P],
-    "b200ssl_adamw_multi_tensor": [_P, _I, _P, _F, _F, _F, _F, _F, _F, _F, _P],
+    "b200ssl_adamw_multi_tensor": [_P, _I, _P, _F, _F, _F, _F, _F, _F, _F, _F, _F, _P],
     "b200ssl_sumsq_multi_tensor": [_P, _I, _P, _P],
 }
 _RESTYPES = {"b200ssl_last_error": c_char_p}

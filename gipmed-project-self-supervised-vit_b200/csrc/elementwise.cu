@@ -1,0 +1,347 @@
+// Small HBM-bound kernels around the GEMMs: patch gathering, token assembly (+CLS, +pos),
+// column sums (bias gradients), fp32->bf16 weight casts, F.normalize and weight-norm rows.
+//
+// Reference sites: PatchEmbed.forward VT.pyc@L167-170 and prepare_tokens @L235-246 (patchify +
+// assemble_tokens), DINOHead.forward @L326-330 (l2norm = F.normalize(dim=-1,p=2), weight-normed
+// last layer @L315-318).
+#include "common.cuh"
+
+namespace b200ssl {
+
+// img [B,C,H,W] bf16 -> A [B*(H/P)*(W/P), C*P*P] bf16, K index = (c, i, j) as in Conv2d weight.flatten(1).
+// One thread moves one 16-byte piece (8 pixels of one patch row).
+__global__ void patchify_kernel(const __nv_bfloat16* __restrict__ img, __nv_bfloat16* __restrict__ out, int B,
+                                int C, int H, int W, int P) {
+  const int pw = W / P, ph = H / P;
+  const int pieces_per_prow = P / 8;
+  const long long total = static_cast<long long>(B) * C * H * (W / 8);
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // idx enumerates the image in memory order so global reads are fully coalesced
+    const int x8 = static_cast<int>(idx % (W / 8));
+    long long r = idx / (W / 8);
+    const int y = static_cast<int>(r % H);
+    r /= H;
+    const int c = static_cast<int>(r % C);
+    const int b = static_cast<int>(r / C);
+    const int px = (x8 * 8) / P, j = (x8 * 8) % P;
+    const int py = y / P, i = y % P;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(img) + idx);
+    const long long row = (static_cast<long long>(b) * ph + py) * pw + px;
+    const long long col = (static_cast<long long>(c) * P + i) * P + j;
+    *reinterpret_cast<uint4*>(out + row * (static_cast<long long>(C) * P * P) + col) = v;
+    (void)pieces_per_prow;
+  }
+}
+
+// x[b,0,:] = cls + pos[0] ; x[b,1+p,:] = y[b*Np+p,:] + pos[1+p]     (pos, cls fp32; x, y bf16)
+__global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ cls,
+                                       const float* __restrict__ pos, __nv_bfloat16* __restrict__ x, int B, int Np,
+                                       int D) {
+  const int N = Np + 1;
+  const int d8 = D / 8;
+  const long long total = static_cast<long long>(B) * N * d8;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(idx % d8);
+    const long long rn = idx / d8;
+    const int n = static_cast<int>(rn % N);
+    const long long b = rn / N;
+    float v[8];
+    if (n == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = __ldg(cls + c8 * 8 + e);
+    } else {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(y + (b * Np + n - 1) * D) + c8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16x2(w[e]);
+        v[2 * e] = f.x;
+        v[2 * e + 1] = f.y;
+      }
+    }
+    const float* pp = pos + static_cast<long long>(n) * D + c8 * 8;
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2(v[2 * e] + __ldg(pp + 2 * e), v[2 * e + 1] + __ldg(pp + 2 * e + 1));
+    reinterpret_cast<uint4*>(x + rn * D)[c8] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// dy[b*Np+p,:] = dx[b,1+p,:] ; dpos[n,:] += sum_b dx[b,n,:]   (block = (n, batch segment))
+__global__ void assemble_tokens_bwd_kernel(const __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dy,
+                                           float* __restrict__ dpos, int B, int Np, int D, int bseg) {
+  const int N = Np + 1;
+  const int n = blockIdx.x;
+  const int b_lo = blockIdx.y * bseg, b_hi = min(B, b_lo + bseg);
+  for (int c8 = threadIdx.x; c8 < D / 8; c8 += blockDim.x) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = b_lo; b < b_hi; ++b) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(dx + (static_cast<long long>(b) * N + n) * D) + c8);
+      if (n > 0) reinterpret_cast<uint4*>(dy + (static_cast<long long>(b) * Np + n - 1) * D)[c8] = u;
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16x2(w[e]);
+        acc[2 * e] += f.x;
+        acc[2 * e + 1] += f.y;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(dpos + static_cast<long long>(n) * D + c8 * 8 + e, acc[e]);
+  }
+}
+
+// out[c] (+)= sum_r x[r, c]   (bf16 in, fp32 atomics out); block = 32 column-chunks x 8 row lanes
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, float* __restrict__ out, long long rows, int ncols,
+              int rows_per_block) {
+  const int c8 = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  __shared__ float red[8][32][8];
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  if (c8 * 8 < ncols) {
+    for (long long r = r0 + rl; r < r1; r += 8) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * ldx) + c8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16x2(w[e]);
+        acc[2 * e] += f.x;
+        acc[2 * e + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[rl][threadIdx.x & 31][e] = acc[e];
+  __syncthreads();
+  if (rl == 0 && c8 * 8 < ncols) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x][e];
+      atomicAdd(out + c8 * 8 + e, s);
+    }
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long n4 = n / 4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+  for (long long i = n4 * 4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
+// y = x / max(||x||_2, eps) per row (F.normalize, eps 1e-12). One warp per row.
+__global__ void l2norm_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                  float* __restrict__ norm_out, long long rows, int D, float eps) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __nv_bfloat16* px = x + row * D;
+  float ss = 0.f;
+  for (int i = lane * 2; i < D; i += 64) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(px + i));
+    ss += f.x * f.x + f.y * f.y;
+  }
+  ss = warp_sum(ss);
+  const float nrm = sqrtf(ss);
+  const float inv = 1.f / fmaxf(nrm, eps);
+  for (int i = lane * 2; i < D; i += 64) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(px + i));
+    *reinterpret_cast<__nv_bfloat162*>(y + row * D + i) = __floats2bfloat162_rn(f.x * inv, f.y * inv);
+  }
+  if (lane == 0) norm_out[row] = nrm;
+}
+
+// dx = (dy - y * <y, dy>) / max(norm, eps)
+__global__ void l2norm_bwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dy,
+                                  const float* __restrict__ norm, __nv_bfloat16* __restrict__ dx, long long rows,
+                                  int D, float eps) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float dot = 0.f;
+  for (int i = lane * 2; i < D; i += 64) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(y + row * D + i));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dy + row * D + i));
+    dot += a.x * b.x + a.y * b.y;
+  }
+  dot = warp_sum(dot);
+  const float inv = 1.f / fmaxf(norm[row], eps);
+  for (int i = lane * 2; i < D; i += 64) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(y + row * D + i));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dy + row * D + i));
+    *reinterpret_cast<__nv_bfloat162*>(dx + row * D + i) =
+        __floats2bfloat162_rn((b.x - a.x * dot) * inv, (b.y - a.y * dot) * inv);
+  }
+}
+
+// w[r,:] = g[r] * v[r,:] / ||v[r,:]||  (fp32 v, g -> bf16 w); g == nullptr means g = 1
+__global__ void weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                      __nv_bfloat16* __restrict__ w, float* __restrict__ norm_out, long long rows,
+                                      int D) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* pv = v + row * D;
+  float ss = 0.f;
+  for (int i = lane * 4; i < D; i += 128) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(pv + i));
+    ss += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
+  }
+  ss = warp_sum(ss);
+  const float nrm = sqrtf(ss);
+  const float s = (g ? g[row] : 1.f) / nrm;
+  for (int i = lane * 4; i < D; i += 128) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(pv + i));
+    *reinterpret_cast<uint2*>(w + row * D + i) = make_uint2(pack_bf16x2(f.x * s, f.y * s), pack_bf16x2(f.z * s, f.w * s));
+  }
+  if (lane == 0) norm_out[row] = nrm;
+}
+
+// dg[r] = <dw, v>/||v|| ; dv = g/||v|| * dw - g*<dw,v>/||v||^3 * v
+__global__ void weightnorm_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                      const float* __restrict__ norm, const float* __restrict__ dw,
+                                      float* __restrict__ dv, float* __restrict__ dg, long long rows, int D) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float dot = 0.f;
+  for (int i = lane * 4; i < D; i += 128) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(v + row * D + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(dw + row * D + i));
+    dot += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+  }
+  dot = warp_sum(dot);
+  const float nrm = norm[row];
+  const float gg = g ? g[row] : 1.f;
+  const float c1 = gg / nrm, c2 = gg * dot / (nrm * nrm * nrm);
+  for (int i = lane * 4; i < D; i += 128) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(v + row * D + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(dw + row * D + i));
+    *reinterpret_cast<float4*>(dv + row * D + i) =
+        make_float4(c1 * b.x - c2 * a.x, c1 * b.y - c2 * a.y, c1 * b.z - c2 * a.z, c1 * b.w - c2 * a.w);
+  }
+  if (dg && lane == 0) dg[row] = dot / nrm;
+}
+
+static int grid_for(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace b200ssl
+
+using namespace b200ssl;
+
+extern "C" int b200ssl_patchify(const void* img, void* out, int B, int C, int H, int W, int P, void* stream) {
+  B200SSL_CHECK(P % 8 == 0 && H % P == 0 && W % P == 0, -2, "patchify: H=%d W=%d must divide by P=%d (P %% 8 == 0)", H, W, P);
+  const long long total = static_cast<long long>(B) * C * H * (W / 8);
+  patchify_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(img), static_cast<__nv_bfloat16*>(out), B, C, H, W, P);
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200ssl_assemble_tokens(const void* y, const float* cls, const float* pos, void* x, int B, int Np,
+                                       int D, void* stream) {
+  B200SSL_CHECK(D % 8 == 0, -2, "assemble_tokens: D=%d must be a multiple of 8", D);
+  const long long total = static_cast<long long>(B) * (Np + 1) * (D / 8);
+  assemble_tokens_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(y), cls, pos, static_cast<__nv_bfloat16*>(x), B, Np, D);
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// dpos [Np+1, D] fp32 is zeroed here; dcls [D] receives dpos[0] (x[b,0] = cls + pos[0]).
+extern "C" int b200ssl_assemble_tokens_bwd(const void* dx, void* dy, float* dpos, float* dcls, int B, int Np, int D,
+                                           void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  B200SSL_CHECK(D % 8 == 0, -2, "assemble_tokens_bwd: D=%d must be a multiple of 8", D);
+  B200SSL_CUDA(cudaMemsetAsync(dpos, 0, sizeof(float) * static_cast<size_t>(Np + 1) * D, s));
+  const int bseg = 32;
+  dim3 grid(Np + 1, (B + bseg - 1) / bseg);
+  assemble_tokens_bwd_kernel<<<grid, 64, 0, s>>>(static_cast<const __nv_bfloat16*>(dx),
+                                                  static_cast<__nv_bfloat16*>(dy), dpos, B, Np, D, bseg);
+  B200SSL_CUDA(cudaGetLastError());
+  if (dcls) B200SSL_CUDA(cudaMemcpyAsync(dcls, dpos, sizeof(float) * D, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+extern "C" int b200ssl_colsum(const void* x, long long ldx, float* out, long long rows, int ncols, int accumulate,
+                              void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  B200SSL_CHECK(ncols % 8 == 0 && ldx % 8 == 0, -2, "colsum: ncols/ldx must be multiples of 8");
+  if (!accumulate) B200SSL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * ncols, s));
+  const int col_blocks = (ncols / 8 + 31) / 32;
+  int row_blocks = (sm_count() * 4 + col_blocks - 1) / col_blocks;
+  long long rpb = (rows + row_blocks - 1) / row_blocks;
+  if (rpb < 64) rpb = 64;
+  row_blocks = static_cast<int>((rows + rpb - 1) / rpb);
+  dim3 grid(col_blocks, row_blocks);
+  colsum_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ldx, out, rows, ncols,
+                                     static_cast<int>(rpb));
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200ssl_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+  B200SSL_CHECK((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, -2,
+                "cast: pointers must be 16B/8B aligned");
+  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), n);
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200ssl_l2norm_fwd(const void* x, void* y, float* norm, long long rows, int D, float eps,
+                                  void* stream) {
+  B200SSL_CHECK(D % 2 == 0, -2, "l2norm: D must be even");
+  const long long threads = rows * 32;
+  l2norm_fwd_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), norm, rows, D, eps);
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200ssl_l2norm_bwd(const void* y, const void* dy, const float* norm, void* dx, long long rows, int D,
+                                  float eps, void* stream) {
+  const long long threads = rows * 32;
+  l2norm_bwd_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(dy), norm,
+      static_cast<__nv_bfloat16*>(dx), rows, D, eps);
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200ssl_weightnorm_fwd(const float* v, const float* g, void* w, float* norm, long long rows, int D,
+                                      void* stream) {
+  B200SSL_CHECK(D % 4 == 0, -2, "weightnorm: D must be a multiple of 4");
+  const long long threads = rows * 32;
+  weightnorm_fwd_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      v, g, static_cast<__nv_bfloat16*>(w), norm, rows, D);
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200ssl_weightnorm_bwd(const float* v, const float* g, const float* norm, const float* dw, float* dv,
+                                      float* dg, long long rows, int D, void* stream) {
+  B200SSL_CHECK(D % 4 == 0, -2, "weightnorm: D must be a multiple of 4");
+  const long long threads = rows * 32;
+  weightnorm_bwd_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      v, g, norm, dw, dv, dg, rows, D);
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -396,12 +396,19 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
   if (bias) B200SSL_CHECK((reinterpret_cast<uintptr_t>(bias) & 15) == 0, -2, "gemm: bias must be 16B aligned");
 
   const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  int bn = block_n;
+  if (epilogue == EPI_ATOMIC_F32 && split_k <= 0) {
+    // auto split-K: the largest tile that divides N, then as many K splits as fill one wave of SMs
+    if (bn == 0) bn = N % 256 == 0 ? 256 : N % 192 == 0 ? 192 : N % 128 == 0 ? 128 : 64;
+    const int tiles_mn = ((M + BLOCK_M - 1) / BLOCK_M) * (N / bn);
+    split_k = sm_count() / (tiles_mn > 0 ? tiles_mn : 1);
+    if (split_k > k_blocks / 2) split_k = k_blocks / 2;
+  }
   if (split_k < 1) split_k = 1;
   if (split_k > k_blocks) split_k = k_blocks;
   int kbps = (k_blocks + split_k - 1) / split_k;
   split_k = (k_blocks + kbps - 1) / kbps;  // no empty splits
 
-  int bn = block_n;
   if (bn == 0) bn = pick_block_n(N, M, split_k);
   B200SSL_CHECK((bn == 64 || bn == 128 || bn == 192 || bn == 256) && N % bn == 0, -2,
                 "gemm: block_n=%d does not divide N=%d", bn, N);

@@ -1,0 +1,399 @@
+"""DINO-side pieces of the hot path behind the reference's call slots (train.py:1045 ``model(input)``,
+:1053 ``loss_fn(output, target)``, :1063-1078 backward/clip/step, :1081 ``model_ema.update(model)``,
+:634 DDP): fused loss with running centre, multi-crop wrapper, teacher EMA, fused AdamW, the
+bucketed gradient all-reduce and the step that strings them together.
+"""
+from __future__ import annotations
+
+import copy
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import ops
+
+
+# ------------------------------------------------------------------------------------------------
+# loss
+# ------------------------------------------------------------------------------------------------
+class DINOLoss(nn.Module):
+    """``forward(student_output, teacher_output, epoch)`` — rows crop-major ([ncrops*B, K] / [2*B, K]).
+
+    One fused forward kernel (single pass over the logits, online softmax statistics) and one fused
+    backward kernel; the centre update is a column-sum kernel, one all-reduce of [K] fp32 when a
+    process group is initialised, and an in-place EMA kernel. Two-positional-argument compatible with
+    the reference's ``loss_fn(output, target)`` call."""
+
+    def __init__(self, out_dim, ncrops, warmup_teacher_temp, teacher_temp, warmup_teacher_temp_epochs, nepochs,
+                 student_temp=0.1, center_momentum=0.9):
+        super().__init__()
+        self.student_temp = student_temp
+        self.center_momentum = center_momentum
+        self.ncrops = ncrops
+        self.register_buffer("center", torch.zeros(1, out_dim))
+        self.teacher_temp_schedule = np.concatenate((
+            np.linspace(warmup_teacher_temp, teacher_temp, warmup_teacher_temp_epochs),
+            np.ones(nepochs - warmup_teacher_temp_epochs) * teacher_temp))
+        self._pending = None  # (work handle, local column sum, rows) of an in-flight centre all-reduce
+
+    def forward(self, student_output, teacher_output, epoch=0):
+        ops.require_cuda(student_output, "DINOLoss")
+        self.finish_center_update()  # the centre this step reads must include the previous step's update
+        temp = float(self.teacher_temp_schedule[epoch])
+        s = student_output if student_output.dtype == torch.bfloat16 else student_output.to(torch.bfloat16)
+        t = teacher_output.detach()
+        t = t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16)
+        center = self.center.view(-1)
+        if center.dtype != torch.float32:
+            raise RuntimeError("DINOLoss.center must stay fp32")
+        loss = ops.DinoLossFn.apply(s.contiguous(), t.contiguous(), center, self.ncrops, self.student_temp, temp)
+        self.update_center(t)
+        return loss
+
+    @torch.no_grad()
+    def update_center(self, teacher_output):
+        """center <- m*center + (1-m)*mean_rows(teacher_output) over all ranks. The all-reduce is
+        launched asynchronously and only waited for when the centre is next read."""
+        t = teacher_output if teacher_output.dtype == torch.bfloat16 else teacher_output.to(torch.bfloat16)
+        batch_sum = ops.teacher_colsum(t.contiguous())
+        rows, world, work = t.shape[0], 1, None
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size()
+            if world > 1:
+                work = dist.all_reduce(batch_sum, async_op=True)
+        self._pending = (work, batch_sum, rows * world)
+        if work is None:
+            self.finish_center_update()
+
+    @torch.no_grad()
+    def finish_center_update(self):
+        if self._pending is None:
+            return
+        work, batch_sum, total_rows = self._pending
+        self._pending = None
+        if work is not None:
+            work.wait()
+        ops.center_update(self.center.view(-1), batch_sum, total_rows, self.center_momentum)
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-crop wrapper
+# ------------------------------------------------------------------------------------------------
+class MultiCropWrapper(nn.Module):
+    """Runs the backbone once per run of equal-resolution crops and the head once on all rows."""
+
+    def __init__(self, backbone, head):
+        super().__init__()
+        backbone.fc, backbone.head = nn.Identity(), nn.Identity()
+        self.backbone = backbone
+        self.head = head
+
+    def forward(self, x):
+        if not isinstance(x, (list, tuple)):
+            x = [x]
+        sizes = [int(inp.shape[-1]) for inp in x]
+        bounds = [i + 1 for i in range(len(sizes)) if i + 1 == len(sizes) or sizes[i + 1] != sizes[i]]
+        start, outs = 0, []
+        for end in bounds:
+            group = x[start] if end - start == 1 else torch.cat(list(x[start:end]))
+            out = self.backbone(group)
+            if isinstance(out, tuple):
+                out = out[0]
+            outs.append(out)
+            start = end
+        feats = outs[0] if len(outs) == 1 else torch.cat(outs)
+        return self.head(feats)
+
+
+def cosine_momentum(it: int, total_iters: int, base: float = 0.996, final: float = 1.0) -> float:
+    return final - (final - base) * (math.cos(math.pi * it / max(total_iters, 1)) + 1) / 2
+
+
+# ------------------------------------------------------------------------------------------------
+# chunk tables for the multi-tensor kernels
+# ------------------------------------------------------------------------------------------------
+_CHUNK = 65536
+
+
+def _chunk_rows(tensors_per_row, numels):
+    """int64 table: one row per <=_CHUNK elements; columns = per-tensor byte addresses + count (+extras)."""
+    rows = []
+    for tens, n in zip(tensors_per_row, numels):
+        for off in range(0, n, _CHUNK):
+            cnt = min(_CHUNK, n - off)
+            rows.append([(t.data_ptr() + off * t.element_size()) if isinstance(t, torch.Tensor) else t for t in tens]
+                        + [cnt])
+    return rows
+
+
+class ModelEma(nn.Module):
+    """Teacher as an EMA of the student with timm's ``ModelEmaV2`` call convention (train.py:619-620,
+    :948, :1081): ``.module`` is the averaged copy, ``update(model)`` folds every floating-point
+    state-dict tensor with ONE multi-tensor kernel launch. ``momentum`` overrides ``decay`` per step."""
+
+    def __init__(self, model, decay=0.9998, device=None):
+        super().__init__()
+        self.module = copy.deepcopy(model)
+        self.module.eval()
+        for p in self.module.parameters():
+            p.requires_grad_(False)
+        self.decay = decay
+        self.device = device
+        if device is not None:
+            self.module.to(device=device)
+        self._table = None
+        self._table_key = None
+
+    def _build(self, model):
+        pairs, others = [], []
+        for e, s in zip(self.module.state_dict().values(), model.state_dict().values()):
+            if e.dtype == torch.float32 and s.dtype == torch.float32 and e.is_contiguous() and s.is_contiguous():
+                pairs.append((e, s))
+            else:
+                others.append((e, s))
+        key = tuple((e.data_ptr(), s.data_ptr(), e.numel()) for e, s in pairs)
+        if key != self._table_key:
+            rows = []
+            for e, s in pairs:
+                for off in range(0, e.numel(), _CHUNK):
+                    rows.append([e.data_ptr() + 4 * off, s.data_ptr() + 4 * off, min(_CHUNK, e.numel() - off)])
+            self._table = torch.tensor(rows, dtype=torch.int64).to(pairs[0][0].device) if rows else None
+            self._table_key = key
+            self._pairs, self._others = pairs, others
+        return self._table
+
+    @torch.no_grad()
+    def update(self, model, momentum=None):
+        m = self.decay if momentum is None else momentum
+        model = getattr(model, "module", model) if isinstance(model, GradBucketDataParallel) else model
+        table = self._build(model)
+        if table is not None:
+            ops.require_cuda(table, "ModelEma")
+            ops._call("b200ssl_ema_multi_tensor", table.data_ptr(), table.shape[0], float(m), ops._stream())
+        for e, s in self._others:  # integer buffers etc.: plain copy like timm
+            if e.dtype.is_floating_point:
+                e.mul_(m).add_(s.to(e.dtype), alpha=1.0 - m)
+            else:
+                e.copy_(s)
+        for p in self.module.parameters():
+            ops.shadows.invalidate(p)
+
+
+# ------------------------------------------------------------------------------------------------
+# optimiser
+# ------------------------------------------------------------------------------------------------
+class FusedAdamW(torch.optim.Optimizer):
+    """AdamW + global-norm gradient clipping in two launches (sum of squares, fused update) over a
+    device-resident chunk table; also refreshes the bf16 weight shadows the GEMMs read. Follows
+    ``torch.optim.AdamW`` update rules; ``step(max_grad_norm=...)`` folds in ``clip_grad_norm_``."""
+
+    def __init__(self, params, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.04):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._tables = {}
+        self._gnorm = None
+        self.last_grad_norm_sq = None
+
+    def _table(self, gi, group):
+        params = [p for p in group["params"] if p.grad is not None]
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params)
+        ent = self._tables.get(gi)
+        if ent is not None and ent["key"] == key:
+            return ent
+        rows, grows = [], []
+        for p in params:
+            if p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
+                raise RuntimeError("FusedAdamW needs contiguous fp32 parameters and gradients")
+            st = self.state[p]
+            if "exp_avg" not in st:
+                st["exp_avg"] = torch.zeros_like(p)
+                st["exp_avg_sq"] = torch.zeros_like(p)
+            sh = ops.shadows.shadow_for(p)
+            n = p.numel()
+            for off in range(0, n, _CHUNK):
+                cnt = min(_CHUNK, n - off)
+                rows.append([p.data_ptr() + 4 * off, p.grad.data_ptr() + 4 * off, st["exp_avg"].data_ptr() + 4 * off,
+                             st["exp_avg_sq"].data_ptr() + 4 * off, cnt, 1 if group["weight_decay"] > 0 else 0, 0,
+                             sh.data_ptr() + 2 * off])
+                grows.append([p.grad.data_ptr() + 4 * off, cnt])
+        dev = params[0].device
+        ent = {"key": key, "params": params, "table": torch.tensor(rows, dtype=torch.int64).to(dev),
+               "gtable": torch.tensor(grows, dtype=torch.int64).to(dev)}
+        self._tables[gi] = ent
+        return ent
+
+    @torch.no_grad()
+    def step(self, closure=None, max_grad_norm: float = 0.0):
+        ents = []
+        for gi, group in enumerate(self.param_groups):
+            if any(p.grad is not None for p in group["params"]):
+                ents.append((group, self._table(gi, group)))
+        if not ents:
+            return None
+        dev = ents[0][1]["table"].device
+        gnorm_ptr = None
+        if max_grad_norm and max_grad_norm > 0:
+            if self._gnorm is None or self._gnorm.device != dev:
+                self._gnorm = torch.zeros(len(self.param_groups) + 1, dtype=torch.float32, device=dev)
+            parts = self._gnorm[1:1 + len(ents)]
+            for i, (_, ent) in enumerate(ents):
+                ops._call("b200ssl_sumsq_multi_tensor", ent["gtable"].data_ptr(), ent["gtable"].shape[0],
+                          parts[i:i + 1].data_ptr(), ops._stream(), launches=2)
+            if len(ents) == 1:
+                total = parts[0:1]
+            else:
+                total = self._gnorm[0:1]
+                torch.sum(parts, dim=0, keepdim=True, out=total)
+            self.last_grad_norm_sq = total
+            gnorm_ptr = total.data_ptr()
+        for group, ent in ents:
+            group["step"] = group.get("step", 0) + 1
+            t = group["step"]
+            b1, b2 = group["betas"]
+            ops._call("b200ssl_adamw_multi_tensor", ent["table"].data_ptr(), ent["table"].shape[0], gnorm_ptr,
+                      float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                      float(max_grad_norm or 0.0), 1.0 - b1 ** t, 1.0 - b2 ** t, 0.0, ops._stream())
+            for p in ent["params"]:
+                ops.shadows.mark_fresh(p)
+        return None
+
+
+def param_groups_wd(model, weight_decay):
+    """DINO's grouping: no weight decay on biases and 1-D (norm) parameters."""
+    decay, no_decay = [], []
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        (no_decay if name.endswith(".bias") or p.ndim == 1 else decay).append(p)
+    return [{"params": decay, "weight_decay": weight_decay}, {"params": no_decay, "weight_decay": 0.0}]
+
+
+# ------------------------------------------------------------------------------------------------
+# data parallel
+# ------------------------------------------------------------------------------------------------
+class GradBucketDataParallel(nn.Module):
+    """Data-parallel wrapper (reference: ``NativeDDP(model, device_ids=[device])`` train.py:634).
+
+    Gradients live as views into flat fp32 buckets (reverse parameter order, ``bucket_mb`` each). A
+    post-accumulate hook per parameter counts arrivals; when every parameter of a bucket has received
+    all its contributions for this backward (the backbone is used once per resolution group), the
+    bucket is all-reduced (AVG) asynchronously on NCCL's stream, overlapping the rest of backward.
+    ``finish()`` (called by ``dino_step`` before the optimiser) waits for the outstanding handles.
+    The first backward runs without overlap to learn the per-parameter contribution counts."""
+
+    def __init__(self, module, bucket_mb: float = 25.0, process_group=None):
+        super().__init__()
+        self.module = module
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        params = [p for p in module.parameters() if p.requires_grad]
+        self._params = params
+        cap = int(bucket_mb * 1024 * 1024 / 4)
+        self.buckets, cur, cur_n = [], [], 0
+        for p in reversed(params):
+            if cur and cur_n + p.numel() > cap:
+                self.buckets.append(cur)
+                cur, cur_n = [], 0
+            cur.append(p)
+            cur_n += p.numel()
+        if cur:
+            self.buckets.append(cur)
+        self._flat, self._bucket_of = [], {}
+        for bi, bucket in enumerate(self.buckets):
+            n = sum((p.numel() + 3) // 4 * 4 for p in bucket)
+            flat = torch.zeros(n, dtype=torch.float32, device=bucket[0].device)
+            off = 0
+            for p in bucket:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += (p.numel() + 3) // 4 * 4
+                self._bucket_of[id(p)] = bi
+            self._flat.append(flat)
+        self._expected = None          # id(p) -> hook firings per backward (learned on the first step)
+        self._seen = {}
+        self._pending = [0] * len(self.buckets)
+        self._handles = []
+        self._launched = [False] * len(self.buckets)
+        if self.world > 1:
+            for p in params:  # replicas must start identical (DDP broadcasts rank 0's state)
+                dist.broadcast(p.data, src=0, group=self.pg)
+            for b in module.buffers():
+                dist.broadcast(b.data, src=0, group=self.pg)
+        for p in params:
+            p.register_post_accumulate_grad_hook(self._hook)
+        self._arm()
+
+    def _arm(self):
+        self._seen = {}
+        self._launched = [False] * len(self.buckets)
+        if self._expected is not None:
+            self._pending = [sum(self._expected.get(id(p), 1) for p in b) for b in self.buckets]
+
+    def _hook(self, p):
+        self._seen[id(p)] = self._seen.get(id(p), 0) + 1
+        if self._expected is None or self.world == 1:
+            return
+        bi = self._bucket_of[id(p)]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0 and not self._launched[bi]:
+            self._launch(bi)
+
+    def _launch(self, bi):
+        self._launched[bi] = True
+        self._handles.append(dist.all_reduce(self._flat[bi], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+
+    def zero_grad(self, set_to_none: bool = False):
+        """Zero the flat buckets (gradients stay views into them)."""
+        for flat, bucket in zip(self._flat, self.buckets):
+            flat.zero_()
+            off = 0
+            for p in bucket:
+                if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + 4 * off:
+                    p.grad = flat[off:off + p.numel()].view_as(p)
+                off += (p.numel() + 3) // 4 * 4
+
+    def finish(self):
+        """Wait for the bucket all-reduces of this backward; re-arm the counters for the next one."""
+        if self.world > 1:
+            for bi in range(len(self.buckets)):
+                if not self._launched[bi]:
+                    self._launch(bi)
+            for h in self._handles:
+                h.wait()
+        self._handles = []
+        if self._expected is None:
+            self._expected = dict(self._seen)
+        self._arm()
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+
+# ------------------------------------------------------------------------------------------------
+# the step
+# ------------------------------------------------------------------------------------------------
+def dino_step(student, teacher_ema, loss_fn, optimizer, crops, epoch=0, momentum=0.996, clip_grad=3.0):
+    """One optimisation step: teacher forward on the 2 global crops, student forward on
+    all crops, fused loss (+ centre update), backward (bucketed all-reduce overlapped when ``student`` is
+    a ``GradBucketDataParallel``), clip + AdamW, teacher EMA. Returns (loss, student_out, teacher_out)."""
+    with torch.no_grad():
+        teacher_out = teacher_ema.module(list(crops[:2]))
+    student_out = student(list(crops))
+    loss = loss_fn(student_out, teacher_out, epoch)
+    ddp = student if isinstance(student, GradBucketDataParallel) else None
+    if ddp is not None:
+        ddp.zero_grad()
+    else:
+        optimizer.zero_grad(set_to_none=False)  # keep .grad storage stable: the fused optimiser caches its table
+    loss.backward()
+    if ddp is not None:
+        ddp.finish()
+    if isinstance(optimizer, FusedAdamW):
+        optimizer.step(max_grad_norm=clip_grad or 0.0)
+    else:
+        if clip_grad:
+            torch.nn.utils.clip_grad_norm_([p for p in student.parameters() if p.requires_grad], clip_grad)
+        optimizer.step()
+    teacher_ema.update(ddp.module if ddp is not None else student, momentum=momentum)
+    return loss.detach(), student_out.detach(), teacher_out.detach()

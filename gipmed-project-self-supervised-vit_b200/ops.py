@@ -1,0 +1,492 @@
+"""Thin host layer over the C-ABI kernels: raw-pointer wrappers and the autograd Functions the
+drop-in modules are built from.
+
+Conventions: activations are bf16 row-major 2-D ``[rows, features]`` (rows = B*N tokens); parameters
+stay fp32 ``nn.Parameter`` (state-dict compatible with the reference) and are shadowed in bf16 by
+``bf16_of`` for the tensor-core operands; gradients of parameters are produced in fp32.
+Nothing here computes on the CPU or through PyTorch math kernels: every op is a launch of a kernel
+from ``libb200ssl.so`` on the current CUDA stream (graph-capturable, no host syncs).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_ATOMIC_F32 = 0, 1, 2, 3, 4
+
+_BF16 = torch.bfloat16
+_counters = {"launches": 0}
+
+
+def launch_count() -> int:
+    """Number of b200ssl kernel launches issued by this process (bench.py reports the delta)."""
+    return _counters["launches"]
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _call(name, *args, launches=1):
+    rc = getattr(_lib.lib(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (code {rc}): {_lib.last_error()}")
+    _counters["launches"] += launches
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: b200ssl ops run on sm_100a CUDA tensors only (got {t.device}); "
+                           "there is no CPU fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 shadows of fp32 parameters
+# ------------------------------------------------------------------------------------------------
+class _ShadowCache:
+    """bf16 copies of fp32 parameters keyed by the parameter object; refreshed when the parameter's
+    version counter or storage changes. Writers that update parameters through raw pointers (the fused
+    optimizer / EMA kernels) refresh the shadow themselves and call ``mark_fresh``."""
+
+    def __init__(self):
+        self._d = {}
+
+    def _entry(self, p):
+        key = id(p)
+        ent = self._d.get(key)
+        if ent is None or ent["t"].shape != p.shape or ent["t"].device != p.device or ent["ref"]() is not p:
+            import weakref
+            ent = {"t": torch.empty(p.shape, dtype=_BF16, device=p.device), "ver": -1, "ptr": 0,
+                   "ref": weakref.ref(p)}
+            self._d[key] = ent
+        return ent
+
+    def get(self, p: torch.Tensor) -> torch.Tensor:
+        if p.dtype == _BF16:
+            return p.detach()
+        ent = self._entry(p)
+        if ent["ver"] != p._version or ent["ptr"] != p.data_ptr():
+            src = p.detach()
+            if src.dtype != torch.float32 or not src.is_contiguous():
+                src = src.float().contiguous()
+            cast_f32_to_bf16(src, ent["t"])
+            ent["ver"], ent["ptr"] = p._version, p.data_ptr()
+        return ent["t"]
+
+    def shadow_for(self, p: torch.Tensor) -> torch.Tensor:
+        """Storage the raw-pointer writers fill; call mark_fresh(p) after the write is enqueued."""
+        return self._entry(p)["t"]
+
+    def mark_fresh(self, p: torch.Tensor):
+        ent = self._entry(p)
+        ent["ver"], ent["ptr"] = p._version, p.data_ptr()
+
+    def invalidate(self, p: torch.Tensor):
+        ent = self._d.get(id(p))
+        if ent is not None:
+            ent["ver"] = -1
+
+
+shadows = _ShadowCache()
+
+
+def bf16_of(p: torch.Tensor) -> torch.Tensor:
+    return shadows.get(p)
+
+
+def to_bf16_2d(x: torch.Tensor) -> torch.Tensor:
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.dtype != _BF16:
+        x2 = x2.to(_BF16)
+    return x2.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# raw wrappers
+# ------------------------------------------------------------------------------------------------
+def cast_f32_to_bf16(src: torch.Tensor, dst: torch.Tensor):
+    _call("b200ssl_cast_f32_to_bf16", src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
+
+
+def gemm(A, B, D, M, N, K, *, a_mn=False, b_mn=False, epi=EPI_BIAS, D2=None, bias=None, aux=None, split_k=1,
+         block_n=0):
+    _call("b200ssl_gemm", A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn),
+          D.data_ptr(), D.stride(0), _ptr(D2), _ptr(bias), _ptr(aux), aux.stride(0) if aux is not None else 0,
+          M, N, K, epi, split_k, block_n, _stream())
+
+
+def linear_fwd(x, w16, bias=None, residual=None, gelu=False):
+    """y = x @ w16^T (+bias) (+residual); with gelu=True returns (pre_activation, gelu(pre))."""
+    M, K = x.shape
+    N = w16.shape[0]
+    y = torch.empty(M, N, dtype=_BF16, device=x.device)
+    if gelu:
+        h = torch.empty(M, N, dtype=_BF16, device=x.device)
+        gemm(x, w16, y, M, N, K, epi=EPI_BIAS_GELU, D2=h, bias=bias)
+        return y, h
+    if residual is not None:
+        gemm(x, w16, y, M, N, K, epi=EPI_BIAS_RES, bias=bias, aux=residual)
+    else:
+        gemm(x, w16, y, M, N, K, epi=EPI_BIAS, bias=bias)
+    return y
+
+
+def linear_dgrad(dy, w16, dgelu_of=None):
+    """dx = dy @ w16 ; optionally multiplied by gelu'(dgelu_of) in the epilogue."""
+    M, N = dy.shape
+    K = w16.shape[1]
+    dx = torch.empty(M, K, dtype=_BF16, device=dy.device)
+    if dgelu_of is not None:
+        gemm(dy, w16, dx, M, K, N, b_mn=True, epi=EPI_DGELU, aux=dgelu_of)
+    else:
+        gemm(dy, w16, dx, M, K, N, b_mn=True, epi=EPI_BIAS)
+    return dx
+
+
+def linear_wgrad(dy, x, need_bias=True):
+    """dW[N,K] = dy^T @ x (fp32, split-K atomics), db[N] = column sums of dy."""
+    M, N = dy.shape
+    K = x.shape[1]
+    dw = torch.zeros(N, K, dtype=torch.float32, device=dy.device)
+    gemm(dy, x, dw, N, K, M, a_mn=True, b_mn=True, epi=EPI_ATOMIC_F32, split_k=0)
+    db = None
+    if need_bias:
+        db = torch.empty(N, dtype=torch.float32, device=dy.device)
+        _call("b200ssl_colsum", dy.data_ptr(), dy.stride(0), db.data_ptr(), M, N, 0, _stream(), launches=2)
+    return dw, db
+
+
+def layernorm_fwd(x, w, b, eps):
+    rows, D = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    _call("b200ssl_layernorm_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), mean.data_ptr(),
+          rstd.data_ptr(), rows, D, float(eps), _stream())
+    return y, mean, rstd
+
+
+def layernorm_bwd(x, dy, w, mean, rstd, dres=None):
+    rows, D = x.shape
+    dx = torch.empty_like(x)
+    dwb = torch.zeros(2, D, dtype=torch.float32, device=x.device)
+    _call("b200ssl_layernorm_bwd", x.data_ptr(), dy.data_ptr(), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+          _ptr(dres), dx.data_ptr(), dwb[0].data_ptr(), dwb[1].data_ptr(), rows, D, _stream())
+    return dx, dwb[0], dwb[1]
+
+
+def attention_fwd(qkv, B, N, H, scale):
+    out = torch.empty(B * N, H * 64, dtype=_BF16, device=qkv.device)
+    lse2 = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
+    _call("b200ssl_attention_fwd", qkv.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, N, H, 64, float(scale),
+          _stream())
+    return out, lse2
+
+
+def attention_bwd(qkv, out, dout, lse2, B, N, H, scale):
+    dqkv = torch.empty_like(qkv)
+    _call("b200ssl_attention_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse2.data_ptr(),
+          dqkv.data_ptr(), B, N, H, 64, float(scale), _stream())
+    return dqkv
+
+
+def _f32(p):
+    t = p.detach()
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.float().contiguous()
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd Functions
+# ------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        y, mean, rstd = layernorm_fwd(x, _f32(weight), _f32(bias), eps)
+        ctx.save_for_backward(x, weight, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dx, dw, db = layernorm_bwd(x, dy.contiguous(), _f32(weight), mean, rstd)
+        return dx, dw.to(weight.dtype), db.to(weight.dtype), None
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b (+ residual)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual):
+        w16 = bf16_of(weight)
+        y = linear_fwd(x, w16, _f32(bias) if bias is not None else None, residual)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = linear_dgrad(dy, bf16_of(weight)) if ctx.needs_input_grad[0] else None
+        dw, db = (None, None)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = linear_wgrad(dy, x, ctx.has_bias)
+        return dx, dw, db, (dy if ctx.has_res else None)
+
+
+class MlpChainFn(torch.autograd.Function):
+    """y = L_n(gelu(... gelu(L_1(x)))) (+ residual): GELU fused in each GEMM epilogue forward, its
+    derivative fused in the dgrad epilogues backward. Args: x, residual, w1, b1, ..., wn, bn."""
+
+    @staticmethod
+    def forward(ctx, x, residual, *wb):
+        n = len(wb) // 2
+        saved = [x]
+        h = x
+        for i in range(n):
+            w, b = wb[2 * i], wb[2 * i + 1]
+            b32 = _f32(b) if b is not None else None
+            if i < n - 1:
+                pre, h = linear_fwd(h, bf16_of(w), b32, gelu=True)
+                saved += [pre, h]
+            else:
+                h = linear_fwd(h, bf16_of(w), b32, residual=residual)
+        ctx.n = n
+        ctx.has_res = residual is not None
+        ctx.has_bias = [wb[2 * i + 1] is not None for i in range(n)]
+        ctx.save_for_backward(*saved, *[wb[2 * i] for i in range(n)])
+        return h
+
+    @staticmethod
+    def backward(ctx, dy):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        acts, weights = saved[: 1 + 2 * (n - 1)], saved[1 + 2 * (n - 1):]
+        dy = dy.contiguous()
+        dres = dy if ctx.has_res else None
+        grads = [None] * (2 * n)
+        d = dy
+        for i in range(n - 1, -1, -1):
+            inp = acts[0] if i == 0 else acts[2 * i]            # input of layer i (x or gelu output)
+            dw, db = linear_wgrad(d, inp, ctx.has_bias[i])
+            grads[2 * i], grads[2 * i + 1] = dw, db
+            if i > 0:
+                d = linear_dgrad(d, bf16_of(weights[i]), dgelu_of=acts[2 * i - 1])
+            elif ctx.needs_input_grad[0]:
+                d = linear_dgrad(d, bf16_of(weights[0]))
+            else:
+                d = None
+        return (d, dres, *grads)
+
+
+class AttentionCoreFn(torch.autograd.Function):
+    """softmax(q k^T * scale) v on the packed QKV-GEMM output [B*N, 3*H*64] -> [B*N, H*64]."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, N, H, scale):
+        out, lse2 = attention_fwd(qkv, B, N, H, scale)
+        ctx.save_for_backward(qkv, out, lse2)
+        ctx.dims = (B, N, H, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse2 = ctx.saved_tensors
+        B, N, H, scale = ctx.dims
+        return attention_bwd(qkv, out, dout.contiguous(), lse2, B, N, H, scale), None, None, None, None
+
+
+class AttnHalfFn(torch.autograd.Function):
+    """x + proj(attention(qkv(LN(x)))) — the first residual branch of a Block (VT.pyc@L147,150) as
+    one autograd node; backward fuses the residual gradient into the LayerNorm-backward kernel."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale):
+        ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
+        qkv = linear_fwd(ln, bf16_of(qkv_w), _f32(qkv_b) if qkv_b is not None else None)
+        att, lse2 = attention_fwd(qkv, B, N, H, scale)
+        y = linear_fwd(att, bf16_of(proj_w), _f32(proj_b) if proj_b is not None else None, residual=x)
+        ctx.save_for_backward(x, mean, rstd, ln, qkv, att, lse2, ln_w, qkv_w, proj_w)
+        ctx.meta = (B, N, H, scale, qkv_b is not None, proj_b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, ln, qkv, att, lse2, ln_w, qkv_w, proj_w = ctx.saved_tensors
+        B, N, H, scale, has_qb, has_pb = ctx.meta
+        dy = dy.contiguous()
+        d_att = linear_dgrad(dy, bf16_of(proj_w))
+        d_pw, d_pb = linear_wgrad(dy, att, has_pb)
+        d_qkv = attention_bwd(qkv, att, d_att, lse2, B, N, H, scale)
+        d_ln = linear_dgrad(d_qkv, bf16_of(qkv_w))
+        d_qw, d_qb = linear_wgrad(d_qkv, ln, has_qb)
+        dx, d_lw, d_lb = layernorm_bwd(x, d_ln, _f32(ln_w), mean, rstd, dres=dy)
+        return dx, d_lw, d_lb, d_qw, d_qb, d_pw, d_pb, None, None, None, None, None
+
+
+class MlpHalfFn(torch.autograd.Function):
+    """x + fc2(gelu(fc1(LN(x)))) — the second residual branch of a Block (VT.pyc@L151)."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, eps):
+        ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
+        pre, h = linear_fwd(ln, bf16_of(w1), _f32(b1) if b1 is not None else None, gelu=True)
+        y = linear_fwd(h, bf16_of(w2), _f32(b2) if b2 is not None else None, residual=x)
+        ctx.save_for_backward(x, mean, rstd, ln, pre, h, ln_w, w1, w2)
+        ctx.meta = (b1 is not None, b2 is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, ln, pre, h, ln_w, w1, w2 = ctx.saved_tensors
+        has_b1, has_b2 = ctx.meta
+        dy = dy.contiguous()
+        d_pre = linear_dgrad(dy, bf16_of(w2), dgelu_of=pre)
+        d_w2, d_b2 = linear_wgrad(dy, h, has_b2)
+        d_ln = linear_dgrad(d_pre, bf16_of(w1))
+        d_w1, d_b1 = linear_wgrad(d_pre, ln, has_b1)
+        dx, d_lw, d_lb = layernorm_bwd(x, d_ln, _f32(ln_w), mean, rstd, dres=dy)
+        return dx, d_lw, d_lb, d_w1, d_b1, d_w2, d_b2, None
+
+
+class TokensFn(torch.autograd.Function):
+    """prepare_tokens (VT.pyc@L235-246): patch-embed conv as GEMM, prepend CLS, add position table.
+    img [B,C,H,W] bf16 -> tokens [B*(Np+1), D] bf16. ``pos`` is the (already interpolated) fp32 table
+    [Np+1, D]; its gradient flows back to pos_embed through the caller's interpolation graph."""
+
+    @staticmethod
+    def forward(ctx, img, proj_w, proj_b, cls_token, pos, patch):
+        B, C, H, W = img.shape
+        Np = (H // patch) * (W // patch)
+        D = proj_w.shape[0]
+        Kp = C * patch * patch
+        cols = torch.empty(B * Np, Kp, dtype=_BF16, device=img.device)
+        _call("b200ssl_patchify", img.data_ptr(), cols.data_ptr(), B, C, H, W, patch, _stream())
+        w16 = bf16_of(proj_w).view(D, Kp)
+        y = linear_fwd(cols, w16, _f32(proj_b) if proj_b is not None else None)
+        x = torch.empty(B * (Np + 1), D, dtype=_BF16, device=img.device)
+        _call("b200ssl_assemble_tokens", y.data_ptr(), _f32(cls_token).data_ptr(), _f32(pos).data_ptr(),
+              x.data_ptr(), B, Np, D, _stream())
+        ctx.save_for_backward(cols, proj_w)
+        ctx.meta = (B, Np, D, proj_b is not None, cls_token.shape, pos.shape)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        cols, proj_w = ctx.saved_tensors
+        B, Np, D, has_bias, cls_shape, pos_shape = ctx.meta
+        dx = dx.contiguous()
+        dy = torch.empty(B * Np, D, dtype=_BF16, device=dx.device)
+        dpos = torch.empty(Np + 1, D, dtype=torch.float32, device=dx.device)
+        dcls = torch.empty(D, dtype=torch.float32, device=dx.device)
+        _call("b200ssl_assemble_tokens_bwd", dx.data_ptr(), dy.data_ptr(), dpos.data_ptr(), dcls.data_ptr(), B, Np,
+              D, _stream(), launches=2)
+        dw, db = linear_wgrad(dy, cols, has_bias)
+        return None, dw.view(proj_w.shape), db, dcls.view(cls_shape), dpos.view(pos_shape), None
+
+
+class L2NormFn(torch.autograd.Function):
+    """F.normalize(x, dim=-1, p=2) with the reference's eps=1e-12 clamp (VT.pyc@L328)."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        rows, D = x.shape
+        y = torch.empty_like(x)
+        norm = torch.empty(rows, dtype=torch.float32, device=x.device)
+        _call("b200ssl_l2norm_fwd", x.data_ptr(), y.data_ptr(), norm.data_ptr(), rows, D, float(eps), _stream())
+        ctx.save_for_backward(y, norm)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, norm = ctx.saved_tensors
+        dx = torch.empty_like(y)
+        _call("b200ssl_l2norm_bwd", y.data_ptr(), dy.contiguous().data_ptr(), norm.data_ptr(), dx.data_ptr(),
+              y.shape[0], y.shape[1], float(ctx.eps), _stream())
+        return dx, None
+
+
+class WeightNormLinearFn(torch.autograd.Function):
+    """y = x (g * v / ||v||_row)^T — the weight-normed, bias-free last layer (VT.pyc@L315-318,329)."""
+
+    @staticmethod
+    def forward(ctx, x, weight_v, weight_g):
+        Kout, D = weight_v.shape
+        v32 = _f32(weight_v)
+        g32 = _f32(weight_g).view(-1) if weight_g is not None else None
+        w16 = torch.empty(Kout, D, dtype=_BF16, device=x.device)
+        norm = torch.empty(Kout, dtype=torch.float32, device=x.device)
+        _call("b200ssl_weightnorm_fwd", v32.data_ptr(), _ptr(g32), w16.data_ptr(), norm.data_ptr(), Kout, D,
+              _stream())
+        y = linear_fwd(x, w16)
+        ctx.save_for_backward(x, weight_v, weight_g, w16, norm)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight_v, weight_g, w16, norm = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = linear_dgrad(dy, w16) if ctx.needs_input_grad[0] else None
+        dv = dg = None
+        if ctx.needs_input_grad[1] or (weight_g is not None and ctx.needs_input_grad[2]):
+            dw, _ = linear_wgrad(dy, x, need_bias=False)
+            v32 = _f32(weight_v)
+            g32 = _f32(weight_g).view(-1) if weight_g is not None else None
+            dv = torch.empty_like(v32)
+            want_g = weight_g is not None and ctx.needs_input_grad[2]
+            dg = torch.empty(v32.shape[0], dtype=torch.float32, device=x.device) if want_g else None
+            _call("b200ssl_weightnorm_bwd", v32.data_ptr(), _ptr(g32), norm.data_ptr(), dw.data_ptr(),
+                  dv.data_ptr(), _ptr(dg), v32.shape[0], v32.shape[1], _stream())
+            if dg is not None:
+                dg = dg.view(weight_g.shape)
+        return dx, dv, dg
+
+
+class DinoLossFn(torch.autograd.Function):
+    """Fused teacher-centred cross-entropy (oracle/dino.py::DINOLoss.forward without the centre update)."""
+
+    @staticmethod
+    def forward(ctx, student, teacher, center, ncrops, student_temp, teacher_temp):
+        rows, K = student.shape
+        B = rows // ncrops
+        loss = torch.empty(1, dtype=torch.float32, device=student.device)
+        s_lse = torch.empty(rows, dtype=torch.float32, device=student.device)
+        t_lse = torch.empty(2 * B, dtype=torch.float32, device=student.device)
+        _call("b200ssl_dino_loss_fwd", student.data_ptr(), teacher.data_ptr(), center.data_ptr(), loss.data_ptr(),
+              s_lse.data_ptr(), t_lse.data_ptr(), B, ncrops, K, float(student_temp), float(teacher_temp), _stream(),
+              launches=2)
+        ctx.save_for_backward(student, teacher, center.clone(), s_lse, t_lse)
+        ctx.meta = (B, ncrops, K, float(student_temp), float(teacher_temp))
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        student, teacher, center, s_lse, t_lse = ctx.saved_tensors
+        B, ncrops, K, ts, tt = ctx.meta
+        g = gout.detach().to(torch.float32).contiguous()
+        ds = torch.empty_like(student)
+        _call("b200ssl_dino_loss_bwd", student.data_ptr(), teacher.data_ptr(), center.data_ptr(), s_lse.data_ptr(),
+              t_lse.data_ptr(), g.data_ptr(), ds.data_ptr(), B, ncrops, K, ts, tt, _stream())
+        return ds, None, None, None, None, None
+
+
+def teacher_colsum(teacher: torch.Tensor) -> torch.Tensor:
+    """fp32 column sums of the raw teacher logits (the local part of the centre update)."""
+    rows, K = teacher.shape
+    out = torch.empty(K, dtype=torch.float32, device=teacher.device)
+    _call("b200ssl_colsum", teacher.data_ptr(), teacher.stride(0), out.data_ptr(), rows, K, 0, _stream(), launches=2)
+    return out
+
+
+def center_update(center: torch.Tensor, batch_sum: torch.Tensor, total_rows: int, momentum: float):
+    _call("b200ssl_center_update", center.data_ptr(), batch_sum.data_ptr(), center.numel(), int(total_rows),
+          float(momentum), _stream())

@@ -1,0 +1,194 @@
+"""GPU parity tests of the individual kernels (through the C-ABI) against plain-PyTorch fp32 math.
+
+Tolerances: bf16 tensor-core results vs fp32 reference -> norm-wise relative error <= 1e-2
+(north_star); fp32 HBM-bound kernels (EMA, AdamW, LayerNorm statistics) much tighter, stated per test.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-20)).item()
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_device):
+    import b200ssl
+    from b200ssl import ops as _ops
+    assert b200ssl._lib.lib().b200ssl_device_check() == 0, b200ssl._lib.last_error()
+    return _ops
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 384, 384), (3152, 1152, 384), (777, 1536, 384), (512, 256, 2048)])
+def test_linear_fwd_bias(ops, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    y = ops.linear_fwd(x, w, b)
+    ref = x.float() @ w.float().t() + b
+    assert rel(y, ref) < 1e-2
+
+
+def test_linear_gelu_and_residual(ops):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    M, K, N = 1111, 384, 1536
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    pre, h = ops.linear_fwd(x, w, b, gelu=True)
+    ref = x.float() @ w.float().t() + b
+    assert rel(pre, ref) < 1e-2
+    assert rel(h, torch.nn.functional.gelu(ref)) < 1e-2      # exact-erf GELU (parity hazard 1)
+    res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    y = ops.linear_fwd(x, w, b, residual=res)
+    assert rel(y, ref + res.float()) < 1e-2
+
+
+def test_linear_dgrad_wgrad(ops):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M, K, N = 3152, 384, 1536
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    dy = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    dx = ops.linear_dgrad(dy, w)
+    assert rel(dx, dy.float() @ w.float()) < 1e-2
+    pre = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    dxg = ops.linear_dgrad(dy, w, dgelu_of=pre)
+    p = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(p).sum().backward()
+    assert rel(dxg, (dy.float() @ w.float()) * p.grad) < 1e-2
+    dw, db = ops.linear_wgrad(dy, x)
+    assert rel(dw, dy.float().t() @ x.float()) < 1e-3        # fp32 output, bf16 inputs
+    assert rel(db, dy.float().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("D", [192, 384, 768])
+def test_layernorm(ops, D):
+    g = torch.Generator(device="cuda").manual_seed(4)
+    rows = 1234
+    x = (torch.randn(rows, D, device="cuda", generator=g) * 2 + 0.5).bfloat16()
+    w = torch.randn(D, device="cuda", generator=g)
+    b = torch.randn(D, device="cuda", generator=g)
+    y, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-6)
+    xr = x.float().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), wr, br, 1e-6)
+    assert rel(y, ref) < 5e-3
+    assert rel(mean, x.float().mean(-1)) < 1e-5
+    dy = torch.randn(rows, D, device="cuda", generator=g).bfloat16()
+    dres = torch.randn(rows, D, device="cuda", generator=g).bfloat16()
+    ref.backward(dy.float())
+    dx, dw, db = ops.layernorm_bwd(x, dy, w, mean, rstd, dres=dres)
+    assert rel(dx, xr.grad + dres.float()) < 5e-3
+    assert rel(dw, wr.grad) < 1e-3
+    assert rel(db, br.grad) < 1e-3
+
+
+@pytest.mark.parametrize("B,N,H", [(2, 197, 6), (7, 37, 3), (3, 64, 2), (5, 100, 1), (2, 256, 2), (1, 1, 1)])
+def test_attention(ops, B, N, H):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    scale = 0.125
+    qkv = torch.randn(B * N, 3 * H * 64, device="cuda", generator=g).bfloat16()
+    out, lse2 = ops.attention_fwd(qkv, B, N, H, scale)
+    qr = qkv.float().requires_grad_(True)
+    q, k, v = qr.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    a = (q @ k.transpose(-2, -1)) * scale
+    ref = (a.softmax(-1) @ v).transpose(1, 2).reshape(B * N, H * 64)
+    assert rel(out, ref) < 1e-2
+    assert rel(lse2 * math.log(2.0), torch.logsumexp(a, -1)) < 1e-3
+    dout = torch.randn(B * N, H * 64, device="cuda", generator=g).bfloat16()
+    ref.backward(dout.float())
+    dqkv = ops.attention_bwd(qkv, out, dout, lse2, B, N, H, scale)
+    assert not torch.isnan(dqkv.float()).any()
+    assert rel(dqkv, qr.grad) < 1.5e-2
+
+
+def test_attention_rejects_long_sequences(ops):
+    qkv = torch.zeros(300, 192, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="sequence length"):
+        ops.attention_fwd(qkv, 1, 300, 1, 0.125)
+
+
+@pytest.mark.parametrize("ncrops,B,K", [(2, 8, 1024), (4, 5, 4096), (12, 3, 65536)])
+def test_dino_loss(ops, ncrops, B, K):
+    from oracle.dino import DINOLoss as OracleLoss
+    g = torch.Generator(device="cuda").manual_seed(6)
+    s = (torch.randn(ncrops * B, K, device="cuda", generator=g)).bfloat16()
+    t = (torch.randn(2 * B, K, device="cuda", generator=g)).bfloat16()
+    center = torch.randn(K, device="cuda", generator=g) * 0.1
+    oracle = OracleLoss(K, ncrops, 0.04, 0.04, 0, 10).cuda()
+    oracle.center.copy_(center.view(1, -1))
+    sr = s.float().requires_grad_(True)
+    ref = oracle(sr, t.float(), 0)
+    (ref * 1.7).backward()
+    sg = s.clone().requires_grad_(True)
+    loss = ops.DinoLossFn.apply(sg, t, center, ncrops, 0.1, 0.04)
+    (loss * 1.7).backward()
+    assert abs(loss.item() - ref.item()) / abs(ref.item()) < 1e-4
+    assert rel(sg.grad, sr.grad) < 1e-2
+    # centre update (raw teacher logits, fp32)
+    bs = ops.teacher_colsum(t)
+    c2 = center.clone()
+    ops.center_update(c2, bs, 2 * B, 0.9)
+    assert rel(c2, oracle.center.view(-1)) < 1e-5
+
+
+def test_l2norm_weightnorm(ops):
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(300, 256, device="cuda", generator=g).bfloat16()
+    xr = x.float().requires_grad_(True)
+    ref = torch.nn.functional.normalize(xr, dim=-1, p=2)
+    xg = x.clone().requires_grad_(True)
+    y = ops.L2NormFn.apply(xg, 1e-12)
+    dy = torch.randn(300, 256, device="cuda", generator=g).bfloat16()
+    ref.backward(dy.float())
+    y.backward(dy)
+    assert rel(y, ref) < 5e-3 and rel(xg.grad, xr.grad) < 1e-2
+    v = torch.randn(1024, 256, device="cuda", generator=g).requires_grad_(True)
+    gg = (torch.rand(1024, 1, device="cuda", generator=g) + 0.5).requires_grad_(True)
+    w_ref = gg * v / v.norm(dim=1, keepdim=True)
+    out_ref = ref.detach() @ w_ref.t()
+    dlog = torch.randn(300, 1024, device="cuda", generator=g).bfloat16()
+    out_ref.backward(dlog.float())
+    v2, g2 = v.detach().clone().requires_grad_(True), gg.detach().clone().requires_grad_(True)
+    out = ops.WeightNormLinearFn.apply(y.detach(), v2, g2)
+    out.backward(dlog)
+    assert rel(out, out_ref) < 1e-2
+    assert rel(v2.grad, v.grad) < 1e-2 and rel(g2.grad, gg.grad) < 1e-2
+
+
+def test_ema_and_adamw(ops):
+    import b200ssl
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(300, 200), torch.nn.LayerNorm(200), torch.nn.Linear(200, 77)).cuda()
+    ema = b200ssl.ModelEma(model, decay=0.9)
+    ref_ema = [p.detach().clone() for p in ema.module.parameters()]
+    ref_model = [p.detach().clone().requires_grad_(True) for p in model.parameters()]
+    opt = b200ssl.FusedAdamW(b200ssl.param_groups_wd(model, 0.04), lr=1e-2)
+    decay = [p for p in ref_model if p.ndim > 1]
+    nodecay = [p for p in ref_model if p.ndim == 1]
+    ref_opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.04}, {"params": nodecay, "weight_decay": 0.0}], lr=1e-2)
+    for step in range(3):
+        grads = [torch.randn_like(p) * 3 for p in model.parameters()]
+        for p, r, gr in zip(model.parameters(), ref_model, grads):
+            p.grad = gr.clone()
+            r.grad = gr.clone()
+        torch.nn.utils.clip_grad_norm_(ref_model, 3.0)
+        ref_opt.step()
+        opt.step(max_grad_norm=3.0)
+        ema.update(model, momentum=0.75)
+        for e, r in zip(ref_ema, ref_model):
+            e.mul_(0.75).add_(r.detach(), alpha=0.25)
+    for p, r in zip(model.parameters(), ref_model):
+        assert rel(p, r) < 1e-5                                   # fp32 arithmetic, same update rule
+    for p, r in zip(ema.module.parameters(), ref_ema):
+        assert rel(p, r) < 1e-6
+    # bf16 shadow written by the optimiser matches the updated weights
+    w = next(model.parameters())
+    assert torch.equal(ops.bf16_of(w), w.detach().bfloat16())
