@@ -34,9 +34,9 @@ __global__ void patchify_kernel(const __nv_bfloat16* __restrict__ img, __nv_bflo
   }
 }
 
-// x[b,0,:] = cls + pos[0] ; x[b,1+p,:] = y[b*Np+p,:] + pos[1+p]     (pos, cls fp32; x, y bf16)
+// x[b,0,:] = cls + pos[0] ; x[b,1+p,:] = y[b*Np+p,:] + pos[1+p]   (pos, cls fp32; y bf16; x = fp32 stream)
 __global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ cls,
-                                       const float* __restrict__ pos, __nv_bfloat16* __restrict__ x, int B, int Np,
+                                       const float* __restrict__ pos, float* __restrict__ x, int B, int Np,
                                        int D) {
   const int N = Np + 1;
   const int d8 = D / 8;
@@ -62,10 +62,11 @@ __global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ y, cons
       }
     }
     const float* pp = pos + static_cast<long long>(n) * D + c8 * 8;
-    uint32_t o[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2(v[2 * e] + __ldg(pp + 2 * e), v[2 * e + 1] + __ldg(pp + 2 * e + 1));
-    reinterpret_cast<uint4*>(x + rn * D)[c8] = make_uint4(o[0], o[1], o[2], o[3]);
+    for (int e = 0; e < 8; ++e) v[e] += __ldg(pp + e);
+    float4* px = reinterpret_cast<float4*>(x + rn * D) + 2 * c8;
+    px[0] = make_float4(v[0], v[1], v[2], v[3]);
+    px[1] = make_float4(v[4], v[5], v[6], v[7]);
   }
 }
 
@@ -260,7 +261,7 @@ extern "C" int b200ssl_assemble_tokens(const void* y, const float* cls, const fl
   B200SSL_CHECK(D % 8 == 0, -2, "assemble_tokens: D=%d must be a multiple of 8", D);
   const long long total = static_cast<long long>(B) * (Np + 1) * (D / 8);
   assemble_tokens_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(y), cls, pos, static_cast<__nv_bfloat16*>(x), B, Np, D);
+      static_cast<const __nv_bfloat16*>(y), cls, pos, static_cast<float*>(x), B, Np, D);
   B200SSL_CUDA(cudaGetLastError());
   return 0;
 }

@@ -29,6 +29,7 @@ enum GemmEpilogue : int {
   EPI_BIAS_RES = 2,   // D = acc (+ bias) + aux
   EPI_DGELU = 3,      // D = acc * gelu'(aux)
   EPI_ATOMIC_F32 = 4, // D(fp32) += acc   (split-K)
+  EPI_BIAS_RES_F32 = 5, // D(fp32) = acc (+ bias) + aux(fp32): the fp32 residual stream
 };
 
 struct GemmArgs {
@@ -36,7 +37,7 @@ struct GemmArgs {
   int a_mn, b_mn;
   int num_m_blocks, num_n_blocks, k_splits, k_blocks_per_split, k_blocks_total;
   const float* bias;
-  const __nv_bfloat16* aux;
+  const void* aux;  // bf16 (EPI_BIAS_RES, EPI_DGELU) or fp32 (EPI_BIAS_RES_F32)
   long long ldaux;
   float* out_f32;
   long long ldd;
@@ -251,8 +252,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (EPI == EPI_BIAS_RES || EPI == EPI_DGELU) {
           if (row_ok) {
-            const uint4* ap =
-                reinterpret_cast<const uint4*>(args.aux + static_cast<long long>(row) * args.ldaux + col0);
+            const uint4* ap = reinterpret_cast<const uint4*>(
+                static_cast<const __nv_bfloat16*>(args.aux) + static_cast<long long>(row) * args.ldaux + col0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint4 a = __ldg(ap + j);
@@ -270,6 +271,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
           }
+        }
+
+        if (EPI == EPI_BIAS_RES_F32) {
+          if (row_ok) {
+            const float4* ap = reinterpret_cast<const float4*>(
+                static_cast<const float*>(args.aux) + static_cast<long long>(row) * args.ldaux + col0);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float4 a = __ldg(ap + j);
+              f[4 * j] += a.x; f[4 * j + 1] += a.y; f[4 * j + 2] += a.z; f[4 * j + 3] += a.w;
+            }
+          }
+          // fp32 output: two 32-column boxes (128 B rows) per 64-column chunk
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            uint8_t* buf = stg + (slot & 1) * STAGING_BYTES;
+            if (gtid == 0) tma_store_wait_read<1>();
+            named_bar_sync(1 + group, 128);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(buf + sw128_offset(row_in_tile, j)) =
+                  make_float4(f[32 * o + 4 * j], f[32 * o + 4 * j + 1], f[32 * o + 4 * j + 2], f[32 * o + 4 * j + 3]);
+            fence_proxy_async_smem();
+            named_bar_sync(1 + group, 128);
+            if (gtid == 0) {
+              tma_store_2d(&tmD, buf, col0 + 32 * o, m0);
+              tma_store_commit();
+            }
+            ++slot;
+          }
+          continue;
         }
 
         constexpr int kOutputs = EPI == EPI_BIAS_GELU ? 2 : 1;
@@ -346,6 +378,7 @@ static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b, con
     case EPI_BIAS_RES: return launch_gemm<BN, EPI_BIAS_RES>(a, b, d, d2, args, s);
     case EPI_DGELU: return launch_gemm<BN, EPI_DGELU>(a, b, d, d2, args, s);
     case EPI_ATOMIC_F32: return launch_gemm<BN, EPI_ATOMIC_F32>(a, b, d, d2, args, s);
+    case EPI_BIAS_RES_F32: return launch_gemm<BN, EPI_BIAS_RES_F32>(a, b, d, d2, args, s);
   }
   set_last_error("gemm: unknown epilogue %d", epi);
   return -2;
@@ -382,15 +415,18 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
   B200SSL_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(D) & 15) == 0,
                 -2, "gemm: operands must be 16-byte aligned");
-  B200SSL_CHECK(epilogue >= 0 && epilogue <= 4, -2, "gemm: unknown epilogue %d", epilogue);
+  B200SSL_CHECK(epilogue >= 0 && epilogue <= 5, -2, "gemm: unknown epilogue %d", epilogue);
   if (epilogue == EPI_BIAS_RES || epilogue == EPI_DGELU)
     B200SSL_CHECK(aux != nullptr && ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0, -2,
                   "gemm: epilogue %d needs a 16B-aligned aux operand", epilogue);
+  if (epilogue == EPI_BIAS_RES_F32)
+    B200SSL_CHECK(aux != nullptr && ldaux % 4 == 0 && ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0, -2,
+                  "gemm: fp32 residual epilogue needs a 16B-aligned fp32 aux operand and ldd %% 4 == 0");
   if (epilogue == EPI_BIAS_GELU) B200SSL_CHECK(D2 != nullptr, -2, "gemm: GELU epilogue needs D2");
   if (epilogue == EPI_ATOMIC_F32) {
     B200SSL_CHECK(ldd % 4 == 0, -2, "gemm: fp32 ldd must be a multiple of 4");
   } else {
-    B200SSL_CHECK(ldd % 8 == 0, -2, "gemm: bf16 ldd must be a multiple of 8");
+    if (epilogue != EPI_BIAS_RES_F32) B200SSL_CHECK(ldd % 8 == 0, -2, "gemm: bf16 ldd must be a multiple of 8");
     split_k = 1;
   }
   if (bias) B200SSL_CHECK((reinterpret_cast<uintptr_t>(bias) & 15) == 0, -2, "gemm: bias must be 16B aligned");
@@ -422,7 +458,7 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
   args.k_blocks_per_split = kbps;
   args.k_blocks_total = k_blocks;
   args.bias = bias;
-  args.aux = static_cast<const __nv_bfloat16*>(aux);
+  args.aux = aux;
   args.ldaux = ldaux;
   args.out_f32 = static_cast<float*>(D);
   args.ldd = ldd;
@@ -440,7 +476,12 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
     else             { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = 64; }
     strides[1] = static_cast<uint64_t>(ldb) * 2;
     if (int rc = make_tensor_map(&tmB, B, 2, 2, dims, strides, box, true)) return rc;
-    if (epilogue != EPI_ATOMIC_F32) {
+    if (epilogue == EPI_BIAS_RES_F32) {
+      dims[0] = N; dims[1] = M; box[0] = 32; box[1] = BLOCK_M;
+      strides[0] = 4; strides[1] = static_cast<uint64_t>(ldd) * 4;
+      if (int rc = make_tensor_map(&tmD, D, 4, 2, dims, strides, box, true)) return rc;
+      tmD2 = tmD;
+    } else if (epilogue != EPI_ATOMIC_F32) {
       dims[0] = N; dims[1] = M; box[0] = 64; box[1] = BLOCK_M;
       strides[1] = static_cast<uint64_t>(ldd) * 2;
       if (int rc = make_tensor_map(&tmD, D, 2, 2, dims, strides, box, true)) return rc;

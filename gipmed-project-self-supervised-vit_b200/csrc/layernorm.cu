@@ -8,6 +8,28 @@
 
 namespace b200ssl {
 
+// load 8 consecutive elements (one "chunk") of a bf16 or fp32 row as floats
+template <typename T>
+__device__ __forceinline__ void load_chunk8(const T* row_ptr, int chunk, float (&out)[8]);
+template <>
+__device__ __forceinline__ void load_chunk8<__nv_bfloat16>(const __nv_bfloat16* row_ptr, int chunk, float (&out)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(row_ptr) + chunk);
+  const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack_bf16x2(uw[e]);
+    out[2 * e] = f.x;
+    out[2 * e + 1] = f.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load_chunk8<float>(const float* row_ptr, int chunk, float (&out)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(row_ptr) + 2 * chunk);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(row_ptr) + 2 * chunk + 1);
+  out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+  out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+}
+
 template <int LPR>
 __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
@@ -15,9 +37,9 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
-template <int LPR, int CPL>
+template <int LPR, int CPL, typename XT>
 __global__ void __launch_bounds__(256)
-ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+ln_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
               long long rows, float eps) {
   constexpr int D = LPR * CPL * 8;
@@ -38,20 +60,21 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, 
       gb[c * 8 + e] = __ldg(b + col + e);
     }
   }
-  for (long long row = warp_global * RPW + lane / LPR; row < rows; row += nwarps * RPW) {
-    const uint4* px = reinterpret_cast<const uint4*>(x + row * D);
+  // the loop bound is warp-uniform (full-mask shuffles inside); tail rows are clamped + predicated
+  for (long long base = warp_global * RPW; base < rows; base += nwarps * RPW) {
+    const bool valid = base + lane / LPR < rows;
+    const long long row = valid ? base + lane / LPR : rows - 1;
+    const XT* px = x + row * D;
     float v[CPL * 8];
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
-      const uint4 u = __ldg(px + c * LPR + sub);
-      const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+      float t8[8];
+      load_chunk8<XT>(px, c * LPR + sub, t8);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack_bf16x2(uw[e]);
-        v[c * 8 + 2 * e] = f.x;
-        v[c * 8 + 2 * e + 1] = f.y;
-        s += f.x + f.y;
+      for (int e = 0; e < 8; ++e) {
+        v[c * 8 + e] = t8[e];
+        s += t8[e];
       }
     }
     const float mean = group_sum<LPR>(s) * (1.f / D);
@@ -62,6 +85,7 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, 
       sq += d * d;
     }
     const float rstd = rsqrtf(group_sum<LPR>(sq) * (1.f / D) + eps);
+    if (!valid) continue;
     uint4* py = reinterpret_cast<uint4*>(y + row * D);
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
@@ -83,9 +107,9 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, 
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) + dres, with g = dy * gamma;
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (fp32 atomics, one per column per CTA)
-template <int LPR, int CPL>
+template <int LPR, int CPL, typename XT>
 __global__ void __launch_bounds__(256)
-ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+ln_bwd_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
               const float* __restrict__ w, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw,
               float* __restrict__ db, long long rows) {
@@ -112,19 +136,27 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
       adb[c * 8 + e] = 0.f;
     }
   }
-  for (long long row = warp_global * RPW + lane / LPR; row < rows; row += nwarps * RPW) {
-    const uint4* px = reinterpret_cast<const uint4*>(x + row * D);
+  for (long long base = warp_global * RPW; base < rows; base += nwarps * RPW) {
+    const bool valid = base + lane / LPR < rows;
+    const long long row = valid ? base + lane / LPR : rows - 1;
+    const float vmask = valid ? 1.f : 0.f;  // tail lanes re-read the last row but contribute nothing
+    const XT* px = x + row * D;
     const uint4* pdy = reinterpret_cast<const uint4*>(dy + row * D);
     const float mean = mean_in[row], rstd = rstd_in[row];
     float xh[CPL * 8], g[CPL * 8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
-      const uint4 ux = __ldg(px + c * LPR + sub), ud = __ldg(pdy + c * LPR + sub);
-      const uint32_t xw[4] = {ux.x, ux.y, ux.z, ux.w}, dw4[4] = {ud.x, ud.y, ud.z, ud.w};
+      float x8[8];
+      load_chunk8<XT>(px, c * LPR + sub, x8);
+      const uint4 ud = __ldg(pdy + c * LPR + sub);
+      const uint32_t dw4[4] = {ud.x, ud.y, ud.z, ud.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float2 fx = unpack_bf16x2(xw[e]), fd = unpack_bf16x2(dw4[e]);
+        const float2 fx = make_float2(x8[2 * e], x8[2 * e + 1]);
+        float2 fd = unpack_bf16x2(dw4[e]);
+        fd.x *= vmask;
+        fd.y *= vmask;
         const int i = c * 8 + 2 * e;
         xh[i] = (fx.x - mean) * rstd;
         xh[i + 1] = (fx.y - mean) * rstd;
@@ -140,6 +172,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
     }
     const float m1 = group_sum<LPR>(s1) * (1.f / D);
     const float m2 = group_sum<LPR>(s2) * (1.f / D);
+    if (!valid) continue;
     uint4* pdx = reinterpret_cast<uint4*>(dx + row * D);
     const uint4* pr = dres ? reinterpret_cast<const uint4*>(dres + row * D) : nullptr;
 #pragma unroll
@@ -177,29 +210,38 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
 }
 
 template <int LPR, int CPL>
-static int launch_ln_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd,
+static int launch_ln_fwd(const void* x, int x_f32, const float* w, const float* b, void* y, float* mean, float* rstd,
                          long long rows, float eps, cudaStream_t s) {
   constexpr int RPW = 32 / LPR;
   const long long warps_needed = (rows + RPW - 1) / RPW;
   long long blocks = (warps_needed + 7) / 8;
   const long long cap = static_cast<long long>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
-  ln_fwd_kernel<LPR, CPL><<<static_cast<int>(blocks), 256, 0, s>>>(
-      static_cast<const __nv_bfloat16*>(x), w, b, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, eps);
+  if (x_f32)
+    ln_fwd_kernel<LPR, CPL, float><<<static_cast<int>(blocks), 256, 0, s>>>(
+        static_cast<const float*>(x), w, b, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, eps);
+  else
+    ln_fwd_kernel<LPR, CPL, __nv_bfloat16><<<static_cast<int>(blocks), 256, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(x), w, b, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, eps);
   B200SSL_CUDA(cudaGetLastError());
   return 0;
 }
 template <int LPR, int CPL>
-static int launch_ln_bwd(const void* x, const void* dy, const float* w, const float* mean, const float* rstd,
+static int launch_ln_bwd(const void* x, int x_f32, const void* dy, const float* w, const float* mean, const float* rstd,
                          const void* dres, void* dx, float* dw, float* db, long long rows, cudaStream_t s) {
   constexpr int RPW = 32 / LPR;
   const long long warps_needed = (rows + RPW - 1) / RPW;
   long long blocks = (warps_needed + 7) / 8;
   const long long cap = static_cast<long long>(sm_count()) * 4;
   if (blocks > cap) blocks = cap;
-  ln_bwd_kernel<LPR, CPL><<<static_cast<int>(blocks), 256, 0, s>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), w, mean, rstd,
-      static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dw, db, rows);
+  if (x_f32)
+    ln_bwd_kernel<LPR, CPL, float><<<static_cast<int>(blocks), 256, 0, s>>>(
+        static_cast<const float*>(x), static_cast<const __nv_bfloat16*>(dy), w, mean, rstd,
+        static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dw, db, rows);
+  else
+    ln_bwd_kernel<LPR, CPL, __nv_bfloat16><<<static_cast<int>(blocks), 256, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), w, mean, rstd,
+        static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dw, db, rows);
   B200SSL_CUDA(cudaGetLastError());
   return 0;
 }
@@ -221,22 +263,23 @@ using namespace b200ssl;
       return -2;                                                   \
   }
 
-extern "C" int b200ssl_layernorm_fwd(const void* x, const float* w, const float* b, void* y, float* mean,
+// x is bf16 (x_f32 == 0) or fp32 (the residual stream, x_f32 == 1); y is bf16.
+extern "C" int b200ssl_layernorm_fwd(const void* x, int x_f32, const float* w, const float* b, void* y, float* mean,
                                      float* rstd, long long rows, int D, float eps, void* stream) {
   B200SSL_CHECK(rows > 0, -2, "layernorm: no rows");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define CALL_FWD(L, C) launch_ln_fwd<L, C>(x, w, b, y, mean, rstd, rows, eps, s)
+#define CALL_FWD(L, C) launch_ln_fwd<L, C>(x, x_f32, w, b, y, mean, rstd, rows, eps, s)
   LN_DISPATCH(D, CALL_FWD)
 #undef CALL_FWD
 }
 
 // dw / db are ACCUMULATED into (fp32); the caller zeroes them when starting a fresh gradient.
-extern "C" int b200ssl_layernorm_bwd(const void* x, const void* dy, const float* w, const float* mean,
+extern "C" int b200ssl_layernorm_bwd(const void* x, int x_f32, const void* dy, const float* w, const float* mean,
                                      const float* rstd, const void* dres, void* dx, float* dw, float* db,
                                      long long rows, int D, void* stream) {
   B200SSL_CHECK(rows > 0, -2, "layernorm: no rows");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define CALL_BWD(L, C) launch_ln_bwd<L, C>(x, dy, w, mean, rstd, dres, dx, dw, db, rows, s)
+#define CALL_BWD(L, C) launch_ln_bwd<L, C>(x, x_f32, dy, w, mean, rstd, dres, dx, dw, db, rows, s)
   LN_DISPATCH(D, CALL_BWD)
 #undef CALL_BWD
 }

@@ -129,6 +129,16 @@ def _chunk_rows(tensors_per_row, numels):
     return rows
 
 
+def _detach_weight_norm(model):
+    """Old-style nn.utils.weight_norm leaves a non-leaf ``weight`` attribute that deepcopy refuses;
+    the forward pre-hook recomputes it anyway, so park a detached copy before cloning the module."""
+    from torch.nn.utils.weight_norm import WeightNorm
+    for m in model.modules():
+        for hook in m._forward_pre_hooks.values():
+            if isinstance(hook, WeightNorm) and isinstance(getattr(m, hook.name, None), torch.Tensor):
+                setattr(m, hook.name, getattr(m, hook.name).detach())
+
+
 class ModelEma(nn.Module):
     """Teacher as an EMA of the student with timm's ``ModelEmaV2`` call convention (train.py:619-620,
     :948, :1081): ``.module`` is the averaged copy, ``update(model)`` folds every floating-point
@@ -136,6 +146,7 @@ class ModelEma(nn.Module):
 
     def __init__(self, model, decay=0.9998, device=None):
         super().__init__()
+        _detach_weight_norm(model)
         self.module = copy.deepcopy(model)
         self.module.eval()
         for p in self.module.parameters():

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_ATOMIC_F32 = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_ATOMIC_F32, EPI_BIAS_RES_F32 = 0, 1, 2, 3, 4, 5
 
 _BF16 = torch.bfloat16
 _counters = {"launches": 0}
@@ -106,6 +106,14 @@ def to_bf16_2d(x: torch.Tensor) -> torch.Tensor:
     return x2.contiguous()
 
 
+def to_stream_2d(x: torch.Tensor) -> torch.Tensor:
+    """The residual stream is fp32 [rows, D] (as under torch autocast); only MMA operands are bf16."""
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.dtype != torch.float32:
+        x2 = x2.float()
+    return x2.contiguous()
+
+
 # ------------------------------------------------------------------------------------------------
 # raw wrappers
 # ------------------------------------------------------------------------------------------------
@@ -121,9 +129,14 @@ def gemm(A, B, D, M, N, K, *, a_mn=False, b_mn=False, epi=EPI_BIAS, D2=None, bia
 
 
 def linear_fwd(x, w16, bias=None, residual=None, gelu=False):
-    """y = x @ w16^T (+bias) (+residual); with gelu=True returns (pre_activation, gelu(pre))."""
+    """y = x @ w16^T (+bias) (+residual); with gelu=True returns (pre_activation, gelu(pre)).
+    An fp32 ``residual`` selects the fp32-stream epilogue (fp32 output); bf16 residual -> bf16 output."""
     M, K = x.shape
     N = w16.shape[0]
+    if residual is not None and residual.dtype == torch.float32:
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        gemm(x, w16, y, M, N, K, epi=EPI_BIAS_RES_F32, bias=bias, aux=residual)
+        return y
     y = torch.empty(M, N, dtype=_BF16, device=x.device)
     if gelu:
         h = torch.empty(M, N, dtype=_BF16, device=x.device)
@@ -162,21 +175,24 @@ def linear_wgrad(dy, x, need_bias=True):
 
 
 def layernorm_fwd(x, w, b, eps):
+    """x: bf16 or fp32 (residual stream) [rows, D] -> bf16 y, fp32 mean / rstd."""
     rows, D = x.shape
-    y = torch.empty_like(x)
+    y = torch.empty(rows, D, dtype=_BF16, device=x.device)
     mean = torch.empty(rows, dtype=torch.float32, device=x.device)
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
-    _call("b200ssl_layernorm_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), mean.data_ptr(),
-          rstd.data_ptr(), rows, D, float(eps), _stream())
+    _call("b200ssl_layernorm_fwd", x.data_ptr(), int(x.dtype == torch.float32), w.data_ptr(), b.data_ptr(),
+          y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, D, float(eps), _stream())
     return y, mean, rstd
 
 
 def layernorm_bwd(x, dy, w, mean, rstd, dres=None):
+    """Gradients travel in bf16: dy, dres, dx are bf16 regardless of the stream dtype of x."""
     rows, D = x.shape
-    dx = torch.empty_like(x)
+    dx = torch.empty(rows, D, dtype=_BF16, device=x.device)
     dwb = torch.zeros(2, D, dtype=torch.float32, device=x.device)
-    _call("b200ssl_layernorm_bwd", x.data_ptr(), dy.data_ptr(), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-          _ptr(dres), dx.data_ptr(), dwb[0].data_ptr(), dwb[1].data_ptr(), rows, D, _stream())
+    _call("b200ssl_layernorm_bwd", x.data_ptr(), int(x.dtype == torch.float32), dy.data_ptr(), w.data_ptr(),
+          mean.data_ptr(), rstd.data_ptr(), _ptr(dres), dx.data_ptr(), dwb[0].data_ptr(), dwb[1].data_ptr(), rows, D,
+          _stream())
     return dx, dwb[0], dwb[1]
 
 
@@ -193,6 +209,11 @@ def attention_bwd(qkv, out, dout, lse2, B, N, H, scale):
     _call("b200ssl_attention_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse2.data_ptr(),
           dqkv.data_ptr(), B, N, H, 64, float(scale), _stream())
     return dqkv
+
+
+def _g16(g):
+    """Incoming gradients are carried in bf16 (autograd may hand us fp32 when the forward output was fp32)."""
+    return g.to(_BF16).contiguous() if g.dtype != _BF16 else g.contiguous()
 
 
 def _f32(p):
@@ -215,8 +236,8 @@ class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, weight, mean, rstd = ctx.saved_tensors
-        dx, dw, db = layernorm_bwd(x, dy.contiguous(), _f32(weight), mean, rstd)
-        return dx, dw.to(weight.dtype), db.to(weight.dtype), None
+        dx, dw, db = layernorm_bwd(x, _g16(dy), _f32(weight), mean, rstd)
+        return dx.to(x.dtype), dw.to(weight.dtype), db.to(weight.dtype), None
 
 
 class LinearFn(torch.autograd.Function):
@@ -304,57 +325,143 @@ class AttentionCoreFn(torch.autograd.Function):
         return attention_bwd(qkv, out, dout.contiguous(), lse2, B, N, H, scale), None, None, None, None
 
 
+# ---- residual half-blocks: plain functions shared by the per-block and whole-encoder autograd nodes ----
+def attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale):
+    """x + proj(attention(qkv(LN(x)))) (VT.pyc@L147,150). Returns (y, saved-for-backward)."""
+    ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
+    qkv = linear_fwd(ln, bf16_of(qkv_w), _f32(qkv_b) if qkv_b is not None else None)
+    att, lse2 = attention_fwd(qkv, B, N, H, scale)
+    y = linear_fwd(att, bf16_of(proj_w), _f32(proj_b) if proj_b is not None else None, residual=x)
+    return y, (x, mean, rstd, ln, qkv, att, lse2)
+
+
+def attn_half_bwd(dy, saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale):
+    """dy: bf16 gradient of the half-block output. Returns (dx bf16, d_ln_w, d_ln_b, d_qkv_w, d_qkv_b,
+    d_proj_w, d_proj_b); the residual gradient is added inside the LayerNorm-backward kernel."""
+    x, mean, rstd, ln, qkv, att, lse2 = saved
+    d_att = linear_dgrad(dy, bf16_of(proj_w))
+    d_pw, d_pb = linear_wgrad(dy, att, has_pb)
+    d_qkv = attention_bwd(qkv, att, d_att, lse2, B, N, H, scale)
+    d_ln = linear_dgrad(d_qkv, bf16_of(qkv_w))
+    d_qw, d_qb = linear_wgrad(d_qkv, ln, has_qb)
+    dx, d_lw, d_lb = layernorm_bwd(x, d_ln, _f32(ln_w), mean, rstd, dres=dy)
+    return dx, d_lw, d_lb, d_qw, d_qb, d_pw, d_pb
+
+
+def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps):
+    """x + fc2(gelu(fc1(LN(x)))) (VT.pyc@L151)."""
+    ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
+    pre, h = linear_fwd(ln, bf16_of(w1), _f32(b1) if b1 is not None else None, gelu=True)
+    y = linear_fwd(h, bf16_of(w2), _f32(b2) if b2 is not None else None, residual=x)
+    return y, (x, mean, rstd, ln, pre, h)
+
+
+def mlp_half_bwd(dy, saved, ln_w, w1, w2, has_b1, has_b2):
+    x, mean, rstd, ln, pre, h = saved
+    d_pre = linear_dgrad(dy, bf16_of(w2), dgelu_of=pre)
+    d_w2, d_b2 = linear_wgrad(dy, h, has_b2)
+    d_ln = linear_dgrad(d_pre, bf16_of(w1))
+    d_w1, d_b1 = linear_wgrad(d_pre, ln, has_b1)
+    dx, d_lw, d_lb = layernorm_bwd(x, d_ln, _f32(ln_w), mean, rstd, dres=dy)
+    return dx, d_lw, d_lb, d_w1, d_b1, d_w2, d_b2
+
+
 class AttnHalfFn(torch.autograd.Function):
-    """x + proj(attention(qkv(LN(x)))) — the first residual branch of a Block (VT.pyc@L147,150) as
-    one autograd node; backward fuses the residual gradient into the LayerNorm-backward kernel."""
+    """First residual branch of a Block as one autograd node (standalone Block.forward path)."""
 
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale):
-        ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
-        qkv = linear_fwd(ln, bf16_of(qkv_w), _f32(qkv_b) if qkv_b is not None else None)
-        att, lse2 = attention_fwd(qkv, B, N, H, scale)
-        y = linear_fwd(att, bf16_of(proj_w), _f32(proj_b) if proj_b is not None else None, residual=x)
-        ctx.save_for_backward(x, mean, rstd, ln, qkv, att, lse2, ln_w, qkv_w, proj_w)
+        y, saved = attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale)
+        ctx.save_for_backward(*saved, ln_w, qkv_w, proj_w)
         ctx.meta = (B, N, H, scale, qkv_b is not None, proj_b is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, mean, rstd, ln, qkv, att, lse2, ln_w, qkv_w, proj_w = ctx.saved_tensors
+        *saved, ln_w, qkv_w, proj_w = ctx.saved_tensors
         B, N, H, scale, has_qb, has_pb = ctx.meta
-        dy = dy.contiguous()
-        d_att = linear_dgrad(dy, bf16_of(proj_w))
-        d_pw, d_pb = linear_wgrad(dy, att, has_pb)
-        d_qkv = attention_bwd(qkv, att, d_att, lse2, B, N, H, scale)
-        d_ln = linear_dgrad(d_qkv, bf16_of(qkv_w))
-        d_qw, d_qb = linear_wgrad(d_qkv, ln, has_qb)
-        dx, d_lw, d_lb = layernorm_bwd(x, d_ln, _f32(ln_w), mean, rstd, dres=dy)
-        return dx, d_lw, d_lb, d_qw, d_qb, d_pw, d_pb, None, None, None, None, None
+        dx, *g = attn_half_bwd(_g16(dy), saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale)
+        return (dx.to(dy.dtype), *g, None, None, None, None, None)
 
 
 class MlpHalfFn(torch.autograd.Function):
-    """x + fc2(gelu(fc1(LN(x)))) — the second residual branch of a Block (VT.pyc@L151)."""
+    """Second residual branch of a Block as one autograd node (standalone Block.forward path)."""
 
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, eps):
-        ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
-        pre, h = linear_fwd(ln, bf16_of(w1), _f32(b1) if b1 is not None else None, gelu=True)
-        y = linear_fwd(h, bf16_of(w2), _f32(b2) if b2 is not None else None, residual=x)
-        ctx.save_for_backward(x, mean, rstd, ln, pre, h, ln_w, w1, w2)
+        y, saved = mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps)
+        ctx.save_for_backward(*saved, ln_w, w1, w2)
         ctx.meta = (b1 is not None, b2 is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, mean, rstd, ln, pre, h, ln_w, w1, w2 = ctx.saved_tensors
+        *saved, ln_w, w1, w2 = ctx.saved_tensors
         has_b1, has_b2 = ctx.meta
-        dy = dy.contiguous()
-        d_pre = linear_dgrad(dy, bf16_of(w2), dgelu_of=pre)
-        d_w2, d_b2 = linear_wgrad(dy, h, has_b2)
-        d_ln = linear_dgrad(d_pre, bf16_of(w1))
-        d_w1, d_b1 = linear_wgrad(d_pre, ln, has_b1)
-        dx, d_lw, d_lb = layernorm_bwd(x, d_ln, _f32(ln_w), mean, rstd, dres=dy)
-        return dx, d_lw, d_lb, d_w1, d_b1, d_w2, d_b2, None
+        dx, *g = mlp_half_bwd(_g16(dy), saved, ln_w, w1, w2, has_b1, has_b2)
+        return (dx.to(dy.dtype), *g, None)
+
+
+BLOCK_PARAMS = 12  # ln1 w,b | qkv w,b | proj w,b | ln2 w,b | fc1 w,b | fc2 w,b
+
+
+class EncoderFn(torch.autograd.Function):
+    """All transformer blocks + the final LayerNorm on the CLS rows as ONE autograd node
+    (VisionTransformer.forward VT.pyc@L248-253). The residual stream is fp32 forward; gradients flow in
+    bf16 between blocks without touching autograd (no per-block dtype casts, ~2*depth fewer graph nodes).
+
+    apply(tokens[B*N, D] fp32, meta, *params) with params = depth * BLOCK_PARAMS tensors (None for absent
+    biases) followed by (norm_w, norm_b); meta = (B, N, H, scale, [eps1, eps2] per block, norm_eps).
+    Returns the normalised CLS embedding [B, D] bf16."""
+
+    @staticmethod
+    def forward(ctx, tok, meta, *params):
+        B, N, H, scale, eps_list, norm_eps = meta
+        depth = (len(params) - 2) // BLOCK_PARAMS
+        keep = any(ctx.needs_input_grad)  # False under no_grad (teacher): nothing is retained
+        saved = []
+        x = tok
+        for i in range(depth):
+            ln1w, ln1b, qw, qb, pw, pb, ln2w, ln2b, w1, b1, w2, b2 = params[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS]
+            x, s1 = attn_half_fwd(x, ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale)
+            x, s2 = mlp_half_fwd(x, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1])
+            if keep:
+                saved.append((s1, s2))
+        D = x.shape[1]
+        cls = x.view(B, N, D)[:, 0].contiguous()
+        norm_w, norm_b = params[-2], params[-1]
+        out, mean, rstd = layernorm_fwd(cls, _f32(norm_w), _f32(norm_b), norm_eps)
+        if keep:
+            ctx.saved = saved          # activations live exactly as long as the graph node
+            ctx.final = (cls, mean, rstd)
+            ctx.params = params
+            ctx.meta = meta
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, N, H, scale, eps_list, norm_eps = ctx.meta
+        params = ctx.params
+        depth = (len(params) - 2) // BLOCK_PARAMS
+        cls, mean, rstd = ctx.final
+        d_cls, d_nw, d_nb = layernorm_bwd(cls, _g16(dout), _f32(params[-2]), mean, rstd)
+        D = cls.shape[1]
+        dx = torch.zeros(B, N, D, dtype=_BF16, device=cls.device)
+        dx[:, 0] = d_cls
+        dx = dx.view(B * N, D)
+        grads = [None] * len(params)
+        for i in range(depth - 1, -1, -1):
+            ln1w, ln1b, qw, qb, pw, pb, ln2w, ln2b, w1, b1, w2, b2 = params[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS]
+            s1, s2 = ctx.saved[i]
+            dx, g_l2w, g_l2b, g_w1, g_b1, g_w2, g_b2 = mlp_half_bwd(dx, s2, ln2w, w1, w2, b1 is not None, b2 is not None)
+            dx, g_l1w, g_l1b, g_qw, g_qb, g_pw, g_pb = attn_half_bwd(dx, s1, ln1w, qw, pw, qb is not None,
+                                                                      pb is not None, B, N, H, scale)
+            grads[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS] = [g_l1w, g_l1b, g_qw, g_qb, g_pw, g_pb, g_l2w, g_l2b,
+                                                              g_w1, g_b1, g_w2, g_b2]
+            ctx.saved[i] = None  # free this block's activations as soon as they are consumed
+        grads[-2], grads[-1] = d_nw, d_nb
+        d_tok = dx.float() if ctx.needs_input_grad[0] else None
+        return (d_tok, None, *grads)
 
 
 class TokensFn(torch.autograd.Function):
@@ -372,7 +479,7 @@ class TokensFn(torch.autograd.Function):
         _call("b200ssl_patchify", img.data_ptr(), cols.data_ptr(), B, C, H, W, patch, _stream())
         w16 = bf16_of(proj_w).view(D, Kp)
         y = linear_fwd(cols, w16, _f32(proj_b) if proj_b is not None else None)
-        x = torch.empty(B * (Np + 1), D, dtype=_BF16, device=img.device)
+        x = torch.empty(B * (Np + 1), D, dtype=torch.float32, device=img.device)
         _call("b200ssl_assemble_tokens", y.data_ptr(), _f32(cls_token).data_ptr(), _f32(pos).data_ptr(),
               x.data_ptr(), B, Np, D, _stream())
         ctx.save_for_backward(cols, proj_w)
@@ -383,7 +490,7 @@ class TokensFn(torch.autograd.Function):
     def backward(ctx, dx):
         cols, proj_w = ctx.saved_tensors
         B, Np, D, has_bias, cls_shape, pos_shape = ctx.meta
-        dx = dx.contiguous()
+        dx = _g16(dx)
         dy = torch.empty(B * Np, D, dtype=_BF16, device=dx.device)
         dpos = torch.empty(Np + 1, D, dtype=torch.float32, device=dx.device)
         dcls = torch.empty(D, dtype=torch.float32, device=dx.device)

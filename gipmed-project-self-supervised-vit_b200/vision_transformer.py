@@ -139,8 +139,13 @@ class Block(nn.Module):
         no_dp = isinstance(self.drop_path, nn.Identity) or not self.training or not self.drop_path.drop_prob
         return no_dp and _is_plain_layernorm(self.norm1) and _is_plain_layernorm(self.norm2) and self.mlp._fusable()
 
+    def _param_list(self):
+        a, m = self.attn, self.mlp
+        return [self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
+                self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias]
+
     def forward_tokens(self, x2, B, N):
-        """Fused path on the packed token matrix [B*N, C] (bf16): two autograd nodes per block."""
+        """Fused path on the packed fp32 token stream [B*N, C]: two autograd nodes per block."""
         a = self.attn
         a._check(x2.shape[1])
         if not self._fused_ok():
@@ -156,10 +161,10 @@ class Block(nn.Module):
         ops.require_cuda(x, "Block")
         B, N, C = x.shape
         if return_attention:
-            y, attn = self.attn(_layer_norm(self.norm1, ops.to_bf16_2d(x)).view(B, N, C))
-            return attn
+            y, attn = self.attn(_layer_norm(self.norm1, ops.to_stream_2d(x)).view(B, N, C))
+            return attn.to(x.dtype)
         dtype = x.dtype
-        return self.forward_tokens(ops.to_bf16_2d(x), B, N).view(B, N, C).to(dtype)
+        return self.forward_tokens(ops.to_stream_2d(x), B, N).view(B, N, C).to(dtype)
 
 
 class PatchEmbed(nn.Module):
@@ -182,7 +187,7 @@ class PatchEmbed(nn.Module):
         zeros_pos = torch.zeros(Np + 1, D, device=x.device)
         tok = ops.TokensFn.apply(x.to(torch.bfloat16).contiguous(), self.proj.weight, self.proj.bias, zeros_cls,
                                  zeros_pos, self.patch_size)
-        return tok.view(B, Np + 1, D)[:, 1:].to(x.dtype)
+        return tok.view(B, Np + 1, D)[:, 1:].to(x.dtype)  # fp32 stream -> caller's dtype
 
 
 class VisionTransformer(nn.Module):
@@ -265,14 +270,19 @@ class VisionTransformer(nn.Module):
 
     def forward(self, x):
         tok, B, N = self._tokens(x)
-        for blk in self.blocks:
-            tok = blk.forward_tokens(tok, B, N)
-        # the reference normalises every token and then keeps row 0; only the CLS rows are needed
-        cls = tok.view(B, N, -1)[:, 0].contiguous()
-        if _is_plain_layernorm(self.norm):
-            cls = _layer_norm(self.norm, cls)
-        else:
-            cls = self.norm(cls)
+        blk0 = self.blocks[0]
+        blk0.attn._check(tok.shape[1])
+        if not (all(b._fused_ok() for b in self.blocks) and _is_plain_layernorm(self.norm)):
+            raise NotImplementedError("b200ssl VisionTransformer: stochastic depth / custom norm or activation "
+                                      "layers are not on the accelerated path (SURVEY.md §8f)")
+        params = []
+        for b in self.blocks:
+            params += b._param_list()
+        params += [self.norm.weight, self.norm.bias]
+        meta = (B, N, blk0.attn.num_heads, blk0.attn.scale, [(b.norm1.eps, b.norm2.eps) for b in self.blocks],
+                self.norm.eps)
+        # the reference normalises every token then keeps row 0 (@L252-253); only CLS rows are normalised here
+        cls = ops.EncoderFn.apply(tok, meta, *params)
         return cls.to(x.dtype)
 
     def get_last_selfattention(self, x):

@@ -90,6 +90,16 @@ def cosine_momentum(it: int, total_iters: int, base: float = 0.996, final: float
     return final - (final - base) * (math.cos(math.pi * it / max(total_iters, 1)) + 1) / 2
 
 
+def _detach_weight_norm(model):
+    """Old-style nn.utils.weight_norm leaves a non-leaf ``weight`` attribute that deepcopy refuses;
+    the forward pre-hook recomputes it anyway, so park a detached copy before cloning the module."""
+    from torch.nn.utils.weight_norm import WeightNorm
+    for m in model.modules():
+        for hook in m._forward_pre_hooks.values():
+            if isinstance(hook, WeightNorm) and isinstance(getattr(m, hook.name, None), torch.Tensor):
+                setattr(m, hook.name, getattr(m, hook.name).detach())
+
+
 class ModelEma(nn.Module):
     """timm ``ModelEmaV2`` call convention (train.py:619-620, :1081): ``.module`` is the EMA copy and
     ``update(model)`` folds every state-dict tensor; ``momentum`` overrides the fixed decay per step."""
@@ -97,6 +107,7 @@ class ModelEma(nn.Module):
     def __init__(self, model, decay=0.9998, device=None):
         super().__init__()
         import copy
+        _detach_weight_norm(model)
         self.module = copy.deepcopy(model)
         self.module.eval()
         for p in self.module.parameters():

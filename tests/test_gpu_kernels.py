@@ -48,6 +48,9 @@ def test_linear_gelu_and_residual(ops):
     res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
     y = ops.linear_fwd(x, w, b, residual=res)
     assert rel(y, ref + res.float()) < 1e-2
+    res32 = torch.randn(M, N, device="cuda", generator=g)            # fp32 residual stream epilogue
+    y32 = ops.linear_fwd(x, w, b, residual=res32)
+    assert y32.dtype == torch.float32 and rel(y32, ref + res32) < 5e-3
 
 
 def test_linear_dgrad_wgrad(ops):
@@ -68,11 +71,12 @@ def test_linear_dgrad_wgrad(ops):
     assert rel(db, dy.float().sum(0)) < 1e-4
 
 
-@pytest.mark.parametrize("D", [192, 384, 768])
-def test_layernorm(ops, D):
+@pytest.mark.parametrize("D,dtype", [(192, torch.bfloat16), (384, torch.bfloat16), (768, torch.bfloat16),
+                                     (192, torch.float32), (384, torch.float32)])
+def test_layernorm(ops, D, dtype):
     g = torch.Generator(device="cuda").manual_seed(4)
     rows = 1234
-    x = (torch.randn(rows, D, device="cuda", generator=g) * 2 + 0.5).bfloat16()
+    x = (torch.randn(rows, D, device="cuda", generator=g) * 2 + 0.5).to(dtype)
     w = torch.randn(D, device="cuda", generator=g)
     b = torch.randn(D, device="cuda", generator=g)
     y, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-6)
@@ -188,7 +192,7 @@ def test_ema_and_adamw(ops):
     for p, r in zip(model.parameters(), ref_model):
         assert rel(p, r) < 1e-5                                   # fp32 arithmetic, same update rule
     for p, r in zip(ema.module.parameters(), ref_ema):
-        assert rel(p, r) < 1e-6
+        assert rel(p, r) < 1e-5                                   # fp32, fma vs mul+add rounding
     # bf16 shadow written by the optimiser matches the updated weights
     w = next(model.parameters())
     assert torch.equal(ops.bf16_of(w), w.detach().bfloat16())
