@@ -25,9 +25,9 @@ namespace b200ssl {
 
 enum GemmEpilogue : int {
   EPI_BIAS = 0,       // D = acc (+ bias)
-  EPI_BIAS_GELU = 1,  // D = acc + bias ; D2 = gelu(D)
+  EPI_BIAS_GELU = 1,  // x = acc + bias ; D = gelu'(x) (saved for backward) ; D2 = gelu(x)
   EPI_BIAS_RES = 2,   // D = acc (+ bias) + aux
-  EPI_DGELU = 3,      // D = acc * gelu'(aux)
+  EPI_MUL_AUX = 3,    // D = acc * aux   (dgrad through GELU: aux = saved gelu'(x))
   EPI_ATOMIC_F32 = 4, // D(fp32) += acc   (split-K)
   EPI_BIAS_RES_F32 = 5, // D(fp32) = acc (+ bias) + aux(fp32): the fp32 residual stream
 };
@@ -36,8 +36,8 @@ struct GemmArgs {
   int M, N, K;
   int a_mn, b_mn;
   int num_m_blocks, num_n_blocks, k_splits, k_blocks_per_split, k_blocks_total;
-  const float* bias;
-  const void* aux;  // bf16 (EPI_BIAS_RES, EPI_DGELU) or fp32 (EPI_BIAS_RES_F32)
+  const float* bias;  // fprop bias [N]; for EPI_ATOMIC_F32 (wgrad) the OUTPUT db[M] += column sums of A, or null
+  const void* aux;  // bf16 (EPI_BIAS_RES, EPI_MUL_AUX) or fp32 (EPI_BIAS_RES_F32)
   long long ldaux;
   float* out_f32;
   long long ldd;
@@ -92,7 +92,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], EPI == EPI_ATOMIC_F32 ? 1 + NUM_EPI_GROUPS * 4 : 1);  // wgrad: + the epilogue warps (bias grad)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -194,12 +194,60 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t slot = 0;  // staging buffer ring position (per group)
     constexpr int kChunks = BN / 64;
 
+    int cs_stage = 0;       // wgrad only: position in the smem ring (bias-gradient pass)
+    uint32_t cs_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t % args.num_n_blocks;
       const int m_blk = (t / args.num_n_blocks) % args.num_m_blocks;
       const int m0 = m_blk * BLOCK_M, n0 = n_blk * BN;
       const int row = m0 + row_in_tile;
       const bool row_ok = row < args.M;
+
+      if (EPI == EPI_ATOMIC_F32) {
+        // wgrad: the epilogue warps are idle during the (long, split-K) mainloop, and the A stages
+        // (dY^T, MN-major [64 k][64 m] x 2 chunks) are already in smem for the MMA, so they fold the bias
+        // gradient db[m] += sum_k A[k, m] from there (n_blk == 0 tiles only: each (m block, k split) once)
+        // and release every stage like a second consumer.
+        const int ks = t / tiles_per_split;
+        const int kb0 = ks * args.k_blocks_per_split;
+        const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks_total);
+        float* db = const_cast<float*>(args.bias);
+        const bool mine = n_blk == 0 && db != nullptr && args.a_mn;
+        const int etid = threadIdx.x - 128;  // 0..255
+        const int jc = etid & 15;            // 16-byte chunk (8 columns) within the 128-wide m range
+        const int sub = etid >> 4;           // k rows sub, sub+16, sub+32, sub+48
+        float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[cs_stage], cs_phase);
+          if (mine) {
+            const uint8_t* sA = smem + cs_stage * Cfg::kStageBytes + (jc >> 3) * 8192;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              const int r = sub + 16 * rr;
+              const uint4 u = *reinterpret_cast<const uint4*>(sA + r * 128 + (((jc & 7) ^ (r & 7)) << 4));
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f2 = unpack_bf16x2(w[e]);
+                cs[2 * e] += f2.x;
+                cs[2 * e + 1] += f2.y;
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[cs_stage]);
+          if (++cs_stage == kStages) { cs_stage = 0; cs_phase ^= 1; }
+        }
+        if (mine) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
+          if (lane < 16) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (m0 + jc * 8 + e < args.M) atomicAdd(db + m0 + jc * 8 + e, cs[e]);
+          }
+        }
+      }
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
@@ -242,7 +290,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         float f[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) f[j] = __uint_as_float(v[j]);
-        if (EPI != EPI_DGELU && args.bias != nullptr) {
+        if (EPI != EPI_MUL_AUX && args.bias != nullptr) {
           const float4* bp = reinterpret_cast<const float4*>(args.bias + col0);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -250,7 +298,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
           }
         }
-        if (EPI == EPI_BIAS_RES || EPI == EPI_DGELU) {
+        if (EPI == EPI_BIAS_RES || EPI == EPI_MUL_AUX) {
           if (row_ok) {
             const uint4* ap = reinterpret_cast<const uint4*>(
                 static_cast<const __nv_bfloat16*>(args.aux) + static_cast<long long>(row) * args.ldaux + col0);
@@ -265,8 +313,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   f[8 * j + 2 * e] += x.x;
                   f[8 * j + 2 * e + 1] += x.y;
                 } else {
-                  f[8 * j + 2 * e] *= dgelu_erf(x.x);
-                  f[8 * j + 2 * e + 1] *= dgelu_erf(x.y);
+                  f[8 * j + 2 * e] *= x.x;
+                  f[8 * j + 2 * e + 1] *= x.y;
                 }
               }
             }
@@ -305,6 +353,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
 
         constexpr int kOutputs = EPI == EPI_BIAS_GELU ? 2 : 1;
+        uint32_t hpk[EPI == EPI_BIAS_GELU ? 32 : 1];  // gelu(x) packed, written as the second output
+        if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float h0, h1, g0, g1;
+            gelu_and_grad(f[2 * j], h0, g0);
+            gelu_and_grad(f[2 * j + 1], h1, g1);
+            f[2 * j] = g0;
+            f[2 * j + 1] = g1;
+            hpk[j] = pack_bf16x2(h0, h1);
+          }
+        }
 #pragma unroll
         for (int o = 0; o < kOutputs; ++o) {
           uint8_t* buf = stg + (slot & 1) * STAGING_BYTES;
@@ -319,10 +379,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               pk.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
               pk.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
             } else {
-              pk.x = pack_bf16x2(gelu_erf(f[8 * j + 0]), gelu_erf(f[8 * j + 1]));
-              pk.y = pack_bf16x2(gelu_erf(f[8 * j + 2]), gelu_erf(f[8 * j + 3]));
-              pk.z = pack_bf16x2(gelu_erf(f[8 * j + 4]), gelu_erf(f[8 * j + 5]));
-              pk.w = pack_bf16x2(gelu_erf(f[8 * j + 6]), gelu_erf(f[8 * j + 7]));
+              pk = make_uint4(hpk[(4 * j) % (EPI == EPI_BIAS_GELU ? 32 : 1)], hpk[(4 * j + 1) % (EPI == EPI_BIAS_GELU ? 32 : 1)],
+                              hpk[(4 * j + 2) % (EPI == EPI_BIAS_GELU ? 32 : 1)], hpk[(4 * j + 3) % (EPI == EPI_BIAS_GELU ? 32 : 1)]);
             }
             *reinterpret_cast<uint4*>(buf + sw128_offset(row_in_tile, j)) = pk;
           }
@@ -376,7 +434,7 @@ static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b, con
     case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(a, b, d, d2, args, s);
     case EPI_BIAS_GELU: return launch_gemm<BN, EPI_BIAS_GELU>(a, b, d, d2, args, s);
     case EPI_BIAS_RES: return launch_gemm<BN, EPI_BIAS_RES>(a, b, d, d2, args, s);
-    case EPI_DGELU: return launch_gemm<BN, EPI_DGELU>(a, b, d, d2, args, s);
+    case EPI_MUL_AUX: return launch_gemm<BN, EPI_MUL_AUX>(a, b, d, d2, args, s);
     case EPI_ATOMIC_F32: return launch_gemm<BN, EPI_ATOMIC_F32>(a, b, d, d2, args, s);
     case EPI_BIAS_RES_F32: return launch_gemm<BN, EPI_BIAS_RES_F32>(a, b, d, d2, args, s);
   }
@@ -416,7 +474,7 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
                     (reinterpret_cast<uintptr_t>(D) & 15) == 0,
                 -2, "gemm: operands must be 16-byte aligned");
   B200SSL_CHECK(epilogue >= 0 && epilogue <= 5, -2, "gemm: unknown epilogue %d", epilogue);
-  if (epilogue == EPI_BIAS_RES || epilogue == EPI_DGELU)
+  if (epilogue == EPI_BIAS_RES || epilogue == EPI_MUL_AUX)
     B200SSL_CHECK(aux != nullptr && ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0, -2,
                   "gemm: epilogue %d needs a 16B-aligned aux operand", epilogue);
   if (epilogue == EPI_BIAS_RES_F32)
@@ -429,7 +487,8 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
     if (epilogue != EPI_BIAS_RES_F32) B200SSL_CHECK(ldd % 8 == 0, -2, "gemm: bf16 ldd must be a multiple of 8");
     split_k = 1;
   }
-  if (bias) B200SSL_CHECK((reinterpret_cast<uintptr_t>(bias) & 15) == 0, -2, "gemm: bias must be 16B aligned");
+  if (bias && epilogue != EPI_ATOMIC_F32)
+    B200SSL_CHECK((reinterpret_cast<uintptr_t>(bias) & 15) == 0, -2, "gemm: bias must be 16B aligned");
 
   const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   int bn = block_n;

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_ATOMIC_F32, EPI_BIAS_RES_F32 = 0, 1, 2, 3, 4, 5
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_MUL_AUX, EPI_ATOMIC_F32, EPI_BIAS_RES_F32 = 0, 1, 2, 3, 4, 5
 
 _BF16 = torch.bfloat16
 _counters = {"launches": 0}
@@ -129,7 +129,8 @@ def gemm(A, B, D, M, N, K, *, a_mn=False, b_mn=False, epi=EPI_BIAS, D2=None, bia
 
 
 def linear_fwd(x, w16, bias=None, residual=None, gelu=False):
-    """y = x @ w16^T (+bias) (+residual); with gelu=True returns (pre_activation, gelu(pre)).
+    """y = x @ w16^T (+bias) (+residual); with gelu=True returns (gelu'(pre), gelu(pre)) — the derivative is
+    what backward needs, so it is saved instead of the pre-activation (one erf evaluation serves both).
     An fp32 ``residual`` selects the fp32-stream epilogue (fp32 output); bf16 residual -> bf16 output."""
     M, K = x.shape
     N = w16.shape[0]
@@ -150,12 +151,12 @@ def linear_fwd(x, w16, bias=None, residual=None, gelu=False):
 
 
 def linear_dgrad(dy, w16, dgelu_of=None):
-    """dx = dy @ w16 ; optionally multiplied by gelu'(dgelu_of) in the epilogue."""
+    """dx = dy @ w16 ; optionally multiplied in the epilogue by ``dgelu_of`` = the saved gelu'(pre)."""
     M, N = dy.shape
     K = w16.shape[1]
     dx = torch.empty(M, K, dtype=_BF16, device=dy.device)
     if dgelu_of is not None:
-        gemm(dy, w16, dx, M, K, N, b_mn=True, epi=EPI_DGELU, aux=dgelu_of)
+        gemm(dy, w16, dx, M, K, N, b_mn=True, epi=EPI_MUL_AUX, aux=dgelu_of)
     else:
         gemm(dy, w16, dx, M, K, N, b_mn=True, epi=EPI_BIAS)
     return dx
@@ -165,12 +166,11 @@ def linear_wgrad(dy, x, need_bias=True):
     """dW[N,K] = dy^T @ x (fp32, split-K atomics), db[N] = column sums of dy."""
     M, N = dy.shape
     K = x.shape[1]
-    dw = torch.zeros(N, K, dtype=torch.float32, device=dy.device)
-    gemm(dy, x, dw, N, K, M, a_mn=True, b_mn=True, epi=EPI_ATOMIC_F32, split_k=0)
-    db = None
-    if need_bias:
-        db = torch.empty(N, dtype=torch.float32, device=dy.device)
-        _call("b200ssl_colsum", dy.data_ptr(), dy.stride(0), db.data_ptr(), M, N, 0, _stream(), launches=2)
+    buf = torch.zeros(N * K + (N if need_bias else 0), dtype=torch.float32, device=dy.device)
+    dw = buf[:N * K].view(N, K)
+    db = buf[N * K:] if need_bias else None
+    # the bias gradient (column sums of dy) is folded by idle warps of the wgrad kernel from the smem stages
+    gemm(dy, x, dw, N, K, M, a_mn=True, b_mn=True, epi=EPI_ATOMIC_F32, split_k=0, bias=db)
     return dw, db
 
 

@@ -50,6 +50,8 @@ def run_case(name, M, N, K, a_mn, b_mn, epi, bn, split_k=1, results=None):
     B_in = B.t().contiguous() if b_mn else B
     ref = A.float() @ B.float().t()
     bias = torch.randn(N, device="cuda", generator=g) if epi in (0, 1, 2) else None
+    if epi == 4 and a_mn:
+        bias = torch.zeros(M, device="cuda")  # wgrad: receives db = column sums of A^T (i.e. A.sum over K)
     aux = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16) if epi in (2, 3) else None
     D2 = None
     if epi == 4:
@@ -62,12 +64,13 @@ def run_case(name, M, N, K, a_mn, b_mn, epi, bn, split_k=1, results=None):
     if epi == 1:
         D2 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
         ref2 = torch.nn.functional.gelu(ref)
+        xr = ref.clone().requires_grad_(True)
+        torch.nn.functional.gelu(xr).sum().backward()
+        ref = xr.grad
     if epi == 2:
         ref = ref + aux.float()
     if epi == 3:
-        x = aux.float().requires_grad_(True)
-        (torch.nn.functional.gelu(x)).sum().backward()
-        ref = ref * x.grad
+        ref = ref * aux.float()
     try:
         gemm(A_in, a_mn, B_in, b_mn, D, M, N, K, epi, D2, bias, aux, split_k, bn)
         torch.cuda.synchronize()
@@ -80,6 +83,11 @@ def run_case(name, M, N, K, a_mn, b_mn, epi, bn, split_k=1, results=None):
     err = (D.float() - ref).abs().max().item() / scale
     nan = int(torch.isnan(D.float()).sum().item())
     ok = err < 1.5e-2 and nan == 0
+    if epi == 4 and a_mn:
+        dbref = A.float().sum(1)
+        errb = (bias - dbref).abs().max().item() / (dbref.abs().max().item() + 1e-6)
+        ok = ok and errb < 1e-3
+        err = max(err, errb)
     if ref2 is not None:
         err2 = (D2.float() - ref2).abs().max().item() / (ref2.abs().max().item() + 1e-6)
         ok = ok and err2 < 1.5e-2
@@ -103,7 +111,7 @@ def bench_case(M, N, K, a_mn, b_mn, epi, bn, split_k=1, iters=20):
     B = torch.randn(N, K, device="cuda").to(torch.bfloat16)
     A_in = A.t().contiguous() if a_mn else A
     B_in = B.t().contiguous() if b_mn else B
-    bias = torch.randn(N, device="cuda")
+    bias = torch.randn(N, device="cuda") if epi != 4 else torch.zeros(M, device="cuda")
     aux = torch.randn(M, N, device="cuda").to(torch.bfloat16) if epi in (2, 3) else None
     D = torch.zeros(M, N, device="cuda", dtype=torch.float32 if epi == 4 else torch.bfloat16)
     D2 = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16) if epi == 1 else None

@@ -41,10 +41,12 @@ def test_linear_gelu_and_residual(ops):
     x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
     w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
     b = torch.randn(N, device="cuda", generator=g)
-    pre, h = ops.linear_fwd(x, w, b, gelu=True)
+    dact, h = ops.linear_fwd(x, w, b, gelu=True)
     ref = x.float() @ w.float().t() + b
-    assert rel(pre, ref) < 1e-2
     assert rel(h, torch.nn.functional.gelu(ref)) < 1e-2      # exact-erf GELU (parity hazard 1)
+    pr = ref.clone().requires_grad_(True)
+    torch.nn.functional.gelu(pr).sum().backward()
+    assert rel(dact, pr.grad) < 1e-2                          # saved derivative gelu'(pre)
     res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
     y = ops.linear_fwd(x, w, b, residual=res)
     assert rel(y, ref + res.float()) < 1e-2
@@ -61,11 +63,9 @@ def test_linear_dgrad_wgrad(ops):
     dy = torch.randn(M, N, device="cuda", generator=g).bfloat16()
     dx = ops.linear_dgrad(dy, w)
     assert rel(dx, dy.float() @ w.float()) < 1e-2
-    pre = torch.randn(M, K, device="cuda", generator=g).bfloat16()
-    dxg = ops.linear_dgrad(dy, w, dgelu_of=pre)
-    p = pre.float().requires_grad_(True)
-    torch.nn.functional.gelu(p).sum().backward()
-    assert rel(dxg, (dy.float() @ w.float()) * p.grad) < 1e-2
+    dact = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    dxg = ops.linear_dgrad(dy, w, dgelu_of=dact)
+    assert rel(dxg, (dy.float() @ w.float()) * dact.float()) < 1e-2
     dw, db = ops.linear_wgrad(dy, x)
     assert rel(dw, dy.float().t() @ x.float()) < 1e-3        # fp32 output, bf16 inputs
     assert rel(db, dy.float().sum(0)) < 1e-4
