@@ -299,6 +299,7 @@ class GradBucketDataParallel(nn.Module):
         self.module = module
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self._avg_native = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
         params = [p for p in module.parameters() if p.requires_grad]
         self._params = params
         cap = int(bucket_mb * 1024 * 1024 / 4)
@@ -352,7 +353,12 @@ class GradBucketDataParallel(nn.Module):
 
     def _launch(self, bi):
         self._launched[bi] = True
-        self._handles.append(dist.all_reduce(self._flat[bi], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+        if self._avg_native:
+            op = dist.ReduceOp.AVG
+        else:  # gloo (CPU tests) has no AVG: pre-scale, then SUM
+            op = dist.ReduceOp.SUM
+            self._flat[bi].div_(self.world)
+        self._handles.append(dist.all_reduce(self._flat[bi], op=op, group=self.pg, async_op=True))
 
     def zero_grad(self, set_to_none: bool = False):
         """Zero the flat buckets (gradients stay views into them)."""

@@ -33,6 +33,11 @@ def trunc_normal_(tensor, mean=0.0, std=1.0, a=-2.0, b=2.0):
     return tensor
 
 
+def _no_grad_trunc_normal_(tensor, mean, std, a, b):
+    """VT.pyc@L25-57: the worker trunc_normal_ wraps (same routine, positional arguments)."""
+    return trunc_normal_(tensor, mean, std, a, b)
+
+
 def drop_path(x, drop_prob: float = 0.0, training: bool = False):
     """Per-sample stochastic depth (VT.pyc@L66-74). Identity at the constructor default (0.0)."""
     if drop_prob == 0.0 or not training:

@@ -1,0 +1,115 @@
+/*
+ * b200ssl — C ABI of the B200-native (sm_100a) hot path of the GipMed self-supervised ViT:
+ * the DINO-style training step (ViT encoder, projection head, centred cross-entropy, teacher EMA,
+ * fused optimiser). Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative code otherwise; b200ssl_last_error() then holds a
+ *    human-readable message (thread-local). Nothing throws across the boundary.
+ *  - all pointers are DEVICE pointers owned by the caller (16-byte aligned unless stated); the library
+ *    allocates nothing persistent and never synchronises: kernels are enqueued on `stream`
+ *    (a cudaStream_t passed as void*), so every call is CUDA-graph capturable.
+ *  - activations are bf16 row-major [rows, features]; parameters / statistics / gradients of
+ *    parameters are fp32. "ld*" are leading dimensions in ELEMENTS.
+ *  - VT.pyc@Lnn = source line nn of the reference's nn_encoder_arch/__pycache__/
+ *    vision_transformer.cpython-37.pyc (the reference ships this path as bytecode only);
+ *    train.py:nn = /root/reference/train.py line nn.
+ */
+#ifndef B200SSL_H_
+#define B200SSL_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------------- */
+int b200ssl_version(void);
+const char* b200ssl_last_error(void);
+/* 0 iff the current CUDA device is compute capability 10.x (there is no fallback path). */
+int b200ssl_device_check(void);
+
+/* ---- K3: tcgen05 GEMM  D[M,N] = epilogue(A . B^T), bf16 x bf16 -> fp32 accumulate in TMEM -------
+ * Replaces every nn.Linear fprop / dgrad / wgrad cuBLASLt call of the encoder and head
+ * (qkv VT.pyc@L114,121; proj @L116,129; fc1/fc2 @L93-95,99-102; DINOHead @L303-318,327-329) and the
+ * patch-embed Conv2d-as-GEMM (@L165,169).
+ *   a_mn_major / b_mn_major: 0 = operand stored [M|N, K] row-major (K-major), 1 = stored [K, M|N].
+ *   epilogue: 0 D=acc+bias | 1 D=gelu'(acc+bias), D2=gelu(acc+bias) (exact erf) | 2 D=acc+bias+aux(bf16)
+ *             3 D=acc*aux(bf16) | 4 D(fp32)+=acc split-K atomics, and bias (if non-null) is the OUTPUT
+ *             db[M] += column sums of A (wgrad bias gradient) | 5 D(fp32)=acc+bias+aux(fp32) (residual stream)
+ *   split_k: K splits for epilogue 4 (0 = auto); block_n: 0 = auto, else 64/128/192/256 dividing N.
+ * Constraints: N % 64 == 0, lda/ldb % 8 == 0. */
+int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
+                 void* D, long long ldd, void* D2, const float* bias, const void* aux, long long ldaux,
+                 int M, int N, int K, int epilogue, int split_k, int block_n, void* stream);
+
+/* ---- K2: LayerNorm (Block.norm1/norm2 VT.pyc@L138,142,147,151; VisionTransformer.norm @L195,252) -----
+ * x is bf16 (x_f32 = 0) or the fp32 residual stream (x_f32 = 1); y bf16; mean/rstd fp32 [rows].
+ * bwd: dx(bf16) = LN'(dy) + dres (dres nullable: the residual-branch gradient is added in-kernel);
+ * dw/db fp32 [D] are ACCUMULATED into. D in {192,256,384,512,768,1024}. */
+int b200ssl_layernorm_fwd(const void* x, int x_f32, const float* w, const float* b, void* y, float* mean,
+                          float* rstd, long long rows, int D, float eps, void* stream);
+int b200ssl_layernorm_bwd(const void* x, int x_f32, const void* dy, const float* w, const float* mean,
+                          const float* rstd, const void* dres, void* dx, float* dw, float* db, long long rows,
+                          int D, void* stream);
+
+/* ---- K4: fused attention (Attention.forward VT.pyc@L119-131) --------------------------------------
+ * qkv [B,N,3,H,64] bf16 (the QKV GEMM output as is), out/dout [B,N,H,64] bf16, lse2 [B,H,N] fp32
+ * (log2-sum-exp of the scaled scores), dqkv like qkv. head_dim must be 64, 1 <= N <= 256. */
+int b200ssl_attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, int head_dim,
+                          float scale, void* stream);
+int b200ssl_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv,
+                          int B, int N, int H, int head_dim, float scale, void* stream);
+
+/* ---- K1 helpers: patch gathering and token assembly (PatchEmbed.forward VT.pyc@L167-170,
+ *      prepare_tokens @L235-246). img [B,C,H,W] bf16 -> cols [B*Np, C*P*P] bf16 (then b200ssl_gemm);
+ *      x(fp32)[b,0]=cls+pos[0], x[b,1+p]=y[b*Np+p]+pos[1+p]; bwd: dy=dx[:,1:], dpos=sum_b dx, dcls=dpos[0]. */
+int b200ssl_patchify(const void* img, void* cols, int B, int C, int H, int W, int P, void* stream);
+int b200ssl_assemble_tokens(const void* y, const float* cls, const float* pos, void* x, int B, int Np, int D,
+                            void* stream);
+int b200ssl_assemble_tokens_bwd(const void* dx, void* dy, float* dpos, float* dcls, int B, int Np, int D,
+                                void* stream);
+
+/* ---- small HBM-bound helpers ------------------------------------------------------------------------ */
+/* out[c] (+)= sum_r x[r,c]; bf16 in, fp32 out (accumulate != 0 keeps the previous content). */
+int b200ssl_colsum(const void* x, long long ldx, float* out, long long rows, int ncols, int accumulate,
+                   void* stream);
+int b200ssl_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+/* F.normalize(dim=-1, p=2, eps) (DINOHead.forward VT.pyc@L328): y = x / max(||x||, eps). */
+int b200ssl_l2norm_fwd(const void* x, void* y, float* norm, long long rows, int D, float eps, void* stream);
+int b200ssl_l2norm_bwd(const void* y, const void* dy, const float* norm, void* dx, long long rows, int D,
+                       float eps, void* stream);
+/* weight_norm(Linear) rows (VT.pyc@L315-318): w(bf16) = g * v / ||v||; g nullable (= 1). */
+int b200ssl_weightnorm_fwd(const float* v, const float* g, void* w, float* norm, long long rows, int D,
+                           void* stream);
+int b200ssl_weightnorm_bwd(const float* v, const float* g, const float* norm, const float* dw, float* dv,
+                           float* dg, long long rows, int D, void* stream);
+
+/* ---- K7: DINO loss (not in the reference; call slot train.py:1053 loss_fn(output, target)) -----------
+ * student [ncrops*B, K], teacher [2*B, K] bf16, crop-major rows; center fp32 [K]; loss fp32 [1];
+ * s_lse [ncrops*B], t_lse [2*B] fp32 saved for backward; gout: device scalar (nullable = 1). */
+int b200ssl_dino_loss_fwd(const void* student, const void* teacher, const float* center, float* loss,
+                          float* s_lse, float* t_lse, int B, int ncrops, int K, float student_temp,
+                          float teacher_temp, void* stream);
+int b200ssl_dino_loss_bwd(const void* student, const void* teacher, const float* center, const float* s_lse,
+                          const float* t_lse, const float* gout, void* dstudent, int B, int ncrops, int K,
+                          float student_temp, float teacher_temp, void* stream);
+/* center = m*center + (1-m)*batch_sum/total_rows (batch_sum = all-reduced column sums of teacher logits). */
+int b200ssl_center_update(float* center, const float* batch_sum, int K, long long total_rows, float momentum,
+                          void* stream);
+
+/* ---- K8: multi-tensor EMA / AdamW / grad-norm (train.py:1081 model_ema.update; :1063-1078 clip+step) --
+ * `table` is a device array of int64 rows, one per <= 65536-element chunk:
+ *   ema   : {dst*, src*, n}                    dst = m*dst + (1-m)*src
+ *   sumsq : {g*, n}                            out[0] = sum g^2
+ *   adamw : {p*, g*, m*, v*, n, decay, ema*, bf16_shadow*}   torch.optim.AdamW rule, grads pre-scaled by
+ *           min(1, max_norm/(sqrt(*gnorm_sq)+1e-6)) when gnorm_sq != NULL and max_norm > 0. */
+int b200ssl_ema_multi_tensor(const void* table, int n_rows, float momentum, void* stream);
+int b200ssl_sumsq_multi_tensor(const void* table, int n_rows, float* out, void* stream);
+int b200ssl_adamw_multi_tensor(const void* table, int n_rows, const float* gnorm_sq, float lr, float beta1,
+                               float beta2, float eps, float weight_decay, float max_norm, float bias_corr1,
+                               float bias_corr2, float ema_momentum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SSL_H_ */

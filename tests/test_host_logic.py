@@ -1,0 +1,134 @@
+"""CPU tests of the host side: the C-ABI library loads and exports exactly what include/b200ssl.h
+declares, the product path refuses to run without CUDA (no fallback), bench.py's FLOP accounting, and
+the data-parallel bucket logic on a 2-rank gloo group."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "b200ssl.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200ssl_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import b200ssl
+    h = b200ssl._lib.lib()                     # raises if the .so is missing: there is no fallback
+    declared = _header_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(h, name), f"{name} declared in include/b200ssl.h but not exported"
+    assert sorted(b200ssl._lib.exported_symbols()) == declared
+    assert h.b200ssl_version() >= 100
+    nm = subprocess.run(["nm", "-D", "--defined-only", b200ssl._lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (b200ssl_\w+)", nm)))
+    assert exported == declared, "library exports symbols the header does not declare (or vice versa)"
+
+
+def test_library_holds_blackwell_kernels():
+    """The shipped cubin must contain tcgen05 MMA / TMEM / TMA instructions (SASS mnemonics)."""
+    import b200ssl
+    r = subprocess.run(["cuobjdump", "-sass", b200ssl._lib.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    sass = r.stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_ops_refuse_cpu_tensors():
+    import b200ssl
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        b200ssl.vit_tiny()(torch.randn(1, 3, 224, 224))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        b200ssl.DINOHead(192, 256)(torch.randn(2, 192))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        b200ssl.DINOLoss(256, 2, 0.04, 0.04, 0, 1)(torch.randn(4, 256), torch.randn(4, 256))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        b200ssl.Mlp(64)(torch.randn(2, 64))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gipmed-project-self-supervised-vit_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_flop_accounting_matches_baseline_md():
+    sys.path.insert(0, ROOT)
+    import bench
+    tot, gemm, attn = bench.flops_per_sample("vit_small", 65536, 10)
+    assert abs(tot / 1e9 - 123.80) < 0.05
+    assert abs(bench.flops_per_sample("vit_base", 65536, 10)[0] / 1e9 - 474.11) < 0.1
+    assert abs(bench.flops_per_sample("vit_tiny", 65536, 10)[0] / 1e9 - 34.20) < 0.05
+    assert gemm + attn == tot and attn / tot < 0.1
+
+
+def test_teacher_temp_schedule_and_param_groups():
+    import b200ssl
+    from oracle import dino as odino
+    a = b200ssl.DINOLoss(64, 4, 0.04, 0.07, 3, 10).teacher_temp_schedule
+    b = odino.DINOLoss(64, 4, 0.04, 0.07, 3, 10).teacher_temp_schedule
+    assert list(a) == list(b) and len(a) == 10
+    groups = b200ssl.param_groups_wd(b200ssl.vit_tiny(), 0.04)
+    assert groups[1]["weight_decay"] == 0.0 and all(p.ndim == 1 for p in groups[1]["params"])
+    assert all(p.ndim > 1 for p in groups[0]["params"])
+
+
+_DDP_SCRIPT = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import b200ssl
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+torch.manual_seed(1234 + rank)                      # different init per rank: the wrapper must broadcast rank 0
+model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 8))
+ddp = b200ssl.GradBucketDataParallel(model, bucket_mb=0.001)   # tiny buckets -> several all-reduces
+assert len(ddp.buckets) > 1
+ref = [p.detach().clone() for p in model.parameters()]
+gathered = [torch.zeros_like(ref[0]) for _ in range(world)]
+dist.all_gather(gathered, ref[0])
+assert all(torch.equal(g, gathered[0]) for g in gathered), "parameters were not broadcast from rank 0"
+for step in range(3):                               # step 0 learns the arrival counts, steps 1-2 overlap
+    torch.manual_seed(100 * step + rank)
+    x = torch.randn(4, 16)
+    ddp.zero_grad()
+    ddp(x).pow(2).sum().backward()
+    ddp.finish()
+    local = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 8))
+    local.load_state_dict(model.state_dict())
+    total = [torch.zeros_like(p) for p in local.parameters()]
+    for r in range(world):                          # serial reference: mean over every rank's batch
+        torch.manual_seed(100 * step + r)
+        xr = torch.randn(4, 16)
+        local.zero_grad()
+        local(xr).pow(2).sum().backward()
+        for t, p in zip(total, local.parameters()):
+            t += p.grad / world
+    for t, p in zip(total, model.parameters()):
+        assert torch.allclose(p.grad, t, atol=1e-5), (step, (p.grad - t).abs().max())
+        assert p.grad.data_ptr() != 0 and p.grad.is_contiguous()
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_grad_bucket_data_parallel_gloo_world2(tmp_path):
+    script = tmp_path / "ddp_check.py"
+    script.write_text(_DDP_SCRIPT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), ROOT],
+                       capture_output=True, text=True, env=env, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("ok") == 2
