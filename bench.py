@@ -229,8 +229,16 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = ops.launch_count()
-    ms_total = timed(lambda i: step(crops, args.warmup + i), args.steps)
+    host_t = [0.0]
+
+    def step_host_timed(i):
+        t0 = time.perf_counter()
+        step(crops, args.warmup + i)
+        host_t[0] += time.perf_counter() - t0
+
+    ms_total = timed(step_host_timed, args.steps)
     launches = ops.launch_count() - launches0
+    host_ms = host_t[0] * 1e3 / args.steps   # host time to ENQUEUE one step (GPU runs asynchronously)
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = B * world / (ms_step / 1e3)
@@ -319,7 +327,8 @@ def main():
             "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2_policy": "inputs + activations per step (>20 GB) far exceed the 126 MB L2",
                        "flop_per_image": total_f},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms,
+            "roofline": roofline}
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
     print(json.dumps(line))

@@ -145,6 +145,12 @@ ln_bwd_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
     const float mean = mean_in[row], rstd = rstd_in[row];
     float xh[CPL * 8], g[CPL * 8];
     float s1 = 0.f, s2 = 0.f;
+    // the residual-branch gradient is only needed at the end: fetch it now so its latency overlaps the
+    // reductions instead of being exposed after them
+    const uint4* pr = dres ? reinterpret_cast<const uint4*>(dres + row * D) : nullptr;
+    uint4 r4[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) r4[c] = pr ? __ldg(pr + c * LPR + sub) : make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
       float x8[8];
@@ -174,12 +180,9 @@ ln_bwd_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
     const float m2 = group_sum<LPR>(s2) * (1.f / D);
     if (!valid) continue;
     uint4* pdx = reinterpret_cast<uint4*>(dx + row * D);
-    const uint4* pr = dres ? reinterpret_cast<const uint4*>(dres + row * D) : nullptr;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
-      uint4 r4 = make_uint4(0, 0, 0, 0);
-      if (pr) r4 = __ldg(pr + c * LPR + sub);
-      const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+      const uint32_t rw[4] = {r4[c].x, r4[c].y, r4[c].z, r4[c].w};
       uint32_t o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
