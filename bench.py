@@ -152,6 +152,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=4, help="images per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying "
+                    "the captured CUDA graph of the step")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -201,8 +203,20 @@ def main():
     crops = make_crops(B, n_local, device, torch.bfloat16, 1234 + 1000 * rank)
     total_steps = args.steps + args.warmup
 
-    def step(cr, it):
+    def eager_step(cr, it):
         m = b200ssl.cosine_momentum(it, max(total_steps, 1))
+        return b200ssl.dino_step(ddp, teacher, loss_fn, opt, cr, epoch=0, momentum=m, clip_grad=3.0)
+
+    use_graph = not args.no_graph
+    graphed = None
+    if use_graph:
+        graphed = b200ssl.GraphedDinoStep(ddp, teacher, loss_fn, opt, crops, clip_grad=3.0)
+
+    def step(cr, it):
+        """The public step API: GraphedDinoStep (whole step = one CUDA-graph replay) or eager dino_step."""
+        m = b200ssl.cosine_momentum(it, max(total_steps, 1))
+        if graphed is not None:
+            return graphed(cr, epoch=0, momentum=m), None, None
         return b200ssl.dino_step(ddp, teacher, loss_fn, opt, cr, epoch=0, momentum=m, clip_grad=3.0)
 
     def barrier():
@@ -239,6 +253,12 @@ def main():
     ms_total = timed(step_host_timed, args.steps)
     launches = ops.launch_count() - launches0
     host_ms = host_t[0] * 1e3 / args.steps   # host time to ENQUEUE one step (GPU runs asynchronously)
+    if graphed is not None:
+        # replays launch the captured kernels without going through Python: count them on one eager step
+        l0 = ops.launch_count()
+        eager_step(crops, total_steps)
+        torch.cuda.synchronize()
+        launches = (ops.launch_count() - l0) * args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = B * world / (ms_step / 1e3)
@@ -292,7 +312,7 @@ def main():
         gemm_events.append((e0, e1))
 
     ops.gemm = timed_gemm
-    step(crops, total_steps)
+    eager_step(crops, total_steps)
     torch.cuda.synchronize()
     ops.gemm = real_gemm
     gemm_ms = sum(a.elapsed_time(b) for a, b in gemm_events)
@@ -325,6 +345,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "step_api": "b200ssl.GraphedDinoStep (CUDA graph replay)" if use_graph else "b200ssl.dino_step (eager)",
                        "l2_policy": "inputs + activations per step (>20 GB) far exceed the 126 MB L2",
                        "flop_per_image": total_f},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms,

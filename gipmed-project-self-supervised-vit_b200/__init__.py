@@ -8,8 +8,8 @@ The compute path is the in-tree C-ABI library ``libb200ssl.so`` (hand-written CU
 There is no CPU, PyTorch-math or Triton fallback: ops raise if the library or an sm_100 GPU is missing.
 """
 from . import _lib, ops  # noqa: F401
-from .dino import (DINOLoss, FusedAdamW, GradBucketDataParallel, ModelEma, MultiCropWrapper,  # noqa: F401
-                   cosine_momentum, dino_step, param_groups_wd)
+from .dino import (DINOLoss, FusedAdamW, GradBucketDataParallel, GraphedDinoStep, ModelEma,  # noqa: F401
+                   MultiCropWrapper, cosine_momentum, dino_step, param_groups_wd)
 from .vision_transformer import (Attention, Block, DINOHead, DropPath, Mlp, PatchEmbed,  # noqa: F401
                                  VisionTransformer, drop_path, trunc_normal_, vit_base, vit_small, vit_tiny)
 

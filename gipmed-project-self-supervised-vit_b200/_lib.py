@@ -37,8 +37,8 @@ SIGNATURES = {
     "b200ssl_dino_loss_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P],
     "b200ssl_dino_loss_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P],
     "b200ssl_center_update": [_P, _P, _I, _L, _F, _P],
-    "b200ssl_ema_multi_tensor": [_P, _I, _F, _P],
-    "b200ssl_adamw_multi_tensor": [_P, _I, _P, _F, _F, _F, _F, _F, _F, _F, _F, _F, _P],
+    "b200ssl_ema_multi_tensor": [_P, _I, _P, _P],
+    "b200ssl_adamw_multi_tensor": [_P, _I, _P, _P, _F, _F, _F, _F, _P],
     "b200ssl_sumsq_multi_tensor": [_P, _I, _P, _P],
 }
 _RESTYPES = {"b200ssl_last_error": c_char_p}

@@ -19,10 +19,12 @@ struct EmaRow {  // int64 x 3
   long long n;
 };
 
-// dst = m * dst + (1 - m) * src
+// dst = m * dst + (1 - m) * src ; the momentum is read from device memory so that a captured CUDA graph
+// can be replayed with a new value every step (cosine schedule)
 __global__ void __launch_bounds__(OPT_THREADS)
-ema_kernel(const EmaRow* __restrict__ table, float m) {
+ema_kernel(const EmaRow* __restrict__ table, const float* __restrict__ momentum) {
   const EmaRow row = table[blockIdx.x];
+  const float m = __ldg(momentum);
   const float om = 1.f - m;
   const bool vec = ((reinterpret_cast<uintptr_t>(row.dst) | reinterpret_cast<uintptr_t>(row.src)) & 15) == 0;
   if (vec) {
@@ -86,6 +88,8 @@ struct AdamRow {  // int64 x 8
 struct AdamHyper {
   float lr, beta1, beta2, eps, wd, max_norm, bc1, bc2, ema_m;
 };
+// per-step scalars live in device memory (graph replay): {lr, weight_decay, 1-beta1^t, 1-beta2^t, ema_m}
+constexpr int ADAM_DEV_HYPER = 5;
 
 __device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, const AdamHyper& h, float clip,
                                           bool decay) {
@@ -100,8 +104,14 @@ __device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, 
 // torch.optim.AdamW semantics (decoupled decay first, bias-corrected moments); gradient clipping by
 // global norm as torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6)).
 __global__ void __launch_bounds__(OPT_THREADS)
-adamw_kernel(const AdamRow* __restrict__ table, const float* __restrict__ gnorm_sq, AdamHyper h) {
+adamw_kernel(const AdamRow* __restrict__ table, const float* __restrict__ gnorm_sq,
+             const float* __restrict__ dev_hyper, AdamHyper h) {
   const AdamRow row = table[blockIdx.x];
+  h.lr = __ldg(dev_hyper + 0);
+  h.wd = __ldg(dev_hyper + 1);
+  h.bc1 = __ldg(dev_hyper + 2);
+  h.bc2 = __ldg(dev_hyper + 3);
+  h.ema_m = __ldg(dev_hyper + 4);
   float clip = 1.f;
   if (gnorm_sq != nullptr && h.max_norm > 0.f) {
     const float norm = sqrtf(__ldg(gnorm_sq));
@@ -147,10 +157,11 @@ adamw_kernel(const AdamRow* __restrict__ table, const float* __restrict__ gnorm_
 
 using namespace b200ssl;
 
-extern "C" int b200ssl_ema_multi_tensor(const void* table, int n_rows, float momentum, void* stream) {
+extern "C" int b200ssl_ema_multi_tensor(const void* table, int n_rows, const float* momentum_dev, void* stream) {
   if (n_rows <= 0) return 0;
+  B200SSL_CHECK(momentum_dev != nullptr, -2, "ema: momentum must be a device pointer");
   ema_kernel<<<n_rows, OPT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const EmaRow*>(table),
-                                                                           momentum);
+                                                                           momentum_dev);
   B200SSL_CUDA(cudaGetLastError());
   return 0;
 }
@@ -165,13 +176,15 @@ extern "C" int b200ssl_sumsq_multi_tensor(const void* table, int n_rows, float* 
   return 0;
 }
 
-extern "C" int b200ssl_adamw_multi_tensor(const void* table, int n_rows, const float* gnorm_sq, float lr,
-                                          float beta1, float beta2, float eps, float weight_decay, float max_norm,
-                                          float bias_corr1, float bias_corr2, float ema_momentum, void* stream) {
+// dev_hyper: device float[5] = {lr, weight_decay, 1-beta1^t, 1-beta2^t, ema_momentum} for THIS step.
+extern "C" int b200ssl_adamw_multi_tensor(const void* table, int n_rows, const float* gnorm_sq,
+                                          const float* dev_hyper, float beta1, float beta2, float eps,
+                                          float max_norm, void* stream) {
   if (n_rows <= 0) return 0;
-  AdamHyper h{lr, beta1, beta2, eps, weight_decay, max_norm, bias_corr1, bias_corr2, ema_momentum};
+  B200SSL_CHECK(dev_hyper != nullptr, -2, "adamw: dev_hyper must be a device pointer");
+  AdamHyper h{0.f, beta1, beta2, eps, 0.f, max_norm, 1.f, 1.f, 0.f};
   adamw_kernel<<<n_rows, OPT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const AdamRow*>(table),
-                                                                             gnorm_sq, h);
+                                                                             gnorm_sq, dev_hyper, h);
   B200SSL_CUDA(cudaGetLastError());
   return 0;
 }

@@ -157,6 +157,9 @@ class ModelEma(nn.Module):
             self.module.to(device=device)
         self._table = None
         self._table_key = None
+        self._m_dev = self._m_host = None
+        self._m_value = decay
+        self._pairs, self._others = [], []
 
     def _build(self, model):
         pairs, others = [], []
@@ -176,14 +179,28 @@ class ModelEma(nn.Module):
             self._pairs, self._others = pairs, others
         return self._table
 
-    @torch.no_grad()
-    def update(self, model, momentum=None):
+    def prepare(self, model, momentum=None):
+        """Host-side part of an update: (re)build the chunk table if storages moved and stage this step's
+        momentum in device memory (pinned host -> device, async). Must run OUTSIDE a CUDA-graph capture."""
         m = self.decay if momentum is None else momentum
         model = getattr(model, "module", model) if isinstance(model, GradBucketDataParallel) else model
         table = self._build(model)
         if table is not None:
             ops.require_cuda(table, "ModelEma")
-            ops._call("b200ssl_ema_multi_tensor", table.data_ptr(), table.shape[0], float(m), ops._stream())
+            if self._m_dev is None:
+                self._m_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+                self._m_dev = torch.zeros(1, dtype=torch.float32, device=table.device)
+            self._m_host[0] = float(m)
+            self._m_dev.copy_(self._m_host, non_blocking=True)
+        self._m_value = float(m)
+
+    @torch.no_grad()
+    def launch(self):
+        """Device-side part: one multi-tensor kernel over every fp32 state-dict tensor (graph-capturable)."""
+        if self._table is not None:
+            ops._call("b200ssl_ema_multi_tensor", self._table.data_ptr(), self._table.shape[0],
+                      self._m_dev.data_ptr(), ops._stream())
+        m = self._m_value
         for e, s in self._others:  # integer buffers etc.: plain copy like timm
             if e.dtype.is_floating_point:
                 e.mul_(m).add_(s.to(e.dtype), alpha=1.0 - m)
@@ -191,6 +208,11 @@ class ModelEma(nn.Module):
                 e.copy_(s)
         for p in self.module.parameters():
             ops.shadows.invalidate(p)
+
+    @torch.no_grad()
+    def update(self, model, momentum=None):
+        self.prepare(model, momentum)
+        self.launch()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -205,6 +227,7 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._tables = {}
         self._gnorm = None
+        self._hyper_dev = self._hyper_host = None
         self.last_grad_norm_sq = None
 
     def _table(self, gi, group):
@@ -235,21 +258,48 @@ class FusedAdamW(torch.optim.Optimizer):
         self._tables[gi] = ent
         return ent
 
-    @torch.no_grad()
-    def step(self, closure=None, max_grad_norm: float = 0.0):
+    def _entries(self):
         ents = []
         for gi, group in enumerate(self.param_groups):
             if any(p.grad is not None for p in group["params"]):
-                ents.append((group, self._table(gi, group)))
+                ents.append((gi, group, self._table(gi, group)))
+        return ents
+
+    def prepare_step(self):
+        """Host-side part of a step: advance the step counters and stage {lr, weight_decay, 1-beta1^t,
+        1-beta2^t, 0} per group in device memory (pinned -> device, async). Runs OUTSIDE graph capture, so
+        schedulers may change lr / weight_decay between replays."""
+        ents = self._entries()
         if not ents:
-            return None
-        dev = ents[0][1]["table"].device
+            return ents
+        dev = ents[0][2]["table"].device
+        if self._hyper_dev is None or self._hyper_dev.device != dev:
+            n = len(self.param_groups)
+            self._hyper_host = torch.zeros(n, 8, dtype=torch.float32).pin_memory()
+            self._hyper_dev = torch.zeros(n, 8, dtype=torch.float32, device=dev)
+            self._gnorm = torch.zeros(n + 1, dtype=torch.float32, device=dev)
+        for gi, group, _ in ents:
+            group["step"] = group.get("step", 0) + 1
+            t = group["step"]
+            b1, b2 = group["betas"]
+            self._hyper_host[gi, 0] = float(group["lr"])
+            self._hyper_host[gi, 1] = float(group["weight_decay"])
+            self._hyper_host[gi, 2] = 1.0 - b1 ** t
+            self._hyper_host[gi, 3] = 1.0 - b2 ** t
+            self._hyper_host[gi, 4] = 0.0
+        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+        return ents
+
+    @torch.no_grad()
+    def launch_step(self, max_grad_norm: float = 0.0, ents=None):
+        """Device-side part: grad sum-of-squares (when clipping) + one fused AdamW launch per group."""
+        ents = self._entries() if ents is None else ents
+        if not ents:
+            return
         gnorm_ptr = None
         if max_grad_norm and max_grad_norm > 0:
-            if self._gnorm is None or self._gnorm.device != dev:
-                self._gnorm = torch.zeros(len(self.param_groups) + 1, dtype=torch.float32, device=dev)
             parts = self._gnorm[1:1 + len(ents)]
-            for i, (_, ent) in enumerate(ents):
+            for i, (_, _, ent) in enumerate(ents):
                 ops._call("b200ssl_sumsq_multi_tensor", ent["gtable"].data_ptr(), ent["gtable"].shape[0],
                           parts[i:i + 1].data_ptr(), ops._stream(), launches=2)
             if len(ents) == 1:
@@ -259,15 +309,17 @@ class FusedAdamW(torch.optim.Optimizer):
                 torch.sum(parts, dim=0, keepdim=True, out=total)
             self.last_grad_norm_sq = total
             gnorm_ptr = total.data_ptr()
-        for group, ent in ents:
-            group["step"] = group.get("step", 0) + 1
-            t = group["step"]
+        for gi, group, ent in ents:
             b1, b2 = group["betas"]
             ops._call("b200ssl_adamw_multi_tensor", ent["table"].data_ptr(), ent["table"].shape[0], gnorm_ptr,
-                      float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                      float(max_grad_norm or 0.0), 1.0 - b1 ** t, 1.0 - b2 ** t, 0.0, ops._stream())
+                      self._hyper_dev[gi].data_ptr(), float(b1), float(b2), float(group["eps"]),
+                      float(max_grad_norm or 0.0), ops._stream())
             for p in ent["params"]:
                 ops.shadows.mark_fresh(p)
+
+    @torch.no_grad()
+    def step(self, closure=None, max_grad_norm: float = 0.0):
+        self.launch_step(max_grad_norm, self.prepare_step())
         return None
 
 
@@ -390,10 +442,16 @@ class GradBucketDataParallel(nn.Module):
 # ------------------------------------------------------------------------------------------------
 # the step
 # ------------------------------------------------------------------------------------------------
-def dino_step(student, teacher_ema, loss_fn, optimizer, crops, epoch=0, momentum=0.996, clip_grad=3.0):
-    """One optimisation step (SURVEY.md §3.3): teacher forward on the 2 global crops, student forward on
-    all crops, fused loss (+ centre update), backward (bucketed all-reduce overlapped when ``student`` is
-    a ``GradBucketDataParallel``), clip + AdamW, teacher EMA. Returns (loss, student_out, teacher_out)."""
+def _step_prepare(student, teacher_ema, optimizer, momentum):
+    """Host-only work of a step (tables, per-step scalars -> device). Never captured in a graph."""
+    ddp = student if isinstance(student, GradBucketDataParallel) else None
+    ents = optimizer.prepare_step() if isinstance(optimizer, FusedAdamW) else None
+    teacher_ema.prepare(ddp.module if ddp is not None else student, momentum)
+    return ents
+
+
+def _step_launch(student, teacher_ema, loss_fn, optimizer, crops, epoch, clip_grad, ents):
+    """Device work of a step: only kernel launches / NCCL calls on the current stream (graph-capturable)."""
     with torch.no_grad():
         teacher_out = teacher_ema.module(list(crops[:2]))
     student_out = student(list(crops))
@@ -407,10 +465,98 @@ def dino_step(student, teacher_ema, loss_fn, optimizer, crops, epoch=0, momentum
     if ddp is not None:
         ddp.finish()
     if isinstance(optimizer, FusedAdamW):
-        optimizer.step(max_grad_norm=clip_grad or 0.0)
+        optimizer.launch_step(clip_grad or 0.0, ents)
     else:
         if clip_grad:
             torch.nn.utils.clip_grad_norm_([p for p in student.parameters() if p.requires_grad], clip_grad)
         optimizer.step()
+    teacher_ema.launch()
+    return loss.detach(), student_out.detach(), teacher_out.detach()
+
+
+def dino_step(student, teacher_ema, loss_fn, optimizer, crops, epoch=0, momentum=0.996, clip_grad=3.0):
+    """One optimisation step (SURVEY.md §3.3): teacher forward on the 2 global crops, student forward on
+    all crops, fused loss (+ centre update), backward (bucketed all-reduce overlapped when ``student`` is
+    a ``GradBucketDataParallel``), clip + AdamW, teacher EMA. Returns (loss, student_out, teacher_out)."""
+    if isinstance(optimizer, FusedAdamW) and optimizer._hyper_dev is None:
+        # very first step: gradients (hence the optimiser tables) do not exist before the first backward
+        out = _step_launch_first(student, teacher_ema, loss_fn, optimizer, crops, epoch, momentum, clip_grad)
+        return out
+    ents = _step_prepare(student, teacher_ema, optimizer, momentum)
+    return _step_launch(student, teacher_ema, loss_fn, optimizer, crops, epoch, clip_grad, ents)
+
+
+def _step_launch_first(student, teacher_ema, loss_fn, optimizer, crops, epoch, momentum, clip_grad):
+    ddp = student if isinstance(student, GradBucketDataParallel) else None
+    with torch.no_grad():
+        teacher_out = teacher_ema.module(list(crops[:2]))
+    student_out = student(list(crops))
+    loss = loss_fn(student_out, teacher_out, epoch)
+    if ddp is not None:
+        ddp.zero_grad()
+    else:
+        optimizer.zero_grad(set_to_none=False)
+    loss.backward()
+    if ddp is not None:
+        ddp.finish()
+    optimizer.step(max_grad_norm=clip_grad or 0.0)
     teacher_ema.update(ddp.module if ddp is not None else student, momentum=momentum)
     return loss.detach(), student_out.detach(), teacher_out.detach()
+
+
+class GraphedDinoStep:
+    """The whole step captured ONCE as a CUDA graph and replayed: one graph launch per step instead of
+    ~1,000 kernel launches from Python (the eager step needs ~55 ms of host time to enqueue, more than the
+    GPU needs to execute it). Per-step scalars (lr, weight decay, Adam bias corrections, EMA momentum) are
+    staged in device memory before each replay, so schedules keep working; a change of teacher temperature
+    (epoch warm-up) triggers a re-capture.
+
+        step = GraphedDinoStep(student, teacher, loss_fn, optimizer, example_crops)
+        loss = step(crops, epoch=e, momentum=m)          # crops are copied into the graph's static inputs
+
+    ``student`` may be a GradBucketDataParallel (its NCCL all-reduces are captured with the graph)."""
+
+    def __init__(self, student, teacher_ema, loss_fn, optimizer, example_crops, clip_grad=3.0, warmup=3):
+        if not isinstance(optimizer, FusedAdamW):
+            raise TypeError("GraphedDinoStep needs b200ssl.FusedAdamW (device-resident step scalars)")
+        self.student, self.teacher, self.loss_fn, self.opt = student, teacher_ema, loss_fn, optimizer
+        self.clip_grad = clip_grad
+        self.static_crops = [torch.empty_like(c) for c in example_crops]
+        for dst, src in zip(self.static_crops, example_crops):
+            dst.copy_(src)
+        self._warmup = warmup
+        self._graph = None
+        self._temp = None
+        self.loss = self.student_out = self.teacher_out = None
+
+    def _capture(self, epoch, momentum):
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up on a side stream (allocator, tables, DP arrival counts)
+            for _ in range(self._warmup):
+                dino_step(self.student, self.teacher, self.loss_fn, self.opt, self.static_crops, epoch, momentum,
+                          self.clip_grad)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        ents = _step_prepare(self.student, self.teacher, self.opt, momentum)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.loss, self.student_out, self.teacher_out = _step_launch(
+                self.student, self.teacher, self.loss_fn, self.opt, self.static_crops, epoch, self.clip_grad, ents)
+        self._temp = float(self.loss_fn.teacher_temp_schedule[epoch])
+
+    def load(self, crops, non_blocking=True):
+        """Copy a batch of crops into the graph's static input buffers (same stream as the replay)."""
+        for dst, src in zip(self.static_crops, crops):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=non_blocking)
+
+    def __call__(self, crops=None, epoch=0, momentum=0.996):
+        if crops is not None:
+            self.load(crops)
+        if self._graph is None or float(self.loss_fn.teacher_temp_schedule[epoch]) != self._temp:
+            self._capture(epoch, momentum)      # the capture itself executes nothing: fall through to replay
+        _step_prepare(self.student, self.teacher, self.opt, momentum)
+        self._graph.replay()
+        return self.loss

@@ -103,11 +103,12 @@ int b200ssl_center_update(float* center, const float* batch_sum, int K, long lon
  *   sumsq : {g*, n}                            out[0] = sum g^2
  *   adamw : {p*, g*, m*, v*, n, decay, ema*, bf16_shadow*}   torch.optim.AdamW rule, grads pre-scaled by
  *           min(1, max_norm/(sqrt(*gnorm_sq)+1e-6)) when gnorm_sq != NULL and max_norm > 0. */
-int b200ssl_ema_multi_tensor(const void* table, int n_rows, float momentum, void* stream);
+/* momentum_dev / dev_hyper are DEVICE pointers: per-step scalars are read on the GPU so a captured CUDA
+ * graph can be replayed with new values. dev_hyper = float[5] {lr, weight_decay, 1-beta1^t, 1-beta2^t, ema_m}. */
+int b200ssl_ema_multi_tensor(const void* table, int n_rows, const float* momentum_dev, void* stream);
 int b200ssl_sumsq_multi_tensor(const void* table, int n_rows, float* out, void* stream);
-int b200ssl_adamw_multi_tensor(const void* table, int n_rows, const float* gnorm_sq, float lr, float beta1,
-                               float beta2, float eps, float weight_decay, float max_norm, float bias_corr1,
-                               float bias_corr2, float ema_momentum, void* stream);
+int b200ssl_adamw_multi_tensor(const void* table, int n_rows, const float* gnorm_sq, const float* dev_hyper,
+                               float beta1, float beta2, float eps, float max_norm, void* stream);
 
 #ifdef __cplusplus
 }
