@@ -54,7 +54,7 @@ static EncodeTiledFn get_encode_fn() {
 
 int make_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, int rank,
                     const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                    bool swizzle128) {
+                    int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   B200SSL_CHECK(fn != nullptr, -3, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
   B200SSL_CHECK(rank >= 1 && rank <= 5, -2, "tensor map rank %d unsupported", rank);
@@ -75,7 +75,8 @@ int make_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, int rank
       elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = fn(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims, gstrides, gbox,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200SSL_CHECK(r == CUDA_SUCCESS, -3,
                 "cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu box %u,%u)",

@@ -46,59 +46,82 @@ __device__ __forceinline__ void key_range(const AttnArgs& a, int nt, int r_in_gr
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward: one 128-row query tile per CTA, two CTAs per SM
+// forward: persistent CTAs (one per SM), two query tiles in flight
 // ------------------------------------------------------------------------------------------------
-// smem : Q tile (16K, re-used as the output staging tile) | K (NT x 16K) | V (NT x 16K) | barriers
-// TMEM : S fp32 in columns [0, keys_n); after the softmax has read it, P (bf16 pairs, the A operand of
-//        the second MMA, read straight from TMEM) overwrites columns [0, keys_n/2) and O accumulates in
-//        the last 64 columns of the allocation, which lie in the dead tail of S.
-// warps: 0 = control (TMA + tcgen05.mma issue), 1..8 = softmax/epilogue, two threads per query row.
-constexpr int FWD_THREADS = 32 + 256;
+// A "round" is two 128-row query tiles ("slots"): for 128 < N <= 256 the two tiles of one (sequence, head)
+// sharing K/V; for N <= 128 two consecutive (packed group, head) items with their own K/V. Slot s is
+// owned by softmax group s (8 warps, two threads per query row) and TMEM columns [256 s, 256 s + 256).
+//   warp 16 : TMA producer — prefetches round r+1 into the other 96 KB smem buffer while round r computes
+//   warp 17 : tcgen05.mma issuer — S = Q K^T for both slots, then P V per slot as its softmax finishes
+//   warps 0-15: softmax + epilogue. Two passes over S straight from TMEM (max, then exp2 / sum / bf16
+//             pack); P overwrites the first columns of S and is the A operand of the second MMA (read from
+//             TMEM); O accumulates in the last 64 columns of the slot, the dead tail of S.
+// smem per buffer: NT==2: Q0 | Q1 | K (2 tiles) | V (2 tiles); NT==1: per slot Q | K | V. The Q tile of a
+// slot is re-used as the staging tile of its TMA output store.
+constexpr int FWD_THREADS = 18 * 32;
+constexpr int FWD_BUF_BYTES = 6 * TILE_BYTES;
 
 template <int NT>
-__global__ void __launch_bounds__(FWD_THREADS, 2)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
-                     const AttnArgs args) {
+                     const AttnArgs args, const int num_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + TILE_BYTES;
-  uint8_t* sV = sK + NT * TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NT * TILE_BYTES);
-  uint64_t* bar_load = bars;
-  uint64_t* bar_s = bars + 1;
-  uint64_t* bar_p = bars + 2;
-  uint64_t* bar_o = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  float* xchg = reinterpret_cast<float*>(bars + 6);  // [2][128]
-  constexpr int TMEM_COLS = 128 * NT;
-  constexpr int O_COL = TMEM_COLS - 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * FWD_BUF_BYTES);
+  uint64_t* load_full = bars;       // [2] per smem buffer
+  uint64_t* buf_free = bars + 2;    // [2] per smem buffer (both groups' stores drained)
+  uint64_t* bar_s = bars + 4;       // [2] per slot: S ready
+  uint64_t* bar_p = bars + 6;       // [2] per slot: P written to TMEM
+  uint64_t* bar_o = bars + 8;       // [2] per slot: O ready
+  uint64_t* tmem_free = bars + 10;  // [2] per slot: O read back, slot's TMEM reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* xchg_all = reinterpret_cast<float*>(bars + 14);  // [2 groups][2 (max,sum)][2 halves][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = NT == 2 ? blockIdx.x >> 1 : blockIdx.x;
-  const int t = NT == 2 ? (blockIdx.x & 1) : 0;  // query tile within the sequence
-  const int head = item % args.H;
-  const int b0 = (item / args.H) * args.G;
+  // rounds: NT==2 -> one item (sequence, head) per round; NT==1 -> two items per round
+  const int num_rounds = NT == 2 ? num_items : (num_items + 1) / 2;
 
-  if (warp == 0) {
+  auto q_tile = [&](int buf, int slot) -> uint8_t* {
+    return smem + buf * FWD_BUF_BYTES + (NT == 2 ? slot * TILE_BYTES : slot * 3 * TILE_BYTES);
+  };
+  auto k_tile = [&](int buf, int slot) -> uint8_t* {
+    return smem + buf * FWD_BUF_BYTES + (NT == 2 ? 2 * TILE_BYTES : slot * 3 * TILE_BYTES + TILE_BYTES);
+  };
+  auto v_tile = [&](int buf, int slot) -> uint8_t* {
+    return smem + buf * FWD_BUF_BYTES + (NT == 2 ? 4 * TILE_BYTES : slot * 3 * TILE_BYTES + 2 * TILE_BYTES);
+  };
+  // item handled by (round, slot); -1 when the slot is empty (odd tail of NT == 1)
+  auto slot_item = [&](int round, int slot) -> int {
+    if (NT == 2) return round;
+    const int it = 2 * round + slot;
+    return it < num_items ? it : -1;
+  };
+
+  if (warp == 17) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQKV);
       tma_prefetch_desc(&tmO);
-      mbar_init(bar_load, 1);
-      mbar_init(bar_s, 1);
-      mbar_init(bar_p, 256);
-      mbar_init(bar_o, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&load_full[i], 1);
+        mbar_init(&buf_free[i], 2);
+        mbar_init(&bar_s[i], 1);
+        mbar_init(&bar_p[i], 256);
+        mbar_init(&bar_o[i], 1);
+        mbar_init(&tmem_free[i], 256);
+      }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<TMEM_COLS>(tmem_slot);
+    tmem_alloc<512>(tmem_slot);
   }
   if (NT == 1) {
-    // V rows the TMA box never writes must not feed NaN bit patterns into P(=0) x V
+    // V rows the TMA boxes never write must not feed NaN bit patterns into P(=0) x V
     const int first = args.rows * 128, last = args.keys_n * 128;
-    for (int i = first + threadIdx.x * 16; i < last; i += FWD_THREADS * 16)
-      *reinterpret_cast<uint4*>(sV + i) = make_uint4(0, 0, 0, 0);
+    for (int buf = 0; buf < 2; ++buf)
+      for (int slot = 0; slot < 2; ++slot)
+        for (int i = first + threadIdx.x * 16; i < last; i += FWD_THREADS * 16)
+          *reinterpret_cast<uint4*>(v_tile(buf, slot) + i) = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
   tcgen05_fence_before();
@@ -106,148 +129,232 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 16) {
+    // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const int cq = head * 64, ck = (args.H + head) * 64, cv = (2 * args.H + head) * 64;
-      if (NT == 1) {
-        mbar_expect_tx(bar_load, 3 * args.rows * 128);
-        tma_load_3d(sQ, &tmQKV, bar_load, cq, 0, b0);
-        tma_load_3d(sK, &tmQKV, bar_load, ck, 0, b0);
-        tma_load_3d(sV, &tmQKV, bar_load, cv, 0, b0);
-      } else {
-        mbar_expect_tx(bar_load, (1 + 2 * NT) * TILE_BYTES);
-        tma_load_3d(sQ, &tmQKV, bar_load, cq, t * 128, b0);
-        for (int u = 0; u < NT; ++u) {
-          tma_load_3d(sK + u * TILE_BYTES, &tmQKV, bar_load, ck, u * 128, b0);
-          tma_load_3d(sV + u * TILE_BYTES, &tmQKV, bar_load, cv, u * 128, b0);
+      int k = 0;
+      for (int round = blockIdx.x; round < num_rounds; round += gridDim.x, ++k) {
+        const int buf = k & 1;
+        mbar_wait(&buf_free[buf], ((k >> 1) & 1) ^ 1);
+        if (NT == 2) {
+          const int head = round % args.H, b0 = round / args.H;
+          const int cq = head * 64, ck = (args.H + head) * 64, cv = (2 * args.H + head) * 64;
+          mbar_expect_tx(&load_full[buf], 6 * TILE_BYTES);
+          for (int t = 0; t < 2; ++t) {
+            tma_load_3d(q_tile(buf, t), &tmQKV, &load_full[buf], cq, t * 128, b0);
+            tma_load_3d(k_tile(buf, 0) + t * TILE_BYTES, &tmQKV, &load_full[buf], ck, t * 128, b0);
+            tma_load_3d(v_tile(buf, 0) + t * TILE_BYTES, &tmQKV, &load_full[buf], cv, t * 128, b0);
+          }
+        } else {
+          const int n_valid = slot_item(round, 1) >= 0 ? 2 : 1;
+          mbar_expect_tx(&load_full[buf], n_valid * 3 * args.rows * 128);
+          for (int slot = 0; slot < n_valid; ++slot) {
+            const int item = slot_item(round, slot);
+            const int head = item % args.H, b0 = (item / args.H) * args.G;
+            tma_load_3d(q_tile(buf, slot), &tmQKV, &load_full[buf], head * 64, 0, b0);
+            tma_load_3d(k_tile(buf, slot), &tmQKV, &load_full[buf], (args.H + head) * 64, 0, b0);
+            tma_load_3d(v_tile(buf, slot), &tmQKV, &load_full[buf], (2 * args.H + head) * 64, 0, b0);
+          }
         }
       }
-      mbar_wait(bar_load, 0);
-      tcgen05_fence_after();
+    }
+  } else if (warp == 17) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(128, args.keys_n, false, false);
       const uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
-      const uint32_t a0 = smem_u32(sQ), bk = smem_u32(sK), v0 = smem_u32(sV);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16_ss(tmem_base, make_smem_desc_sw128(a0 + k * 32, 16, 1024),
-                     make_smem_desc_sw128(bk + k * 32, 16, 1024), idesc_s, k > 0);
-      umma_commit(bar_s);
-      mbar_wait(bar_p, 0);
-      tcgen05_fence_after();
       const int ksteps = args.keys_n / 16;
-      for (int j = 0; j < ksteps; ++j)
-        umma_bf16_ts(tmem_base + O_COL, tmem_base + j * 8, make_smem_desc_sw128(v0 + j * 2048, 8192, 1024),
-                     idesc_o, j > 0);
-      umma_commit(bar_o);
-    }
-  } else {
-    const int q = warp & 3;
-    const int hf = (warp - 1) >> 2;
-    const int r = q * 32 + lane;
-    const int nchunks = args.keys_n / 16;
-    const int c_begin = hf == 0 ? 0 : (nchunks + 1) / 2;
-    const int c_end = hf == 0 ? (nchunks + 1) / 2 : nchunks;
-    int lo, hi;
-    bool row_valid;
-    key_range(args, NT, NT == 1 ? r : t * 128 + r, lo, hi, row_valid);
-    if (!row_valid) hi = lo;  // no valid keys: the row is all padding
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-
-    mbar_wait(bar_s, 0);
-    tcgen05_fence_after();
-    // ---- pass 1: row max of the raw scores over this thread's column range
-    float mx = -INFINITY;
-    for (int c = c_begin; c < c_end; ++c) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(trow + c * 16, v);
-      tmem_ld_wait();
-      const int col0 = c * 16;
-      if (col0 >= lo && col0 + 16 <= hi) {
+      int k = 0;
+      for (int round = blockIdx.x; round < num_rounds; round += gridDim.x, ++k) {
+        const int buf = k & 1;
+        const uint32_t par = k & 1;
+        mbar_wait(&load_full[buf], (k >> 1) & 1);
+        tcgen05_fence_after();
+        for (int slot = 0; slot < 2; ++slot) {
+          if (slot_item(round, slot) < 0) continue;
+          mbar_wait(&tmem_free[slot], par ^ 1);
+          tcgen05_fence_after();
+          const uint32_t a0 = smem_u32(q_tile(buf, slot)), bk = smem_u32(k_tile(buf, slot));
 #pragma unroll
-        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (col0 + j >= lo && col0 + j < hi) mx = fmaxf(mx, __uint_as_float(v[j]));
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ss(tmem_base + slot * 256, make_smem_desc_sw128(a0 + kk * 32, 16, 1024),
+                         make_smem_desc_sw128(bk + kk * 32, 16, 1024), idesc_s, kk > 0);
+          umma_commit(&bar_s[slot]);
+        }
+        for (int slot = 0; slot < 2; ++slot) {
+          if (slot_item(round, slot) < 0) continue;
+          mbar_wait(&bar_p[slot], par);
+          tcgen05_fence_after();
+          const uint32_t v0 = smem_u32(v_tile(buf, slot));
+          const int ch0 = (ksteps + 1) / 2;  // P column map of the softmax halves (see below)
+          for (int j = 0; j < ksteps; ++j)
+            umma_bf16_ts(tmem_base + slot * 256 + 192,
+                         tmem_base + slot * 256 + (j < ch0 ? 8 * j : 16 * ch0 + 8 * (j - ch0)),
+                         make_smem_desc_sw128(v0 + j * 2048, 8192, 1024), idesc_o, j > 0);
+          umma_commit(&bar_o[slot]);
+        }
       }
     }
-    xchg[hf * 128 + r] = mx;
-    named_bar_sync(1, 256);
-    mx = fmaxf(mx, xchg[(hf ^ 1) * 128 + r]);
-    const float m2 = mx == -INFINITY ? 0.f : mx * args.scale_log2;
-    // ---- pass 2: p = 2^(s*c - m), packed to bf16 in registers (P aliases S, so no TMEM write yet)
-    uint32_t pk[8][8];
-    float sum = 0.f;
-#pragma unroll
-    for (int ci = 0; ci < 8; ++ci) {
-      const int c = c_begin + ci;
-      if (c < c_end) {
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue groups
+    const int slot = warp >> 3;          // group 0: warps 0-7, group 1: warps 8-15
+    const int q = warp & 3;              // TMEM lane quarter
+    const int hf = (warp >> 2) & 1;      // which half of the key columns this thread owns
+    const int r = q * 32 + lane;         // row within the tile
+    const int gtid = threadIdx.x - slot * 256;
+    float* xchg = xchg_all + slot * 512;
+    const int nchunks = args.keys_n / 16;
+    const int ch0 = (nchunks + 1) / 2;  // half 0 owns key chunks [0, ch0), half 1 owns [ch0, nchunks)
+    const int c_begin = hf == 0 ? 0 : ch0;
+    const int c_end = hf == 0 ? ch0 : nchunks;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * 256;
+    // P (bf16 pairs, 8 columns per 16-key chunk) is written into the thread's OWN S columns, behind its
+    // read pointer, so no cross-thread hazard exists and nothing has to be buffered in registers:
+    // half 0 -> columns [0, 8 ch0), half 1 -> columns [16 ch0, ...). The MMA issuer uses the same map.
+    const uint32_t p_base = trow + (hf == 0 ? 0 : 16 * ch0) - 8 * c_begin;
+    constexpr int O_COL = 192;
+
+    int k = 0;
+    for (int round = blockIdx.x; round < num_rounds; round += gridDim.x, ++k) {
+      const int item = slot_item(round, slot);
+      if (item < 0) {  // empty tail slot: still hand the smem buffer back
+        if (gtid == 0) mbar_arrive(&buf_free[k & 1]);
+        continue;
+      }
+      const int buf = k & 1;
+      const uint32_t par = k & 1;
+      const int head = item % args.H;
+      const int b0 = (item / args.H) * args.G;
+      const int t = NT == 2 ? slot : 0;  // query tile within the sequence
+      int lo, hi;
+      bool row_valid;
+      key_range(args, NT, NT == 1 ? r : t * 128 + r, lo, hi, row_valid);
+      if (!row_valid) hi = lo;  // no valid keys: the row is all padding
+      // NT == 2: no masking. Key rows >= N are zero-filled by TMA, so their scores are exactly 0 (harmless
+      // in the max), their V rows are 0 (no contribution to O) and their exp2(-m) terms are subtracted
+      // from the row sum below. NT == 1 (packed sequences): whole 16-key chunks are classified as
+      // outside / inside / straddling the row's own sequence [lo, hi).
+      auto chunk_class = [&](int c) -> int {
+        if (NT == 2) return 1;
+        const int c0 = c * 16;
+        if (c0 + 16 <= lo || c0 >= hi) return 0;
+        return (c0 >= lo && c0 + 16 <= hi) ? 1 : 2;
+      };
+
+      mbar_wait(&bar_s[slot], par);
+      tcgen05_fence_after();
+      // ---- pass 1: row max of the raw scores over this thread's column range
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; ++c) {
+        // tcgen05.ld/st are warp-collective (.sync.aligned): every lane issues them for every chunk; only the
+        // arithmetic in between may diverge on the per-row chunk class
+        const int cls = chunk_class(c);
         uint32_t v[16];
         tmem_ld_32x32b_x16(trow + c * 16, v);
         tmem_ld_wait();
-        const int col0 = c * 16;
-        const bool full = col0 >= lo && col0 + 16 <= hi;
+        if (cls == 1) {
+          float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+          float m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float x0 = fmaf(__uint_as_float(v[2 * j]), args.scale_log2, -m2);
-          float x1 = fmaf(__uint_as_float(v[2 * j + 1]), args.scale_log2, -m2);
-          if (!full) {
-            if (!(col0 + 2 * j >= lo && col0 + 2 * j < hi)) x0 = -INFINITY;
-            if (!(col0 + 2 * j + 1 >= lo && col0 + 2 * j + 1 < hi)) x1 = -INFINITY;
+          for (int j = 4; j < 16; j += 4) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
           }
-          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-          sum += p0 + p1;
-          pk[ci][j] = pack_bf16x2(p0, p1);
+          mx = fmaxf(mx, fmaxf(m0, m1));
+        } else if (cls == 2) {
+          for (int j = 0; j < 16; ++j)
+            if (c * 16 + j >= lo && c * 16 + j < hi) mx = fmaxf(mx, __uint_as_float(v[j]));
         }
       }
-    }
-    xchg[256 + hf * 128 + r] = sum;
-    tcgen05_fence_before();
-    named_bar_sync(1, 256);  // every thread has finished reading S: P may now overwrite it
-    tcgen05_fence_after();
-    sum += xchg[256 + (hf ^ 1) * 128 + r];
+      xchg[hf * 128 + r] = mx;
+      named_bar_sync(1 + slot, 256);  // also: every thread of the group is done with pass 1
+      mx = fmaxf(mx, xchg[(hf ^ 1) * 128 + r]);
+      const float m2 = mx == -INFINITY ? 0.f : mx * args.scale_log2;
+      // ---- pass 2: p = 2^(s*c - m) -> bf16 pairs -> written over the already-consumed S columns
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; ++c) {
+        const int cls = chunk_class(c);
+        uint32_t pk[8];
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(trow + c * 16, v);
+        tmem_ld_wait();
+        if (cls == 0) {
 #pragma unroll
-    for (int ci = 0; ci < 8; ++ci) {
-      const int c = c_begin + ci;
-      if (c < c_end) tmem_st_32x32b_x8(trow + c * 8, pk[ci]);
-    }
-    tmem_st_wait();
-    tcgen05_fence_before();
-    mbar_arrive(bar_p);
-    const float inv = sum > 0.f ? 1.f / sum : 0.f;
-    if (hf == 0 && row_valid) {
-      const int rr = NT == 1 ? r : t * 128 + r;
-      const int b = b0 + (NT == 1 ? rr / args.N : 0);
-      const int n = NT == 1 ? rr % args.N : rr;
-      if (b < args.B) args.lse2[(static_cast<long long>(b) * args.H + head) * args.N + n] = m2 + log2f(sum);
-    }
-    // ---- epilogue: O / rowsum -> bf16 -> swizzled staging (the dead Q tile) -> TMA store
-    mbar_wait(bar_o, 0);
-    tcgen05_fence_after();
-    uint32_t v[32];
-    tmem_ld_32x32b_x32(trow + O_COL + hf * 32, v);
-    tmem_ld_wait();
+          for (int j = 0; j < 8; ++j) pk[j] = 0u;
+        } else {
+          if (cls == 1) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 o;
-      o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
-      o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
-      o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
-      o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
-      *reinterpret_cast<uint4*>(sQ + sw128_offset(r, hf * 4 + j)) = o;
+            for (int j = 0; j < 8; ++j) {
+              const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), args.scale_log2, -m2));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), args.scale_log2, -m2));
+              sum0 += p0;
+              sum1 += p1;
+              pk[j] = pack_bf16x2(p0, p1);
+            }
+          } else {
+            for (int j = 0; j < 8; ++j) {
+              float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), args.scale_log2, -m2));
+              float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), args.scale_log2, -m2));
+              if (!(c * 16 + 2 * j >= lo && c * 16 + 2 * j < hi)) p0 = 0.f;
+              if (!(c * 16 + 2 * j + 1 >= lo && c * 16 + 2 * j + 1 < hi)) p1 = 0.f;
+              sum0 += p0;
+              sum1 += p1;
+              pk[j] = pack_bf16x2(p0, p1);
+            }
+          }
+        }
+        tmem_st_32x32b_x8(p_base + c * 8, pk);
+      }
+      float sum = sum0 + sum1;
+      xchg[256 + hf * 128 + r] = sum;
+      tmem_st_wait();
+      tcgen05_fence_before();
+      mbar_arrive(&bar_p[slot]);
+      named_bar_sync(1 + slot, 256);
+      sum += xchg[256 + (hf ^ 1) * 128 + r];
+      if (NT == 2) sum -= static_cast<float>(args.keys_n - args.N) * ex2_approx(-m2);  // zero-padded keys
+      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+      if (hf == 0 && row_valid) {
+        const int rr = NT == 1 ? r : t * 128 + r;
+        const int b = b0 + (NT == 1 ? rr / args.N : 0);
+        const int n = NT == 1 ? rr % args.N : rr;
+        if (b < args.B) args.lse2[(static_cast<long long>(b) * args.H + head) * args.N + n] = m2 + log2f(sum);
+      }
+      // ---- epilogue: O / rowsum -> bf16 -> swizzled staging (the dead Q tile) -> TMA store
+      mbar_wait(&bar_o[slot], par);
+      tcgen05_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(trow + O_COL + hf * 32, v);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_free[slot]);  // S of the next round may overwrite this slot's TMEM
+      uint8_t* stg = q_tile(buf, slot);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
+        *reinterpret_cast<uint4*>(stg + sw128_offset(r, hf * 4 + j)) = o;
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + slot, 256);
+      if (gtid == 0) {
+        tma_store_3d(&tmO, stg, head * 64, NT == 1 ? 0 : t * 128, b0);
+        tma_store_commit();
+        tma_store_wait_read<0>();      // staging (and with it the whole buffer, for this group) is reusable
+        mbar_arrive(&buf_free[buf]);
+      }
     }
-    fence_proxy_async_smem();
-    named_bar_sync(1, 256);
-    if (threadIdx.x == 32) {
-      tma_store_3d(&tmO, sQ, head * 64, NT == 1 ? 0 : t * 128, b0);
-      tma_store_commit();
-      tma_store_wait_all<0>();
-    }
+    if (gtid == 0) tma_store_wait_all<0>();
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 17) tmem_dealloc<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -544,7 +651,7 @@ static int make_bnd_map(CUtensorMap* tm, const void* base, int cols, int N, int 
   uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   uint64_t strides[3] = {2, static_cast<uint64_t>(cols) * 2, static_cast<uint64_t>(cols) * 2 * N};
   uint32_t box[3] = {64, static_cast<uint32_t>(nt == 1 ? N : 128), static_cast<uint32_t>(nt == 1 ? G : 1)};
-  return make_tensor_map(tm, base, 2, 3, dims, strides, box, true);
+  return make_tensor_map(tm, base, 2, 3, dims, strides, box, 128);
 }
 
 }  // namespace b200ssl
@@ -563,22 +670,24 @@ extern "C" int b200ssl_attention_fwd(const void* qkv, void* out, float* lse2, in
   CUtensorMap tq, to;
   if (int rc = make_bnd_map(&tq, qkv, 3 * H * 64, N, B, nt, a.G)) return rc;
   if (int rc = make_bnd_map(&to, out, H * 64, N, B, nt, a.G)) return rc;
+  const int num_items = groups * H;
+  const int num_rounds = nt == 2 ? num_items : (num_items + 1) / 2;
+  const int grid = num_rounds < sm_count() ? num_rounds : sm_count();
+  const int smem = 2 * FWD_BUF_BYTES + 8192 + 1024;
   if (nt == 1) {
-    const int smem = 3 * TILE_BYTES + 2048 + 1024 + 1024;
     static bool cfg = false;
     if (!cfg) {
       B200SSL_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       cfg = true;
     }
-    attention_fwd_kernel<1><<<groups * H, FWD_THREADS, smem, stream>>>(tq, to, a);
+    attention_fwd_kernel<1><<<grid, FWD_THREADS, smem, stream>>>(tq, to, a, num_items);
   } else {
-    const int smem = 5 * TILE_BYTES + 2048 + 1024 + 1024;
     static bool cfg = false;
     if (!cfg) {
       B200SSL_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       cfg = true;
     }
-    attention_fwd_kernel<2><<<groups * H * 2, FWD_THREADS, smem, stream>>>(tq, to, a);
+    attention_fwd_kernel<2><<<grid, FWD_THREADS, smem, stream>>>(tq, to, a, num_items);
   }
   B200SSL_CUDA(cudaGetLastError());
   return 0;

@@ -41,7 +41,7 @@ int sm_count();
 // dims 1..rank-1 (dim 0 is contiguous). Returns 0 on success.
 int make_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, int rank,
                     const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                    bool swizzle128);
+                    int swizzle_bytes /* 0, 64 or 128 */);
 
 #ifdef __CUDACC__
 
@@ -328,6 +328,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // 16-byte chunk address inside a 128B-swizzled tile whose rows are 128 B (row r, chunk c in 0..7).
 __device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
   return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4));
+}
+
+// 16-byte chunk address inside a 64B-swizzled tile whose rows are 64 B (row r, chunk c in 0..3).
+__device__ __forceinline__ uint32_t sw64_offset(int r, int c) {
+  return static_cast<uint32_t>(r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
 }
 
 #endif  // __CUDACC__

@@ -17,8 +17,9 @@
 //   warp 0      : TMA producer   (global -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : MMA issuer     (one elected lane issues tcgen05.mma; accumulators in TMEM,
 //                                 2 accumulator stages so tile i's epilogue overlaps tile i+1's MMAs)
-//   warps 4..11 : epilogue       (2 groups x 4 warps; tcgen05.ld -> bias/GELU/residual -> bf16 ->
-//                                 swizzled smem -> TMA store; or fp32 red.add for split-K wgrad)
+//   warps 4..19 : epilogue       (4 groups x 4 warps, 32 columns at a time; tcgen05.ld -> bias / GELU+GELU' /
+//                                 residual / x aux -> bf16|fp32 -> swizzled smem -> TMA store; or fp32 red.add
+//                                 for split-K wgrad, whose bias gradient they fold from the smem stages)
 #include "common.cuh"
 
 namespace b200ssl {
@@ -47,8 +48,9 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int STAGING_BYTES = BLOCK_M * 128;           // 128 rows x 64 bf16
-constexpr int NUM_EPI_GROUPS = 2;
+constexpr int EPI_CHUNK = 32;                          // columns an epilogue thread handles at a time
+constexpr int STAGING_BYTES = BLOCK_M * 128;           // per epilogue group: 2 x (128 rows x 32 bf16) or 1 x (128 x 32 fp32)
+constexpr int NUM_EPI_GROUPS = 4;                      // 4 groups x 4 warps: 4 warps per TMEM lane quarter
 constexpr int GEMM_THREADS = 128 + NUM_EPI_GROUPS * 128;
 
 template <int BN>
@@ -58,7 +60,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = A_STAGE_BYTES + kBStageBytes;
   static constexpr int kTmemCols = BN * 2 <= 128 ? 128 : BN * 2 <= 256 ? 256 : 512;
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + NUM_EPI_GROUPS * 2 * STAGING_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+      kStages * kStageBytes + NUM_EPI_GROUPS * STAGING_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
 };
 
 template <int BN, int EPI>
@@ -73,7 +75,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* staging = smem + kStages * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + NUM_EPI_GROUPS * 2 * STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + NUM_EPI_GROUPS * STAGING_BYTES);
   uint64_t* full_bar = bars;                 // [kStages]
   uint64_t* empty_bar = bars + kStages;      // [kStages]
   uint64_t* tmem_full = bars + 2 * kStages;  // [2]
@@ -184,18 +186,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int group = (warp - 4) >> 2;  // 0 or 1: which 64-column chunks this warp owns
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int group = (warp - 4) >> 2;  // 0..3: which 32-column chunks this warp owns (c = group, group+4, ..)
     const int gtid = threadIdx.x - 128 - group * 128;
-    uint8_t* stg = staging + group * 2 * STAGING_BYTES;
+    uint8_t* stg = staging + group * STAGING_BYTES;
     const int row_in_tile = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t slot = 0;  // staging buffer ring position (per group)
-    constexpr int kChunks = BN / 64;
-
-    int cs_stage = 0;       // wgrad only: position in the smem ring (bias-gradient pass)
+    uint32_t slot = 0;  // bf16 staging ring position (per group, two 8 KB buffers)
+    constexpr int kChunks = BN / EPI_CHUNK;
+    int cs_stage = 0;   // wgrad only: position in the smem ring (bias-gradient pass)
     uint32_t cs_phase = 0;
+
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t % args.num_n_blocks;
       const int m_blk = (t / args.num_n_blocks) % args.num_m_blocks;
@@ -213,17 +215,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks_total);
         float* db = const_cast<float*>(args.bias);
         const bool mine = n_blk == 0 && db != nullptr && args.a_mn;
-        const int etid = threadIdx.x - 128;  // 0..255
+        const int etid = threadIdx.x - 128;  // 0..511
         const int jc = etid & 15;            // 16-byte chunk (8 columns) within the 128-wide m range
-        const int sub = etid >> 4;           // k rows sub, sub+16, sub+32, sub+48
+        const int sub = etid >> 4;           // k rows sub and sub+32
         float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[cs_stage], cs_phase);
           if (mine) {
             const uint8_t* sA = smem + cs_stage * Cfg::kStageBytes + (jc >> 3) * 8192;
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-              const int r = sub + 16 * rr;
+            for (int rr = 0; rr < 2; ++rr) {
+              const int r = sub + 32 * rr;
               const uint4 u = *reinterpret_cast<const uint4*>(sA + r * 128 + (((jc & 7) ^ (r & 7)) << 4));
               const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -254,16 +256,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
       bool released = false;
       for (int c = group; c < kChunks; c += NUM_EPI_GROUPS) {
-        uint32_t v[64];
+        float f[EPI_CHUNK];
         {
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                 static_cast<uint32_t>(acc * BN + c * 64);
-          uint32_t lo[32], hi[32];
-          tmem_ld_32x32b_x32(taddr, lo);
-          tmem_ld_32x32b_x32(taddr + 32, hi);
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 static_cast<uint32_t>(acc * BN + c * EPI_CHUNK), v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { v[j] = lo[j]; v[32 + j] = hi[j]; }
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         }
         if (c + NUM_EPI_GROUPS >= kChunks) {
           // last TMEM read of this tile by this thread: hand the accumulator stage back
@@ -271,29 +271,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_arrive(&tmem_empty[acc]);
           released = true;
         }
-        const int col0 = n0 + c * 64;
+        const int col0 = n0 + c * EPI_CHUNK;
 
         if (EPI == EPI_ATOMIC_F32) {
           if (row_ok) {
             float* dst = args.out_f32 + static_cast<long long>(row) * args.ldd + col0;
 #pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
-                           "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
-                           "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+            for (int j = 0; j < EPI_CHUNK; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(f[j]), "f"(f[j + 1]),
+                           "f"(f[j + 2]), "f"(f[j + 3])
                            : "memory");
-            }
           }
           continue;
         }
 
-        float f[64];
-#pragma unroll
-        for (int j = 0; j < 64; ++j) f[j] = __uint_as_float(v[j]);
         if (EPI != EPI_MUL_AUX && args.bias != nullptr) {
           const float4* bp = reinterpret_cast<const float4*>(args.bias + col0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < EPI_CHUNK / 4; ++j) {
             const float4 b = __ldg(bp + j);
             f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
           }
@@ -303,7 +298,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint4* ap = reinterpret_cast<const uint4*>(
                 static_cast<const __nv_bfloat16*>(args.aux) + static_cast<long long>(row) * args.ldaux + col0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < EPI_CHUNK / 8; ++j) {
               const uint4 a = __ldg(ap + j);
               const uint32_t w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
@@ -326,52 +321,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const float4* ap = reinterpret_cast<const float4*>(
                 static_cast<const float*>(args.aux) + static_cast<long long>(row) * args.ldaux + col0);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < EPI_CHUNK / 4; ++j) {
               const float4 a = __ldg(ap + j);
               f[4 * j] += a.x; f[4 * j + 1] += a.y; f[4 * j + 2] += a.z; f[4 * j + 3] += a.w;
             }
           }
-          // fp32 output: two 32-column boxes (128 B rows) per 64-column chunk
+          // fp32 output: one 32-column box (128 B rows, 128B swizzle); single staging buffer per group
+          if (gtid == 0) tma_store_wait_read<0>();
+          named_bar_sync(1 + group, 128);
 #pragma unroll
-          for (int o = 0; o < 2; ++o) {
-            uint8_t* buf = stg + (slot & 1) * STAGING_BYTES;
-            if (gtid == 0) tma_store_wait_read<1>();
-            named_bar_sync(1 + group, 128);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(buf + sw128_offset(row_in_tile, j)) =
-                  make_float4(f[32 * o + 4 * j], f[32 * o + 4 * j + 1], f[32 * o + 4 * j + 2], f[32 * o + 4 * j + 3]);
-            fence_proxy_async_smem();
-            named_bar_sync(1 + group, 128);
-            if (gtid == 0) {
-              tma_store_2d(&tmD, buf, col0 + 32 * o, m0);
-              tma_store_commit();
-            }
-            ++slot;
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg + sw128_offset(row_in_tile, j)) =
+                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          fence_proxy_async_smem();
+          named_bar_sync(1 + group, 128);
+          if (gtid == 0) {
+            tma_store_2d(&tmD, stg, col0, m0);
+            tma_store_commit();
           }
           continue;
         }
 
         constexpr int kOutputs = EPI == EPI_BIAS_GELU ? 2 : 1;
-        uint32_t hpk[EPI == EPI_BIAS_GELU ? 32 : 1];  // gelu(x) packed, written as the second output
+        uint32_t hpk[EPI == EPI_BIAS_GELU ? EPI_CHUNK / 2 : 1];  // gelu(x) packed: the second output
         if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < EPI_CHUNK / 2; ++j) {
             float h0, h1, g0, g1;
             gelu_and_grad(f[2 * j], h0, g0);
             gelu_and_grad(f[2 * j + 1], h1, g1);
             f[2 * j] = g0;
             f[2 * j + 1] = g1;
-            hpk[j] = pack_bf16x2(h0, h1);
+            hpk[j % (EPI == EPI_BIAS_GELU ? EPI_CHUNK / 2 : 1)] = pack_bf16x2(h0, h1);
           }
         }
 #pragma unroll
         for (int o = 0; o < kOutputs; ++o) {
-          uint8_t* buf = stg + (slot & 1) * STAGING_BYTES;
+          // bf16 output: 32-column box = 64 B rows, 64B swizzle; two 8 KB buffers per group
+          uint8_t* buf = stg + (slot & 1) * (STAGING_BYTES / 2);
           if (gtid == 0) tma_store_wait_read<1>();  // the store that last used this buffer has drained
           named_bar_sync(1 + group, 128);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             uint4 pk;
             if (o == 0) {
               pk.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
@@ -379,10 +370,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               pk.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
               pk.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
             } else {
-              pk = make_uint4(hpk[(4 * j) % (EPI == EPI_BIAS_GELU ? 32 : 1)], hpk[(4 * j + 1) % (EPI == EPI_BIAS_GELU ? 32 : 1)],
-                              hpk[(4 * j + 2) % (EPI == EPI_BIAS_GELU ? 32 : 1)], hpk[(4 * j + 3) % (EPI == EPI_BIAS_GELU ? 32 : 1)]);
+              constexpr int HM = EPI == EPI_BIAS_GELU ? EPI_CHUNK / 2 : 1;
+              pk = make_uint4(hpk[(4 * j) % HM], hpk[(4 * j + 1) % HM], hpk[(4 * j + 2) % HM], hpk[(4 * j + 3) % HM]);
             }
-            *reinterpret_cast<uint4*>(buf + sw128_offset(row_in_tile, j)) = pk;
+            *reinterpret_cast<uint4*>(buf + sw64_offset(row_in_tile, j)) = pk;
           }
           fence_proxy_async_smem();
           named_bar_sync(1 + group, 128);
@@ -530,21 +521,21 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
     if (!a_mn_major) { dims[0] = K; dims[1] = M; box[0] = 64; box[1] = BLOCK_M; }
     else             { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = 64; }
     strides[0] = 2; strides[1] = static_cast<uint64_t>(lda) * 2;
-    if (int rc = make_tensor_map(&tmA, A, 2, 2, dims, strides, box, true)) return rc;
+    if (int rc = make_tensor_map(&tmA, A, 2, 2, dims, strides, box, 128)) return rc;
     if (!b_mn_major) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = bn; }
     else             { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = 64; }
     strides[1] = static_cast<uint64_t>(ldb) * 2;
-    if (int rc = make_tensor_map(&tmB, B, 2, 2, dims, strides, box, true)) return rc;
+    if (int rc = make_tensor_map(&tmB, B, 2, 2, dims, strides, box, 128)) return rc;
     if (epilogue == EPI_BIAS_RES_F32) {
       dims[0] = N; dims[1] = M; box[0] = 32; box[1] = BLOCK_M;
       strides[0] = 4; strides[1] = static_cast<uint64_t>(ldd) * 4;
-      if (int rc = make_tensor_map(&tmD, D, 4, 2, dims, strides, box, true)) return rc;
+      if (int rc = make_tensor_map(&tmD, D, 4, 2, dims, strides, box, 128)) return rc;
       tmD2 = tmD;
     } else if (epilogue != EPI_ATOMIC_F32) {
-      dims[0] = N; dims[1] = M; box[0] = 64; box[1] = BLOCK_M;
+      dims[0] = N; dims[1] = M; box[0] = EPI_CHUNK; box[1] = BLOCK_M;   // 64 B rows, 64B swizzle
       strides[1] = static_cast<uint64_t>(ldd) * 2;
-      if (int rc = make_tensor_map(&tmD, D, 2, 2, dims, strides, box, true)) return rc;
-      if (int rc = make_tensor_map(&tmD2, D2 ? D2 : D, 2, 2, dims, strides, box, true)) return rc;
+      if (int rc = make_tensor_map(&tmD, D, 2, 2, dims, strides, box, 64)) return rc;
+      if (int rc = make_tensor_map(&tmD2, D2 ? D2 : D, 2, 2, dims, strides, box, 64)) return rc;
     } else {
       tmD = tmA; tmD2 = tmA;  // unused
     }
