@@ -406,6 +406,24 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     mbar_init(bar_pds, BWD_MATH_THREADS);
     mbar_init(bar_mma, 1);
     fence_barrier_init();
+    // the operand loads only need bar_load: issue them now so they fly while the other warps allocate TMEM
+    // and compute the per-row constants (NT == 1 zero-fills disjoint rows, so there is no conflict)
+    const int cq = head * 64, ck = (args.H + head) * 64, cv = (2 * args.H + head) * 64;
+    if (NT == 1) {
+      mbar_expect_tx(bar_load, 4 * args.rows * 128);
+      tma_load_3d(sQ, &tmQKV, bar_load, cq, 0, b0);
+      tma_load_3d(sK, &tmQKV, bar_load, ck, 0, b0);
+      tma_load_3d(sV, &tmQKV, bar_load, cv, 0, b0);
+      tma_load_3d(sdO, &tmDO, bar_load, cq, 0, b0);
+    } else {
+      mbar_expect_tx(bar_load, 4 * NT * TILE_BYTES);
+      for (int t = 0; t < NT; ++t) {
+        tma_load_3d(sQ + t * TILE_BYTES, &tmQKV, bar_load, cq, t * 128, b0);
+        tma_load_3d(sK + t * TILE_BYTES, &tmQKV, bar_load, ck, t * 128, b0);
+        tma_load_3d(sV + t * TILE_BYTES, &tmQKV, bar_load, cv, t * 128, b0);
+        tma_load_3d(sdO + t * TILE_BYTES, &tmDO, bar_load, cq, t * 128, b0);
+      }
+    }
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   if (NT == 1) {
@@ -457,22 +475,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      const int cq = head * 64, ck = (args.H + head) * 64, cv = (2 * args.H + head) * 64;
-      if (NT == 1) {
-        mbar_expect_tx(bar_load, 4 * args.rows * 128);
-        tma_load_3d(sQ, &tmQKV, bar_load, cq, 0, b0);
-        tma_load_3d(sK, &tmQKV, bar_load, ck, 0, b0);
-        tma_load_3d(sV, &tmQKV, bar_load, cv, 0, b0);
-        tma_load_3d(sdO, &tmDO, bar_load, cq, 0, b0);
-      } else {
-        mbar_expect_tx(bar_load, 4 * NT * TILE_BYTES);
-        for (int t = 0; t < NT; ++t) {
-          tma_load_3d(sQ + t * TILE_BYTES, &tmQKV, bar_load, cq, t * 128, b0);
-          tma_load_3d(sK + t * TILE_BYTES, &tmQKV, bar_load, ck, t * 128, b0);
-          tma_load_3d(sV + t * TILE_BYTES, &tmQKV, bar_load, cv, t * 128, b0);
-          tma_load_3d(sdO + t * TILE_BYTES, &tmDO, bar_load, cq, t * 128, b0);
-        }
-      }
       mbar_wait(bar_load, 0);
       tcgen05_fence_after();
       const uint32_t idesc_q = make_idesc_bf16(128, 64, false, true);  // dQ: A K-major, B MN-major
@@ -535,13 +537,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       lse2[t] = rowc[(t * 128 + r) * 2 + 1];
     }
 
-    // 128x64 fp32 accumulator at TMEM column `tcol` -> bf16 -> staging -> TMA store at (col, row0, b0)
-    auto store_tile = [&](uint32_t tcol, int gcol, int row0) {
+    // 128x64 fp32 accumulator at TMEM column `tcol` -> bf16 -> staging tile `stage` -> TMA store at
+    // (col, row0, b0). Staging tiles are the P / dS chunk buffers, dead at the points of use, so several
+    // stores are in flight at once; `stores_pending` makes the next writer of those buffers wait.
+    bool stores_pending = false;
+    auto store_tile = [&](uint32_t tcol, uint8_t* stage, int gcol, int row0) {
       uint32_t v[16];
       tmem_ld_32x32b_x16(tcol + lane_off + qc * 16, v);
       tmem_ld_wait();
-      if (leader) tma_store_wait_read<0>();
-      named_bar_sync(1, BWD_MATH_THREADS);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         uint4 pk;
@@ -549,14 +552,15 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         pk.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
         pk.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
         pk.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-        *reinterpret_cast<uint4*>(stg + sw128_offset(r, qc * 2 + j)) = pk;
+        *reinterpret_cast<uint4*>(stage + sw128_offset(r, qc * 2 + j)) = pk;
       }
       fence_proxy_async_smem();
       named_bar_sync(1, BWD_MATH_THREADS);
       if (leader) {
-        tma_store_3d(&tmDQKV, stg, gcol, row0, b0);
+        tma_store_3d(&tmDQKV, stage, gcol, row0, b0);
         tma_store_commit();
       }
+      stores_pending = true;
     };
 
 #pragma unroll
@@ -571,7 +575,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const int col0 = qc * 32;             // first key column (within the tile) of this thread
         const bool active = col0 < ku;
         uint32_t pp[16], dd[16];              // 32 columns of P and dS, packed bf16 pairs
-        if (active) {
+        if (active) {                         // warp-uniform: col0 depends on the warp only
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t sv[16], dv[16];
@@ -579,25 +583,47 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             tmem_ld_32x32b_x16(T_DP + lane_off + col0 + h * 16, dv);
             tmem_ld_wait();
             const int gcol = u * 128 + col0 + h * 16;
-            const bool full = gcol >= lo[t] && gcol + 16 <= hi[t];
+            // NT == 2 needs no key masking: K / V rows >= N are zero-filled by TMA, so whatever P and dS hold
+            // in those columns only reaches dQ through zero K rows and dK / dV rows the TMA store clips;
+            // padded query rows have lse2 = +inf, hence P = dS = 0. NT == 1 (packed sequences): classify the
+            // 16-key chunk against the row's own sequence [lo, hi) — 0 outside, 1 inside, 2 straddling.
+            int cls = 1;
+            if (NT == 1) cls = (gcol + 16 <= lo[t] || gcol >= hi[t]) ? 0 : ((gcol >= lo[t] && gcol + 16 <= hi[t]) ? 1 : 2);
+            if (cls == 0) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), args.scale_log2, -lse2[t]));
-              float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), args.scale_log2, -lse2[t]));
-              if (!full) {
+              for (int e = 0; e < 8; ++e) { pp[h * 8 + e] = 0u; dd[h * 8 + e] = 0u; }
+            } else if (cls == 1) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), args.scale_log2, -lse2[t]));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), args.scale_log2, -lse2[t]));
+                const float d0 = p0 * ((__uint_as_float(dv[2 * e]) - delta[t]) * args.scale);
+                const float d1 = p1 * ((__uint_as_float(dv[2 * e + 1]) - delta[t]) * args.scale);
+                pp[h * 8 + e] = pack_bf16x2(p0, p1);
+                dd[h * 8 + e] = pack_bf16x2(d0, d1);
+              }
+            } else {
+              for (int e = 0; e < 8; ++e) {
+                float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), args.scale_log2, -lse2[t]));
+                float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), args.scale_log2, -lse2[t]));
                 if (!(gcol + 2 * e >= lo[t] && gcol + 2 * e < hi[t])) p0 = 0.f;
                 if (!(gcol + 2 * e + 1 >= lo[t] && gcol + 2 * e + 1 < hi[t])) p1 = 0.f;
+                const float d0 = p0 * ((__uint_as_float(dv[2 * e]) - delta[t]) * args.scale);
+                const float d1 = p1 * ((__uint_as_float(dv[2 * e + 1]) - delta[t]) * args.scale);
+                pp[h * 8 + e] = pack_bf16x2(p0, p1);
+                dd[h * 8 + e] = pack_bf16x2(d0, d1);
               }
-              const float d0 = p0 * (__uint_as_float(dv[2 * e]) - delta[t]) * args.scale;
-              const float d1 = p1 * (__uint_as_float(dv[2 * e + 1]) - delta[t]) * args.scale;
-              pp[h * 8 + e] = pack_bf16x2(p0, p1);
-              dd[h * 8 + e] = pack_bf16x2(d0, d1);
             }
           }
         }
         tcgen05_fence_before();
         mbar_arrive(bar_sdp_free);
         if (pair > 0) mbar_wait(bar_mma, (pair - 1) & 1);  // previous MMAs done with sP / sdS
+        if (stores_pending) {  // dK / dV of the previous key tile were staged in sP: let those stores drain
+          if (leader) tma_store_wait_read<0>();
+          named_bar_sync(1, BWD_MATH_THREADS);
+          stores_pending = false;
+        }
         if (active) {
           uint8_t* pc = sP + (qc >> 1) * TILE_BYTES;
           uint8_t* dc = sdS + (qc >> 1) * TILE_BYTES;
@@ -615,8 +641,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           // dK_u and dV_u are complete once this pair's MMAs retire
           mbar_wait(bar_mma, pair & 1);
           tcgen05_fence_after();
-          store_tile(T_DK, (args.H + head) * 64, NT == 1 ? 0 : u * 128);
-          store_tile(T_DV, (2 * args.H + head) * 64, NT == 1 ? 0 : u * 128);
+          store_tile(T_DK, sP, (args.H + head) * 64, NT == 1 ? 0 : u * 128);
+          store_tile(T_DV, sP + TILE_BYTES, (2 * args.H + head) * 64, NT == 1 ? 0 : u * 128);
           // the dK/dV accumulators are re-used by the next key tile: order these reads before its MMAs
           tcgen05_fence_before();
         }
@@ -624,7 +650,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     }
     // dQ tiles (complete after the last pair; bar_mma already waited on above)
 #pragma unroll
-    for (int t = 0; t < NT; ++t) store_tile(T_DQ + t * 64, head * 64, NT == 1 ? 0 : t * 128);
+    for (int t = 0; t < NT; ++t) store_tile(T_DQ + t * 64, sdS + t * TILE_BYTES, head * 64, NT == 1 ? 0 : t * 128);
     if (leader) tma_store_wait_all<0>();
   }
 
