@@ -386,6 +386,9 @@ class GradBucketDataParallel(nn.Module):
                 dist.broadcast(b.data, src=0, group=self.pg)
         for p in params:
             p.register_post_accumulate_grad_hook(self._hook)
+            # our wgrad / LayerNorm-backward kernels add straight into these bucket views (no autograd
+            # accumulation); they call the same arrival hook once per contribution
+            ops.register_grad_sink(p, self._hook)
         self._arm()
 
     def _arm(self):

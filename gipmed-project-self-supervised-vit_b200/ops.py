@@ -115,6 +115,45 @@ def to_stream_2d(x: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
+# gradient sinks: accumulate parameter gradients straight into a persistent fp32 buffer
+# ------------------------------------------------------------------------------------------------
+# The wgrad GEMM (fp32 atomics), its folded bias gradient and the LayerNorm dgamma/dbeta reductions all
+# ACCUMULATE into their output. When a parameter is registered here (GradBucketDataParallel does it for
+# the views into its flat buckets), backward adds into ``param.grad`` directly and hands autograd ``None``:
+# no per-step zero-filled temporaries and no autograd accumulation kernels (~470 launches per step).
+_grad_sinks = {}
+
+
+def register_grad_sink(param, callback=None):
+    import weakref
+    _grad_sinks[id(param)] = (weakref.ref(param), callback)
+
+
+def unregister_grad_sink(param):
+    _grad_sinks.pop(id(param), None)
+
+
+def _sink(param):
+    """The buffer to accumulate ``param``'s gradient into, or None (then the gradient goes through autograd)."""
+    if param is None:
+        return None
+    ent = _grad_sinks.get(id(param))
+    if ent is None or ent[0]() is not param:
+        return None
+    g = param.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != param.shape:
+        return None
+    return g
+
+
+def _sunk(param):
+    """Tell the sink's owner that one more contribution to ``param.grad`` has been enqueued."""
+    cb = _grad_sinks[id(param)][1]
+    if cb is not None:
+        cb(param)
+
+
+# ------------------------------------------------------------------------------------------------
 # raw wrappers
 # ------------------------------------------------------------------------------------------------
 def cast_f32_to_bf16(src: torch.Tensor, dst: torch.Tensor):
@@ -162,14 +201,23 @@ def linear_dgrad(dy, w16, dgelu_of=None):
     return dx
 
 
-def linear_wgrad(dy, x, need_bias=True):
-    """dW[N,K] = dy^T @ x (fp32, split-K atomics), db[N] = column sums of dy."""
+def linear_wgrad(dy, x, need_bias=True, weight=None, bias=None):
+    """dW[N,K] = dy^T @ x (fp32, split-K atomics), db[N] = column sums of dy (folded by idle warps of the
+    wgrad kernel from its smem stages). With ``weight`` / ``bias`` parameters that have a registered
+    gradient sink the result is accumulated into ``.grad`` in place and ``None`` is returned for it."""
     M, N = dy.shape
     K = x.shape[1]
+    w_sink = _sink(weight)
+    b_sink = _sink(bias) if need_bias else None
+    if w_sink is not None and (not need_bias or b_sink is not None):
+        gemm(dy, x, w_sink.view(N, K), N, K, M, a_mn=True, b_mn=True, epi=EPI_ATOMIC_F32, split_k=0, bias=b_sink)
+        _sunk(weight)
+        if b_sink is not None:
+            _sunk(bias)
+        return None, None
     buf = torch.zeros(N * K + (N if need_bias else 0), dtype=torch.float32, device=dy.device)
     dw = buf[:N * K].view(N, K)
     db = buf[N * K:] if need_bias else None
-    # the bias gradient (column sums of dy) is folded by idle warps of the wgrad kernel from the smem stages
     gemm(dy, x, dw, N, K, M, a_mn=True, b_mn=True, epi=EPI_ATOMIC_F32, split_k=0, bias=db)
     return dw, db
 
@@ -185,15 +233,25 @@ def layernorm_fwd(x, w, b, eps):
     return y, mean, rstd
 
 
-def layernorm_bwd(x, dy, w, mean, rstd, dres=None):
-    """Gradients travel in bf16: dy, dres, dx are bf16 regardless of the stream dtype of x."""
+def layernorm_bwd(x, dy, w, mean, rstd, dres=None, weight=None, bias=None):
+    """Gradients travel in bf16: dy, dres, dx are bf16 regardless of the stream dtype of x. dgamma / dbeta
+    are accumulated into the parameters' gradient sinks when registered (then returned as None)."""
     rows, D = x.shape
     dx = torch.empty(rows, D, dtype=_BF16, device=x.device)
-    dwb = torch.zeros(2, D, dtype=torch.float32, device=x.device)
+    w_sink, b_sink = _sink(weight), _sink(bias)
+    if w_sink is not None and b_sink is not None:
+        dw, db, ret = w_sink, b_sink, (None, None)
+    else:
+        dwb = torch.zeros(2, D, dtype=torch.float32, device=x.device)
+        dw, db = dwb[0], dwb[1]
+        ret = (dw, db)
     _call("b200ssl_layernorm_bwd", x.data_ptr(), int(x.dtype == torch.float32), dy.data_ptr(), w.data_ptr(),
-          mean.data_ptr(), rstd.data_ptr(), _ptr(dres), dx.data_ptr(), dwb[0].data_ptr(), dwb[1].data_ptr(), rows, D,
+          mean.data_ptr(), rstd.data_ptr(), _ptr(dres), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), rows, D,
           _stream())
-    return dx, dwb[0], dwb[1]
+    if ret[0] is None:
+        _sunk(weight)
+        _sunk(bias)
+    return dx, ret[0], ret[1]
 
 
 def attention_fwd(qkv, B, N, H, scale):
@@ -283,6 +341,7 @@ class MlpChainFn(torch.autograd.Function):
         ctx.n = n
         ctx.has_res = residual is not None
         ctx.has_bias = [wb[2 * i + 1] is not None for i in range(n)]
+        ctx.biases = [wb[2 * i + 1] for i in range(n)]
         ctx.save_for_backward(*saved, *[wb[2 * i] for i in range(n)])
         return h
 
@@ -297,7 +356,7 @@ class MlpChainFn(torch.autograd.Function):
         d = dy
         for i in range(n - 1, -1, -1):
             inp = acts[0] if i == 0 else acts[2 * i]            # input of layer i (x or gelu output)
-            dw, db = linear_wgrad(d, inp, ctx.has_bias[i])
+            dw, db = linear_wgrad(d, inp, ctx.has_bias[i], weights[i], ctx.biases[i])
             grads[2 * i], grads[2 * i + 1] = dw, db
             if i > 0:
                 d = linear_dgrad(d, bf16_of(weights[i]), dgelu_of=acts[2 * i - 1])
@@ -335,16 +394,17 @@ def attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, sca
     return y, (x, mean, rstd, ln, qkv, att, lse2)
 
 
-def attn_half_bwd(dy, saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale):
+def attn_half_bwd(dy, saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale, ln_b=None, qkv_b=None,
+                  proj_b=None):
     """dy: bf16 gradient of the half-block output. Returns (dx bf16, d_ln_w, d_ln_b, d_qkv_w, d_qkv_b,
     d_proj_w, d_proj_b); the residual gradient is added inside the LayerNorm-backward kernel."""
     x, mean, rstd, ln, qkv, att, lse2 = saved
     d_att = linear_dgrad(dy, bf16_of(proj_w))
-    d_pw, d_pb = linear_wgrad(dy, att, has_pb)
+    d_pw, d_pb = linear_wgrad(dy, att, has_pb, proj_w, proj_b)
     d_qkv = attention_bwd(qkv, att, d_att, lse2, B, N, H, scale)
     d_ln = linear_dgrad(d_qkv, bf16_of(qkv_w))
-    d_qw, d_qb = linear_wgrad(d_qkv, ln, has_qb)
-    dx, d_lw, d_lb = layernorm_bwd(x, d_ln, _f32(ln_w), mean, rstd, dres=dy)
+    d_qw, d_qb = linear_wgrad(d_qkv, ln, has_qb, qkv_w, qkv_b)
+    dx, d_lw, d_lb = layernorm_bwd(x, d_ln, _f32(ln_w), mean, rstd, dres=dy, weight=ln_w, bias=ln_b)
     return dx, d_lw, d_lb, d_qw, d_qb, d_pw, d_pb
 
 
@@ -356,13 +416,13 @@ def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps):
     return y, (x, mean, rstd, ln, pre, h)
 
 
-def mlp_half_bwd(dy, saved, ln_w, w1, w2, has_b1, has_b2):
+def mlp_half_bwd(dy, saved, ln_w, w1, w2, has_b1, has_b2, ln_b=None, b1=None, b2=None):
     x, mean, rstd, ln, pre, h = saved
     d_pre = linear_dgrad(dy, bf16_of(w2), dgelu_of=pre)
-    d_w2, d_b2 = linear_wgrad(dy, h, has_b2)
+    d_w2, d_b2 = linear_wgrad(dy, h, has_b2, w2, b2)
     d_ln = linear_dgrad(d_pre, bf16_of(w1))
-    d_w1, d_b1 = linear_wgrad(d_pre, ln, has_b1)
-    dx, d_lw, d_lb = layernorm_bwd(x, d_ln, _f32(ln_w), mean, rstd, dres=dy)
+    d_w1, d_b1 = linear_wgrad(d_pre, ln, has_b1, w1, b1)
+    dx, d_lw, d_lb = layernorm_bwd(x, d_ln, _f32(ln_w), mean, rstd, dres=dy, weight=ln_w, bias=ln_b)
     return dx, d_lw, d_lb, d_w1, d_b1, d_w2, d_b2
 
 
@@ -444,7 +504,8 @@ class EncoderFn(torch.autograd.Function):
         params = ctx.params
         depth = (len(params) - 2) // BLOCK_PARAMS
         cls, mean, rstd = ctx.final
-        d_cls, d_nw, d_nb = layernorm_bwd(cls, _g16(dout), _f32(params[-2]), mean, rstd)
+        d_cls, d_nw, d_nb = layernorm_bwd(cls, _g16(dout), _f32(params[-2]), mean, rstd, weight=params[-2],
+                                          bias=params[-1])
         D = cls.shape[1]
         dx = torch.zeros(B, N, D, dtype=_BF16, device=cls.device)
         dx[:, 0] = d_cls
@@ -453,9 +514,10 @@ class EncoderFn(torch.autograd.Function):
         for i in range(depth - 1, -1, -1):
             ln1w, ln1b, qw, qb, pw, pb, ln2w, ln2b, w1, b1, w2, b2 = params[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS]
             s1, s2 = ctx.saved[i]
-            dx, g_l2w, g_l2b, g_w1, g_b1, g_w2, g_b2 = mlp_half_bwd(dx, s2, ln2w, w1, w2, b1 is not None, b2 is not None)
+            dx, g_l2w, g_l2b, g_w1, g_b1, g_w2, g_b2 = mlp_half_bwd(dx, s2, ln2w, w1, w2, b1 is not None, b2 is not None,
+                                                                    ln2b, b1, b2)
             dx, g_l1w, g_l1b, g_qw, g_qb, g_pw, g_pb = attn_half_bwd(dx, s1, ln1w, qw, pw, qb is not None,
-                                                                      pb is not None, B, N, H, scale)
+                                                                      pb is not None, B, N, H, scale, ln1b, qb, pb)
             grads[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS] = [g_l1w, g_l1b, g_qw, g_qb, g_pw, g_pb, g_l2w, g_l2b,
                                                               g_w1, g_b1, g_w2, g_b2]
             ctx.saved[i] = None  # free this block's activations as soon as they are consumed
@@ -483,6 +545,7 @@ class TokensFn(torch.autograd.Function):
         _call("b200ssl_assemble_tokens", y.data_ptr(), _f32(cls_token).data_ptr(), _f32(pos).data_ptr(),
               x.data_ptr(), B, Np, D, _stream())
         ctx.save_for_backward(cols, proj_w)
+        ctx.proj_b = proj_b
         ctx.meta = (B, Np, D, proj_b is not None, cls_token.shape, pos.shape)
         return x
 
@@ -496,8 +559,9 @@ class TokensFn(torch.autograd.Function):
         dcls = torch.empty(D, dtype=torch.float32, device=dx.device)
         _call("b200ssl_assemble_tokens_bwd", dx.data_ptr(), dy.data_ptr(), dpos.data_ptr(), dcls.data_ptr(), B, Np,
               D, _stream(), launches=2)
-        dw, db = linear_wgrad(dy, cols, has_bias)
-        return None, dw.view(proj_w.shape), db, dcls.view(cls_shape), dpos.view(pos_shape), None
+        dw, db = linear_wgrad(dy, cols, has_bias, proj_w, ctx.proj_b)
+        return None, (dw.view(proj_w.shape) if dw is not None else None), db, dcls.view(cls_shape), \
+            dpos.view(pos_shape), None
 
 
 class L2NormFn(torch.autograd.Function):

@@ -180,3 +180,50 @@ def test_dino_step_bf16_autocast_oracle_agrees(libs):
     l, s, _ = b200ssl.dino_step(student, teacher, loss_fn, opt, [c.bfloat16() for c in crops])
     assert abs(l.item() - l_ref.item()) / abs(l_ref.item()) < 1e-2
     assert rel(s, s_ref) < 2e-2
+
+
+def test_grad_sinks_and_graphed_step_match_eager(libs):
+    """(a) GradBucketDataParallel's gradient sinks (kernels accumulate straight into the flat buckets) give
+    the same gradients as plain autograd accumulation; (b) the CUDA-graph step reproduces the eager step."""
+    b200ssl, ovt, odino = libs
+    out_dim, ncrops, B = 1024, 4, 4
+
+    def build():
+        torch.manual_seed(0)
+        m = b200ssl.MultiCropWrapper(b200ssl.vit_tiny(), b200ssl.DINOHead(192, out_dim, hidden_dim=256, bottleneck_dim=64)).cuda()
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.ndim == 1:
+                    p.add_(torch.randn_like(p) * 0.02)
+        return m
+
+    g = torch.Generator(device="cuda").manual_seed(7)
+    crops = [torch.randn(B, 3, 224, 224, device="cuda", generator=g).bfloat16() for _ in range(2)] + \
+            [torch.randn(B, 3, 96, 96, device="cuda", generator=g).bfloat16() for _ in range(ncrops - 2)]
+    plain, wrapped_mod, graphed_mod = build(), build(), build()
+    wrapped_mod.load_state_dict(plain.state_dict())
+    graphed_mod.load_state_dict(plain.state_dict())
+    wrapped = b200ssl.GradBucketDataParallel(wrapped_mod)
+    graphed_ddp = b200ssl.GradBucketDataParallel(graphed_mod)
+    runs = {}
+    for name, student, mod in (("plain", plain, plain), ("wrapped", wrapped, wrapped_mod)):
+        teacher = b200ssl.ModelEma(mod)
+        loss_fn = b200ssl.DINOLoss(out_dim, ncrops, 0.04, 0.04, 0, 10).cuda()
+        opt = b200ssl.FusedAdamW(b200ssl.param_groups_wd(mod, 0.04), lr=5e-4)
+        losses = [b200ssl.dino_step(student, teacher, loss_fn, opt, crops, momentum=0.99)[0].item()]
+        grads = {n: p.grad.clone() for n, p in mod.named_parameters() if p.grad is not None}   # step 0: same weights
+        losses += [b200ssl.dino_step(student, teacher, loss_fn, opt, crops, momentum=0.99)[0].item() for _ in range(3)]
+        runs[name] = (losses, grads)
+    for n, gp in runs["plain"][1].items():
+        assert cos(runs["wrapped"][1][n], gp) > 0.9999, n
+        assert rel(runs["wrapped"][1][n], gp) < 1e-2, n
+    # later steps run on independently updated weights (Adam amplifies rounding noise): loose bound only
+    assert max(abs(a - b) / abs(a) for a, b in zip(runs["plain"][0], runs["wrapped"][0])) < 1e-2
+    # graph replay vs eager (same wrapped configuration); fp32 atomics make runs equal only up to rounding
+    teacher = b200ssl.ModelEma(graphed_mod)
+    loss_fn = b200ssl.DINOLoss(out_dim, ncrops, 0.04, 0.04, 0, 10).cuda()
+    opt = b200ssl.FusedAdamW(b200ssl.param_groups_wd(graphed_mod, 0.04), lr=5e-4)
+    step = b200ssl.GraphedDinoStep(graphed_ddp, teacher, loss_fn, opt, crops, warmup=1)
+    # the capture warm-up ran 1 eager step; replays continue from there
+    glosses = [step(crops, momentum=0.99).item() for _ in range(3)]
+    assert max(abs(a - b) / abs(a) for a, b in zip(runs["wrapped"][0][1:], glosses)) < 1e-2, (runs["wrapped"][0], glosses)
