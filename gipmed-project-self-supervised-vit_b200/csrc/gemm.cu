@@ -53,22 +53,37 @@ constexpr int STAGING_BYTES = BLOCK_M * 128;           // per epilogue group: 2 
 constexpr int NUM_EPI_GROUPS = 4;                      // 4 groups x 4 warps: 4 warps per TMEM lane quarter
 constexpr int GEMM_THREADS = 128 + NUM_EPI_GROUPS * 128;
 
-template <int BN>
+constexpr int kSmemBudget = 232448 - 2048;  // 227 KB opt-in limit minus barrier block and alignment slack
+
+template <int BN, int CL>
 struct GemmCfg {
-  static constexpr int kStages = BN == 256 ? 3 : BN == 192 ? 4 : BN == 128 ? 5 : 6;
-  static constexpr int kBStageBytes = BN * BLOCK_K * 2;
+  // per-CTA bytes of one pipeline stage: 128 rows of A and (in CTA-pair mode half of) the B tile
+  static constexpr int kBStageBytes = BN * BLOCK_K * 2 / CL;
   static constexpr int kStageBytes = A_STAGE_BYTES + kBStageBytes;
+  static constexpr int kStagingBytes = NUM_EPI_GROUPS * STAGING_BYTES;
+  // as many stages as fit: the operand feed is latency bound (bytes in flight per SM / ~1 us L2 latency),
+  // so depth matters more than anything else; pair mode gets 5-6 stages where single-CTA mode gets 3-4
+  static constexpr int kStagesFit = (kSmemBudget - kStagingBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kTmemCols = BN * 2 <= 128 ? 128 : BN * 2 <= 256 ? 256 : 512;
-  static constexpr int kSmemBytes =
-      kStages * kStageBytes + NUM_EPI_GROUPS * STAGING_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*barriers*/ + 1024 /*align*/;
 };
 
-template <int BN, int EPI>
+// CL = CTAs per cluster (1 or 2). CL == 2 is the CTA-pair mode (tcgen05 cta_group::2): the two CTAs of a
+// cluster own vertically adjacent 128-row tiles of one 256 x BN output tile. Each CTA loads its own 128 rows
+// of A and only HALF of the B tile; the leader CTA (rank 0) issues 256 x BN x 16 MMAs that read both halves
+// of B from the two SMs' shared memory and write each CTA's 128 rows into its own TMEM. L2 -> smem bytes per
+// MMA drop by a third (the 128 x BN tiling is L2-bandwidth bound, ~11 TB/s measured).
+//   * both CTAs' TMA loads complete on the LEADER's full barrier (peer-bit mask), count 2 = leader's
+//     arrive.expect_tx (both CTAs' bytes) + the peer's remote arrive;
+//   * the leader's tcgen05.commit is multicast to both CTAs (stage-empty / accumulator-full barriers);
+//   * both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.
+template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
             const GemmArgs args) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   constexpr int kStages = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -80,10 +95,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* empty_bar = bars + kStages;      // [kStages]
   uint64_t* tmem_full = bars + 2 * kStages;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* consumed_bar = tmem_empty + 2;   // [kStages] CTA-pair wgrad: "MMA is done reading this stage"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(consumed_bar + kStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cluster_id = CL > 1 ? blockIdx.x / CL : blockIdx.x;
+  const int num_clusters = CL > 1 ? gridDim.x / CL : gridDim.x;
+  const int num_m_units = (args.num_m_blocks + CL - 1) / CL;  // CL vertically adjacent m blocks per unit
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -92,23 +112,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (EPI == EPI_BIAS_GELU) tma_prefetch_desc(&tmD2);
   }
   if (warp == 1 && lane == 0) {
+    constexpr int kEpiWarps = NUM_EPI_GROUPS * 4;
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], EPI == EPI_ATOMIC_F32 ? 1 + NUM_EPI_GROUPS * 4 : 1);  // wgrad: + the epilogue warps (bias grad)
+      mbar_init(&full_bar[s], CL);
+      // stage release: the MMA commit, plus (wgrad) the epilogue warps that fold the bias gradient from the
+      // stage; in CTA-pair wgrad the commit goes to consumed_bar instead and only the warps release
+      mbar_init(&empty_bar[s], EPI == EPI_ATOMIC_F32 ? (CL == 1 ? 1 + kEpiWarps : kEpiWarps) : 1);
+      mbar_init(&consumed_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], NUM_EPI_GROUPS * 128);
+      mbar_init(&tmem_empty[s], CL * kEpiWarps);  // one arrive per epilogue warp of every CTA of the pair
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if (CL == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
+  }
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_per_split = args.num_m_blocks * args.num_n_blocks;
+  const int tiles_per_split = num_m_units * args.num_n_blocks;  // work units (CL tiles each) per k split
   const int total_tiles = tiles_per_split * args.k_splits;
 
   if (warp == 0) {
@@ -116,9 +144,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
         const int n_blk = t % args.num_n_blocks;
-        const int m_blk = (t / args.num_n_blocks) % args.num_m_blocks;
+        const int m_blk = ((t / args.num_n_blocks) % num_m_units) * CL + cta_rank;
         const int ks = t / tiles_per_split;
         const int kb0 = ks * args.k_blocks_per_split;
         const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks_total);
@@ -127,21 +155,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * Cfg::kStageBytes;
           uint8_t* sB = sA + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int k0 = kb * BLOCK_K;
-          if (!args.a_mn) {
-            tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
-          } else {
+          if (CL == 1) {
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            if (!args.a_mn) {
+              tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BLOCK_M / 64; ++c)
-              tma_load_2d(sA + c * 8192, &tmA, &full_bar[stage], m0 + c * 64, k0);
-          }
-          if (!args.b_mn) {
-            tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
-          } else {
+              for (int c = 0; c < BLOCK_M / 64; ++c)
+                tma_load_2d(sA + c * 8192, &tmA, &full_bar[stage], m0 + c * 64, k0);
+            }
+            if (!args.b_mn) {
+              tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(sB + c * 8192, &tmB, &full_bar[stage], n0 + c * 64, k0);
+              for (int c = 0; c < BN / 64; ++c)
+                tma_load_2d(sB + c * 8192, &tmB, &full_bar[stage], n0 + c * 64, k0);
+            }
+          } else {
+            // CTA pair: own 128 rows of A, own half of the B tile; completion lands on the leader's barrier
+            constexpr int kHalfN = BN / 2;
+            if (!args.a_mn) {
+              tma_load_2d_2sm(sA, &tmA, &full_bar[stage], k0, m0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BLOCK_M / 64; ++c)
+                tma_load_2d_2sm(sA + c * 8192, &tmA, &full_bar[stage], m0 + c * 64, k0);
+            }
+            if (!args.b_mn) {
+              tma_load_2d_2sm(sB, &tmB, &full_bar[stage], k0, n0 + cta_rank * kHalfN);
+            } else {
+#pragma unroll
+              for (int c = 0; c < kHalfN / 64; ++c)
+                tma_load_2d_2sm(sB + c * 8192, &tmB, &full_bar[stage], n0 + cta_rank * kHalfN + c * 64, k0);
+            }
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            else mbar_arrive_leader(&full_bar[stage]);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -149,8 +198,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, args.a_mn != 0, args.b_mn != 0);
+    if (lane == 0 && cta_rank == 0) {  // CTA pair: only the leader issues MMAs
+      const uint32_t idesc = make_idesc_bf16(BLOCK_M * CL, BN, args.a_mn != 0, args.b_mn != 0);
       const uint32_t a_lbo = args.a_mn ? 8192u : 16u;
       const uint32_t b_lbo = args.b_mn ? 8192u : 16u;
       const uint32_t a_kstep = args.a_mn ? UMMA_K * 128u : UMMA_K * 2u;
@@ -159,7 +208,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
         const int ks = t / tiles_per_split;
         const int kb0 = ks * args.k_blocks_per_split;
         const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks_total);
@@ -175,12 +224,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(sA + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(sB + k * b_kstep, b_lbo, 1024);
-            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CL == 1) umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (CL == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_2sm_mc(EPI == EPI_ATOMIC_F32 ? &consumed_bar[stage] : &empty_bar[stage], 3);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
+        if (CL == 1) umma_commit(&tmem_full[acc]);
+        else umma_commit_2sm_mc(&tmem_full[acc], 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -198,9 +250,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int cs_stage = 0;   // wgrad only: position in the smem ring (bias-gradient pass)
     uint32_t cs_phase = 0;
 
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
       const int n_blk = t % args.num_n_blocks;
-      const int m_blk = (t / args.num_n_blocks) % args.num_m_blocks;
+      const int m_blk = ((t / args.num_n_blocks) % num_m_units) * CL + cta_rank;
       const int m0 = m_blk * BLOCK_M, n0 = n_blk * BN;
       const int row = m0 + row_in_tile;
       const bool row_ok = row < args.M;
@@ -220,7 +272,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int sub = etid >> 4;           // k rows sub and sub+32
         float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[cs_stage], cs_phase);
+          // single CTA: the stage is readable as soon as TMA filled it; CTA pair: only the leader's full
+          // barrier is signalled, so wait for the (multicast) "MMA consumed this stage" commit instead
+          mbar_wait(CL == 1 ? &full_bar[cs_stage] : &consumed_bar[cs_stage], cs_phase);
           if (mine) {
             const uint8_t* sA = smem + cs_stage * Cfg::kStageBytes + (jc >> 3) * 8192;
 #pragma unroll
@@ -256,6 +310,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
       bool released = false;
       for (int c = group; c < kChunks; c += NUM_EPI_GROUPS) {
+        // aux operand (residual / saved gelu'): each thread owns a ROW of the tile (TMEM lane), but loading it
+        // that way touches 32 cache lines per warp instruction. Fetch the warp's 32-row slab with a coalesced
+        // lane mapping instead (issued first, so it flies during the TMEM read) and transpose it through the
+        // staging buffer further down.
+        constexpr bool kAuxBf16 = EPI == EPI_BIAS_RES || EPI == EPI_MUL_AUX;
+        constexpr bool kAuxF32 = EPI == EPI_BIAS_RES_F32;
+        constexpr int kAuxLoads = kAuxBf16 ? 4 : (kAuxF32 ? 8 : 1);
+        uint4 auxv[kAuxLoads];
+        if (kAuxBf16 || kAuxF32) {
+          constexpr int kLanesPerRow = kAuxBf16 ? 4 : 8;   // 16-byte pieces per 32-column row
+          constexpr int kRowsPerLoad = 32 / kLanesPerRow;
+          const int piece = lane % kLanesPerRow;
+          const int acol = n0 + c * EPI_CHUNK;
+#pragma unroll
+          for (int i = 0; i < kAuxLoads; ++i) {
+            const int arow = m0 + q * 32 + i * kRowsPerLoad + lane / kLanesPerRow;
+            auxv[i] = make_uint4(0, 0, 0, 0);
+            if (arow < args.M) {
+              const uint8_t* base = static_cast<const uint8_t*>(args.aux) +
+                                    (static_cast<long long>(arow) * args.ldaux + acol) * (kAuxBf16 ? 2 : 4);
+              auxv[i] = __ldg(reinterpret_cast<const uint4*>(base) + piece);
+            }
+          }
+        }
         float f[EPI_CHUNK];
         {
           uint32_t v[32];
@@ -266,9 +344,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         }
         if (c + NUM_EPI_GROUPS >= kChunks) {
-          // last TMEM read of this tile by this thread: hand the accumulator stage back
+          // last TMEM read of this tile by this warp: hand the accumulator stage back (to the leader's MMA)
           tcgen05_fence_before();
-          mbar_arrive(&tmem_empty[acc]);
+          __syncwarp();
+          if (lane == 0) {
+            if (CL == 1) mbar_arrive(&tmem_empty[acc]);
+            else mbar_arrive_leader(&tmem_empty[acc]);
+          }
           released = true;
         }
         const int col0 = n0 + c * EPI_CHUNK;
@@ -293,46 +375,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
           }
         }
-        if (EPI == EPI_BIAS_RES || EPI == EPI_MUL_AUX) {
-          if (row_ok) {
-            const uint4* ap = reinterpret_cast<const uint4*>(
-                static_cast<const __nv_bfloat16*>(args.aux) + static_cast<long long>(row) * args.ldaux + col0);
-#pragma unroll
-            for (int j = 0; j < EPI_CHUNK / 8; ++j) {
-              const uint4 a = __ldg(ap + j);
-              const uint32_t w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 x = unpack_bf16x2(w[e]);
-                if (EPI == EPI_BIAS_RES) {
-                  f[8 * j + 2 * e] += x.x;
-                  f[8 * j + 2 * e + 1] += x.y;
-                } else {
-                  f[8 * j + 2 * e] *= x.x;
-                  f[8 * j + 2 * e + 1] *= x.y;
-                }
-              }
-            }
-          }
-        }
-
         if (EPI == EPI_BIAS_RES_F32) {
-          if (row_ok) {
-            const float4* ap = reinterpret_cast<const float4*>(
-                static_cast<const float*>(args.aux) + static_cast<long long>(row) * args.ldaux + col0);
-#pragma unroll
-            for (int j = 0; j < EPI_CHUNK / 4; ++j) {
-              const float4 a = __ldg(ap + j);
-              f[4 * j] += a.x; f[4 * j + 1] += a.y; f[4 * j + 2] += a.z; f[4 * j + 3] += a.w;
-            }
-          }
-          // fp32 output: one 32-column box (128 B rows, 128B swizzle); single staging buffer per group
+          // fp32 output: one 32-column box (128 B rows, 128B swizzle); single staging buffer per group.
           if (gtid == 0) tma_store_wait_read<0>();
           named_bar_sync(1 + group, 128);
+          // residual slab -> staging (coalesced mapping), then each thread reads back ITS row, adds and
+          // overwrites it in place; only this warp touches these 32 rows, so a __syncwarp orders it
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(stg + sw128_offset(row_in_tile, j)) =
-                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<uint4*>(stg + sw128_offset(q * 32 + i * 4 + (lane >> 3), lane & 7)) = auxv[i];
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4* p4 = reinterpret_cast<float4*>(stg + sw128_offset(row_in_tile, j));
+            const float4 a = *p4;
+            *p4 = make_float4(f[4 * j] + a.x, f[4 * j + 1] + a.y, f[4 * j + 2] + a.z, f[4 * j + 3] + a.w);
+          }
           fence_proxy_async_smem();
           named_bar_sync(1 + group, 128);
           if (gtid == 0) {
@@ -361,6 +419,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint8_t* buf = stg + (slot & 1) * (STAGING_BYTES / 2);
           if (gtid == 0) tma_store_wait_read<1>();  // the store that last used this buffer has drained
           named_bar_sync(1 + group, 128);
+          if (kAuxBf16) {
+            // aux slab -> staging (coalesced mapping) -> own row back (conflict-free), combine with acc
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(buf + sw64_offset(q * 32 + i * 8 + (lane >> 2), lane & 3)) = auxv[i % kAuxLoads];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 a = *reinterpret_cast<const uint4*>(buf + sw64_offset(row_in_tile, j));
+              const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 x = unpack_bf16x2(w[e]);
+                if (EPI == EPI_BIAS_RES) {
+                  f[8 * j + 2 * e] += x.x;
+                  f[8 * j + 2 * e + 1] += x.y;
+                } else {
+                  f[8 * j + 2 * e] *= x.x;
+                  f[8 * j + 2 * e + 1] *= x.y;
+                }
+              }
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 pk;
@@ -386,7 +467,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       if (!released) {
         tcgen05_fence_before();
-        mbar_arrive(&tmem_empty[acc]);
+        __syncwarp();
+        if (lane == 0) {
+          if (CL == 1) mbar_arrive(&tmem_empty[acc]);
+          else mbar_arrive_leader(&tmem_empty[acc]);
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -395,39 +480,64 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  if (CL > 1) cluster_sync_all();  // the peer may still arrive on / read from this CTA until it is done
+  if (warp == 2) {
+    if (CL == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
-template <int BN, int EPI>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
-                       const CUtensorMap& tmD2, const GemmArgs& args, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+static int g_gemm_cluster = 2;  // CTAs per cluster for the B-multicast variant (1 disables it)
+
+template <int BN, int EPI, int CL>
+static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                          const CUtensorMap& tmD2, const GemmArgs& args, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CL>;
   static bool configured = false;
   if (!configured) {
-    B200SSL_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    B200SSL_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::kSmemBytes));
     configured = true;
   }
-  const int total = args.num_m_blocks * args.num_n_blocks * args.k_splits;
-  const int grid = total < sm_count() ? total : sm_count();
-  gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmD, tmD2, args);
-  B200SSL_CUDA(cudaGetLastError());
+  const int units = ((args.num_m_blocks + CL - 1) / CL) * args.num_n_blocks * args.k_splits;
+  const int max_clusters = sm_count() / CL;
+  const int clusters = units < max_clusters ? units : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  B200SSL_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, CL>, tmA, tmB, tmD, tmD2, args));
   return 0;
+}
+
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                       const CUtensorMap& tmD2, const GemmArgs& args, int cluster, cudaStream_t stream) {
+  if (cluster == 2) return launch_gemm_cl<BN, EPI, 2>(tmA, tmB, tmD, tmD2, args, stream);
+  return launch_gemm_cl<BN, EPI, 1>(tmA, tmB, tmD, tmD2, args, stream);
 }
 
 template <int BN>
 static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d,
-                        const CUtensorMap& d2, const GemmArgs& args, cudaStream_t s) {
+                        const CUtensorMap& d2, const GemmArgs& args, int cl, cudaStream_t s) {
   switch (epi) {
-    case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(a, b, d, d2, args, s);
-    case EPI_BIAS_GELU: return launch_gemm<BN, EPI_BIAS_GELU>(a, b, d, d2, args, s);
-    case EPI_BIAS_RES: return launch_gemm<BN, EPI_BIAS_RES>(a, b, d, d2, args, s);
-    case EPI_MUL_AUX: return launch_gemm<BN, EPI_MUL_AUX>(a, b, d, d2, args, s);
-    case EPI_ATOMIC_F32: return launch_gemm<BN, EPI_ATOMIC_F32>(a, b, d, d2, args, s);
-    case EPI_BIAS_RES_F32: return launch_gemm<BN, EPI_BIAS_RES_F32>(a, b, d, d2, args, s);
+    case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(a, b, d, d2, args, cl, s);
+    case EPI_BIAS_GELU: return launch_gemm<BN, EPI_BIAS_GELU>(a, b, d, d2, args, cl, s);
+    case EPI_BIAS_RES: return launch_gemm<BN, EPI_BIAS_RES>(a, b, d, d2, args, cl, s);
+    case EPI_MUL_AUX: return launch_gemm<BN, EPI_MUL_AUX>(a, b, d, d2, args, cl, s);
+    case EPI_ATOMIC_F32: return launch_gemm<BN, EPI_ATOMIC_F32>(a, b, d, d2, args, cl, s);
+    case EPI_BIAS_RES_F32: return launch_gemm<BN, EPI_BIAS_RES_F32>(a, b, d, d2, args, cl, s);
   }
   set_last_error("gemm: unknown epilogue %d", epi);
   return -2;
@@ -486,8 +596,9 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
   if (epilogue == EPI_ATOMIC_F32 && split_k <= 0) {
     // auto split-K: the largest tile that divides N, then as many K splits as fill one wave of SMs
     if (bn == 0) bn = N % 256 == 0 ? 256 : N % 192 == 0 ? 192 : N % 128 == 0 ? 128 : 64;
-    const int tiles_mn = ((M + BLOCK_M - 1) / BLOCK_M) * (N / bn);
-    split_k = sm_count() / (tiles_mn > 0 ? tiles_mn : 1);
+    const int cl_ = (g_gemm_cluster == 2 && M > BLOCK_M && (!b_mn_major || bn % 128 == 0)) ? 2 : 1;
+    const int tiles_mn = (((M + BLOCK_M - 1) / BLOCK_M + cl_ - 1) / cl_) * (N / bn);  // work units per k split
+    split_k = (sm_count() / cl_) / (tiles_mn > 0 ? tiles_mn : 1);
     if (split_k > k_blocks / 2) split_k = k_blocks / 2;
   }
   if (split_k < 1) split_k = 1;
@@ -513,6 +624,8 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
   args.out_f32 = static_cast<float*>(D);
   args.ldd = ldd;
 
+  // CTA-pair mode needs two m blocks and, for an MN-major B, a half tile made of whole 64-column chunks
+  const int cluster = (g_gemm_cluster == 2 && args.num_m_blocks > 1 && (!b_mn_major || bn % 128 == 0)) ? 2 : 1;
   CUtensorMap tmA, tmB, tmD, tmD2;
   {
     // A: K-major -> dims (K, M), box (64, 128); MN-major -> dims (M, K), box (64, 64)
@@ -522,7 +635,7 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
     else             { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = 64; }
     strides[0] = 2; strides[1] = static_cast<uint64_t>(lda) * 2;
     if (int rc = make_tensor_map(&tmA, A, 2, 2, dims, strides, box, 128)) return rc;
-    if (!b_mn_major) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = bn; }
+    if (!b_mn_major) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = bn / cluster; }  // pair: half the rows
     else             { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = 64; }
     strides[1] = static_cast<uint64_t>(ldb) * 2;
     if (int rc = make_tensor_map(&tmB, B, 2, 2, dims, strides, box, 128)) return rc;
@@ -542,9 +655,16 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
   }
 
   switch (bn) {
-    case 64: return dispatch_epi<64>(epilogue, tmA, tmB, tmD, tmD2, args, stream);
-    case 128: return dispatch_epi<128>(epilogue, tmA, tmB, tmD, tmD2, args, stream);
-    case 192: return dispatch_epi<192>(epilogue, tmA, tmB, tmD, tmD2, args, stream);
-    default: return dispatch_epi<256>(epilogue, tmA, tmB, tmD, tmD2, args, stream);
+    case 64: return dispatch_epi<64>(epilogue, tmA, tmB, tmD, tmD2, args, cluster, stream);
+    case 128: return dispatch_epi<128>(epilogue, tmA, tmB, tmD, tmD2, args, cluster, stream);
+    case 192: return dispatch_epi<192>(epilogue, tmA, tmB, tmD, tmD2, args, cluster, stream);
+    default: return dispatch_epi<256>(epilogue, tmA, tmB, tmD, tmD2, args, cluster, stream);
   }
+}
+
+// 1 = independent CTAs, 2 = clusters of two CTAs sharing the B tile through TMA multicast (default).
+extern "C" int b200ssl_set_gemm_cluster(int ctas) {
+  B200SSL_CHECK(ctas == 1 || ctas == 2, -2, "gemm cluster size must be 1 or 2");
+  b200ssl::g_gemm_cluster = ctas;
+  return 0;
 }

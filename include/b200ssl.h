@@ -42,6 +42,9 @@ int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const void* B, lo
                  void* D, long long ldd, void* D2, const float* bias, const void* aux, long long ldaux,
                  int M, int N, int K, int epilogue, int split_k, int block_n, void* stream);
 
+/* 1 = independent CTAs; 2 (default) = clusters of two CTAs that share each B tile through TMA multicast. */
+int b200ssl_set_gemm_cluster(int ctas);
+
 /* ---- K2: LayerNorm (Block.norm1/norm2 VT.pyc@L138,142,147,151; VisionTransformer.norm @L195,252) -----
  * x is bf16 (x_f32 = 0) or the fp32 residual stream (x_f32 = 1); y bf16; mean/rstd fp32 [rows].
  * bwd: dx(bf16) = LN'(dy) + dres (dres nullable: the residual-branch gradient is added in-kernel);

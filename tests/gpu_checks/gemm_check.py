@@ -145,6 +145,11 @@ def bench_case(M, N, K, a_mn, b_mn, epi, bn, split_k=1, iters=20):
 
 def main():
     assert torch.cuda.is_available()
+    if "--cluster" in sys.argv:
+        n = int(sys.argv[sys.argv.index("--cluster") + 1])
+        h.b200ssl_set_gemm_cluster.argtypes = [I]
+        assert h.b200ssl_set_gemm_cluster(n) == 0
+        print("gemm cluster size", n)
     results = []
     allok = True
     # 1. smallest K-major case first: one tile, one k-block

@@ -1,0 +1,63 @@
+"""Developer bench: every GEMM of one ViT-S block (fprop / dgrad / wgrad) at config-2 row counts,
+single-CTA vs CTA-pair mode, through the same ops-level entry points the model uses."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch
+
+import b200ssl
+from b200ssl import ops
+
+lib = b200ssl._lib.lib()
+D, H4 = 384, 1536
+
+
+def timeit(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+def run(rows):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    x, x4 = r(rows, D).bfloat16(), r(rows, H4).bfloat16()
+    x3 = r(rows, 3 * D).bfloat16()
+    wq, wp, w1, w2 = (r(3 * D, D) * .05).bfloat16(), (r(D, D) * .05).bfloat16(), (r(H4, D) * .05).bfloat16(), (r(D, H4) * .05).bfloat16()
+    bq, bp, b1, b2 = r(3 * D), r(D), r(H4), r(D)
+    res = r(rows, D)
+    cases = {
+        "qkv fwd": (lambda: ops.linear_fwd(x, wq, bq), 2 * rows * D * 3 * D),
+        "proj fwd+res32": (lambda: ops.linear_fwd(x, wp, bp, residual=res), 2 * rows * D * D),
+        "fc1 fwd+gelu": (lambda: ops.linear_fwd(x, w1, b1, gelu=True), 2 * rows * D * H4),
+        "fc2 fwd+res32": (lambda: ops.linear_fwd(x4, w2, b2, residual=res), 2 * rows * D * H4),
+        "proj dgrad": (lambda: ops.linear_dgrad(x, wp), 2 * rows * D * D),
+        "qkv dgrad": (lambda: ops.linear_dgrad(x3, wq), 2 * rows * D * 3 * D),
+        "fc2 dgrad*aux": (lambda: ops.linear_dgrad(x, w2, dgelu_of=x4), 2 * rows * D * H4),
+        "fc1 dgrad": (lambda: ops.linear_dgrad(x4, w1), 2 * rows * D * H4),
+        "proj wgrad": (lambda: ops.linear_wgrad(x, x), 2 * rows * D * D),
+        "qkv wgrad": (lambda: ops.linear_wgrad(x3, x), 2 * rows * D * 3 * D),
+        "fc1 wgrad": (lambda: ops.linear_wgrad(x4, x), 2 * rows * D * H4),
+        "fc2 wgrad": (lambda: ops.linear_wgrad(x, x4), 2 * rows * D * H4),
+    }
+    tot = {1: 0.0, 2: 0.0}
+    for name, (fn, fl) in cases.items():
+        ts = {}
+        for cl in (1, 2):
+            lib.b200ssl_set_gemm_cluster(cl)
+            ts[cl] = timeit(fn)
+            tot[cl] += ts[cl]
+        print(f"rows={rows:7d} {name:16s} single {ts[1]:7.1f} us ({fl/ts[1]/1e6:5.0f} TF)   pair {ts[2]:7.1f} us ({fl/ts[2]/1e6:5.0f} TF)")
+    print(f"rows={rows:7d} TOTAL single {tot[1]:.0f} us   pair {tot[2]:.0f} us")
+
+
+run(100864)
+run(94720)
