@@ -70,7 +70,24 @@ sumsq_kernel(const SumsqRow* __restrict__ table, float* __restrict__ out) {
   if (threadIdx.x < 32) {
     float v = threadIdx.x < OPT_THREADS / 32 ? red[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(out, v);
+    if (threadIdx.x == 0) out[1 + blockIdx.x] = v;  // per-chunk partial; summed in a fixed order below
+  }
+}
+
+// out[0] = sum of the n partials in out[1..n], in an order that does not depend on scheduling: data-parallel
+// replicas must compute bit-identical clipping coefficients or they drift apart
+__global__ void __launch_bounds__(1024)
+sumsq_final_kernel(float* __restrict__ out, int n) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) acc += out[1 + i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = red[threadIdx.x];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] = v;
   }
 }
 
@@ -166,12 +183,16 @@ extern "C" int b200ssl_ema_multi_tensor(const void* table, int n_rows, const flo
   return 0;
 }
 
-// out[0] is overwritten with sum over all rows of g^2.
+// out is a float[1 + n_rows] workspace: out[0] receives sum over all rows of g^2 (deterministic order),
+// out[1..] the per-row partials.
 extern "C" int b200ssl_sumsq_multi_tensor(const void* table, int n_rows, float* out, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  B200SSL_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
-  if (n_rows <= 0) return 0;
+  if (n_rows <= 0) {
+    B200SSL_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
+    return 0;
+  }
   sumsq_kernel<<<n_rows, OPT_THREADS, 0, s>>>(static_cast<const SumsqRow*>(table), out);
+  sumsq_final_kernel<<<1, 1024, 0, s>>>(out, n_rows);
   B200SSL_CUDA(cudaGetLastError());
   return 0;
 }

@@ -38,6 +38,7 @@ class DINOLoss(nn.Module):
             np.linspace(warmup_teacher_temp, teacher_temp, warmup_teacher_temp_epochs),
             np.ones(nepochs - warmup_teacher_temp_epochs) * teacher_temp))
         self._pending = None  # (work handle, local column sum, rows) of an in-flight centre all-reduce
+        self.defer_comm = False  # True: forward only computes the local column sums; the caller all-reduces
 
     def forward(self, student_output, teacher_output, epoch=0):
         ops.require_cuda(student_output, "DINOLoss")
@@ -62,11 +63,18 @@ class DINOLoss(nn.Module):
         rows, world, work = t.shape[0], 1, None
         if dist.is_available() and dist.is_initialized():
             world = dist.get_world_size()
-            if world > 1:
+            if world > 1 and not self.defer_comm:
                 work = dist.all_reduce(batch_sum, async_op=True)
         self._pending = (work, batch_sum, rows * world)
-        if work is None:
+        if work is None and not (self.defer_comm and world > 1):
             self.finish_center_update()
+
+    @torch.no_grad()
+    def allreduce_center_now(self):
+        """Deferred mode (two-graph step): sum the pending local column sums over ranks, eagerly."""
+        if self._pending is not None and self._pending[0] is None and dist.is_initialized() \
+                and dist.get_world_size() > 1:
+            dist.all_reduce(self._pending[1])
 
     @torch.no_grad()
     def finish_center_update(self):
@@ -278,6 +286,7 @@ class FusedAdamW(torch.optim.Optimizer):
             self._hyper_host = torch.zeros(n, 8, dtype=torch.float32).pin_memory()
             self._hyper_dev = torch.zeros(n, 8, dtype=torch.float32, device=dev)
             self._gnorm = torch.zeros(n + 1, dtype=torch.float32, device=dev)
+            self._gnorm_ws = {}
         for gi, group, _ in ents:
             group["step"] = group.get("step", 0) + 1
             t = group["step"]
@@ -298,15 +307,22 @@ class FusedAdamW(torch.optim.Optimizer):
             return
         gnorm_ptr = None
         if max_grad_norm and max_grad_norm > 0:
-            parts = self._gnorm[1:1 + len(ents)]
-            for i, (_, _, ent) in enumerate(ents):
-                ops._call("b200ssl_sumsq_multi_tensor", ent["gtable"].data_ptr(), ent["gtable"].shape[0],
-                          parts[i:i + 1].data_ptr(), ops._stream(), launches=2)
-            if len(ents) == 1:
-                total = parts[0:1]
+            parts = []
+            for gi, _, ent in ents:
+                n_rows = ent["gtable"].shape[0]
+                ws = self._gnorm_ws.get(gi)
+                if ws is None or ws.numel() < n_rows + 1:
+                    ws = self._gnorm_ws[gi] = torch.zeros(n_rows + 1, dtype=torch.float32, device=self._gnorm.device)
+                ops._call("b200ssl_sumsq_multi_tensor", ent["gtable"].data_ptr(), n_rows, ws.data_ptr(),
+                          ops._stream(), launches=2)
+                parts.append(ws[0:1])
+            if len(parts) == 1:
+                total = parts[0]
             else:
                 total = self._gnorm[0:1]
-                torch.sum(parts, dim=0, keepdim=True, out=total)
+                torch.add(parts[0], parts[1], out=total)
+                for extra in parts[2:]:
+                    total.add_(extra)
             self.last_grad_norm_sq = total
             gnorm_ptr = total.data_ptr()
         for gi, group, ent in ents:
@@ -374,6 +390,7 @@ class GradBucketDataParallel(nn.Module):
                 off += (p.numel() + 3) // 4 * 4
                 self._bucket_of[id(p)] = bi
             self._flat.append(flat)
+        self.defer_comm = False        # True: hooks / finish() launch nothing; the caller runs allreduce_now()
         self._expected = None          # id(p) -> hook firings per backward (learned on the first step)
         self._seen = {}
         self._pending = [0] * len(self.buckets)
@@ -399,7 +416,7 @@ class GradBucketDataParallel(nn.Module):
 
     def _hook(self, p):
         self._seen[id(p)] = self._seen.get(id(p), 0) + 1
-        if self._expected is None or self.world == 1:
+        if self._expected is None or self.world == 1 or self.defer_comm:
             return
         bi = self._bucket_of[id(p)]
         self._pending[bi] -= 1
@@ -425,8 +442,20 @@ class GradBucketDataParallel(nn.Module):
                     p.grad = flat[off:off + p.numel()].view_as(p)
                 off += (p.numel() + 3) // 4 * 4
 
+    def allreduce_now(self):
+        """Deferred mode (two-graph step): average every flat bucket over ranks, eagerly, in bucket order."""
+        if self.world > 1:
+            for bi in range(len(self.buckets)):
+                if self._avg_native:
+                    dist.all_reduce(self._flat[bi], op=dist.ReduceOp.AVG, group=self.pg)
+                else:
+                    self._flat[bi].div_(self.world)
+                    dist.all_reduce(self._flat[bi], op=dist.ReduceOp.SUM, group=self.pg)
+
     def finish(self):
         """Wait for the bucket all-reduces of this backward; re-arm the counters for the next one."""
+        if self.defer_comm:
+            return
         if self.world > 1:
             for bi in range(len(self.buckets)):
                 if not self._launched[bi]:
@@ -453,8 +482,8 @@ def _step_prepare(student, teacher_ema, optimizer, momentum):
     return ents
 
 
-def _step_launch(student, teacher_ema, loss_fn, optimizer, crops, epoch, clip_grad, ents):
-    """Device work of a step: only kernel launches / NCCL calls on the current stream (graph-capturable)."""
+def _step_compute(student, teacher_ema, loss_fn, optimizer, crops, epoch):
+    """Forward (teacher + student), loss, backward. Kernel launches (and, unless deferred, NCCL calls) only."""
     with torch.no_grad():
         teacher_out = teacher_ema.module(list(crops[:2]))
     student_out = student(list(crops))
@@ -467,6 +496,11 @@ def _step_launch(student, teacher_ema, loss_fn, optimizer, crops, epoch, clip_gr
     loss.backward()
     if ddp is not None:
         ddp.finish()
+    return loss.detach(), student_out.detach(), teacher_out.detach()
+
+
+def _step_update(student, teacher_ema, loss_fn, optimizer, clip_grad, ents):
+    """Gradient clipping + AdamW, teacher EMA, centre update. Kernel launches only."""
     if isinstance(optimizer, FusedAdamW):
         optimizer.launch_step(clip_grad or 0.0, ents)
     else:
@@ -474,7 +508,17 @@ def _step_launch(student, teacher_ema, loss_fn, optimizer, crops, epoch, clip_gr
             torch.nn.utils.clip_grad_norm_([p for p in student.parameters() if p.requires_grad], clip_grad)
         optimizer.step()
     teacher_ema.launch()
-    return loss.detach(), student_out.detach(), teacher_out.detach()
+    # the centre all-reduce was launched right after the loss forward and has overlapped with backward and
+    # the optimiser; close it inside the step so a step is self-contained
+    if hasattr(loss_fn, "finish_center_update"):
+        loss_fn.finish_center_update()
+
+
+def _step_launch(student, teacher_ema, loss_fn, optimizer, crops, epoch, clip_grad, ents):
+    """Device work of a whole step on the current stream."""
+    out = _step_compute(student, teacher_ema, loss_fn, optimizer, crops, epoch)
+    _step_update(student, teacher_ema, loss_fn, optimizer, clip_grad, ents)
+    return out
 
 
 def dino_step(student, teacher_ema, loss_fn, optimizer, crops, epoch=0, momentum=0.996, clip_grad=3.0):
@@ -504,6 +548,8 @@ def _step_launch_first(student, teacher_ema, loss_fn, optimizer, crops, epoch, m
         ddp.finish()
     optimizer.step(max_grad_norm=clip_grad or 0.0)
     teacher_ema.update(ddp.module if ddp is not None else student, momentum=momentum)
+    if hasattr(loss_fn, "finish_center_update"):
+        loss_fn.finish_center_update()
     return loss.detach(), student_out.detach(), teacher_out.detach()
 
 
@@ -528,11 +574,27 @@ class GraphedDinoStep:
         for dst, src in zip(self.static_crops, example_crops):
             dst.copy_(src)
         self._warmup = warmup
-        self._graph = None
+        self._graph = self._graph_update = None
+        self._multi = False
+        self._pending_static = None
         self._temp = None
         self.loss = self.student_out = self.teacher_out = None
 
+    def _set_defer(self, flag):
+        if isinstance(self.student, GradBucketDataParallel):
+            self.student.defer_comm = flag
+        if hasattr(self.loss_fn, "defer_comm"):
+            self.loss_fn.defer_comm = flag
+
+    def _comm(self):
+        """Eager collectives between the two graphs (N > 1): gradient buckets and the centre column sums."""
+        if isinstance(self.student, GradBucketDataParallel):
+            self.student.allreduce_now()
+        if hasattr(self.loss_fn, "allreduce_center_now"):
+            self.loss_fn.allreduce_center_now()
+
     def _capture(self, epoch, momentum):
+        self._multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         torch.cuda.synchronize()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -542,11 +604,29 @@ class GraphedDinoStep:
                           self.clip_grad)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        ents = _step_prepare(self.student, self.teacher, self.opt, momentum)
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self.loss, self.student_out, self.teacher_out = _step_launch(
-                self.student, self.teacher, self.loss_fn, self.opt, self.static_crops, epoch, self.clip_grad, ents)
+        # capture records launches only: it needs the optimiser's chunk tables but must NOT advance the step
+        # counter / restage scalars (that is _step_prepare's job, once per replay)
+        ents = self.opt._entries()
+        if not self._multi:
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self.loss, self.student_out, self.teacher_out = _step_launch(
+                    self.student, self.teacher, self.loss_fn, self.opt, self.static_crops, epoch, self.clip_grad, ents)
+        else:
+            # NCCL stays out of the graphs: compute graph -> eager all-reduces (176 MB of gradients + the
+            # 256 KB centre, well under a millisecond on NVLink) -> update graph
+            self._set_defer(True)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self.loss, self.student_out, self.teacher_out = _step_compute(
+                    self.student, self.teacher, self.loss_fn, self.opt, self.static_crops, epoch)
+            # capture executed nothing; loss_fn._pending holds the static (graph-pool) column-sum buffer that
+            # every replay of the compute graph refills
+            self._pending_static = self.loss_fn._pending
+            self._graph_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_update, pool=self._graph.pool()):
+                _step_update(self.student, self.teacher, self.loss_fn, self.opt, self.clip_grad, ents)
+            self._set_defer(False)   # the flags only matter while capturing; eager steps stay self-contained
         self._temp = float(self.loss_fn.teacher_temp_schedule[epoch])
 
     def load(self, crops, non_blocking=True):
@@ -562,4 +642,9 @@ class GraphedDinoStep:
             self._capture(epoch, momentum)      # the capture itself executes nothing: fall through to replay
         _step_prepare(self.student, self.teacher, self.opt, momentum)
         self._graph.replay()
+        if self._multi:
+            self.loss_fn._pending = self._pending_static   # the compute graph refilled this buffer
+            self._comm()
+            self._graph_update.replay()
+            self.loss_fn._pending = None
         return self.loss
