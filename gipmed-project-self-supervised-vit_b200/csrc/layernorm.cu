@@ -108,7 +108,7 @@ ln_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, const float
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) + dres, with g = dy * gamma;
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (fp32 atomics, one per column per CTA)
 template <int LPR, int CPL, typename XT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 ln_bwd_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
               const float* __restrict__ w, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw,
@@ -125,17 +125,11 @@ ln_bwd_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
 
-  float gw[CPL * 8], adw[CPL * 8], adb[CPL * 8];
+  // dgamma / dbeta partials live in registers for the whole kernel; gamma is re-read per row (L1-resident) so
+  // that two 256-thread blocks fit per SM (the kernel is latency bound at one)
+  float adw[CPL * 8], adb[CPL * 8];
 #pragma unroll
-  for (int c = 0; c < CPL; ++c) {
-    const int col = (c * LPR + sub) * 8;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      gw[c * 8 + e] = __ldg(w + col + e);
-      adw[c * 8 + e] = 0.f;
-      adb[c * 8 + e] = 0.f;
-    }
-  }
+  for (int i = 0; i < CPL * 8; ++i) { adw[i] = 0.f; adb[i] = 0.f; }
   for (long long base = warp_global * RPW; base < rows; base += nwarps * RPW) {
     const bool valid = base + lane / LPR < rows;
     const long long row = valid ? base + lane / LPR : rows - 1;
@@ -153,8 +147,9 @@ ln_bwd_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
     for (int c = 0; c < CPL; ++c) r4[c] = pr ? __ldg(pr + c * LPR + sub) : make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
-      float x8[8];
+      float x8[8], gw[8];
       load_chunk8<XT>(px, c * LPR + sub, x8);
+      load_chunk8<float>(w, c * LPR + sub, gw);
       const uint4 ud = __ldg(pdy + c * LPR + sub);
       const uint32_t dw4[4] = {ud.x, ud.y, ud.z, ud.w};
 #pragma unroll
@@ -170,8 +165,8 @@ ln_bwd_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
         adw[i + 1] += fd.y * xh[i + 1];
         adb[i] += fd.x;
         adb[i + 1] += fd.y;
-        g[i] = fd.x * gw[i];
-        g[i + 1] = fd.y * gw[i + 1];
+        g[i] = fd.x * gw[2 * e];
+        g[i + 1] = fd.y * gw[2 * e + 1];
         s1 += g[i] + g[i + 1];
         s2 += g[i] * xh[i] + g[i + 1] * xh[i + 1];
       }
@@ -235,7 +230,7 @@ static int launch_ln_bwd(const void* x, int x_f32, const void* dy, const float* 
   constexpr int RPW = 32 / LPR;
   const long long warps_needed = (rows + RPW - 1) / RPW;
   long long blocks = (warps_needed + 7) / 8;
-  const long long cap = static_cast<long long>(sm_count()) * 4;
+  const long long cap = static_cast<long long>(sm_count()) * 2;  // two resident blocks per SM, one wave
   if (blocks > cap) blocks = cap;
   if (x_f32)
     ln_bwd_kernel<LPR, CPL, float><<<static_cast<int>(blocks), 256, 0, s>>>(
