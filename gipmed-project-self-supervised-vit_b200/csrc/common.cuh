@@ -86,6 +86,17 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // exact-erf GELU (nn.GELU() default in the reference: VT.pyc@L89) and its derivative, sharing one
 // erf evaluation: erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32-exact for a bf16
 // result) with the two transcendentals on the MUFU pipe (rcp, ex2); exp(-x^2/2) is re-used for the pdf.
@@ -103,6 +114,80 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& h, float& g) {
   const float cdf = fmaf(copysignf(0.5f, x), erf_abs, 0.5f);  // Phi(x)
   h = x * cdf;
   g = fmaf(x * e, 0.39894228040143268f, cdf);                 // Phi(x) + x * phi(x)
+}
+
+// ----------------------------------------------------------------------------------------------
+// explicit shared-space accesses (32-bit shared addresses; generic pointers into dynamic smem lose their
+// address space after the alignment cast and would compile to generic LD/ST)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 — two fp32 lanes per issue slot). The epilogues
+// are issue-bound, not FP32-pipe-bound, so halving the instruction count is what counts.
+// ----------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack_f32x2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 splat_f32x2(float c) { return pack_f32x2(c, c); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// gelu_and_grad on a pair of pre-activations: same A&S 7.1.26 evaluation as above, all FMA-class
+// operations packed; the four transcendentals (2 x rcp, 2 x ex2) stay scalar on the MUFU pipe.
+__device__ __forceinline__ void gelu_and_grad2(float x0, float x1, f32x2& h, f32x2& g) {
+  const float az0 = fabsf(x0) * 0.70710678118654752f, az1 = fabsf(x1) * 0.70710678118654752f;
+  const f32x2 az = pack_f32x2(az0, az1);
+  const f32x2 x = pack_f32x2(x0, x1);
+  float d0, d1;
+  unpack_f32x2(ffma2(splat_f32x2(0.3275911f), az, splat_f32x2(1.0f)), d0, d1);
+  const f32x2 t = pack_f32x2(rcp_approx(d0), rcp_approx(d1));
+  // npoly = -(a1 t + a2 t^2 + ... + a5 t^5)  (coefficients negated so that erf = 1 + npoly * e)
+  f32x2 np = ffma2(t, splat_f32x2(-1.061405429f), splat_f32x2(1.453152027f));
+  np = ffma2(np, t, splat_f32x2(-1.421413741f));
+  np = ffma2(np, t, splat_f32x2(0.284496736f));
+  np = ffma2(np, t, splat_f32x2(-0.254829592f));
+  np = fmul2(np, t);
+  float a0, a1;
+  unpack_f32x2(fmul2(fmul2(az, splat_f32x2(-1.4426950408889634f)), az), a0, a1);
+  const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+  const f32x2 e = pack_f32x2(e0, e1);
+  const f32x2 erf_abs = ffma2(np, e, splat_f32x2(1.0f));                       // erf(|x|/sqrt2)
+  const f32x2 half_s = pack_f32x2(copysignf(0.5f, x0), copysignf(0.5f, x1));
+  const f32x2 cdf = ffma2(half_s, erf_abs, splat_f32x2(0.5f));                 // Phi(x)
+  h = fmul2(x, cdf);
+  g = ffma2(fmul2(x, e), splat_f32x2(0.39894228040143268f), cdf);              // Phi(x) + x phi(x)
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -213,6 +298,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* 
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(tm)),
                "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// same, source given as a 32-bit shared address
+__device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1,
@@ -357,16 +449,6 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
 }
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");

@@ -48,8 +48,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int EPI_CHUNK = 32;                          // columns an epilogue thread handles at a time
-constexpr int STAGING_BYTES = BLOCK_M * 128;           // per epilogue group: 2 x (128 rows x 32 bf16) or 1 x (128 x 32 fp32)
+constexpr int SLAB_BYTES = 32 * 64;                    // one epilogue slab: 32 rows x 64 B (32 bf16 or 16 fp32 columns)
+constexpr int STAGING_BYTES = 4 * 2 * SLAB_BYTES;      // per epilogue group: 4 warps x ring of two slabs
 constexpr int NUM_EPI_GROUPS = 4;                      // 4 groups x 4 warps: 4 warps per TMEM lane quarter
 constexpr int GEMM_THREADS = 128 + NUM_EPI_GROUPS * 128;
 
@@ -238,24 +238,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int group = (warp - 4) >> 2;  // 0..3: which 32-column chunks this warp owns (c = group, group+4, ..)
-    const int gtid = threadIdx.x - 128 - group * 128;
-    uint8_t* stg = staging + group * STAGING_BYTES;
-    const int row_in_tile = q * 32 + lane;
+    // 16 fully independent warps. Warp (q, group) owns TMEM lane quarter q (rows 32q .. 32q+31 of the tile) and
+    // the column chunks c with (c + tile_iter) % 4 == group (rotating, so uneven chunk counts even out). Its
+    // private staging is a ring of two 2 KB slabs (32 rows x 64 B, 64B swizzle) from which lane 0 issues 32-row
+    // TMA stores -- no block-level barrier anywhere in the epilogue. Everything with global-memory latency
+    // (bias, the aux slab of the first chunk) is fetched BEFORE the wait for the accumulator; the aux slab of
+    // chunk i+1 is fetched while chunk i is processed.
+    const int q = warp & 3;
+    const int group = (warp - 4) >> 2;
+    const uint32_t slab_base = smem_u32(staging) + static_cast<uint32_t>(warp - 4) * (2 * SLAB_BYTES);
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    constexpr int W = EPI == EPI_BIAS_RES_F32 ? 16 : 32;  // columns per chunk (one slab row = 64 B)
+    constexpr int kChunks = BN / W;
+    constexpr int kMaxOwn = (kChunks + NUM_EPI_GROUPS - 1) / NUM_EPI_GROUPS;
+    constexpr bool kAuxBf16 = EPI == EPI_BIAS_RES || EPI == EPI_MUL_AUX;
+    constexpr bool kAuxF32 = EPI == EPI_BIAS_RES_F32;
+    constexpr bool kAux = kAuxBf16 || kAuxF32;
+    constexpr int kAuxEsize = kAuxF32 ? 4 : 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t slot = 0;  // bf16 staging ring position (per group, two 8 KB buffers)
-    constexpr int kChunks = BN / EPI_CHUNK;
+    uint32_t ring = 0;  // slab ring position
     int cs_stage = 0;   // wgrad only: position in the smem ring (bias-gradient pass)
     uint32_t cs_phase = 0;
+    int tile_iter = 0;
 
-    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+    for (int t = cluster_id; t < total_tiles; t += num_clusters, ++tile_iter) {
       const int n_blk = t % args.num_n_blocks;
       const int m_blk = ((t / args.num_n_blocks) % num_m_units) * CL + cta_rank;
       const int m0 = m_blk * BLOCK_M, n0 = n_blk * BN;
-      const int row = m0 + row_in_tile;
-      const bool row_ok = row < args.M;
+      const int row0 = m0 + q * 32;  // first row of this warp's 32-row slab
 
       if (EPI == EPI_ATOMIC_F32) {
         // wgrad: the epilogue warps are idle during the (long, split-K) mainloop, and the A stages
@@ -276,11 +287,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // barrier is signalled, so wait for the (multicast) "MMA consumed this stage" commit instead
           mbar_wait(CL == 1 ? &full_bar[cs_stage] : &consumed_bar[cs_stage], cs_phase);
           if (mine) {
-            const uint8_t* sA = smem + cs_stage * Cfg::kStageBytes + (jc >> 3) * 8192;
+            const uint32_t sA = smem_u32(smem) + cs_stage * Cfg::kStageBytes + (jc >> 3) * 8192;
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
               const int r = sub + 32 * rr;
-              const uint4 u = *reinterpret_cast<const uint4*>(sA + r * 128 + (((jc & 7) ^ (r & 7)) << 4));
+              const uint4 u = lds128(sA + r * 128 + (((jc & 7) ^ (r & 7)) << 4));
               const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -303,46 +314,85 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (m0 + jc * 8 + e < args.M) atomicAdd(db + m0 + jc * 8 + e, cs[e]);
           }
         }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tcgen05_fence_after();
+        const int row = row0 + lane;
+        for (int c = group; c < BN / 32; c += NUM_EPI_GROUPS) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(lane_taddr + static_cast<uint32_t>(acc * BN + c * 32), v);
+          tmem_ld_wait();
+          if (row < args.M) {
+            float* dst = args.out_f32 + static_cast<long long>(row) * args.ldd + n0 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                           "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
+                           "f"(__uint_as_float(v[j + 3]))
+                           : "memory");
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CL == 1) mbar_arrive(&tmem_empty[acc]);
+          else mbar_arrive_leader(&tmem_empty[acc]);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
       }
+
+      const int c_first = (group - tile_iter) & 3;
+      // aux slab of chunk c in a coalesced mapping: lane -> (row i*8 + lane/4, 16-byte piece lane%4)
+      auto load_aux = [&](int c, uint4 (&dst)[4]) {
+        const int col0 = n0 + c * W;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int arow = row0 + i * 8 + (lane >> 2);
+          dst[i] = make_uint4(0, 0, 0, 0);
+          if (arow < args.M) {
+            const uint8_t* p = static_cast<const uint8_t*>(args.aux) +
+                               (static_cast<long long>(arow) * args.ldaux + col0) * kAuxEsize;
+            dst[i] = __ldg(reinterpret_cast<const uint4*>(p) + (lane & 3));
+          }
+        }
+      };
+      const bool has_bias = EPI != EPI_MUL_AUX && args.bias != nullptr;
+      float bias_r[kMaxOwn];  // lane l: bias[n0 + c*W + l] of the i-th owned chunk
+#pragma unroll
+      for (int i = 0; i < kMaxOwn; ++i) {
+        const int c = c_first + NUM_EPI_GROUPS * i;
+        bias_r[i] = 0.f;
+        if (has_bias && c < kChunks && lane < W) bias_r[i] = __ldg(args.bias + n0 + c * W + lane);
+      }
+      uint4 aux_next[4];
+      if (kAux && c_first < kChunks) load_aux(c_first, aux_next);
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
 
       bool released = false;
-      for (int c = group; c < kChunks; c += NUM_EPI_GROUPS) {
-        // aux operand (residual / saved gelu'): each thread owns a ROW of the tile (TMEM lane), but loading it
-        // that way touches 32 cache lines per warp instruction. Fetch the warp's 32-row slab with a coalesced
-        // lane mapping instead (issued first, so it flies during the TMEM read) and transpose it through the
-        // staging buffer further down.
-        constexpr bool kAuxBf16 = EPI == EPI_BIAS_RES || EPI == EPI_MUL_AUX;
-        constexpr bool kAuxF32 = EPI == EPI_BIAS_RES_F32;
-        constexpr int kAuxLoads = kAuxBf16 ? 4 : (kAuxF32 ? 8 : 1);
-        uint4 auxv[kAuxLoads];
-        if (kAuxBf16 || kAuxF32) {
-          constexpr int kLanesPerRow = kAuxBf16 ? 4 : 8;   // 16-byte pieces per 32-column row
-          constexpr int kRowsPerLoad = 32 / kLanesPerRow;
-          const int piece = lane % kLanesPerRow;
-          const int acol = n0 + c * EPI_CHUNK;
 #pragma unroll
-          for (int i = 0; i < kAuxLoads; ++i) {
-            const int arow = m0 + q * 32 + i * kRowsPerLoad + lane / kLanesPerRow;
-            auxv[i] = make_uint4(0, 0, 0, 0);
-            if (arow < args.M) {
-              const uint8_t* base = static_cast<const uint8_t*>(args.aux) +
-                                    (static_cast<long long>(arow) * args.ldaux + acol) * (kAuxBf16 ? 2 : 4);
-              auxv[i] = __ldg(reinterpret_cast<const uint4*>(base) + piece);
-            }
-          }
-        }
-        float f[EPI_CHUNK];
-        {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                 static_cast<uint32_t>(acc * BN + c * EPI_CHUNK), v);
-          tmem_ld_wait();
+      for (int i = 0; i < kMaxOwn; ++i) {
+        const int c = c_first + NUM_EPI_GROUPS * i;
+        if (c >= kChunks) break;
+        const int col0 = n0 + c * W;
+        uint32_t v[W];
+        if constexpr (W == 32) tmem_ld_32x32b_x32(lane_taddr + static_cast<uint32_t>(acc * BN + c * W), v);
+        else tmem_ld_32x32b_x16(lane_taddr + static_cast<uint32_t>(acc * BN + c * W), v);
+        uint4 aux_cur[4];
+        if (kAux) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          for (int k = 0; k < 4; ++k) aux_cur[k] = aux_next[k];
+          if (c + NUM_EPI_GROUPS < kChunks) load_aux(c + NUM_EPI_GROUPS, aux_next);
         }
+        uint32_t slab = slab_base + (ring & 1) * SLAB_BYTES;
+        if (lane == 0) tma_store_wait_read<1>();  // the store that last read this slab has drained
+        __syncwarp();
+        if (has_bias) {
+          if (lane < W) sts32(slab + lane * 4, __float_as_uint(bias_r[i]));
+          __syncwarp();
+        }
+        tmem_ld_wait();
         if (c + NUM_EPI_GROUPS >= kChunks) {
           // last TMEM read of this tile by this warp: hand the accumulator stage back (to the leader's MMA)
           tcgen05_fence_before();
@@ -353,116 +403,104 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           released = true;
         }
-        const int col0 = n0 + c * EPI_CHUNK;
-
-        if (EPI == EPI_ATOMIC_F32) {
-          if (row_ok) {
-            float* dst = args.out_f32 + static_cast<long long>(row) * args.ldd + col0;
+        float f[W];
 #pragma unroll
-            for (int j = 0; j < EPI_CHUNK; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(f[j]), "f"(f[j + 1]),
-                           "f"(f[j + 2]), "f"(f[j + 3])
-                           : "memory");
+        for (int j = 0; j < W; ++j) f[j] = __uint_as_float(v[j]);
+        if (has_bias) {
+#pragma unroll
+          for (int j = 0; j < W / 4; ++j) {
+            const uint4 b = lds128(slab + j * 16);  // broadcast read
+            f[4 * j] += __uint_as_float(b.x);
+            f[4 * j + 1] += __uint_as_float(b.y);
+            f[4 * j + 2] += __uint_as_float(b.z);
+            f[4 * j + 3] += __uint_as_float(b.w);
           }
-          continue;
+          __syncwarp();  // every lane has its bias before the slab is overwritten
         }
-
-        if (EPI != EPI_MUL_AUX && args.bias != nullptr) {
-          const float4* bp = reinterpret_cast<const float4*>(args.bias + col0);
+        if (kAux) {
+          // aux slab -> staging (coalesced mapping) -> own row back (conflict-free), combined with the accumulator
 #pragma unroll
-          for (int j = 0; j < EPI_CHUNK / 4; ++j) {
-            const float4 b = __ldg(bp + j);
-            f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-          }
-        }
-        if (EPI == EPI_BIAS_RES_F32) {
-          // fp32 output: one 32-column box (128 B rows, 128B swizzle); single staging buffer per group.
-          if (gtid == 0) tma_store_wait_read<0>();
-          named_bar_sync(1 + group, 128);
-          // residual slab -> staging (coalesced mapping), then each thread reads back ITS row, adds and
-          // overwrites it in place; only this warp touches these 32 rows, so a __syncwarp orders it
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<uint4*>(stg + sw128_offset(q * 32 + i * 4 + (lane >> 3), lane & 7)) = auxv[i];
+          for (int k = 0; k < 4; ++k) sts128(slab + sw64_offset(k * 8 + (lane >> 2), lane & 3), aux_cur[k]);
           __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4* p4 = reinterpret_cast<float4*>(stg + sw128_offset(row_in_tile, j));
-            const float4 a = *p4;
-            *p4 = make_float4(f[4 * j] + a.x, f[4 * j + 1] + a.y, f[4 * j + 2] + a.z, f[4 * j + 3] + a.w);
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(1 + group, 128);
-          if (gtid == 0) {
-            tma_store_2d(&tmD, stg, col0, m0);
-            tma_store_commit();
-          }
-          continue;
-        }
-
-        constexpr int kOutputs = EPI == EPI_BIAS_GELU ? 2 : 1;
-        uint32_t hpk[EPI == EPI_BIAS_GELU ? EPI_CHUNK / 2 : 1];  // gelu(x) packed: the second output
-        if (EPI == EPI_BIAS_GELU) {
+          for (int j = 0; j < 4; ++j) {
+            const uint4 a = lds128(slab + sw64_offset(lane, j));
+            const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+            if (kAuxF32) {
 #pragma unroll
-          for (int j = 0; j < EPI_CHUNK / 2; ++j) {
-            float h0, h1, g0, g1;
-            gelu_and_grad(f[2 * j], h0, g0);
-            gelu_and_grad(f[2 * j + 1], h1, g1);
-            f[2 * j] = g0;
-            f[2 * j + 1] = g1;
-            hpk[j % (EPI == EPI_BIAS_GELU ? EPI_CHUNK / 2 : 1)] = pack_bf16x2(h0, h1);
-          }
-        }
-#pragma unroll
-        for (int o = 0; o < kOutputs; ++o) {
-          // bf16 output: 32-column box = 64 B rows, 64B swizzle; two 8 KB buffers per group
-          uint8_t* buf = stg + (slot & 1) * (STAGING_BYTES / 2);
-          if (gtid == 0) tma_store_wait_read<1>();  // the store that last used this buffer has drained
-          named_bar_sync(1 + group, 128);
-          if (kAuxBf16) {
-            // aux slab -> staging (coalesced mapping) -> own row back (conflict-free), combine with acc
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              *reinterpret_cast<uint4*>(buf + sw64_offset(q * 32 + i * 8 + (lane >> 2), lane & 3)) = auxv[i % kAuxLoads];
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 a = *reinterpret_cast<const uint4*>(buf + sw64_offset(row_in_tile, j));
-              const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+              for (int e = 0; e < 4; ++e) f[(4 * j + e) % W] += __uint_as_float(w[e]);
+            } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 x = unpack_bf16x2(w[e]);
                 if (EPI == EPI_BIAS_RES) {
-                  f[8 * j + 2 * e] += x.x;
-                  f[8 * j + 2 * e + 1] += x.y;
+                  f[(8 * j + 2 * e) % W] += x.x;
+                  f[(8 * j + 2 * e + 1) % W] += x.y;
                 } else {
-                  f[8 * j + 2 * e] *= x.x;
-                  f[8 * j + 2 * e + 1] *= x.y;
+                  f[(8 * j + 2 * e) % W] *= x.x;
+                  f[(8 * j + 2 * e + 1) % W] *= x.y;
                 }
               }
             }
           }
+          // each lane re-uses only its own row below, so no further warp sync is needed before the writes
+        }
+        const bool rows_ok = row0 < args.M;
+        if (EPI == EPI_BIAS_RES_F32) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 pk;
-            if (o == 0) {
-              pk.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-              pk.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              pk.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-              pk.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-            } else {
-              constexpr int HM = EPI == EPI_BIAS_GELU ? EPI_CHUNK / 2 : 1;
-              pk = make_uint4(hpk[(4 * j) % HM], hpk[(4 * j + 1) % HM], hpk[(4 * j + 2) % HM], hpk[(4 * j + 3) % HM]);
-            }
-            *reinterpret_cast<uint4*>(buf + sw64_offset(row_in_tile, j)) = pk;
-          }
+          for (int j = 0; j < 4; ++j)
+            sts128(slab + sw64_offset(lane, j),
+                   make_uint4(__float_as_uint(f[(4 * j) % W]), __float_as_uint(f[(4 * j + 1) % W]),
+                              __float_as_uint(f[(4 * j + 2) % W]), __float_as_uint(f[(4 * j + 3) % W])));
           fence_proxy_async_smem();
-          named_bar_sync(1 + group, 128);
-          if (gtid == 0) {
-            tma_store_2d(o == 0 ? &tmD : &tmD2, buf, col0, m0);
+          __syncwarp();
+          if (lane == 0 && rows_ok) {
+            tma_store_2d_s(&tmD, slab, col0, row0);
             tma_store_commit();
           }
-          ++slot;
+          ++ring;
+          continue;
+        }
+        uint32_t hpk[EPI == EPI_BIAS_GELU ? W / 2 : 1];  // gelu(x) packed: the second output
+        if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+          for (int j = 0; j < W / 2; ++j) {
+            f32x2 h2, g2;
+            gelu_and_grad2(f[2 * j], f[2 * j + 1], h2, g2);
+            float h0, h1;
+            unpack_f32x2(h2, h0, h1);
+            unpack_f32x2(g2, f[2 * j], f[2 * j + 1]);
+            hpk[j % (EPI == EPI_BIAS_GELU ? W / 2 : 1)] = pack_bf16x2(h0, h1);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128(slab + sw64_offset(lane, j),
+                 make_uint4(pack_bf16x2(f[(8 * j) % W], f[(8 * j + 1) % W]), pack_bf16x2(f[(8 * j + 2) % W], f[(8 * j + 3) % W]),
+                            pack_bf16x2(f[(8 * j + 4) % W], f[(8 * j + 5) % W]), pack_bf16x2(f[(8 * j + 6) % W], f[(8 * j + 7) % W])));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && rows_ok) {
+          tma_store_2d_s(&tmD, slab, col0, row0);
+          tma_store_commit();
+        }
+        ++ring;
+        if (EPI == EPI_BIAS_GELU) {
+          slab = slab_base + (ring & 1) * SLAB_BYTES;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          constexpr int HM = EPI == EPI_BIAS_GELU ? W / 2 : 1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128(slab + sw64_offset(lane, j),
+                   make_uint4(hpk[(4 * j) % HM], hpk[(4 * j + 1) % HM], hpk[(4 * j + 2) % HM], hpk[(4 * j + 3) % HM]));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && rows_ok) {
+            tma_store_2d_s(&tmD2, slab, col0, row0);
+            tma_store_commit();
+          }
+          ++ring;
         }
       }
       if (!released) {
@@ -475,7 +513,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (gtid == 0) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tcgen05_fence_before();
@@ -640,12 +678,12 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
     strides[1] = static_cast<uint64_t>(ldb) * 2;
     if (int rc = make_tensor_map(&tmB, B, 2, 2, dims, strides, box, 128)) return rc;
     if (epilogue == EPI_BIAS_RES_F32) {
-      dims[0] = N; dims[1] = M; box[0] = 32; box[1] = BLOCK_M;
+      dims[0] = N; dims[1] = M; box[0] = 16; box[1] = 32;               // per-warp slab: 32 rows x 64 B
       strides[0] = 4; strides[1] = static_cast<uint64_t>(ldd) * 4;
-      if (int rc = make_tensor_map(&tmD, D, 4, 2, dims, strides, box, 128)) return rc;
+      if (int rc = make_tensor_map(&tmD, D, 4, 2, dims, strides, box, 64)) return rc;
       tmD2 = tmD;
     } else if (epilogue != EPI_ATOMIC_F32) {
-      dims[0] = N; dims[1] = M; box[0] = EPI_CHUNK; box[1] = BLOCK_M;   // 64 B rows, 64B swizzle
+      dims[0] = N; dims[1] = M; box[0] = 32; box[1] = 32;               // per-warp slab: 32 rows x 64 B, 64B swizzle
       strides[1] = static_cast<uint64_t>(ldd) * 2;
       if (int rc = make_tensor_map(&tmD, D, 2, 2, dims, strides, box, 64)) return rc;
       if (int rc = make_tensor_map(&tmD2, D2 ? D2 : D, 2, 2, dims, strides, box, 64)) return rc;

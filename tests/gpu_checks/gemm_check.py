@@ -49,16 +49,20 @@ def run_case(name, M, N, K, a_mn, b_mn, epi, bn, split_k=1, results=None):
     A_in = A.t().contiguous() if a_mn else A
     B_in = B.t().contiguous() if b_mn else B
     ref = A.float() @ B.float().t()
-    bias = torch.randn(N, device="cuda", generator=g) if epi in (0, 1, 2) else None
+    bias = torch.randn(N, device="cuda", generator=g) if epi in (0, 1, 2, 5) else None
     if epi == 4 and a_mn:
         bias = torch.zeros(M, device="cuda")  # wgrad: receives db = column sums of A^T (i.e. A.sum over K)
     aux = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16) if epi in (2, 3) else None
+    if epi == 5:
+        aux = torch.randn(M, N, device="cuda", generator=g) * 3.0   # fp32 residual stream
     D2 = None
     if epi == 4:
         D = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    elif epi == 5:
+        D = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
     else:
         D = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
-    if epi in (0, 1, 2):
+    if epi in (0, 1, 2, 5):
         ref = ref + bias
     ref2 = None
     if epi == 1:
@@ -67,7 +71,7 @@ def run_case(name, M, N, K, a_mn, b_mn, epi, bn, split_k=1, results=None):
         xr = ref.clone().requires_grad_(True)
         torch.nn.functional.gelu(xr).sum().backward()
         ref = xr.grad
-    if epi == 2:
+    if epi in (2, 5):
         ref = ref + aux.float()
     if epi == 3:
         ref = ref * aux.float()
@@ -113,7 +117,9 @@ def bench_case(M, N, K, a_mn, b_mn, epi, bn, split_k=1, iters=20):
     B_in = B.t().contiguous() if b_mn else B
     bias = torch.randn(N, device="cuda") if epi != 4 else torch.zeros(M, device="cuda")
     aux = torch.randn(M, N, device="cuda").to(torch.bfloat16) if epi in (2, 3) else None
-    D = torch.zeros(M, N, device="cuda", dtype=torch.float32 if epi == 4 else torch.bfloat16)
+    if epi == 5:
+        aux = torch.randn(M, N, device="cuda")
+    D = torch.zeros(M, N, device="cuda", dtype=torch.float32 if epi in (4, 5) else torch.bfloat16)
     D2 = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16) if epi == 1 else None
     for _ in range(3):
         gemm(A_in, a_mn, B_in, b_mn, D, M, N, K, epi, D2, bias, aux, split_k, bn)
@@ -163,6 +169,11 @@ def main():
     allok &= run_case("kk_gelu", 1000, 1536, 384, 0, 0, 1, 256, results=results)
     allok &= run_case("kk_res", 1000, 384, 1536, 0, 0, 2, 192, results=results)
     allok &= run_case("kk_dgelu", 1000, 1536, 384, 0, 0, 3, 256, results=results)
+    allok &= run_case("kk_res32_k384", 1000, 384, 384, 0, 0, 5, 192, results=results)
+    allok &= run_case("kk_res32_k1536", 5000, 384, 1536, 0, 0, 5, 192, results=results)
+    allok &= run_case("kk_res32_bn128", 700, 768, 384, 0, 0, 5, 128, results=results)
+    allok &= run_case("kk_gelu_many", 128 * 300 + 5, 1536, 384, 0, 0, 1, 256, results=results)
+    allok &= run_case("kk_bn64_many", 128 * 40 + 77, 256, 2048, 0, 0, 0, 64, results=results)
     # dgrad layout: B MN-major
     allok &= run_case("kmn_small", 128, 64, 64, 0, 1, 0, 64, results=results)
     allok &= run_case("kmn", 1000, 384, 1536, 0, 1, 0, 192, results=results)
@@ -179,10 +190,10 @@ def main():
         rows = 100864
         b.append(bench_case(rows, 1152, 384, 0, 0, 0, 192))
         b.append(bench_case(rows, 1152, 384, 0, 0, 0, 128))
-        b.append(bench_case(rows, 384, 384, 0, 0, 2, 192))
+        b.append(bench_case(rows, 384, 384, 0, 0, 5, 192))
         b.append(bench_case(rows, 1536, 384, 0, 0, 1, 256))
         b.append(bench_case(rows, 1536, 384, 0, 0, 0, 256))
-        b.append(bench_case(rows, 384, 1536, 0, 0, 2, 192))
+        b.append(bench_case(rows, 384, 1536, 0, 0, 5, 192))
         b.append(bench_case(rows, 384, 1536, 0, 1, 0, 192))
         b.append(bench_case(rows, 1536, 384, 0, 1, 3, 256))
         b.append(bench_case(1536, 384, rows, 1, 1, 4, 128, split_k=8))
