@@ -31,7 +31,9 @@ enum GemmEpilogue : int {
   EPI_MUL_AUX = 3,    // D = acc * aux   (dgrad through GELU: aux = saved gelu'(x))
   EPI_ATOMIC_F32 = 4, // D(fp32) += acc   (split-K)
   EPI_BIAS_RES_F32 = 5, // D(fp32) = acc (+ bias) + aux(fp32): the fp32 residual stream
+  EPI_ATOMIC_F32_T = 6, // D(fp32)[n, m] += acc[m, n] (split-K, TRANSPOSED store); bias output = column sums of B
 };
+__host__ __device__ constexpr bool is_wgrad_epi(int e) { return e == EPI_ATOMIC_F32 || e == EPI_ATOMIC_F32_T; }
 
 struct GemmArgs {
   int M, N, K;
@@ -42,6 +44,7 @@ struct GemmArgs {
   long long ldaux;
   float* out_f32;
   long long ldd;
+  unsigned long long* prof;  // developer instrumentation (null = off): per-role wait / busy cycle counters
 };
 
 constexpr int BLOCK_M = 128;
@@ -55,18 +58,62 @@ constexpr int GEMM_THREADS = 128 + NUM_EPI_GROUPS * 128;
 
 constexpr int kSmemBudget = 232448 - 2048;  // 227 KB opt-in limit minus barrier block and alignment slack
 
-template <int BN, int CL>
+constexpr int kMaxPanelKBlocks = 6;  // B-stationary mode: the whole K extent (<= 384) of the B tile stays in smem
+
+template <int BN, int CL, bool BS = false>
 struct GemmCfg {
-  // per-CTA bytes of one pipeline stage: 128 rows of A and (in CTA-pair mode half of) the B tile
+  // per-CTA bytes of one k-block of B: (in CTA-pair mode half of) the B tile
   static constexpr int kBStageBytes = BN * BLOCK_K * 2 / CL;
-  static constexpr int kStageBytes = A_STAGE_BYTES + kBStageBytes;
+  // B-stationary: B lives in a panel of kMaxPanelKBlocks k-blocks loaded once; the ring carries A only
+  static constexpr int kPanelBytes = BS ? kMaxPanelKBlocks * kBStageBytes : 0;
+  static constexpr int kStageBytes = BS ? A_STAGE_BYTES : A_STAGE_BYTES + kBStageBytes;
   static constexpr int kStagingBytes = NUM_EPI_GROUPS * STAGING_BYTES;
   // as many stages as fit: the operand feed is latency bound (bytes in flight per SM / ~1 us L2 latency),
   // so depth matters more than anything else; pair mode gets 5-6 stages where single-CTA mode gets 3-4
-  static constexpr int kStagesFit = (kSmemBudget - kStagingBytes) / kStageBytes;
+  static constexpr int kStagesFit = (kSmemBudget - kStagingBytes - kPanelBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
-  static constexpr int kTmemCols = BN * 2 <= 128 ? 128 : BN * 2 <= 256 ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*barriers*/ + 1024 /*align*/;
+  // BN = 384 (CTA pair only): one 128 x 384 accumulator (MMAs of N = 256 + 128 per k step); else two stages
+  static constexpr int kAccStages = BN > 256 ? 1 : 2;
+  static constexpr int kTmemCols = BN * kAccStages <= 128 ? 128 : BN * kAccStages <= 256 ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kPanelBytes + kStagingBytes + 1024 /*barriers*/ + 1024 /*align*/;
+};
+
+// Work distribution. Default: output tiles round-robin over the clusters, n fastest (all n blocks of an m unit
+// run at about the same time on different clusters, so A is read from HBM once and hits L2 afterwards).
+// B-stationary (BS): cluster c keeps ONE n block (c % num_n_blocks) for the whole kernel and sweeps the m
+// units rank, rank + group_size, ...; the groups of different n blocks sweep m in the same order at the same
+// pace, which keeps the L2 reuse of A.
+struct TileIter {
+  int t, step, total;        // default mode: linear tile index
+  int n_blk, m_unit, ks;
+  template <bool BS>
+  __device__ __forceinline__ void init(const GemmArgs& a, int cluster_id, int num_clusters, int num_m_units) {
+    if (BS) {
+      n_blk = cluster_id % a.num_n_blocks;
+      const int rank = cluster_id / a.num_n_blocks;
+      step = num_clusters / a.num_n_blocks + (n_blk < num_clusters % a.num_n_blocks ? 1 : 0);
+      t = rank;
+      total = num_m_units;
+    } else {
+      t = cluster_id;
+      step = num_clusters;
+      total = num_m_units * a.num_n_blocks * a.k_splits;
+    }
+  }
+  template <bool BS>
+  __device__ __forceinline__ bool valid(const GemmArgs& a, int num_m_units) {
+    if (t >= total) return false;
+    if (BS) {
+      m_unit = t;
+      ks = 0;
+    } else {
+      n_blk = t % a.num_n_blocks;
+      m_unit = (t / a.num_n_blocks) % num_m_units;
+      ks = t / (num_m_units * a.num_n_blocks);
+    }
+    return true;
+  }
+  __device__ __forceinline__ void next() { t += step; }
 };
 
 // CL = CTAs per cluster (1 or 2). CL == 2 is the CTA-pair mode (tcgen05 cta_group::2): the two CTAs of a
@@ -78,26 +125,35 @@ struct GemmCfg {
 //     arrive.expect_tx (both CTAs' bytes) + the peer's remote arrive;
 //   * the leader's tcgen05.commit is multicast to both CTAs (stage-empty / accumulator-full barriers);
 //   * both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.
-template <int BN, int EPI, int CL>
+template <int BN, int EPI, int CL, bool BS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
             const GemmArgs args) {
-  using Cfg = GemmCfg<BN, CL>;
+  using Cfg = GemmCfg<BN, CL, BS>;
   constexpr int kStages = Cfg::kStages;
+  static_assert(kStages >= 2, "smem ring too shallow");
+  constexpr int kAccStages = Cfg::kAccStages;
+  constexpr bool kWgrad = is_wgrad_epi(EPI);
+  static_assert(!BS || !kWgrad, "B-stationary mode is for the non-split-K epilogues");
+  static_assert(BN <= 256 || CL == 2, "BN = 384 needs the CTA-pair mode");
+  static_assert(EPI != EPI_ATOMIC_F32_T || BN == 384, "the transposed wgrad store is built for BN = 384");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* staging = smem + kStages * Cfg::kStageBytes;
+  uint8_t* panel = smem + kStages * Cfg::kStageBytes;  // BS: the stationary B tile, kMaxPanelKBlocks k-blocks
+  uint8_t* staging = panel + Cfg::kPanelBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + NUM_EPI_GROUPS * STAGING_BYTES);
   uint64_t* full_bar = bars;                 // [kStages]
   uint64_t* empty_bar = bars + kStages;      // [kStages]
   uint64_t* tmem_full = bars + 2 * kStages;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint64_t* consumed_bar = tmem_empty + 2;   // [kStages] CTA-pair wgrad: "MMA is done reading this stage"
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(consumed_bar + kStages);
+  uint64_t* panel_full = consumed_bar + kStages;  // [1] BS: the B panel has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(panel_full + 1);
 
+  const long long t_entry = args.prof ? clock64() : 0;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cta_rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
@@ -108,7 +164,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (EPI != EPI_ATOMIC_F32) tma_prefetch_desc(&tmD);
+    if (!kWgrad) tma_prefetch_desc(&tmD);
     if (EPI == EPI_BIAS_GELU) tma_prefetch_desc(&tmD2);
   }
   if (warp == 1 && lane == 0) {
@@ -117,9 +173,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&full_bar[s], CL);
       // stage release: the MMA commit, plus (wgrad) the epilogue warps that fold the bias gradient from the
       // stage; in CTA-pair wgrad the commit goes to consumed_bar instead and only the warps release
-      mbar_init(&empty_bar[s], EPI == EPI_ATOMIC_F32 ? (CL == 1 ? 1 + kEpiWarps : kEpiWarps) : 1);
+      mbar_init(&empty_bar[s], kWgrad ? (CL == 1 ? 1 + kEpiWarps : kEpiWarps) : 1);
       mbar_init(&consumed_bar[s], 1);
     }
+    mbar_init(panel_full, CL);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], CL * kEpiWarps);  // one arrive per epilogue warp of every CTA of the pair
@@ -136,19 +193,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_per_split = num_m_units * args.num_n_blocks;  // work units (CL tiles each) per k split
-  const int total_tiles = tiles_per_split * args.k_splits;
+  TileIter it;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-        const int n_blk = t % args.num_n_blocks;
-        const int m_blk = ((t / args.num_n_blocks) % num_m_units) * CL + cta_rank;
-        const int ks = t / tiles_per_split;
-        const int kb0 = ks * args.k_blocks_per_split;
+      it.init<BS>(args, cluster_id, num_clusters, num_m_units);
+      if (BS && it.t < it.total) {
+        // the stationary B tile: all k-blocks of this cluster's n block, (pair mode) own half of the rows
+        constexpr int kHalfN = BN / CL;
+        const int n0 = it.n_blk * BN + cta_rank * kHalfN;
+        for (int kb = 0; kb < args.k_blocks_total; ++kb) {
+          uint8_t* sB = panel + kb * Cfg::kBStageBytes;
+          const int k0 = kb * BLOCK_K;
+          if (!args.b_mn) {
+            if (CL == 1) tma_load_2d(sB, &tmB, panel_full, k0, n0);
+            else tma_load_2d_2sm(sB, &tmB, panel_full, k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < kHalfN / 64; ++c) {
+              if (CL == 1) tma_load_2d(sB + c * 8192, &tmB, panel_full, n0 + c * 64, k0);
+              else tma_load_2d_2sm(sB + c * 8192, &tmB, panel_full, n0 + c * 64, k0);
+            }
+          }
+        }
+        if (cta_rank == 0) mbar_expect_tx(panel_full, CL * args.k_blocks_total * Cfg::kBStageBytes);
+        else mbar_arrive_leader(panel_full);
+      }
+      for (; it.valid<BS>(args, num_m_units); it.next()) {
+        const int n_blk = it.n_blk;
+        const int m_blk = it.m_unit * CL + cta_rank;
+        const int kb0 = it.ks * args.k_blocks_per_split;
         const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks_total);
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -165,7 +242,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int c = 0; c < BLOCK_M / 64; ++c)
                 tma_load_2d(sA + c * 8192, &tmA, &full_bar[stage], m0 + c * 64, k0);
             }
-            if (!args.b_mn) {
+            if (BS) {
+              // B is stationary
+            } else if (!args.b_mn) {
               tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
             } else {
 #pragma unroll
@@ -182,7 +261,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int c = 0; c < BLOCK_M / 64; ++c)
                 tma_load_2d_2sm(sA + c * 8192, &tmA, &full_bar[stage], m0 + c * 64, k0);
             }
-            if (!args.b_mn) {
+            if (BS) {
+              // B is stationary
+            } else if (BN == 384) {
+              // per CTA 192 of the 384 columns as three 64-wide pieces: two for the N = 256 MMA (columns
+              // [128 r, 128 r + 128)) and one for the N = 128 MMA (columns 256 + [64 r, 64 r + 64))
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                const int col = c < 2 ? n0 + cta_rank * 128 + c * 64 : n0 + 256 + cta_rank * 64;
+                if (!args.b_mn) tma_load_2d_2sm(sB + c * 8192, &tmB, &full_bar[stage], k0, col);
+                else tma_load_2d_2sm(sB + c * 8192, &tmB, &full_bar[stage], col, k0);
+              }
+            } else if (!args.b_mn) {
               tma_load_2d_2sm(sB, &tmB, &full_bar[stage], k0, n0 + cta_rank * kHalfN);
             } else {
 #pragma unroll
@@ -199,7 +289,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && cta_rank == 0) {  // CTA pair: only the leader issues MMAs
-      const uint32_t idesc = make_idesc_bf16(BLOCK_M * CL, BN, args.a_mn != 0, args.b_mn != 0);
+      const uint32_t idesc = make_idesc_bf16(BLOCK_M * CL, BN == 384 ? 256 : BN, args.a_mn != 0, args.b_mn != 0);
+      const uint32_t idesc2 = make_idesc_bf16(BLOCK_M * CL, 128, args.a_mn != 0, args.b_mn != 0);  // BN = 384 only
       const uint32_t a_lbo = args.a_mn ? 8192u : 16u;
       const uint32_t b_lbo = args.b_mn ? 8192u : 16u;
       const uint32_t a_kstep = args.a_mn ? UMMA_K * 128u : UMMA_K * 2u;
@@ -208,32 +299,53 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-        const int ks = t / tiles_per_split;
-        const int kb0 = ks * args.k_blocks_per_split;
+      it.init<BS>(args, cluster_id, num_clusters, num_m_units);
+      if (BS && it.t < it.total) {
+        mbar_wait(panel_full, 0);
+        tcgen05_fence_after();
+      }
+      long long w_full = 0, w_acc = 0;
+      const long long t_begin = clock64();
+      for (; it.valid<BS>(args, num_m_units); it.next()) {
+        const int kb0 = it.ks * args.k_blocks_per_split;
         const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks_total);
+        long long tw = clock64();
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        w_acc += clock64() - tw;
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
+          tw = clock64();
           mbar_wait(&full_bar[stage], phase);
+          w_full += clock64() - tw;
           tcgen05_fence_after();
           const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sB = sA + A_STAGE_BYTES;
+          const uint32_t sB = BS ? smem_u32(panel + kb * Cfg::kBStageBytes) : sA + A_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(sA + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(sB + k * b_kstep, b_lbo, 1024);
             if (CL == 1) umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else umma_bf16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (BN == 384) {
+              // second MMA of the k step: output columns [256, 384) from the third 64-wide B piece of each CTA
+              const uint64_t bdesc2 = make_smem_desc_sw128(sB + 16384 + k * b_kstep, b_lbo, 1024);
+              umma_bf16_ss_2sm(d_tmem + 256, adesc, bdesc2, idesc2, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           if (CL == 1) umma_commit(&empty_bar[stage]);
-          else umma_commit_2sm_mc(EPI == EPI_ATOMIC_F32 ? &consumed_bar[stage] : &empty_bar[stage], 3);
+          else umma_commit_2sm_mc(kWgrad ? &consumed_bar[stage] : &empty_bar[stage], 3);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (CL == 1) umma_commit(&tmem_full[acc]);
         else umma_commit_2sm_mc(&tmem_full[acc], 3);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+      if (args.prof) {
+        atomicAdd(args.prof + 0, static_cast<unsigned long long>(w_full));
+        atomicAdd(args.prof + 1, static_cast<unsigned long long>(w_acc));
+        atomicAdd(args.prof + 2, static_cast<unsigned long long>(clock64() - t_begin));
+        atomicAdd(args.prof + 3, 1ull);
       }
     }
   } else if (warp >= 4) {
@@ -262,42 +374,85 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t cs_phase = 0;
     int tile_iter = 0;
 
-    for (int t = cluster_id; t < total_tiles; t += num_clusters, ++tile_iter) {
-      const int n_blk = t % args.num_n_blocks;
-      const int m_blk = ((t / args.num_n_blocks) % num_m_units) * CL + cta_rank;
+    // aux operand (fp32 residual / bf16 residual / saved gelu'): fetched TWO owned chunks ahead -- across tile
+    // boundaries -- into two alternating register sets, in a coalesced mapping (lane -> row k*8 + lane/4,
+    // 16-byte piece lane%4 of the 32-row x 64-byte slab); the set is parked in the slab and refilled right away.
+    TileIter pit;
+    int p_tile_iter = 0, p_i = 0;
+    uint4 aux_a[4], aux_b[4];
+    uint32_t aux_par = 0;
+    auto prefetch_aux = [&](uint4 (&dst)[4]) {
+      while (pit.valid<BS>(args, num_m_units)) {
+        const int c = ((group - p_tile_iter) & 3) + NUM_EPI_GROUPS * p_i;
+        if (c < kChunks) {
+          const int prow0 = (pit.m_unit * CL + cta_rank) * BLOCK_M + q * 32;
+          const int pcol0 = pit.n_blk * BN + c * W;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int arow = prow0 + k * 8 + (lane >> 2);
+            dst[k] = make_uint4(0, 0, 0, 0);
+            if (arow < args.M) {
+              const uint8_t* ap = static_cast<const uint8_t*>(args.aux) +
+                                  (static_cast<long long>(arow) * args.ldaux + pcol0) * kAuxEsize;
+              dst[k] = __ldg(reinterpret_cast<const uint4*>(ap) + (lane & 3));
+            }
+          }
+          ++p_i;
+          return;
+        }
+        pit.next();
+        ++p_tile_iter;
+        p_i = 0;
+      }
+    };
+    if (kAux) {
+      pit.init<BS>(args, cluster_id, num_clusters, num_m_units);
+      prefetch_aux(aux_a);
+      prefetch_aux(aux_b);
+    }
+
+    it.init<BS>(args, cluster_id, num_clusters, num_m_units);
+    for (; it.valid<BS>(args, num_m_units); it.next(), ++tile_iter) {
+      const int n_blk = it.n_blk;
+      const int m_blk = it.m_unit * CL + cta_rank;
       const int m0 = m_blk * BLOCK_M, n0 = n_blk * BN;
       const int row0 = m0 + q * 32;  // first row of this warp's 32-row slab
 
-      if (EPI == EPI_ATOMIC_F32) {
-        // wgrad: the epilogue warps are idle during the (long, split-K) mainloop, and the A stages
-        // (dY^T, MN-major [64 k][64 m] x 2 chunks) are already in smem for the MMA, so they fold the bias
-        // gradient db[m] += sum_k A[k, m] from there (n_blk == 0 tiles only: each (m block, k split) once)
-        // and release every stage like a second consumer.
-        const int ks = t / tiles_per_split;
-        const int kb0 = ks * args.k_blocks_per_split;
+      if (kWgrad) {
+        // wgrad: the epilogue warps are idle during the (long, split-K) mainloop, and the operand that is dY
+        // (A = dY^T as MN-major [64 k][64 m] pieces; for the transposed variant B) is already in smem for the
+        // MMA, so they fold the bias gradient db[col] += sum_k dY[k, col] from there -- on the tiles that see
+        // each (column block, k split) exactly once -- and release every stage like a second consumer.
+        const int kb0 = it.ks * args.k_blocks_per_split;
         const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks_total);
         float* db = const_cast<float*>(args.bias);
-        const bool mine = n_blk == 0 && db != nullptr && args.a_mn;
+        constexpr bool kT = EPI == EPI_ATOMIC_F32_T;
+        constexpr int kGroups = kT ? 24 : 16;       // 16-byte column groups (8 columns) in the folded operand
+        constexpr int kSubs = 512 / kGroups;        // threads per column group, striding over the 64 k rows
+        const bool mine = db != nullptr && args.a_mn && (kT ? it.m_unit == 0 : n_blk == 0);
         const int etid = threadIdx.x - 128;  // 0..511
-        const int jc = etid & 15;            // 16-byte chunk (8 columns) within the 128-wide m range
-        const int sub = etid >> 4;           // k rows sub and sub+32
+        const int jc = etid % kGroups;
+        const int sub = etid / kGroups;
+        const int piece = jc >> 3;           // 64-column piece of the operand tile
         float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int kb = kb0; kb < kb1; ++kb) {
           // single CTA: the stage is readable as soon as TMA filled it; CTA pair: only the leader's full
           // barrier is signalled, so wait for the (multicast) "MMA consumed this stage" commit instead
           mbar_wait(CL == 1 ? &full_bar[cs_stage] : &consumed_bar[cs_stage], cs_phase);
-          if (mine) {
-            const uint32_t sA = smem_u32(smem) + cs_stage * Cfg::kStageBytes + (jc >> 3) * 8192;
+          if (mine && sub < kSubs) {
+            const uint32_t src = smem_u32(smem) + cs_stage * Cfg::kStageBytes + (kT ? A_STAGE_BYTES : 0) + piece * 8192;
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-              const int r = sub + 32 * rr;
-              const uint4 u = lds128(sA + r * 128 + (((jc & 7) ^ (r & 7)) << 4));
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+            for (int rr = 0; rr < (64 + kSubs - 1) / kSubs; ++rr) {
+              const int r = sub + kSubs * rr;
+              if (r < 64) {
+                const uint4 u = lds128(src + r * 128 + (((jc & 7) ^ (r & 7)) << 4));
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f2 = unpack_bf16x2(w[e]);
-                cs[2 * e] += f2.x;
-                cs[2 * e + 1] += f2.y;
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f2 = unpack_bf16x2(w[e]);
+                  cs[2 * e] += f2.x;
+                  cs[2 * e + 1] += f2.y;
+                }
               }
             }
           }
@@ -305,30 +460,61 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (lane == 0) mbar_arrive(&empty_bar[cs_stage]);
           if (++cs_stage == kStages) { cs_stage = 0; cs_phase ^= 1; }
         }
-        if (mine) {
+        if (mine && sub < kSubs) {
+          if (!kT) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
-          if (lane < 16) {
+            for (int e = 0; e < 8; ++e) cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
+            if (lane < 16) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (m0 + jc * 8 + e < args.M) atomicAdd(db + m0 + jc * 8 + e, cs[e]);
+            }
+          } else {
+            const int colbase = (piece < 2 ? n0 + cta_rank * 128 + piece * 64 : n0 + 256 + cta_rank * 64) + (jc & 7) * 8;
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-              if (m0 + jc * 8 + e < args.M) atomicAdd(db + m0 + jc * 8 + e, cs[e]);
+              if (colbase + e < args.N) atomicAdd(db + colbase + e, cs[e]);
           }
         }
         mbar_wait(&tmem_full[acc], acc_phase);
         tcgen05_fence_after();
+        const long long te0 = args.prof ? clock64() : 0;
         const int row = row0 + lane;
         for (int c = group; c < BN / 32; c += NUM_EPI_GROUPS) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(lane_taddr + static_cast<uint32_t>(acc * BN + c * 32), v);
           tmem_ld_wait();
           if (row < args.M) {
-            float* dst = args.out_f32 + static_cast<long long>(row) * args.ldd + n0 + c * 32;
+            if (!kT) {
+              // handled below (needs the whole warp)
+            } else {
+              // transposed store: lanes hold consecutive rows m, i.e. consecutive addresses of D[n, :]
+              float* dst = args.out_f32 + static_cast<long long>(n0 + c * 32) * args.ldd + row;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
-                           "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
-                           "f"(__uint_as_float(v[j + 3]))
+              for (int j = 0; j < 32; ++j)
+                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + static_cast<long long>(j) * args.ldd),
+                             "f"(__uint_as_float(v[j]))
+                             : "memory");
+            }
+          }
+          if (!kT) {
+            // row-major store: a lane owns a ROW, so reds straight from its registers touch 32 cache lines per
+            // instruction (measured 3x slower than the mainloop could hide). Transpose the 32 x 32 fp32 chunk
+            // through the warp's two slabs (4 KB, 16-byte pieces XOR-swizzled by row) and issue one coalesced
+            // 128-byte red per row instead.
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(slab_base + lane * 128 + ((j ^ (lane & 7)) << 4), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            __syncwarp();
+            float* dst = args.out_f32 + static_cast<long long>(row0) * args.ldd + n0 + c * 32 + lane;
+            const int rows_here = min(32, args.M - row0);
+            for (int r = 0; r < rows_here; ++r) {
+              uint32_t x;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x) : "r"(slab_base + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4) : "memory");
+              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + static_cast<long long>(r) * args.ldd), "f"(__uint_as_float(x))
                            : "memory");
+            }
           }
         }
         tcgen05_fence_before();
@@ -337,37 +523,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (CL == 1) mbar_arrive(&tmem_empty[acc]);
           else mbar_arrive_leader(&tmem_empty[acc]);
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (args.prof && threadIdx.x == 128) atomicAdd(args.prof + 6, static_cast<unsigned long long>(clock64() - te0));
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         continue;
       }
 
       const int c_first = (group - tile_iter) & 3;
-      // aux slab of chunk c in a coalesced mapping: lane -> (row i*8 + lane/4, 16-byte piece lane%4)
-      auto load_aux = [&](int c, uint4 (&dst)[4]) {
-        const int col0 = n0 + c * W;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int arow = row0 + i * 8 + (lane >> 2);
-          dst[i] = make_uint4(0, 0, 0, 0);
-          if (arow < args.M) {
-            const uint8_t* p = static_cast<const uint8_t*>(args.aux) +
-                               (static_cast<long long>(arow) * args.ldaux + col0) * kAuxEsize;
-            dst[i] = __ldg(reinterpret_cast<const uint4*>(p) + (lane & 3));
-          }
-        }
-      };
       const bool has_bias = EPI != EPI_MUL_AUX && args.bias != nullptr;
+      // bias: the fp32-residual epilogue adds it to the aux registers (per-lane float4 of its column piece);
+      // the others broadcast it through the slab from one register per lane, loaded before the accumulator wait
+      const bool slab_bias = has_bias && EPI != EPI_BIAS_RES_F32;
       float bias_r[kMaxOwn];  // lane l: bias[n0 + c*W + l] of the i-th owned chunk
 #pragma unroll
       for (int i = 0; i < kMaxOwn; ++i) {
         const int c = c_first + NUM_EPI_GROUPS * i;
         bias_r[i] = 0.f;
-        if (has_bias && c < kChunks && lane < W) bias_r[i] = __ldg(args.bias + n0 + c * W + lane);
+        if (slab_bias && c < kChunks && lane < W) bias_r[i] = __ldg(args.bias + n0 + c * W + lane);
       }
-      uint4 aux_next[4];
-      if (kAux && c_first < kChunks) load_aux(c_first, aux_next);
 
+      const long long te0 = args.prof ? clock64() : 0;
       mbar_wait(&tmem_full[acc], acc_phase);
+      if (args.prof && threadIdx.x == 128) atomicAdd(args.prof + 4, static_cast<unsigned long long>(clock64() - te0));
       tcgen05_fence_after();
 
       bool released = false;
@@ -379,18 +555,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint32_t v[W];
         if constexpr (W == 32) tmem_ld_32x32b_x32(lane_taddr + static_cast<uint32_t>(acc * BN + c * W), v);
         else tmem_ld_32x32b_x16(lane_taddr + static_cast<uint32_t>(acc * BN + c * W), v);
-        uint4 aux_cur[4];
-        if (kAux) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) aux_cur[k] = aux_next[k];
-          if (c + NUM_EPI_GROUPS < kChunks) load_aux(c + NUM_EPI_GROUPS, aux_next);
-        }
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EPI == EPI_BIAS_RES_F32 && has_bias) b4 = __ldg(reinterpret_cast<const float4*>(args.bias + col0) + (lane & 3));
         uint32_t slab = slab_base + (ring & 1) * SLAB_BYTES;
         if (lane == 0) tma_store_wait_read<1>();  // the store that last read this slab has drained
         __syncwarp();
-        if (has_bias) {
+        // park this chunk's aux set in the slab (coalesced mapping) and refill the registers two chunks ahead
+        auto stage_and_refill = [&](uint4 (&cur)[4]) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 a = cur[k];
+            if (EPI == EPI_BIAS_RES_F32) {
+              a.x = __float_as_uint(__uint_as_float(a.x) + b4.x);
+              a.y = __float_as_uint(__uint_as_float(a.y) + b4.y);
+              a.z = __float_as_uint(__uint_as_float(a.z) + b4.z);
+              a.w = __float_as_uint(__uint_as_float(a.w) + b4.w);
+            }
+            sts128(slab + sw64_offset(k * 8 + (lane >> 2), lane & 3), a);
+          }
+          prefetch_aux(cur);
+        };
+        auto stage_aux = [&]() {
+          if (aux_par) stage_and_refill(aux_b);
+          else stage_and_refill(aux_a);
+          aux_par ^= 1;
+          __syncwarp();
+        };
+        if (slab_bias) {
           if (lane < W) sts32(slab + lane * 4, __float_as_uint(bias_r[i]));
           __syncwarp();
+        } else if (kAux) {
+          stage_aux();  // while the TMEM load is in flight
         }
         tmem_ld_wait();
         if (c + NUM_EPI_GROUPS >= kChunks) {
@@ -406,7 +601,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         float f[W];
 #pragma unroll
         for (int j = 0; j < W; ++j) f[j] = __uint_as_float(v[j]);
-        if (has_bias) {
+        if (slab_bias) {
 #pragma unroll
           for (int j = 0; j < W / 4; ++j) {
             const uint4 b = lds128(slab + j * 16);  // broadcast read
@@ -416,12 +611,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             f[4 * j + 3] += __uint_as_float(b.w);
           }
           __syncwarp();  // every lane has its bias before the slab is overwritten
+          if (kAux) stage_aux();
         }
         if (kAux) {
-          // aux slab -> staging (coalesced mapping) -> own row back (conflict-free), combined with the accumulator
-#pragma unroll
-          for (int k = 0; k < 4; ++k) sts128(slab + sw64_offset(k * 8 + (lane >> 2), lane & 3), aux_cur[k]);
-          __syncwarp();
+          // own row back from the slab (conflict-free), combined with the accumulator
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 a = lds128(slab + sw64_offset(lane, j));
@@ -511,7 +704,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           else mbar_arrive_leader(&tmem_empty[acc]);
         }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
@@ -519,6 +712,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tcgen05_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // the peer may still arrive on / read from this CTA until it is done
+  if (args.prof && threadIdx.x == 32) {
+    atomicAdd(args.prof + 5, static_cast<unsigned long long>(clock64() - t_entry));
+    atomicAdd(args.prof + 7, 1ull);
+  }
   if (warp == 2) {
     if (CL == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     else tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
@@ -528,15 +725,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
-static int g_gemm_cluster = 2;  // CTAs per cluster for the B-multicast variant (1 disables it)
+static int g_gemm_cluster = 2;     // CTAs per cluster (1 disables the CTA-pair mode)
+static int g_gemm_stationary = 1;  // 0 disables the B-stationary mode (developer A/B switch)
+static int g_gemm_wide = 1;        // 0 disables the automatic choice of 256 x 384 CTA-pair tiles
+static unsigned long long* g_gemm_prof = nullptr;
 
-template <int BN, int EPI, int CL>
+template <int BN, int EPI, int CL, bool BS>
 static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                           const CUtensorMap& tmD2, const GemmArgs& args, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CL>;
+  using Cfg = GemmCfg<BN, CL, BS>;
   static bool configured = false;
   if (!configured) {
-    B200SSL_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200SSL_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, CL, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::kSmemBytes));
     configured = true;
   }
@@ -555,15 +755,31 @@ static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
-  B200SSL_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, CL>, tmA, tmB, tmD, tmD2, args));
+  B200SSL_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, CL, BS>, tmA, tmB, tmD, tmD2, args));
   return 0;
 }
 
+// mode: 1 = independent CTAs, 2 = CTA pairs, 3 = CTA pairs with a stationary B tile (K <= 384)
 template <int BN, int EPI>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
-                       const CUtensorMap& tmD2, const GemmArgs& args, int cluster, cudaStream_t stream) {
-  if (cluster == 2) return launch_gemm_cl<BN, EPI, 2>(tmA, tmB, tmD, tmD2, args, stream);
-  return launch_gemm_cl<BN, EPI, 1>(tmA, tmB, tmD, tmD2, args, stream);
+                       const CUtensorMap& tmD2, const GemmArgs& args, int mode, cudaStream_t stream) {
+  if constexpr (BN == 384) {
+    // 256 x 384 CTA-pair tiles: wgrad (both store orders), plain dgrad and the fp32-residual fprop
+    if constexpr (EPI == EPI_BIAS || EPI == EPI_ATOMIC_F32 || EPI == EPI_ATOMIC_F32_T || EPI == EPI_BIAS_RES_F32) {
+      if (mode >= 2) return launch_gemm_cl<BN, EPI, 2, false>(tmA, tmB, tmD, tmD2, args, stream);
+    }
+    set_last_error("gemm: block_n 384 needs the CTA-pair mode and epilogue 0, 4, 5 or 6 (got %d)", EPI);
+    return -2;
+  } else if constexpr (EPI == EPI_ATOMIC_F32_T) {
+    set_last_error("gemm: epilogue 6 (transposed wgrad store) needs block_n 384");
+    return -2;
+  } else {
+    if constexpr (!is_wgrad_epi(EPI) && (BN == 192 || BN == 256)) {
+      if (mode == 3) return launch_gemm_cl<BN, EPI, 2, true>(tmA, tmB, tmD, tmD2, args, stream);
+    }
+    if (mode >= 2) return launch_gemm_cl<BN, EPI, 2, false>(tmA, tmB, tmD, tmD2, args, stream);
+    return launch_gemm_cl<BN, EPI, 1, false>(tmA, tmB, tmD, tmD2, args, stream);
+  }
 }
 
 template <int BN>
@@ -576,6 +792,7 @@ static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b, con
     case EPI_MUL_AUX: return launch_gemm<BN, EPI_MUL_AUX>(a, b, d, d2, args, cl, s);
     case EPI_ATOMIC_F32: return launch_gemm<BN, EPI_ATOMIC_F32>(a, b, d, d2, args, cl, s);
     case EPI_BIAS_RES_F32: return launch_gemm<BN, EPI_BIAS_RES_F32>(a, b, d, d2, args, cl, s);
+    case EPI_ATOMIC_F32_T: return launch_gemm<BN, EPI_ATOMIC_F32_T>(a, b, d, d2, args, cl, s);
   }
   set_last_error("gemm: unknown epilogue %d", epi);
   return -2;
@@ -612,7 +829,8 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
   B200SSL_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(D) & 15) == 0,
                 -2, "gemm: operands must be 16-byte aligned");
-  B200SSL_CHECK(epilogue >= 0 && epilogue <= 5, -2, "gemm: unknown epilogue %d", epilogue);
+  B200SSL_CHECK(epilogue >= 0 && epilogue <= 6, -2, "gemm: unknown epilogue %d", epilogue);
+  const bool wgrad = is_wgrad_epi(epilogue);
   if (epilogue == EPI_BIAS_RES || epilogue == EPI_MUL_AUX)
     B200SSL_CHECK(aux != nullptr && ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0, -2,
                   "gemm: epilogue %d needs a 16B-aligned aux operand", epilogue);
@@ -620,21 +838,29 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
     B200SSL_CHECK(aux != nullptr && ldaux % 4 == 0 && ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0, -2,
                   "gemm: fp32 residual epilogue needs a 16B-aligned fp32 aux operand and ldd %% 4 == 0");
   if (epilogue == EPI_BIAS_GELU) B200SSL_CHECK(D2 != nullptr, -2, "gemm: GELU epilogue needs D2");
-  if (epilogue == EPI_ATOMIC_F32) {
+  if (wgrad) {
     B200SSL_CHECK(ldd % 4 == 0, -2, "gemm: fp32 ldd must be a multiple of 4");
   } else {
     if (epilogue != EPI_BIAS_RES_F32) B200SSL_CHECK(ldd % 8 == 0, -2, "gemm: bf16 ldd must be a multiple of 8");
     split_k = 1;
   }
-  if (bias && epilogue != EPI_ATOMIC_F32)
+  if (bias && !wgrad)
     B200SSL_CHECK((reinterpret_cast<uintptr_t>(bias) & 15) == 0, -2, "gemm: bias must be 16B aligned");
 
   const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   int bn = block_n;
-  if (epilogue == EPI_ATOMIC_F32 && split_k <= 0) {
+  const bool pair_ok = g_gemm_cluster == 2 && M > BLOCK_M;
+  // 256 x 384 CTA-pair tiles (one accumulator, no mainloop/epilogue overlap) halve the shared-memory traffic per
+  // MMA: used for wgrad (one tile per CTA anyway) and for long-K problems with a plain or fp32-residual epilogue
+  if (bn == 0 && N % 384 == 0 && pair_ok &&
+      (epilogue == EPI_ATOMIC_F32_T ||
+       (g_gemm_wide && ((epilogue == EPI_ATOMIC_F32 && M >= 512) || (epilogue == EPI_BIAS && K >= 768)))))
+    bn = 384;
+  if (epilogue == EPI_ATOMIC_F32_T) B200SSL_CHECK(bn == 384, -2, "gemm: epilogue 6 needs N %% 384 == 0 and M > 128");
+  if (wgrad && split_k <= 0) {
     // auto split-K: the largest tile that divides N, then as many K splits as fill one wave of SMs
     if (bn == 0) bn = N % 256 == 0 ? 256 : N % 192 == 0 ? 192 : N % 128 == 0 ? 128 : 64;
-    const int cl_ = (g_gemm_cluster == 2 && M > BLOCK_M && (!b_mn_major || bn % 128 == 0)) ? 2 : 1;
+    const int cl_ = (g_gemm_cluster == 2 && M > BLOCK_M && (!b_mn_major || bn % 128 == 0 || bn == 384)) ? 2 : 1;
     const int tiles_mn = (((M + BLOCK_M - 1) / BLOCK_M + cl_ - 1) / cl_) * (N / bn);  // work units per k split
     split_k = (sm_count() / cl_) / (tiles_mn > 0 ? tiles_mn : 1);
     if (split_k > k_blocks / 2) split_k = k_blocks / 2;
@@ -645,8 +871,9 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
   split_k = (k_blocks + kbps - 1) / kbps;  // no empty splits
 
   if (bn == 0) bn = pick_block_n(N, M, split_k);
-  B200SSL_CHECK((bn == 64 || bn == 128 || bn == 192 || bn == 256) && N % bn == 0, -2,
+  B200SSL_CHECK((bn == 64 || bn == 128 || bn == 192 || bn == 256 || bn == 384) && N % bn == 0, -2,
                 "gemm: block_n=%d does not divide N=%d", bn, N);
+  B200SSL_CHECK(bn != 384 || pair_ok, -2, "gemm: block_n 384 needs the CTA-pair mode (M > 128)");
 
   GemmArgs args;
   args.M = M; args.N = N; args.K = K;
@@ -661,9 +888,14 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
   args.ldaux = ldaux;
   args.out_f32 = static_cast<float*>(D);
   args.ldd = ldd;
+  args.prof = g_gemm_prof;
 
   // CTA-pair mode needs two m blocks and, for an MN-major B, a half tile made of whole 64-column chunks
-  const int cluster = (g_gemm_cluster == 2 && args.num_m_blocks > 1 && (!b_mn_major || bn % 128 == 0)) ? 2 : 1;
+  int cluster = (g_gemm_cluster == 2 && args.num_m_blocks > 1 && (!b_mn_major || bn % 128 == 0 || bn == 384)) ? 2 : 1;
+  // B-stationary: short K (the whole B tile fits beside the A ring), enough clusters to give every n block one
+  if (cluster == 2 && g_gemm_stationary && !wgrad && k_blocks <= kMaxPanelKBlocks &&
+      (bn == 192 || bn == 256) && args.num_n_blocks <= sm_count() / 2 && args.num_m_blocks >= 8)
+    cluster = 3;
   CUtensorMap tmA, tmB, tmD, tmD2;
   {
     // A: K-major -> dims (K, M), box (64, 128); MN-major -> dims (M, K), box (64, 64)
@@ -673,7 +905,7 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
     else             { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = 64; }
     strides[0] = 2; strides[1] = static_cast<uint64_t>(lda) * 2;
     if (int rc = make_tensor_map(&tmA, A, 2, 2, dims, strides, box, 128)) return rc;
-    if (!b_mn_major) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = bn / cluster; }  // pair: half the rows
+    if (!b_mn_major) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = bn == 384 ? 64 : bn / (cluster >= 2 ? 2 : 1); }  // pair: half the rows
     else             { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = 64; }
     strides[1] = static_cast<uint64_t>(ldb) * 2;
     if (int rc = make_tensor_map(&tmB, B, 2, 2, dims, strides, box, 128)) return rc;
@@ -682,7 +914,7 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
       strides[0] = 4; strides[1] = static_cast<uint64_t>(ldd) * 4;
       if (int rc = make_tensor_map(&tmD, D, 4, 2, dims, strides, box, 64)) return rc;
       tmD2 = tmD;
-    } else if (epilogue != EPI_ATOMIC_F32) {
+    } else if (!wgrad) {
       dims[0] = N; dims[1] = M; box[0] = 32; box[1] = 32;               // per-warp slab: 32 rows x 64 B, 64B swizzle
       strides[1] = static_cast<uint64_t>(ldd) * 2;
       if (int rc = make_tensor_map(&tmD, D, 2, 2, dims, strides, box, 64)) return rc;
@@ -696,6 +928,7 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
     case 64: return dispatch_epi<64>(epilogue, tmA, tmB, tmD, tmD2, args, cluster, stream);
     case 128: return dispatch_epi<128>(epilogue, tmA, tmB, tmD, tmD2, args, cluster, stream);
     case 192: return dispatch_epi<192>(epilogue, tmA, tmB, tmD, tmD2, args, cluster, stream);
+    case 384: return dispatch_epi<384>(epilogue, tmA, tmB, tmD, tmD2, args, cluster, stream);
     default: return dispatch_epi<256>(epilogue, tmA, tmB, tmD, tmD2, args, cluster, stream);
   }
 }
@@ -704,5 +937,25 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
 extern "C" int b200ssl_set_gemm_cluster(int ctas) {
   B200SSL_CHECK(ctas == 1 || ctas == 2, -2, "gemm cluster size must be 1 or 2");
   b200ssl::g_gemm_cluster = ctas;
+  return 0;
+}
+
+// Developer instrumentation: device buffer of 8 uint64 counters the GEMM kernels add to (null = off):
+// [0] MMA-issuer cycles waiting for operand stages, [1] waiting for a free accumulator, [2] MMA-issuer loop cycles,
+// [3] number of issuing CTAs, [4] cycles the first epilogue warp waited for accumulators.
+extern "C" int b200ssl_set_gemm_prof(void* counters) {
+  b200ssl::g_gemm_prof = static_cast<unsigned long long*>(counters);
+  return 0;
+}
+
+// 1 (default) = pick 256 x 384 CTA-pair tiles automatically where they apply; 0 = only when block_n = 384 is asked for.
+extern "C" int b200ssl_set_gemm_wide(int on) {
+  b200ssl::g_gemm_wide = on ? 1 : 0;
+  return 0;
+}
+
+// 1 = keep the B tile stationary in shared memory for K <= 384 problems (default), 0 = always stream it.
+extern "C" int b200ssl_set_gemm_stationary(int on) {
+  b200ssl::g_gemm_stationary = on ? 1 : 0;
   return 0;
 }

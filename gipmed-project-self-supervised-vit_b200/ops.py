@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_MUL_AUX, EPI_ATOMIC_F32, EPI_BIAS_RES_F32 = 0, 1, 2, 3, 4, 5
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_MUL_AUX, EPI_ATOMIC_F32, EPI_BIAS_RES_F32, EPI_ATOMIC_F32_T = 0, 1, 2, 3, 4, 5, 6
 
 _BF16 = torch.bfloat16
 _counters = {"launches": 0}
@@ -209,8 +209,17 @@ def linear_wgrad(dy, x, need_bias=True, weight=None, bias=None):
     K = x.shape[1]
     w_sink = _sink(weight)
     b_sink = _sink(bias) if need_bias else None
+
+    def run(dw, db):
+        if N % 384 == 0 and K > N:
+            # more inputs than outputs (fc2): compute dW^T = x^T dy with the long dimension as GEMM-M so the
+            # 256 x 384 CTA-pair tiles are full, and store it transposed; db folds from the B operand (dy)
+            gemm(x, dy, dw, K, N, M, a_mn=True, b_mn=True, epi=EPI_ATOMIC_F32_T, split_k=0, bias=db)
+        else:
+            gemm(dy, x, dw, N, K, M, a_mn=True, b_mn=True, epi=EPI_ATOMIC_F32, split_k=0, bias=db)
+
     if w_sink is not None and (not need_bias or b_sink is not None):
-        gemm(dy, x, w_sink.view(N, K), N, K, M, a_mn=True, b_mn=True, epi=EPI_ATOMIC_F32, split_k=0, bias=b_sink)
+        run(w_sink.view(N, K), b_sink)
         _sunk(weight)
         if b_sink is not None:
             _sunk(bias)
@@ -218,7 +227,7 @@ def linear_wgrad(dy, x, need_bias=True, weight=None, bias=None):
     buf = torch.zeros(N * K + (N if need_bias else 0), dtype=torch.float32, device=dy.device)
     dw = buf[:N * K].view(N, K)
     db = buf[N * K:] if need_bias else None
-    gemm(dy, x, dw, N, K, M, a_mn=True, b_mn=True, epi=EPI_ATOMIC_F32, split_k=0, bias=db)
+    run(dw, db)
     return dw, db
 
 

@@ -36,14 +36,23 @@ int b200ssl_device_check(void);
  *   epilogue: 0 D=acc+bias | 1 D=gelu'(acc+bias), D2=gelu(acc+bias) (exact erf) | 2 D=acc+bias+aux(bf16)
  *             3 D=acc*aux(bf16) | 4 D(fp32)+=acc split-K atomics, and bias (if non-null) is the OUTPUT
  *             db[M] += column sums of A (wgrad bias gradient) | 5 D(fp32)=acc+bias+aux(fp32) (residual stream)
- *   split_k: K splits for epilogue 4 (0 = auto); block_n: 0 = auto, else 64/128/192/256 dividing N.
+ *             6 like 4 but stored TRANSPOSED: D(fp32)[n, m] += acc[m, n] (ldd >= M) and bias is the OUTPUT
+ *             db[N] += column sums of B (wgrad of a layer with more inputs than outputs; needs block_n 384)
+ *   split_k: K splits for epilogues 4/6 (0 = auto); block_n: 0 = auto, else 64/128/192/256/384 dividing N
+ *   (384 = 256 x 384 CTA-pair tiles: M > 128, epilogues 0, 4, 5, 6).
  * Constraints: N % 64 == 0, lda/ldb % 8 == 0. */
 int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
                  void* D, long long ldd, void* D2, const float* bias, const void* aux, long long ldaux,
                  int M, int N, int K, int epilogue, int split_k, int block_n, void* stream);
 
-/* 1 = independent CTAs; 2 (default) = clusters of two CTAs that share each B tile through TMA multicast. */
+/* 1 = independent CTAs; 2 (default) = CTA pairs (tcgen05 cta_group::2: 256-row tiles, each CTA loads half of B). */
 int b200ssl_set_gemm_cluster(int ctas);
+/* 1 (default) = for K <= 384 keep the B tile stationary in shared memory and stream only A; 0 = always stream both. */
+int b200ssl_set_gemm_stationary(int on);
+/* 1 (default) = choose 256 x 384 CTA-pair tiles automatically (wgrad; long-K plain / fp32-residual epilogues). */
+int b200ssl_set_gemm_wide(int on);
+/* Developer instrumentation: device buffer of 8 uint64 cycle counters the GEMM kernels accumulate into (NULL = off). */
+int b200ssl_set_gemm_prof(void* counters);
 
 /* ---- K2: LayerNorm (Block.norm1/norm2 VT.pyc@L138,142,147,151; VisionTransformer.norm @L195,252) -----
  * x is bf16 (x_f32 = 0) or the fp32 residual stream (x_f32 = 1); y bf16; mean/rstd fp32 [rows].

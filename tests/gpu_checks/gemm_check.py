@@ -52,12 +52,16 @@ def run_case(name, M, N, K, a_mn, b_mn, epi, bn, split_k=1, results=None):
     bias = torch.randn(N, device="cuda", generator=g) if epi in (0, 1, 2, 5) else None
     if epi == 4 and a_mn:
         bias = torch.zeros(M, device="cuda")  # wgrad: receives db = column sums of A^T (i.e. A.sum over K)
+    if epi == 6:
+        bias = torch.zeros(N, device="cuda")  # transposed wgrad: receives db = B.sum over K
     aux = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16) if epi in (2, 3) else None
     if epi == 5:
         aux = torch.randn(M, N, device="cuda", generator=g) * 3.0   # fp32 residual stream
     D2 = None
     if epi == 4:
         D = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    elif epi == 6:
+        D = torch.zeros(N, M, device="cuda", dtype=torch.float32)   # stored transposed
     elif epi == 5:
         D = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
     else:
@@ -83,10 +87,17 @@ def run_case(name, M, N, K, a_mn, b_mn, epi, bn, split_k=1, results=None):
         if results is not None:
             results.append({"name": name, "ok": False, "err": str(e)})
         return False
+    if epi == 6:
+        D = D.t()
     scale = ref.abs().max().item() + 1e-6
     err = (D.float() - ref).abs().max().item() / scale
     nan = int(torch.isnan(D.float()).sum().item())
     ok = err < 1.5e-2 and nan == 0
+    if epi == 6:
+        dbref = B.float().sum(1)
+        errb = (bias - dbref).abs().max().item() / (dbref.abs().max().item() + 1e-6)
+        ok = ok and errb < 1e-3
+        err = max(err, errb)
     if epi == 4 and a_mn:
         dbref = A.float().sum(1)
         errb = (bias - dbref).abs().max().item() / (dbref.abs().max().item() + 1e-6)
@@ -115,11 +126,13 @@ def bench_case(M, N, K, a_mn, b_mn, epi, bn, split_k=1, iters=20):
     B = torch.randn(N, K, device="cuda").to(torch.bfloat16)
     A_in = A.t().contiguous() if a_mn else A
     B_in = B.t().contiguous() if b_mn else B
-    bias = torch.randn(N, device="cuda") if epi != 4 else torch.zeros(M, device="cuda")
+    bias = torch.randn(N, device="cuda") if epi not in (4, 6) else torch.zeros(max(M, N), device="cuda")
     aux = torch.randn(M, N, device="cuda").to(torch.bfloat16) if epi in (2, 3) else None
     if epi == 5:
         aux = torch.randn(M, N, device="cuda")
-    D = torch.zeros(M, N, device="cuda", dtype=torch.float32 if epi in (4, 5) else torch.bfloat16)
+    D = torch.zeros(M, N, device="cuda", dtype=torch.float32 if epi in (4, 5, 6) else torch.bfloat16)
+    if epi == 6:
+        D = torch.zeros(N, M, device="cuda", dtype=torch.float32)
     D2 = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16) if epi == 1 else None
     for _ in range(3):
         gemm(A_in, a_mn, B_in, b_mn, D, M, N, K, epi, D2, bias, aux, split_k, bn)
@@ -183,6 +196,14 @@ def main():
     allok &= run_case("mnmn_small_bf16", 128, 128, 128, 1, 1, 0, 128, results=results)
     allok &= run_case("mnmn_wgrad", 1536, 384, 5000, 1, 1, 4, 128, split_k=7, results=results)
     allok &= run_case("mnmn_wgrad_256", 384, 1536, 3152, 1, 1, 4, 256, split_k=5, results=results)
+    # 256 x 384 CTA-pair tiles (one accumulator, MMAs of N = 256 + 128)
+    allok &= run_case("kk_bn384", 1000, 768, 1536, 0, 0, 0, 384, results=results)
+    allok &= run_case("kmn_bn384", 128 * 37 + 5, 384, 1152, 0, 1, 0, 384, results=results)
+    allok &= run_case("kk_res32_bn384", 128 * 21 + 3, 384, 1536, 0, 0, 5, 384, results=results)
+    allok &= run_case("mnmn_wgrad_bn384", 1536, 384, 5000, 1, 1, 4, 384, split_k=7, results=results)
+    allok &= run_case("mnmn_wgrad_bn384_odd", 384, 384, 3000, 1, 1, 4, 384, split_k=0, results=results)
+    allok &= run_case("mnmn_wgrad_T", 1536, 384, 5000, 1, 1, 6, 384, split_k=0, results=results)
+    allok &= run_case("mnmn_wgrad_T_768", 1000, 768, 3152, 1, 1, 6, 384, split_k=3, results=results)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     out = {"all_ok": bool(allok), "cases": results}
     if "--bench" in sys.argv and allok:

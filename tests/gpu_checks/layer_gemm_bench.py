@@ -1,5 +1,5 @@
 """Developer bench: every GEMM of one ViT-S block (fprop / dgrad / wgrad) at config-2 row counts,
-single-CTA vs CTA-pair mode, through the same ops-level entry points the model uses."""
+B tile streamed vs stationary, through the same ops-level entry points the model uses."""
 import os
 import sys
 
@@ -48,15 +48,17 @@ def run(rows):
         "fc1 wgrad": (lambda: ops.linear_wgrad(x4, x), 2 * rows * D * H4),
         "fc2 wgrad": (lambda: ops.linear_wgrad(x, x4), 2 * rows * D * H4),
     }
-    tot = {1: 0.0, 2: 0.0}
+    modes = {"narrow": 0, "wide": 1}   # without / with the automatic 256 x 384 CTA-pair tiles
+    tot = {k: 0.0 for k in modes}
     for name, (fn, fl) in cases.items():
         ts = {}
-        for cl in (1, 2):
-            lib.b200ssl_set_gemm_cluster(cl)
-            ts[cl] = timeit(fn)
-            tot[cl] += ts[cl]
-        print(f"rows={rows:7d} {name:16s} single {ts[1]:7.1f} us ({fl/ts[1]/1e6:5.0f} TF)   pair {ts[2]:7.1f} us ({fl/ts[2]/1e6:5.0f} TF)")
-    print(f"rows={rows:7d} TOTAL single {tot[1]:.0f} us   pair {tot[2]:.0f} us")
+        for mode, bs in modes.items():
+            lib.b200ssl_set_gemm_wide(bs)
+            ts[mode] = timeit(fn)
+            tot[mode] += ts[mode]
+        print(f"rows={rows:7d} {name:16s} " + "   ".join(f"{m} {ts[m]:7.1f} us ({fl/ts[m]/1e6:5.0f} TF)" for m in modes))
+    print(f"rows={rows:7d} TOTAL " + "   ".join(f"{m} {tot[m]:.0f} us" for m in modes))
+    lib.b200ssl_set_gemm_wide(1)
 
 
 run(100864)
