@@ -358,113 +358,73 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: one (sequence | packed group, head) per CTA
+// backward: persistent CTAs (one per SM) looping over (sequence | packed group, head) items
 // ------------------------------------------------------------------------------------------------
-// smem: Q (NT) | dO (NT) | K (NT) | V (NT) | P (2 chunks) | dS (2 chunks) | staging | barriers | row consts
-// TMEM: S [0,128) | dP [128,256) | dQ_t [256+64t) | dK [384,448) | dV [448,512)
-// warps: 0 = control (TMA + MMA issue); 4..19 = math/epilogue, four threads per query row (32 key
-// columns each). Loops over (key tile u, query tile t) are fully unrolled so per-tile row constants
-// stay in registers.
+// smem: operand sets [Q (NT) | dO (NT) | K (NT) | V (NT)] x SETS | P (2 chunks) | dS (2 chunks) | barriers |
+//       row constants (2 buffers). NT == 1 (N <= 128, packed local crops) has two operand sets, so the loads of
+//       item i+1 fly during the whole of item i; NT == 2 re-loads its single set as soon as the last MMA of the
+//       item has retired, under the store epilogue.
+// TMEM: S [0,128) | dP [128,256) | dQ_t [256+64t) | dK [384,448) | dV [448,512), allocated once per CTA.
+// warps: 0      = control: TMA loads + every tcgen05.mma. S/dP of the NEXT pair is issued as soon as the math
+//                 warps hold the current S/dP in registers, i.e. before the dQ/dK/dV MMAs of the current pair.
+//        1..3   = row-constant producers: delta = sum_d dO*O and lse2 of item i+1 while item i computes.
+//        4..19  = math/epilogue, four threads per query row (32 key columns each).
 constexpr int BWD_MATH_THREADS = 512;
+constexpr int BWD_ROWC_THREADS = 96;
 constexpr int BWD_THREADS = 128 + BWD_MATH_THREADS;
 
 template <int NT>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                     const __grid_constant__ CUtensorMap tmDQKV, const AttnArgs args) {
+                     const __grid_constant__ CUtensorMap tmDQKV, const AttnArgs args, const int num_items) {
+  constexpr int SETS = NT == 1 ? 2 : 1;
+  constexpr int PPI = NT * NT;                    // (key tile, query tile) pairs per item
+  constexpr int SET_BYTES = 4 * NT * TILE_BYTES;  // Q | dO | K | V
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sdO = sQ + NT * TILE_BYTES;
-  uint8_t* sK = sdO + NT * TILE_BYTES;
-  uint8_t* sV = sK + NT * TILE_BYTES;
-  uint8_t* sP = sV + NT * TILE_BYTES;
+  uint8_t* sP = smem + SETS * SET_BYTES;
   uint8_t* sdS = sP + 2 * TILE_BYTES;
-  uint8_t* stg = sdS + 2 * TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + TILE_BYTES);
-  uint64_t* bar_load = bars;
-  uint64_t* bar_sdp = bars + 1;       // S and dP ready in TMEM
-  uint64_t* bar_sdp_free = bars + 2;  // math threads done reading S/dP
-  uint64_t* bar_pds = bars + 3;       // P and dS written to smem
-  uint64_t* bar_mma = bars + 4;       // dQ/dK/dV MMAs of the pair finished
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-  float* rowc = reinterpret_cast<float*>(bars + 8);  // [NT][128][2]: delta, lse2
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * TILE_BYTES);
+  uint64_t* bar_load = bars;          // [2] per operand set
+  uint64_t* bar_sdp = bars + 2;       // S and dP ready in TMEM
+  uint64_t* bar_sdp_free = bars + 3;  // math threads hold S/dP in registers
+  uint64_t* bar_pds = bars + 4;       // P and dS written to smem
+  uint64_t* bar_mma = bars + 5;       // dQ/dK/dV MMAs of the pair finished
+  uint64_t* bar_rowc_full = bars + 6; // [2] row constants of an item written
+  uint64_t* bar_rowc_free = bars + 8; // [2] ... and copied to registers by every math thread
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* rowc = reinterpret_cast<float*>(bars + 16);  // [2][NT*128][2]: delta, lse2
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.x % args.H;
-  const int grp = blockIdx.x / args.H;
-  const int b0 = grp * args.G;
+  const int n_my = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  auto item_of = [&](int k) { return static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x); };
+  auto set_base = [&](int k) -> uint8_t* { return smem + (SETS == 2 ? (k & 1) : 0) * SET_BYTES; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmDQKV);
-    mbar_init(bar_load, 1);
+    mbar_init(&bar_load[0], 1);
+    mbar_init(&bar_load[1], 1);
     mbar_init(bar_sdp, 1);
     mbar_init(bar_sdp_free, BWD_MATH_THREADS);
     mbar_init(bar_pds, BWD_MATH_THREADS);
     mbar_init(bar_mma, 1);
-    fence_barrier_init();
-    // the operand loads only need bar_load: issue them now so they fly while the other warps allocate TMEM
-    // and compute the per-row constants (NT == 1 zero-fills disjoint rows, so there is no conflict)
-    const int cq = head * 64, ck = (args.H + head) * 64, cv = (2 * args.H + head) * 64;
-    if (NT == 1) {
-      mbar_expect_tx(bar_load, 4 * args.rows * 128);
-      tma_load_3d(sQ, &tmQKV, bar_load, cq, 0, b0);
-      tma_load_3d(sK, &tmQKV, bar_load, ck, 0, b0);
-      tma_load_3d(sV, &tmQKV, bar_load, cv, 0, b0);
-      tma_load_3d(sdO, &tmDO, bar_load, cq, 0, b0);
-    } else {
-      mbar_expect_tx(bar_load, 4 * NT * TILE_BYTES);
-      for (int t = 0; t < NT; ++t) {
-        tma_load_3d(sQ + t * TILE_BYTES, &tmQKV, bar_load, cq, t * 128, b0);
-        tma_load_3d(sK + t * TILE_BYTES, &tmQKV, bar_load, ck, t * 128, b0);
-        tma_load_3d(sV + t * TILE_BYTES, &tmQKV, bar_load, cv, t * 128, b0);
-        tma_load_3d(sdO + t * TILE_BYTES, &tmDO, bar_load, cq, t * 128, b0);
-      }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_rowc_full[i], BWD_ROWC_THREADS);
+      mbar_init(&bar_rowc_free[i], BWD_MATH_THREADS);
     }
+    fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   if (NT == 1) {
-    // rows never written by the TMA boxes: zero them so 0 x garbage cannot become NaN
+    // rows never written by the TMA boxes: zero them once so 0 x garbage cannot become NaN
     const int first = args.rows * 128, last = 128 * 128;
-    for (int i = first + threadIdx.x * 16; i < last; i += BWD_THREADS * 16) {
-      *reinterpret_cast<uint4*>(sQ + i) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(sdO + i) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(sK + i) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(sV + i) = make_uint4(0, 0, 0, 0);
-    }
+    for (int t = 0; t < SETS * 4; ++t)
+      for (int i = first + threadIdx.x * 16; i < last; i += BWD_THREADS * 16)
+        *reinterpret_cast<uint4*>(smem + t * TILE_BYTES + i) = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
-  }
-  // per-row constants: delta = sum_d dO*O and lse2; invalid rows get lse2 = +inf so that P = 0
-  if (warp >= 4 && threadIdx.x - 128 < NT * 128) {
-    const int idx = threadIdx.x - 128;
-    const int rr = NT == 1 ? idx : idx;  // row within the sequence / packed group
-    int lo_, hi_;
-    bool row_valid;
-    key_range(args, NT, rr, lo_, hi_, row_valid);
-    const int b = b0 + (NT == 1 ? rr / args.N : 0);
-    const int n = NT == 1 ? rr % args.N : rr;
-    float delta = 0.f, l2 = INFINITY;
-    if (row_valid && b < args.B) {
-      const long long off = ((static_cast<long long>(b) * args.N + n) * args.H + head) * 64;
-      const uint4* po = reinterpret_cast<const uint4*>(args.out + off);
-      const uint4* pd = reinterpret_cast<const uint4*>(args.dout + off);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint4 a = __ldg(po + j), d = __ldg(pd + j);
-        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(dw[e]);
-          delta += x.x * y.x + x.y * y.y;
-        }
-      }
-      l2 = args.lse2[(static_cast<long long>(b) * args.H + head) * args.N + n];
-    }
-    rowc[idx * 2] = delta;
-    rowc[idx * 2 + 1] = l2;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -474,183 +434,294 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                  T_DV = tmem_base + 448;
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_wait(bar_load, 0);
-      tcgen05_fence_after();
+    // ------------------------------------------------------------------ control: TMA + MMA issue
+    if (lane == 0 && n_my > 0) {
+      auto issue_load = [&](int k) {
+        const int item = item_of(k);
+        const int head = item % args.H, b0 = (item / args.H) * args.G;
+        uint8_t* sQ = set_base(k);
+        uint8_t* sdO = sQ + NT * TILE_BYTES;
+        uint8_t* sK = sdO + NT * TILE_BYTES;
+        uint8_t* sV = sK + NT * TILE_BYTES;
+        uint64_t* bar = &bar_load[SETS == 2 ? (k & 1) : 0];
+        const int cq = head * 64, ck = (args.H + head) * 64, cv = (2 * args.H + head) * 64;
+        if (NT == 1) {
+          mbar_expect_tx(bar, 4 * args.rows * 128);
+          tma_load_3d(sQ, &tmQKV, bar, cq, 0, b0);
+          tma_load_3d(sK, &tmQKV, bar, ck, 0, b0);
+          tma_load_3d(sV, &tmQKV, bar, cv, 0, b0);
+          tma_load_3d(sdO, &tmDO, bar, cq, 0, b0);
+        } else {
+          mbar_expect_tx(bar, 4 * NT * TILE_BYTES);
+          for (int t = 0; t < NT; ++t) {
+            tma_load_3d(sQ + t * TILE_BYTES, &tmQKV, bar, cq, t * 128, b0);
+            tma_load_3d(sK + t * TILE_BYTES, &tmQKV, bar, ck, t * 128, b0);
+            tma_load_3d(sV + t * TILE_BYTES, &tmQKV, bar, cv, t * 128, b0);
+            tma_load_3d(sdO + t * TILE_BYTES, &tmDO, bar, cq, t * 128, b0);
+          }
+        }
+      };
+      auto wait_load = [&](int k) {
+        const int uses = SETS == 2 ? (k >> 1) : k;  // completed phases of this set's barrier before item k
+        mbar_wait(&bar_load[SETS == 2 ? (k & 1) : 0], uses & 1);
+        tcgen05_fence_after();
+      };
       const uint32_t idesc_q = make_idesc_bf16(128, 64, false, true);  // dQ: A K-major, B MN-major
       const uint32_t idesc_kv = make_idesc_bf16(128, 64, true, true);  // dK/dV: both MN-major
-      int pair = 0;
-      for (int u = 0; u < NT; ++u) {
+      auto issue_sdp = [&](int k, int p) {
+        const int u = p / NT, t = p % NT;
         const int ku = min(128, args.keys_n - u * 128);  // keys in this key tile (multiple of 16)
         const uint32_t idesc_s = make_idesc_bf16(128, ku, false, false);
-        const uint32_t k_u = smem_u32(sK + u * TILE_BYTES), v_u = smem_u32(sV + u * TILE_BYTES);
-        for (int t = 0; t < NT; ++t, ++pair) {
-          const uint32_t q_t = smem_u32(sQ + t * TILE_BYTES), do_t = smem_u32(sdO + t * TILE_BYTES);
-          if (pair > 0) {
-            mbar_wait(bar_sdp_free, (pair - 1) & 1);
-            tcgen05_fence_after();
-          }
+        const uint32_t base = smem_u32(set_base(k));
+        const uint32_t q_t = base + t * TILE_BYTES, do_t = base + (NT + t) * TILE_BYTES;
+        const uint32_t k_u = base + (2 * NT + u) * TILE_BYTES, v_u = base + (3 * NT + u) * TILE_BYTES;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(T_S, make_smem_desc_sw128(q_t + k * 32, 16, 1024),
-                         make_smem_desc_sw128(k_u + k * 32, 16, 1024), idesc_s, k > 0);
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ss(T_S, make_smem_desc_sw128(q_t + kk * 32, 16, 1024), make_smem_desc_sw128(k_u + kk * 32, 16, 1024),
+                       idesc_s, kk > 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(T_DP, make_smem_desc_sw128(do_t + k * 32, 16, 1024),
-                         make_smem_desc_sw128(v_u + k * 32, 16, 1024), idesc_s, k > 0);
-          umma_commit(bar_sdp);
-          mbar_wait(bar_pds, pair & 1);
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ss(T_DP, make_smem_desc_sw128(do_t + kk * 32, 16, 1024),
+                       make_smem_desc_sw128(v_u + kk * 32, 16, 1024), idesc_s, kk > 0);
+        umma_commit(bar_sdp);
+      };
+      auto issue_dqkv = [&](int k, int p) {
+        const int u = p / NT, t = p % NT;
+        const int ku = min(128, args.keys_n - u * 128);
+        const uint32_t base = smem_u32(set_base(k));
+        const uint32_t q_t = base + t * TILE_BYTES, do_t = base + (NT + t) * TILE_BYTES;
+        const uint32_t k_u = base + (2 * NT + u) * TILE_BYTES;
+        const uint32_t p0 = smem_u32(sP), ds0 = smem_u32(sdS);
+        // dQ_t (+)= dS[128 q, ku keys] . K_u[ku keys, 64]
+        for (int j = 0; j < ku / 16; ++j)
+          umma_bf16_ss(T_DQ + t * 64, make_smem_desc_sw128(ds0 + (j >> 2) * TILE_BYTES + (j & 3) * 32, 16, 1024),
+                       make_smem_desc_sw128(k_u + j * 2048, 8192, 1024), idesc_q, (u > 0 || j > 0));
+        // dV_u (+)= P^T[128 keys, 128 q] . dO_t[128 q, 64] ; dK_u (+)= dS^T . Q_t
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_bf16_ss(T_DV, make_smem_desc_sw128(p0 + j * 2048, TILE_BYTES, 1024),
+                       make_smem_desc_sw128(do_t + j * 2048, 8192, 1024), idesc_kv, (t > 0 || j > 0));
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_bf16_ss(T_DK, make_smem_desc_sw128(ds0 + j * 2048, TILE_BYTES, 1024),
+                       make_smem_desc_sw128(q_t + j * 2048, 8192, 1024), idesc_kv, (t > 0 || j > 0));
+        umma_commit(bar_mma);
+      };
+
+      issue_load(0);
+      if (SETS == 2 && n_my > 1) issue_load(1);
+      wait_load(0);
+      issue_sdp(0, 0);
+      int gp = 0;
+      for (int k = 0; k < n_my; ++k) {
+        for (int p = 0; p < PPI; ++p, ++gp) {
+          mbar_wait(bar_sdp_free, gp & 1);  // the math warps hold S/dP(gp) in registers
           tcgen05_fence_after();
-          const uint32_t p0 = smem_u32(sP), ds0 = smem_u32(sdS);
-          // dQ_t (+)= dS[128 q, ku keys] . K_u[ku keys, 64]
-          for (int j = 0; j < ku / 16; ++j)
-            umma_bf16_ss(T_DQ + t * 64,
-                         make_smem_desc_sw128(ds0 + (j >> 2) * TILE_BYTES + (j & 3) * 32, 16, 1024),
-                         make_smem_desc_sw128(k_u + j * 2048, 8192, 1024), idesc_q, (u > 0 || j > 0));
-          // dV_u (+)= P^T[128 keys, 128 q] . dO_t[128 q, 64] ; dK_u (+)= dS^T . Q_t
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            umma_bf16_ss(T_DV, make_smem_desc_sw128(p0 + j * 2048, TILE_BYTES, 1024),
-                         make_smem_desc_sw128(do_t + j * 2048, 8192, 1024), idesc_kv, (t > 0 || j > 0));
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            umma_bf16_ss(T_DK, make_smem_desc_sw128(ds0 + j * 2048, TILE_BYTES, 1024),
-                         make_smem_desc_sw128(q_t + j * 2048, 8192, 1024), idesc_kv, (t > 0 || j > 0));
-          umma_commit(bar_mma);
+          const bool last = p + 1 == PPI;
+          if (!last) {
+            issue_sdp(k, p + 1);
+          } else if (SETS == 2 && k + 1 < n_my) {
+            wait_load(k + 1);
+            issue_sdp(k + 1, 0);
+          }
+          mbar_wait(bar_pds, gp & 1);
+          tcgen05_fence_after();
+          issue_dqkv(k, p);
+          if (last) {
+            mbar_wait(bar_mma, gp & 1);  // every MMA of the item has retired: its operand set is free again
+            if (SETS == 2) {
+              if (k + 2 < n_my) issue_load(k + 2);
+            } else if (k + 1 < n_my) {
+              issue_load(k + 1);
+              wait_load(k + 1);
+              issue_sdp(k + 1, 0);
+            }
+          }
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------ row constants of item k (one ahead)
+    const int ptid = threadIdx.x - 32;  // 0..95
+    for (int k = 0; k < n_my; ++k) {
+      const int item = item_of(k);
+      const int head = item % args.H, b0 = (item / args.H) * args.G;
+      float* rc = rowc + (k & 1) * (NT * 128 * 2);
+      mbar_wait(&bar_rowc_free[k & 1], ((k >> 1) & 1) ^ 1);
+      for (int idx = ptid; idx < NT * 128; idx += BWD_ROWC_THREADS) {
+        int lo_, hi_;
+        bool row_valid;
+        key_range(args, NT, idx, lo_, hi_, row_valid);
+        const int b = b0 + (NT == 1 ? idx / args.N : 0);
+        const int n = NT == 1 ? idx % args.N : idx;
+        float delta = 0.f, l2 = INFINITY;  // invalid rows: lse2 = +inf so that P = 0
+        if (row_valid && b < args.B) {
+          const long long off = ((static_cast<long long>(b) * args.N + n) * args.H + head) * 64;
+          const uint4* po = reinterpret_cast<const uint4*>(args.out + off);
+          const uint4* pd = reinterpret_cast<const uint4*>(args.dout + off);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 a = __ldg(po + j), d = __ldg(pd + j);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(dw[e]);
+              delta += x.x * y.x + x.y * y.y;
+            }
+          }
+          l2 = args.lse2[(static_cast<long long>(b) * args.H + head) * args.N + n];
+        }
+        rc[idx * 2] = delta;
+        rc[idx * 2 + 1] = l2;
+      }
+      mbar_arrive(&bar_rowc_full[k & 1]);
+    }
+  } else {
+    // ------------------------------------------------------------------ math + epilogue
     const int q = warp & 3;           // TMEM lane quarter
     const int qc = (warp - 4) >> 2;   // which 32 key columns of the 128-wide key tile
     const int r = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const bool leader = threadIdx.x == 128;
 
-    float delta[NT], lse2[NT];
     int lo[NT], hi[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       bool row_valid;
       key_range(args, NT, NT == 1 ? r : t * 128 + r, lo[t], hi[t], row_valid);
-      delta[t] = rowc[(t * 128 + r) * 2];
-      lse2[t] = rowc[(t * 128 + r) * 2 + 1];
     }
-
-    // 128x64 fp32 accumulator at TMEM column `tcol` -> bf16 -> staging tile `stage` -> TMA store at
-    // (col, row0, b0). Staging tiles are the P / dS chunk buffers, dead at the points of use, so several
-    // stores are in flight at once; `stores_pending` makes the next writer of those buffers wait.
     bool stores_pending = false;
-    auto store_tile = [&](uint32_t tcol, uint8_t* stage, int gcol, int row0) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(tcol + lane_off + qc * 16, v);
-      tmem_ld_wait();
+    int gp = 0;
+
+    for (int k = 0; k < n_my; ++k) {
+      const int item = item_of(k);
+      const int head = item % args.H, b0 = (item / args.H) * args.G;
+      float delta[NT], lse2[NT];
+      {
+        const float* rc = rowc + (k & 1) * (NT * 128 * 2);
+        mbar_wait(&bar_rowc_full[k & 1], (k >> 1) & 1);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        uint4 pk;
-        pk.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-        pk.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-        pk.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-        pk.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-        *reinterpret_cast<uint4*>(stage + sw128_offset(r, qc * 2 + j)) = pk;
+        for (int t = 0; t < NT; ++t) {
+          delta[t] = rc[(t * 128 + r) * 2];
+          lse2[t] = rc[(t * 128 + r) * 2 + 1];
+        }
+        mbar_arrive(&bar_rowc_free[k & 1]);
       }
-      fence_proxy_async_smem();
-      named_bar_sync(1, BWD_MATH_THREADS);
-      if (leader) {
-        tma_store_3d(&tmDQKV, stage, gcol, row0, b0);
-        tma_store_commit();
-      }
-      stores_pending = true;
-    };
+
+      // 128x64 fp32 accumulator at TMEM column `tcol` -> bf16 -> staging tile `stage` -> TMA store at
+      // (col, row0, b0). Staging tiles are the P / dS chunk buffers, dead at the points of use, so several
+      // stores are in flight at once; `stores_pending` makes the next writer of those buffers wait.
+      auto store_tile = [&](uint32_t tcol, uint8_t* stage, int gcol, int row0) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tcol + lane_off + qc * 16, v);
+        tmem_ld_wait();
+        const uint32_t st = smem_u32(stage);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+          pk.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+          pk.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+          pk.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+          sts128(st + sw128_offset(r, qc * 2 + j), pk);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, BWD_MATH_THREADS);
+        if (leader) {
+          tma_store_3d(&tmDQKV, stage, gcol, row0, b0);
+          tma_store_commit();
+        }
+        stores_pending = true;
+      };
 
 #pragma unroll
-    for (int u = 0; u < NT; ++u) {
-      const int ku = min(128, args.keys_n - u * 128);
+      for (int u = 0; u < NT; ++u) {
+        const int ku = min(128, args.keys_n - u * 128);
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        constexpr int kPairsPerU = NT;
-        const int pair = u * kPairsPerU + t;
-        mbar_wait(bar_sdp, pair & 1);
-        tcgen05_fence_after();
-        const int col0 = qc * 32;             // first key column (within the tile) of this thread
-        const bool active = col0 < ku;
-        uint32_t pp[16], dd[16];              // 32 columns of P and dS, packed bf16 pairs
-        if (active) {                         // warp-uniform: col0 depends on the warp only
+        for (int t = 0; t < NT; ++t, ++gp) {
+          mbar_wait(bar_sdp, gp & 1);
+          tcgen05_fence_after();
+          const int col0 = qc * 32;             // first key column (within the tile) of this thread
+          const bool active = col0 < ku;
+          uint32_t pp[16], dd[16];              // 32 columns of P and dS, packed bf16 pairs
+          if (active) {                         // warp-uniform: col0 depends on the warp only
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t sv[16], dv[16];
-            tmem_ld_32x32b_x16(T_S + lane_off + col0 + h * 16, sv);
-            tmem_ld_32x32b_x16(T_DP + lane_off + col0 + h * 16, dv);
-            tmem_ld_wait();
-            const int gcol = u * 128 + col0 + h * 16;
-            // NT == 2 needs no key masking: K / V rows >= N are zero-filled by TMA, so whatever P and dS hold
-            // in those columns only reaches dQ through zero K rows and dK / dV rows the TMA store clips;
-            // padded query rows have lse2 = +inf, hence P = dS = 0. NT == 1 (packed sequences): classify the
-            // 16-key chunk against the row's own sequence [lo, hi) — 0 outside, 1 inside, 2 straddling.
-            int cls = 1;
-            if (NT == 1) cls = (gcol + 16 <= lo[t] || gcol >= hi[t]) ? 0 : ((gcol >= lo[t] && gcol + 16 <= hi[t]) ? 1 : 2);
-            if (cls == 0) {
+            for (int h = 0; h < 2; ++h) {
+              uint32_t sv[16], dv[16];
+              tmem_ld_32x32b_x16(T_S + lane_off + col0 + h * 16, sv);
+              tmem_ld_32x32b_x16(T_DP + lane_off + col0 + h * 16, dv);
+              tmem_ld_wait();
+              const int gcol = u * 128 + col0 + h * 16;
+              // NT == 2 needs no key masking: K / V rows >= N are zero-filled by TMA, so whatever P and dS hold
+              // in those columns only reaches dQ through zero K rows and dK / dV rows the TMA store clips;
+              // padded query rows have lse2 = +inf, hence P = dS = 0. NT == 1 (packed sequences): classify the
+              // 16-key chunk against the row's own sequence [lo, hi) -- 0 outside, 1 inside, 2 straddling.
+              int cls = 1;
+              if (NT == 1) cls = (gcol + 16 <= lo[t] || gcol >= hi[t]) ? 0 : ((gcol >= lo[t] && gcol + 16 <= hi[t]) ? 1 : 2);
+              if (cls == 0) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) { pp[h * 8 + e] = 0u; dd[h * 8 + e] = 0u; }
-            } else if (cls == 1) {
+                for (int e = 0; e < 8; ++e) { pp[h * 8 + e] = 0u; dd[h * 8 + e] = 0u; }
+              } else if (cls == 1) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), args.scale_log2, -lse2[t]));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), args.scale_log2, -lse2[t]));
-                const float d0 = p0 * ((__uint_as_float(dv[2 * e]) - delta[t]) * args.scale);
-                const float d1 = p1 * ((__uint_as_float(dv[2 * e + 1]) - delta[t]) * args.scale);
-                pp[h * 8 + e] = pack_bf16x2(p0, p1);
-                dd[h * 8 + e] = pack_bf16x2(d0, d1);
-              }
-            } else {
-              for (int e = 0; e < 8; ++e) {
-                float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), args.scale_log2, -lse2[t]));
-                float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), args.scale_log2, -lse2[t]));
-                if (!(gcol + 2 * e >= lo[t] && gcol + 2 * e < hi[t])) p0 = 0.f;
-                if (!(gcol + 2 * e + 1 >= lo[t] && gcol + 2 * e + 1 < hi[t])) p1 = 0.f;
-                const float d0 = p0 * ((__uint_as_float(dv[2 * e]) - delta[t]) * args.scale);
-                const float d1 = p1 * ((__uint_as_float(dv[2 * e + 1]) - delta[t]) * args.scale);
-                pp[h * 8 + e] = pack_bf16x2(p0, p1);
-                dd[h * 8 + e] = pack_bf16x2(d0, d1);
+                for (int e = 0; e < 8; ++e) {
+                  const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), args.scale_log2, -lse2[t]));
+                  const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), args.scale_log2, -lse2[t]));
+                  const float d0 = p0 * ((__uint_as_float(dv[2 * e]) - delta[t]) * args.scale);
+                  const float d1 = p1 * ((__uint_as_float(dv[2 * e + 1]) - delta[t]) * args.scale);
+                  pp[h * 8 + e] = pack_bf16x2(p0, p1);
+                  dd[h * 8 + e] = pack_bf16x2(d0, d1);
+                }
+              } else {
+                for (int e = 0; e < 8; ++e) {
+                  float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), args.scale_log2, -lse2[t]));
+                  float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), args.scale_log2, -lse2[t]));
+                  if (!(gcol + 2 * e >= lo[t] && gcol + 2 * e < hi[t])) p0 = 0.f;
+                  if (!(gcol + 2 * e + 1 >= lo[t] && gcol + 2 * e + 1 < hi[t])) p1 = 0.f;
+                  const float d0 = p0 * ((__uint_as_float(dv[2 * e]) - delta[t]) * args.scale);
+                  const float d1 = p1 * ((__uint_as_float(dv[2 * e + 1]) - delta[t]) * args.scale);
+                  pp[h * 8 + e] = pack_bf16x2(p0, p1);
+                  dd[h * 8 + e] = pack_bf16x2(d0, d1);
+                }
               }
             }
           }
-        }
-        tcgen05_fence_before();
-        mbar_arrive(bar_sdp_free);
-        if (pair > 0) mbar_wait(bar_mma, (pair - 1) & 1);  // previous MMAs done with sP / sdS
-        if (stores_pending) {  // dK / dV of the previous key tile were staged in sP: let those stores drain
-          if (leader) tma_store_wait_read<0>();
-          named_bar_sync(1, BWD_MATH_THREADS);
-          stores_pending = false;
-        }
-        if (active) {
-          uint8_t* pc = sP + (qc >> 1) * TILE_BYTES;
-          uint8_t* dc = sdS + (qc >> 1) * TILE_BYTES;
+          tcgen05_fence_before();
+          mbar_arrive(bar_sdp_free);
+          if (gp > 0) mbar_wait(bar_mma, (gp - 1) & 1);  // previous MMAs done with sP / sdS
+          if (stores_pending) {  // tiles staged in sP / sdS: let those TMA stores finish reading
+            if (leader) tma_store_wait_read<0>();
+            named_bar_sync(1, BWD_MATH_THREADS);
+            stores_pending = false;
+          }
+          if (active) {
+            const uint32_t pc = smem_u32(sP) + (qc >> 1) * TILE_BYTES;
+            const uint32_t dc = smem_u32(sdS) + (qc >> 1) * TILE_BYTES;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t off = sw128_offset(r, (qc & 1) * 4 + j);
-            *reinterpret_cast<uint4*>(pc + off) = make_uint4(pp[4 * j], pp[4 * j + 1], pp[4 * j + 2], pp[4 * j + 3]);
-            *reinterpret_cast<uint4*>(dc + off) = make_uint4(dd[4 * j], dd[4 * j + 1], dd[4 * j + 2], dd[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t off = sw128_offset(r, (qc & 1) * 4 + j);
+              sts128(pc + off, make_uint4(pp[4 * j], pp[4 * j + 1], pp[4 * j + 2], pp[4 * j + 3]));
+              sts128(dc + off, make_uint4(dd[4 * j], dd[4 * j + 1], dd[4 * j + 2], dd[4 * j + 3]));
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(bar_pds);
+
+          if (t == NT - 1) {
+            // dK_u and dV_u are complete once this pair's MMAs retire
+            mbar_wait(bar_mma, gp & 1);
+            tcgen05_fence_after();
+            store_tile(T_DK, sP, (args.H + head) * 64, NT == 1 ? 0 : u * 128);
+            store_tile(T_DV, sP + TILE_BYTES, (2 * args.H + head) * 64, NT == 1 ? 0 : u * 128);
+            // the dK/dV accumulators are re-used by the next key tile: order these reads before its MMAs
+            tcgen05_fence_before();
           }
         }
-        fence_proxy_async_smem();
-        mbar_arrive(bar_pds);
-
-        if (t == NT - 1) {
-          // dK_u and dV_u are complete once this pair's MMAs retire
-          mbar_wait(bar_mma, pair & 1);
-          tcgen05_fence_after();
-          store_tile(T_DK, sP, (args.H + head) * 64, NT == 1 ? 0 : u * 128);
-          store_tile(T_DV, sP + TILE_BYTES, (2 * args.H + head) * 64, NT == 1 ? 0 : u * 128);
-          // the dK/dV accumulators are re-used by the next key tile: order these reads before its MMAs
-          tcgen05_fence_before();
-        }
       }
-    }
-    // dQ tiles (complete after the last pair; bar_mma already waited on above)
+      // dQ tiles (complete after the last pair; bar_mma already waited on above)
 #pragma unroll
-    for (int t = 0; t < NT; ++t) store_tile(T_DQ + t * 64, sdS + t * TILE_BYTES, head * 64, NT == 1 ? 0 : t * 128);
+      for (int t = 0; t < NT; ++t) store_tile(T_DQ + t * 64, sdS + t * TILE_BYTES, head * 64, NT == 1 ? 0 : t * 128);
+      tcgen05_fence_before();
+    }
     if (leader) tma_store_wait_all<0>();
   }
 
@@ -734,23 +805,24 @@ extern "C" int b200ssl_attention_bwd(const void* qkv, const void* out, const voi
   if (int rc = make_bnd_map(&tq, qkv, 3 * H * 64, N, B, nt, a.G)) return rc;
   if (int rc = make_bnd_map(&tdo, dout, H * 64, N, B, nt, a.G)) return rc;
   if (int rc = make_bnd_map(&tdq, dqkv, 3 * H * 64, N, B, nt, a.G)) return rc;
-  const int grid = groups * H;
+  const int num_items = groups * H;
+  const int grid = num_items < sm_count() ? num_items : sm_count();
   if (nt == 1) {
-    const int smem = 9 * TILE_BYTES + 1024 + 2048 + 1024;
+    const int smem = 12 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 2 * 128 * 2 * 4 + 256;
     static bool cfg = false;
     if (!cfg) {
       B200SSL_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       cfg = true;
     }
-    attention_bwd_kernel<1><<<grid, BWD_THREADS, smem, stream>>>(tq, tdo, tdq, a);
+    attention_bwd_kernel<1><<<grid, BWD_THREADS, smem, stream>>>(tq, tdo, tdq, a, num_items);
   } else {
-    const int smem = 13 * TILE_BYTES + 1024 + 2048 + 1024;
+    const int smem = 12 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 2 * 256 * 2 * 4 + 256;
     static bool cfg = false;
     if (!cfg) {
       B200SSL_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       cfg = true;
     }
-    attention_bwd_kernel<2><<<grid, BWD_THREADS, smem, stream>>>(tq, tdo, tdq, a);
+    attention_bwd_kernel<2><<<grid, BWD_THREADS, smem, stream>>>(tq, tdo, tdq, a, num_items);
   }
   B200SSL_CUDA(cudaGetLastError());
   return 0;

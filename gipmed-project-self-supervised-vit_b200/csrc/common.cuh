@@ -190,6 +190,26 @@ __device__ __forceinline__ void gelu_and_grad2(float x0, float x1, f32x2& h, f32
   g = ffma2(fmul2(x, e), splat_f32x2(0.39894228040143268f), cdf);              // Phi(x) + x phi(x)
 }
 
+// gelu only (inference / no-grad forward: the teacher), packed like gelu_and_grad2
+__device__ __forceinline__ f32x2 gelu2(float x0, float x1) {
+  const float az0 = fabsf(x0) * 0.70710678118654752f, az1 = fabsf(x1) * 0.70710678118654752f;
+  const f32x2 az = pack_f32x2(az0, az1);
+  float d0, d1;
+  unpack_f32x2(ffma2(splat_f32x2(0.3275911f), az, splat_f32x2(1.0f)), d0, d1);
+  const f32x2 t = pack_f32x2(rcp_approx(d0), rcp_approx(d1));
+  f32x2 np = ffma2(t, splat_f32x2(-1.061405429f), splat_f32x2(1.453152027f));
+  np = ffma2(np, t, splat_f32x2(-1.421413741f));
+  np = ffma2(np, t, splat_f32x2(0.284496736f));
+  np = ffma2(np, t, splat_f32x2(-0.254829592f));
+  np = fmul2(np, t);
+  float a0, a1;
+  unpack_f32x2(fmul2(fmul2(az, splat_f32x2(-1.4426950408889634f)), az), a0, a1);
+  const f32x2 e = pack_f32x2(ex2_approx(a0), ex2_approx(a1));
+  const f32x2 erf_abs = ffma2(np, e, splat_f32x2(1.0f));
+  const f32x2 half_s = pack_f32x2(copysignf(0.5f, x0), copysignf(0.5f, x1));
+  return fmul2(pack_f32x2(x0, x1), ffma2(half_s, erf_abs, splat_f32x2(0.5f)));
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

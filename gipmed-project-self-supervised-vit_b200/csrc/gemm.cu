@@ -32,6 +32,7 @@ enum GemmEpilogue : int {
   EPI_ATOMIC_F32 = 4, // D(fp32) += acc   (split-K)
   EPI_BIAS_RES_F32 = 5, // D(fp32) = acc (+ bias) + aux(fp32): the fp32 residual stream
   EPI_ATOMIC_F32_T = 6, // D(fp32)[n, m] += acc[m, n] (split-K, TRANSPOSED store); bias output = column sums of B
+  EPI_BIAS_GELU_FWD = 7, // D = gelu(acc + bias): no-grad forward (teacher), nothing saved for backward
 };
 __host__ __device__ constexpr bool is_wgrad_epi(int e) { return e == EPI_ATOMIC_F32 || e == EPI_ATOMIC_F32_T; }
 
@@ -654,6 +655,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           ++ring;
           continue;
         }
+        if (EPI == EPI_BIAS_GELU_FWD) {
+#pragma unroll
+          for (int j = 0; j < W / 2; ++j) unpack_f32x2(gelu2(f[2 * j], f[2 * j + 1]), f[2 * j], f[2 * j + 1]);
+        }
         uint32_t hpk[EPI == EPI_BIAS_GELU ? W / 2 : 1];  // gelu(x) packed: the second output
         if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
@@ -793,6 +798,7 @@ static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b, con
     case EPI_ATOMIC_F32: return launch_gemm<BN, EPI_ATOMIC_F32>(a, b, d, d2, args, cl, s);
     case EPI_BIAS_RES_F32: return launch_gemm<BN, EPI_BIAS_RES_F32>(a, b, d, d2, args, cl, s);
     case EPI_ATOMIC_F32_T: return launch_gemm<BN, EPI_ATOMIC_F32_T>(a, b, d, d2, args, cl, s);
+    case EPI_BIAS_GELU_FWD: return launch_gemm<BN, EPI_BIAS_GELU_FWD>(a, b, d, d2, args, cl, s);
   }
   set_last_error("gemm: unknown epilogue %d", epi);
   return -2;
@@ -829,7 +835,7 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
   B200SSL_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(D) & 15) == 0,
                 -2, "gemm: operands must be 16-byte aligned");
-  B200SSL_CHECK(epilogue >= 0 && epilogue <= 6, -2, "gemm: unknown epilogue %d", epilogue);
+  B200SSL_CHECK(epilogue >= 0 && epilogue <= 7, -2, "gemm: unknown epilogue %d", epilogue);
   const bool wgrad = is_wgrad_epi(epilogue);
   if (epilogue == EPI_BIAS_RES || epilogue == EPI_MUL_AUX)
     B200SSL_CHECK(aux != nullptr && ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0, -2,

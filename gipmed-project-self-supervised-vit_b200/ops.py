@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_MUL_AUX, EPI_ATOMIC_F32, EPI_BIAS_RES_F32, EPI_ATOMIC_F32_T = 0, 1, 2, 3, 4, 5, 6
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_MUL_AUX, EPI_ATOMIC_F32, EPI_BIAS_RES_F32, EPI_ATOMIC_F32_T, EPI_BIAS_GELU_FWD = 0, 1, 2, 3, 4, 5, 6, 7
 
 _BF16 = torch.bfloat16
 _counters = {"launches": 0}
@@ -178,6 +178,10 @@ def linear_fwd(x, w16, bias=None, residual=None, gelu=False):
         gemm(x, w16, y, M, N, K, epi=EPI_BIAS_RES_F32, bias=bias, aux=residual)
         return y
     y = torch.empty(M, N, dtype=_BF16, device=x.device)
+    if gelu == "fwd_only":
+        # no-grad forward (teacher): gelu(pre) only, nothing saved for backward
+        gemm(x, w16, y, M, N, K, epi=EPI_BIAS_GELU_FWD, bias=bias)
+        return None, y
     if gelu:
         h = torch.empty(M, N, dtype=_BF16, device=x.device)
         gemm(x, w16, y, M, N, K, epi=EPI_BIAS_GELU, D2=h, bias=bias)
@@ -339,12 +343,13 @@ class MlpChainFn(torch.autograd.Function):
         n = len(wb) // 2
         saved = [x]
         h = x
+        keep = any(ctx.needs_input_grad)  # False under no_grad (teacher head): gelu' is not produced
         for i in range(n):
             w, b = wb[2 * i], wb[2 * i + 1]
             b32 = _f32(b) if b is not None else None
             if i < n - 1:
-                pre, h = linear_fwd(h, bf16_of(w), b32, gelu=True)
-                saved += [pre, h]
+                pre, h = linear_fwd(h, bf16_of(w), b32, gelu=True if keep else "fwd_only")
+                saved += [pre, h] if keep else []
             else:
                 h = linear_fwd(h, bf16_of(w), b32, residual=residual)
         ctx.n = n
@@ -417,10 +422,10 @@ def attn_half_bwd(dy, saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale
     return dx, d_lw, d_lb, d_qw, d_qb, d_pw, d_pb
 
 
-def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps):
-    """x + fc2(gelu(fc1(LN(x)))) (VT.pyc@L151)."""
+def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, keep=True):
+    """x + fc2(gelu(fc1(LN(x)))) (VT.pyc@L151). keep=False (no-grad forward): gelu' is not produced."""
     ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
-    pre, h = linear_fwd(ln, bf16_of(w1), _f32(b1) if b1 is not None else None, gelu=True)
+    pre, h = linear_fwd(ln, bf16_of(w1), _f32(b1) if b1 is not None else None, gelu=True if keep else "fwd_only")
     y = linear_fwd(h, bf16_of(w2), _f32(b2) if b2 is not None else None, residual=x)
     return y, (x, mean, rstd, ln, pre, h)
 
@@ -493,7 +498,7 @@ class EncoderFn(torch.autograd.Function):
         for i in range(depth):
             ln1w, ln1b, qw, qb, pw, pb, ln2w, ln2b, w1, b1, w2, b2 = params[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS]
             x, s1 = attn_half_fwd(x, ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale)
-            x, s2 = mlp_half_fwd(x, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1])
+            x, s2 = mlp_half_fwd(x, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1], keep=keep)
             if keep:
                 saved.append((s1, s2))
         D = x.shape[1]

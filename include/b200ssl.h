@@ -38,6 +38,7 @@ int b200ssl_device_check(void);
  *             db[M] += column sums of A (wgrad bias gradient) | 5 D(fp32)=acc+bias+aux(fp32) (residual stream)
  *             6 like 4 but stored TRANSPOSED: D(fp32)[n, m] += acc[m, n] (ldd >= M) and bias is the OUTPUT
  *             db[N] += column sums of B (wgrad of a layer with more inputs than outputs; needs block_n 384)
+ *             7 D=gelu(acc+bias) only (no-grad forward, e.g. the teacher: nothing saved for backward)
  *   split_k: K splits for epilogues 4/6 (0 = auto); block_n: 0 = auto, else 64/128/192/256/384 dividing N
  *   (384 = 256 x 384 CTA-pair tiles: M > 128, epilogues 0, 4, 5, 6).
  * Constraints: N % 64 == 0, lda/ldb % 8 == 0. */

@@ -89,6 +89,9 @@ def main():
     ok &= run(2, 197, 2)
     ok &= run(3, 256, 1)
     ok &= run(4, 145, 3)
+    ok &= run(64, 197, 6)     # 384 items: persistent CTAs take 2-3 items each
+    ok &= run(700, 37, 6)     # 1404 packed items: ~9.5 per CTA, two operand sets in flight
+    ok &= run(160, 100, 3)    # N <= 128 without packing
     if "--bench" in sys.argv and ok:
         run(512, 197, 6, bench=True)
         run(2560, 37, 6, bench=True)

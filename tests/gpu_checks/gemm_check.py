@@ -49,7 +49,7 @@ def run_case(name, M, N, K, a_mn, b_mn, epi, bn, split_k=1, results=None):
     A_in = A.t().contiguous() if a_mn else A
     B_in = B.t().contiguous() if b_mn else B
     ref = A.float() @ B.float().t()
-    bias = torch.randn(N, device="cuda", generator=g) if epi in (0, 1, 2, 5) else None
+    bias = torch.randn(N, device="cuda", generator=g) if epi in (0, 1, 2, 5, 7) else None
     if epi == 4 and a_mn:
         bias = torch.zeros(M, device="cuda")  # wgrad: receives db = column sums of A^T (i.e. A.sum over K)
     if epi == 6:
@@ -66,8 +66,10 @@ def run_case(name, M, N, K, a_mn, b_mn, epi, bn, split_k=1, results=None):
         D = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
     else:
         D = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
-    if epi in (0, 1, 2, 5):
+    if epi in (0, 1, 2, 5, 7):
         ref = ref + bias
+    if epi == 7:
+        ref = torch.nn.functional.gelu(ref)
     ref2 = None
     if epi == 1:
         D2 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
@@ -182,6 +184,7 @@ def main():
     allok &= run_case("kk_gelu", 1000, 1536, 384, 0, 0, 1, 256, results=results)
     allok &= run_case("kk_res", 1000, 384, 1536, 0, 0, 2, 192, results=results)
     allok &= run_case("kk_dgelu", 1000, 1536, 384, 0, 0, 3, 256, results=results)
+    allok &= run_case("kk_gelu_fwd_only", 128 * 70 + 9, 1536, 384, 0, 0, 7, 256, results=results)
     allok &= run_case("kk_res32_k384", 1000, 384, 384, 0, 0, 5, 192, results=results)
     allok &= run_case("kk_res32_k1536", 5000, 384, 1536, 0, 0, 5, 192, results=results)
     allok &= run_case("kk_res32_bn128", 700, 768, 384, 0, 0, 5, 128, results=results)

@@ -47,6 +47,8 @@ def test_linear_gelu_and_residual(ops):
     pr = ref.clone().requires_grad_(True)
     torch.nn.functional.gelu(pr).sum().backward()
     assert rel(dact, pr.grad) < 1e-2                          # saved derivative gelu'(pre)
+    none, h_only = ops.linear_fwd(x, w, b, gelu="fwd_only")   # no-grad forward (teacher): gelu only
+    assert none is None and rel(h_only, torch.nn.functional.gelu(ref)) < 1e-2
     res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
     y = ops.linear_fwd(x, w, b, residual=res)
     assert rel(y, ref + res.float()) < 1e-2
@@ -68,6 +70,12 @@ def test_linear_dgrad_wgrad(ops):
     assert rel(dxg, (dy.float() @ w.float()) * dact.float()) < 1e-2
     dw, db = ops.linear_wgrad(dy, x)
     assert rel(dw, dy.float().t() @ x.float()) < 1e-3        # fp32 output, bf16 inputs
+    # more inputs than outputs (fc2-like): 256 x 384 pair tiles with the transposed store
+    dy2 = torch.randn(M, 384, device="cuda", generator=g).bfloat16()
+    x2 = torch.randn(M, 1536, device="cuda", generator=g).bfloat16()
+    dw2, db2 = ops.linear_wgrad(dy2, x2)
+    assert dw2.shape == (384, 1536) and rel(dw2, dy2.float().t() @ x2.float()) < 1e-3
+    assert rel(db2, dy2.float().sum(0)) < 1e-3
     assert rel(db, dy.float().sum(0)) < 1e-4
 
 
