@@ -13,20 +13,22 @@ namespace b200ssl {
 
 constexpr int OPT_THREADS = 256;
 
-struct EmaRow {  // int64 x 3
+struct EmaRow {  // int64 x 4
   float* dst;
   const float* src;
   long long n;
+  __nv_bfloat16* shadow;  // optional bf16 copy of dst the GEMMs read (nullptr: none)
 };
 
-// dst = m * dst + (1 - m) * src ; the momentum is read from device memory so that a captured CUDA graph
-// can be replayed with a new value every step (cosine schedule)
+// dst = m * dst + (1 - m) * src (+ refresh of dst's bf16 shadow in the same pass); the momentum is read from
+// device memory so that a captured CUDA graph can be replayed with a new value every step (cosine schedule)
 __global__ void __launch_bounds__(OPT_THREADS)
 ema_kernel(const EmaRow* __restrict__ table, const float* __restrict__ momentum) {
   const EmaRow row = table[blockIdx.x];
   const float m = __ldg(momentum);
   const float om = 1.f - m;
-  const bool vec = ((reinterpret_cast<uintptr_t>(row.dst) | reinterpret_cast<uintptr_t>(row.src)) & 15) == 0;
+  const bool vec = ((reinterpret_cast<uintptr_t>(row.dst) | reinterpret_cast<uintptr_t>(row.src) |
+                     (reinterpret_cast<uintptr_t>(row.shadow) << 1)) & 15) == 0;
   if (vec) {
     const long long n4 = row.n / 4;
     float4* d = reinterpret_cast<float4*>(row.dst);
@@ -36,10 +38,19 @@ ema_kernel(const EmaRow* __restrict__ table, const float* __restrict__ momentum)
       const float4 b = __ldg(s + i);
       a.x = m * a.x + om * b.x; a.y = m * a.y + om * b.y; a.z = m * a.z + om * b.z; a.w = m * a.w + om * b.w;
       d[i] = a;
+      if (row.shadow) reinterpret_cast<uint2*>(row.shadow)[i] = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
     }
-    for (long long i = n4 * 4 + threadIdx.x; i < row.n; i += OPT_THREADS) row.dst[i] = m * row.dst[i] + om * row.src[i];
+    for (long long i = n4 * 4 + threadIdx.x; i < row.n; i += OPT_THREADS) {
+      const float v = m * row.dst[i] + om * row.src[i];
+      row.dst[i] = v;
+      if (row.shadow) row.shadow[i] = __float2bfloat16_rn(v);
+    }
   } else {
-    for (long long i = threadIdx.x; i < row.n; i += OPT_THREADS) row.dst[i] = m * row.dst[i] + om * row.src[i];
+    for (long long i = threadIdx.x; i < row.n; i += OPT_THREADS) {
+      const float v = m * row.dst[i] + om * row.src[i];
+      row.dst[i] = v;
+      if (row.shadow) row.shadow[i] = __float2bfloat16_rn(v);
+    }
   }
 }
 

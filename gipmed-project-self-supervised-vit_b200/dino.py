@@ -167,7 +167,7 @@ class ModelEma(nn.Module):
         self._table_key = None
         self._m_dev = self._m_host = None
         self._m_value = decay
-        self._pairs, self._others = [], []
+        self._pairs, self._others, self._shadowed = [], [], []
 
     def _build(self, model):
         pairs, others = [], []
@@ -178,13 +178,22 @@ class ModelEma(nn.Module):
                 others.append((e, s))
         key = tuple((e.data_ptr(), s.data_ptr(), e.numel()) for e, s in pairs)
         if key != self._table_key:
-            rows = []
+            # matrices the GEMMs read through a bf16 shadow get it refreshed by the same kernel pass
+            by_ptr = {p.data_ptr(): p for p in self.module.parameters() if p.ndim >= 2}
+            rows, shadowed = [], []
             for e, s in pairs:
+                param = by_ptr.get(e.data_ptr())
+                if param is not None and id(param) not in ops.shadows._d:
+                    param = None   # never read through a bf16 shadow (position table, weight-norm direction, ...)
+                sh = ops.shadows.shadow_for(param).data_ptr() if param is not None else 0
+                if param is not None:
+                    shadowed.append(param)
                 for off in range(0, e.numel(), _CHUNK):
-                    rows.append([e.data_ptr() + 4 * off, s.data_ptr() + 4 * off, min(_CHUNK, e.numel() - off)])
+                    rows.append([e.data_ptr() + 4 * off, s.data_ptr() + 4 * off, min(_CHUNK, e.numel() - off),
+                                 sh + 2 * off if sh else 0])
             self._table = torch.tensor(rows, dtype=torch.int64).to(pairs[0][0].device) if rows else None
             self._table_key = key
-            self._pairs, self._others = pairs, others
+            self._pairs, self._others, self._shadowed = pairs, others, shadowed
         return self._table
 
     def prepare(self, model, momentum=None):
@@ -214,8 +223,12 @@ class ModelEma(nn.Module):
                 e.mul_(m).add_(s.to(e.dtype), alpha=1.0 - m)
             else:
                 e.copy_(s)
+        fresh = {id(p) for p in self._shadowed}
         for p in self.module.parameters():
-            ops.shadows.invalidate(p)
+            if id(p) in fresh:
+                ops.shadows.mark_fresh(p)   # the EMA kernel rewrote the bf16 shadow together with the fp32 value
+            else:
+                ops.shadows.invalidate(p)
 
     @torch.no_grad()
     def update(self, model, momentum=None):

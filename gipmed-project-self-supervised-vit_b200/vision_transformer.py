@@ -243,10 +243,21 @@ class VisionTransformer(nn.Module):
         h0 = h // self.patch_embed.patch_size
         w0, h0 = w0 + 0.1, h0 + 0.1
         side = int(math.sqrt(N))
-        patch_pos_embed = F.interpolate(patch_pos_embed.reshape(1, side, side, dim).permute(0, 3, 1, 2),
-                                        scale_factor=(w0 / math.sqrt(N), h0 / math.sqrt(N)), mode="bicubic")
-        assert int(w0) == patch_pos_embed.shape[-2] and int(h0) == patch_pos_embed.shape[-1]
-        patch_pos_embed = patch_pos_embed.permute(0, 2, 3, 1).view(1, -1, dim)
+        # The resize is a fixed linear map of the table, so it is applied as a cached [Np_out, Np_in] matrix
+        # (built once per resolution by pushing the identity through the very same F.interpolate call) --
+        # one tiny matmul per step and direction instead of the slow bicubic kernels (0.5 ms per step).
+        key = (w, h, N, str(self.pos_embed.device))
+        cache = self.__dict__.setdefault("_interp_cache", {})
+        mat = cache.get(key)
+        if mat is None:
+            with torch.no_grad():
+                eye = torch.eye(N, device=self.pos_embed.device, dtype=torch.float32)
+                out = F.interpolate(eye.reshape(1, side, side, N).permute(0, 3, 1, 2),
+                                    scale_factor=(w0 / math.sqrt(N), h0 / math.sqrt(N)), mode="bicubic")
+                assert int(w0) == out.shape[-2] and int(h0) == out.shape[-1]
+                mat = out.permute(0, 2, 3, 1).reshape(-1, N).contiguous()   # [Np_out, Np_in]
+            cache[key] = mat
+        patch_pos_embed = torch.matmul(mat, patch_pos_embed[0].to(torch.float32)).to(patch_pos_embed.dtype).unsqueeze(0)
         return torch.cat((class_pos_embed.unsqueeze(0), patch_pos_embed), dim=1)
 
     def _pos_table(self, w, h):

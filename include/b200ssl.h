@@ -112,7 +112,7 @@ int b200ssl_center_update(float* center, const float* batch_sum, int K, long lon
 
 /* ---- K8: multi-tensor EMA / AdamW / grad-norm (train.py:1081 model_ema.update; :1063-1078 clip+step) --
  * `table` is a device array of int64 rows, one per <= 65536-element chunk:
- *   ema   : {dst*, src*, n}                    dst = m*dst + (1-m)*src
+ *   ema   : {dst*, src*, n, bf16_shadow*}      dst = m*dst + (1-m)*src; shadow (nullable) = bf16(dst), same pass
  *   sumsq : {g*, n}                            out = float[1+n_rows] workspace, out[0] = sum g^2 (fixed order)
  *   adamw : {p*, g*, m*, v*, n, decay, ema*, bf16_shadow*}   torch.optim.AdamW rule, grads pre-scaled by
  *           min(1, max_norm/(sqrt(*gnorm_sq)+1e-6)) when gnorm_sq != NULL and max_norm > 0. */
