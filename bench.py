@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=4, help="images per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pdl", action="store_true", help="enable programmatic dependent launch (A/B switch; off by default)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying "
                     "the captured CUDA graph of the step")
     args = ap.parse_args()
@@ -191,6 +192,8 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     import b200ssl
     from b200ssl import ops
+    if args.pdl:
+        b200ssl._lib.lib().b200ssl_set_pdl(1)
 
     torch.manual_seed(0)
     D = MODELS[args.model]["D"]

@@ -128,6 +128,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // set-up done: the next kernel may begin its own; then wait for the QKV producer
+  pdl_wait();
 
   if (warp == 16) {
     // ------------------------------------------------------------------ TMA producer
@@ -432,6 +434,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t T_S = tmem_base, T_DP = tmem_base + 128, T_DQ = tmem_base + 256, T_DK = tmem_base + 384,
                  T_DV = tmem_base + 448;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ control: TMA + MMA issue
@@ -777,14 +781,14 @@ extern "C" int b200ssl_attention_fwd(const void* qkv, void* out, float* lse2, in
       B200SSL_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       cfg = true;
     }
-    attention_fwd_kernel<1><<<grid, FWD_THREADS, smem, stream>>>(tq, to, a, num_items);
+    B200SSL_CUDA(launch_pdl(attention_fwd_kernel<1>, dim3(grid), dim3(FWD_THREADS), smem, stream, 1, tq, to, a, num_items));
   } else {
     static bool cfg = false;
     if (!cfg) {
       B200SSL_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       cfg = true;
     }
-    attention_fwd_kernel<2><<<grid, FWD_THREADS, smem, stream>>>(tq, to, a, num_items);
+    B200SSL_CUDA(launch_pdl(attention_fwd_kernel<2>, dim3(grid), dim3(FWD_THREADS), smem, stream, 1, tq, to, a, num_items));
   }
   B200SSL_CUDA(cudaGetLastError());
   return 0;
@@ -814,7 +818,7 @@ extern "C" int b200ssl_attention_bwd(const void* qkv, const void* out, const voi
       B200SSL_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       cfg = true;
     }
-    attention_bwd_kernel<1><<<grid, BWD_THREADS, smem, stream>>>(tq, tdo, tdq, a, num_items);
+    B200SSL_CUDA(launch_pdl(attention_bwd_kernel<1>, dim3(grid), dim3(BWD_THREADS), smem, stream, 1, tq, tdo, tdq, a, num_items));
   } else {
     const int smem = 12 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 2 * 256 * 2 * 4 + 256;
     static bool cfg = false;
@@ -822,7 +826,7 @@ extern "C" int b200ssl_attention_bwd(const void* qkv, const void* out, const voi
       B200SSL_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       cfg = true;
     }
-    attention_bwd_kernel<2><<<grid, BWD_THREADS, smem, stream>>>(tq, tdo, tdq, a, num_items);
+    B200SSL_CUDA(launch_pdl(attention_bwd_kernel<2>, dim3(grid), dim3(BWD_THREADS), smem, stream, 1, tq, tdo, tdq, a, num_items));
   }
   B200SSL_CUDA(cudaGetLastError());
   return 0;

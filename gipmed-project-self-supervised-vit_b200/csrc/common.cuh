@@ -36,6 +36,7 @@ void set_last_error(const char* fmt, ...);
   } while (0)
 
 int sm_count();
+bool pdl_enabled();  // programmatic dependent launch (b200ssl_set_pdl)
 
 // Host: encode a bf16/fp32 tiled tensor map. dims/strides innermost-first, strides in BYTES for
 // dims 1..rank-1 (dim 0 is contiguous). Returns 0 on success.
@@ -44,6 +45,42 @@ int make_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, int rank
                     int swizzle_bytes /* 0, 64 or 128 */);
 
 #ifdef __CUDACC__
+
+// ----------------------------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with the attribute may start (block scheduling, barrier /
+// TMEM set-up, descriptor prefetch) while its predecessor in the stream drains; it must execute pdl_wait()
+// before its first access to global memory, and pdl_launch_dependents() lets ITS successor start early.
+// Both are no-ops for a kernel launched without the attribute.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     int cluster_x, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ----------------------------------------------------------------------------------------------
 // small utilities

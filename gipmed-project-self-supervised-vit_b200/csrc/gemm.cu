@@ -193,6 +193,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only this CTA's shared / tensor memory: let the next kernel in the stream start its
+  // own set-up, then wait for the previous one's results before the first global access
+  pdl_launch_dependents();
+  pdl_wait();
 
   TileIter it;
 
@@ -748,19 +752,8 @@ static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   const int units = ((args.num_m_blocks + CL - 1) / CL) * args.num_n_blocks * args.k_splits;
   const int max_clusters = sm_count() / CL;
   const int clusters = units < max_clusters ? units : max_clusters;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(clusters * CL);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = CL > 1 ? 1 : 0;
-  B200SSL_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, CL, BS>, tmA, tmB, tmD, tmD2, args));
+  B200SSL_CUDA(launch_pdl(gemm_kernel<BN, EPI, CL, BS>, dim3(clusters * CL), dim3(GEMM_THREADS), Cfg::kSmemBytes, stream,
+                          CL, tmA, tmB, tmD, tmD2, args));
   return 0;
 }
 

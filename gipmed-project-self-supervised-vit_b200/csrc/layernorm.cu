@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
               long long rows, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int D = LPR * CPL * 8;
   constexpr int RPW = 32 / LPR;  // rows per warp
   const int lane = threadIdx.x & 31;
@@ -113,6 +115,8 @@ ln_bwd_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
               const float* __restrict__ w, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw,
               float* __restrict__ db, long long rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int D = LPR * CPL * 8;
   constexpr int RPW = 32 / LPR;
   __shared__ float s_dw[D];
@@ -216,12 +220,12 @@ static int launch_ln_fwd(const void* x, int x_f32, const float* w, const float* 
   const long long cap = static_cast<long long>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
   if (x_f32)
-    ln_fwd_kernel<LPR, CPL, float><<<static_cast<int>(blocks), 256, 0, s>>>(
-        static_cast<const float*>(x), w, b, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, eps);
+    B200SSL_CUDA(launch_pdl(ln_fwd_kernel<LPR, CPL, float>, dim3(static_cast<int>(blocks)), dim3(256), 0, s, 1,
+                            static_cast<const float*>(x), w, b, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, eps));
   else
-    ln_fwd_kernel<LPR, CPL, __nv_bfloat16><<<static_cast<int>(blocks), 256, 0, s>>>(
-        static_cast<const __nv_bfloat16*>(x), w, b, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, eps);
-  B200SSL_CUDA(cudaGetLastError());
+    B200SSL_CUDA(launch_pdl(ln_fwd_kernel<LPR, CPL, __nv_bfloat16>, dim3(static_cast<int>(blocks)), dim3(256), 0, s, 1,
+                            static_cast<const __nv_bfloat16*>(x), w, b, static_cast<__nv_bfloat16*>(y), mean, rstd, rows,
+                            eps));
   return 0;
 }
 template <int LPR, int CPL>
@@ -233,14 +237,13 @@ static int launch_ln_bwd(const void* x, int x_f32, const void* dy, const float* 
   const long long cap = static_cast<long long>(sm_count()) * 2;  // two resident blocks per SM, one wave
   if (blocks > cap) blocks = cap;
   if (x_f32)
-    ln_bwd_kernel<LPR, CPL, float><<<static_cast<int>(blocks), 256, 0, s>>>(
-        static_cast<const float*>(x), static_cast<const __nv_bfloat16*>(dy), w, mean, rstd,
-        static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dw, db, rows);
+    B200SSL_CUDA(launch_pdl(ln_bwd_kernel<LPR, CPL, float>, dim3(static_cast<int>(blocks)), dim3(256), 0, s, 1,
+                            static_cast<const float*>(x), static_cast<const __nv_bfloat16*>(dy), w, mean, rstd,
+                            static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dw, db, rows));
   else
-    ln_bwd_kernel<LPR, CPL, __nv_bfloat16><<<static_cast<int>(blocks), 256, 0, s>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), w, mean, rstd,
-        static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dw, db, rows);
-  B200SSL_CUDA(cudaGetLastError());
+    B200SSL_CUDA(launch_pdl(ln_bwd_kernel<LPR, CPL, __nv_bfloat16>, dim3(static_cast<int>(blocks)), dim3(256), 0, s, 1,
+                            static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), w, mean, rstd,
+                            static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dw, db, rows));
   return 0;
 }
 

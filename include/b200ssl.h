@@ -52,6 +52,10 @@ int b200ssl_set_gemm_cluster(int ctas);
 int b200ssl_set_gemm_stationary(int on);
 /* 1 (default) = choose 256 x 384 CTA-pair tiles automatically (wgrad; long-K plain / fp32-residual epilogues). */
 int b200ssl_set_gemm_wide(int on);
+/* 1 = GEMM / LayerNorm / attention kernels use programmatic dependent launch (default 0: measured slower in-step): each kernel's set-up (block
+ * scheduling, mbarrier + TMEM allocation, descriptor prefetch) overlaps the tail of its predecessor in the stream and
+ * it waits (griddepcontrol.wait) before its first global-memory access. 0 = plain stream order. */
+int b200ssl_set_pdl(int on);
 /* Developer instrumentation: device buffer of 8 uint64 cycle counters the GEMM kernels accumulate into (NULL = off). */
 int b200ssl_set_gemm_prof(void* counters);
 
