@@ -320,9 +320,24 @@ def main():
     ops.gemm = real_gemm
     gemm_ms = sum(a.elapsed_time(b) for a, b in gemm_events)
     gemm_tflops = gemm_f * B / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    # DRAM traffic of the same kernel family from the committed ncu capture of one step (profiles/): per launch,
+    # like `achieved` (family total per step / launches per step)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_step_summary_v3.json")) as f:
+            summ = json.load(f)
+        gk = [k for k in summ["kernels"] if k["kernel"].startswith("gemm_kernel")]
+        n_l = sum(k["launches_per_step"] for k in gk)
+        traffic = sum(k["dram_read_mb_per_step"] + k["dram_write_mb_per_step"] for k in gk) * 1e6 / max(n_l, 1)
+        traffic_src = ("profiles/r1_step_summary_v3.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the "
+                       f"{n_l:.0f} gemm_kernel launches of one step, divided by the launch count")
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN,EPI> (tcgen05, all Linear fprop/dgrad/wgrad)",
                 "achieved": gemm_tflops, "peak": peak_sus, "unit": "TFLOP/s", "frac": gemm_tflops / peak_sus,
-                "traffic": None, "peak_source": f"{peak_src} (sustained bf16; burst {peak_burst})",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "flops_per_launch": gemm_f * B / max(len(gemm_events), 1),
+                "peak_source": f"{peak_src} (sustained bf16; burst {peak_burst})",
                 "launches_per_step": len(gemm_events), "gemm_ms_per_step": gemm_ms,
                 "gemm_share_of_step": gemm_ms / ms_step,
                 "step_tflops": total_f * B / (ms_step / 1e3) / 1e12,
