@@ -46,6 +46,15 @@ struct GemmArgs {
   float* out_f32;
   long long ldd;
   unsigned long long* prof;  // developer instrumentation (null = off): per-role wait / busy cycle counters
+  // LayerNorm-fused mode (MODE 2): A = LN(x) is produced inside the kernel from the fp32 residual stream
+  const float* ln_x;
+  long long ln_ldx;
+  const float* ln_gamma;
+  const float* ln_beta;
+  float ln_eps;
+  __nv_bfloat16* ln_out;  // optional: the normalised rows (bf16, [M, K]) saved for the backward wgrad
+  float* ln_mean;         // optional: per-row statistics saved for the LayerNorm backward
+  float* ln_rstd;
 };
 
 constexpr int BLOCK_M = 128;
@@ -61,13 +70,19 @@ constexpr int kSmemBudget = 232448 - 2048;  // 227 KB opt-in limit minus barrier
 
 constexpr int kMaxPanelKBlocks = 6;  // B-stationary mode: the whole K extent (<= 384) of the B tile stays in smem
 
-template <int BN, int CL, bool BS = false>
+// MODE 0: A and B stream through the ring. MODE 1 (B-stationary): the B tile stays in a smem panel, the ring carries
+// A only. MODE 2 (LayerNorm-fused, A-stationary): the epilogue warps normalise 128 rows of the fp32 residual stream
+// straight into a bf16 A panel in the UMMA layout, every n block of those rows is computed from it, the ring
+// carries B only.
+template <int BN, int CL, int MODE = 0>
 struct GemmCfg {
+  static constexpr bool BS = MODE == 1;
+  static constexpr bool LN = MODE == 2;
   // per-CTA bytes of one k-block of B: (in CTA-pair mode half of) the B tile
   static constexpr int kBStageBytes = BN * BLOCK_K * 2 / CL;
   // B-stationary: B lives in a panel of kMaxPanelKBlocks k-blocks loaded once; the ring carries A only
-  static constexpr int kPanelBytes = BS ? kMaxPanelKBlocks * kBStageBytes : 0;
-  static constexpr int kStageBytes = BS ? A_STAGE_BYTES : A_STAGE_BYTES + kBStageBytes;
+  static constexpr int kPanelBytes = BS ? kMaxPanelKBlocks * kBStageBytes : LN ? kMaxPanelKBlocks * A_STAGE_BYTES : 0;
+  static constexpr int kStageBytes = BS ? A_STAGE_BYTES : LN ? kBStageBytes : A_STAGE_BYTES + kBStageBytes;
   static constexpr int kStagingBytes = NUM_EPI_GROUPS * STAGING_BYTES;
   // as many stages as fit: the operand feed is latency bound (bytes in flight per SM / ~1 us L2 latency),
   // so depth matters more than anything else; pair mode gets 5-6 stages where single-CTA mode gets 3-4
@@ -85,15 +100,21 @@ struct GemmCfg {
 // units rank, rank + group_size, ...; the groups of different n blocks sweep m in the same order at the same
 // pace, which keeps the L2 reuse of A.
 struct TileIter {
-  int t, step, total;        // default mode: linear tile index
+  int t, step, total;        // default mode: linear tile index; other modes: m unit index
   int n_blk, m_unit, ks;
-  template <bool BS>
+  template <int MODE>
   __device__ __forceinline__ void init(const GemmArgs& a, int cluster_id, int num_clusters, int num_m_units) {
-    if (BS) {
+    if (MODE == 1) {
       n_blk = cluster_id % a.num_n_blocks;
       const int rank = cluster_id / a.num_n_blocks;
       step = num_clusters / a.num_n_blocks + (n_blk < num_clusters % a.num_n_blocks ? 1 : 0);
       t = rank;
+      total = num_m_units;
+    } else if (MODE == 2) {
+      // LayerNorm-fused: a cluster owns whole m units and walks all their n blocks from one A panel
+      n_blk = 0;
+      t = cluster_id;
+      step = num_clusters;
       total = num_m_units;
     } else {
       t = cluster_id;
@@ -101,10 +122,10 @@ struct TileIter {
       total = num_m_units * a.num_n_blocks * a.k_splits;
     }
   }
-  template <bool BS>
+  template <int MODE>
   __device__ __forceinline__ bool valid(const GemmArgs& a, int num_m_units) {
     if (t >= total) return false;
-    if (BS) {
+    if (MODE == 1 || MODE == 2) {
       m_unit = t;
       ks = 0;
     } else {
@@ -114,7 +135,14 @@ struct TileIter {
     }
     return true;
   }
-  __device__ __forceinline__ void next() { t += step; }
+  template <int MODE>
+  __device__ __forceinline__ void next(const GemmArgs& a) {
+    if (MODE == 2) {
+      if (++n_blk == a.num_n_blocks) { n_blk = 0; t += step; }
+    } else {
+      t += step;
+    }
+  }
 };
 
 // CL = CTAs per cluster (1 or 2). CL == 2 is the CTA-pair mode (tcgen05 cta_group::2): the two CTAs of a
@@ -126,14 +154,17 @@ struct TileIter {
 //     arrive.expect_tx (both CTAs' bytes) + the peer's remote arrive;
 //   * the leader's tcgen05.commit is multicast to both CTAs (stage-empty / accumulator-full barriers);
 //   * both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.
-template <int BN, int EPI, int CL, bool BS>
+template <int BN, int EPI, int CL, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
             const GemmArgs args) {
-  using Cfg = GemmCfg<BN, CL, BS>;
+  using Cfg = GemmCfg<BN, CL, MODE>;
+  constexpr bool BS = MODE == 1;
+  constexpr bool LN = MODE == 2;
   constexpr int kStages = Cfg::kStages;
   static_assert(kStages >= 2, "smem ring too shallow");
+  static_assert(!LN || (CL == 2 && !is_wgrad_epi(EPI)), "the LayerNorm-fused mode is built for CTA pairs, fprop only");
   constexpr int kAccStages = Cfg::kAccStages;
   constexpr bool kWgrad = is_wgrad_epi(EPI);
   static_assert(!BS || !kWgrad, "B-stationary mode is for the non-split-K epilogues");
@@ -151,8 +182,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tmem_full = bars + 2 * kStages;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint64_t* consumed_bar = tmem_empty + 2;   // [kStages] CTA-pair wgrad: "MMA is done reading this stage"
-  uint64_t* panel_full = consumed_bar + kStages;  // [1] BS: the B panel has landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(panel_full + 1);
+  uint64_t* panel_full = consumed_bar + kStages;  // [1] BS: the B panel has landed; LN: the A panel is written
+  uint64_t* panel_empty = panel_full + 1;         // [1] LN: every MMA that reads the A panel has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(panel_empty + 1);
 
   const long long t_entry = args.prof ? clock64() : 0;
   const int warp = threadIdx.x >> 5;
@@ -177,7 +209,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&empty_bar[s], kWgrad ? (CL == 1 ? 1 + kEpiWarps : kEpiWarps) : 1);
       mbar_init(&consumed_bar[s], 1);
     }
-    mbar_init(panel_full, CL);
+    mbar_init(panel_full, LN ? CL * NUM_EPI_GROUPS * 4 : CL);  // LN: one arrive per transform warp of the pair
+    mbar_init(panel_empty, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], CL * kEpiWarps);  // one arrive per epilogue warp of every CTA of the pair
@@ -205,7 +238,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      it.init<BS>(args, cluster_id, num_clusters, num_m_units);
+      it.init<MODE>(args, cluster_id, num_clusters, num_m_units);
       if (BS && it.t < it.total) {
         // the stationary B tile: all k-blocks of this cluster's n block, (pair mode) own half of the rows
         constexpr int kHalfN = BN / CL;
@@ -227,7 +260,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (cta_rank == 0) mbar_expect_tx(panel_full, CL * args.k_blocks_total * Cfg::kBStageBytes);
         else mbar_arrive_leader(panel_full);
       }
-      for (; it.valid<BS>(args, num_m_units); it.next()) {
+      for (; it.valid<MODE>(args, num_m_units); it.next<MODE>(args)) {
         const int n_blk = it.n_blk;
         const int m_blk = it.m_unit * CL + cta_rank;
         const int kb0 = it.ks * args.k_blocks_per_split;
@@ -236,7 +269,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * Cfg::kStageBytes;
-          uint8_t* sB = sA + A_STAGE_BYTES;
+          uint8_t* sB = LN ? sA : sA + A_STAGE_BYTES;  // LN: the ring carries B only (A is produced in-kernel)
           const int k0 = kb * BLOCK_K;
           if (CL == 1) {
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -259,7 +292,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
             // CTA pair: own 128 rows of A, own half of the B tile; completion lands on the leader's barrier
             constexpr int kHalfN = BN / 2;
-            if (!args.a_mn) {
+            if (LN) {
+              // A comes from the in-kernel LayerNorm panel
+            } else if (!args.a_mn) {
               tma_load_2d_2sm(sA, &tmA, &full_bar[stage], k0, m0);
             } else {
 #pragma unroll
@@ -304,16 +339,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      it.init<BS>(args, cluster_id, num_clusters, num_m_units);
+      it.init<MODE>(args, cluster_id, num_clusters, num_m_units);
       if (BS && it.t < it.total) {
         mbar_wait(panel_full, 0);
         tcgen05_fence_after();
       }
-      long long w_full = 0, w_acc = 0;
+      long long w_full = 0, w_acc = 0, w_panel = 0;
+      uint32_t ln_phase = 0;
       const long long t_begin = clock64();
-      for (; it.valid<BS>(args, num_m_units); it.next()) {
+      for (; it.valid<MODE>(args, num_m_units); it.next<MODE>(args)) {
         const int kb0 = it.ks * args.k_blocks_per_split;
         const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks_total);
+        if (LN && it.n_blk == 0) {
+          // a new m unit: both CTAs' transform warps have written (and proxy-fenced) their A panels
+          const long long tp = clock64();
+          mbar_wait_cluster(panel_full, ln_phase);
+          w_panel += clock64() - tp;
+          ln_phase ^= 1;
+          tcgen05_fence_after();
+        }
         long long tw = clock64();
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         w_acc += clock64() - tw;
@@ -324,8 +368,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&full_bar[stage], phase);
           w_full += clock64() - tw;
           tcgen05_fence_after();
-          const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sB = BS ? smem_u32(panel + kb * Cfg::kBStageBytes) : sA + A_STAGE_BYTES;
+          const uint32_t sStage = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sA = LN ? smem_u32(panel + kb * A_STAGE_BYTES) : sStage;
+          const uint32_t sB = BS ? smem_u32(panel + kb * Cfg::kBStageBytes) : LN ? sStage : sStage + A_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(sA + k * a_kstep, a_lbo, 1024);
@@ -344,6 +389,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (CL == 1) umma_commit(&tmem_full[acc]);
         else umma_commit_2sm_mc(&tmem_full[acc], 3);
+        if (LN && it.n_blk == args.num_n_blocks - 1) umma_commit_2sm_mc(panel_empty, 3);  // the A panels may be rewritten
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
       if (args.prof) {
@@ -351,6 +397,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         atomicAdd(args.prof + 1, static_cast<unsigned long long>(w_acc));
         atomicAdd(args.prof + 2, static_cast<unsigned long long>(clock64() - t_begin));
         atomicAdd(args.prof + 3, 1ull);
+        if (LN) atomicAdd(args.prof + 6, static_cast<unsigned long long>(w_panel));
       }
     }
   } else if (warp >= 4) {
@@ -378,6 +425,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int cs_stage = 0;   // wgrad only: position in the smem ring (bias-gradient pass)
     uint32_t cs_phase = 0;
     int tile_iter = 0;
+    int ln_unit = 0;    // LN mode: m units transformed so far
 
     // aux operand (fp32 residual / bf16 residual / saved gelu'): fetched TWO owned chunks ahead -- across tile
     // boundaries -- into two alternating register sets, in a coalesced mapping (lane -> row k*8 + lane/4,
@@ -387,7 +435,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint4 aux_a[4], aux_b[4];
     uint32_t aux_par = 0;
     auto prefetch_aux = [&](uint4 (&dst)[4]) {
-      while (pit.valid<BS>(args, num_m_units)) {
+      while (pit.valid<MODE>(args, num_m_units)) {
         const int c = ((group - p_tile_iter) & 3) + NUM_EPI_GROUPS * p_i;
         if (c < kChunks) {
           const int prow0 = (pit.m_unit * CL + cta_rank) * BLOCK_M + q * 32;
@@ -405,19 +453,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           ++p_i;
           return;
         }
-        pit.next();
+        pit.next<MODE>(args);
         ++p_tile_iter;
         p_i = 0;
       }
     };
     if (kAux) {
-      pit.init<BS>(args, cluster_id, num_clusters, num_m_units);
+      pit.init<MODE>(args, cluster_id, num_clusters, num_m_units);
       prefetch_aux(aux_a);
       prefetch_aux(aux_b);
     }
 
-    it.init<BS>(args, cluster_id, num_clusters, num_m_units);
-    for (; it.valid<BS>(args, num_m_units); it.next(), ++tile_iter) {
+    it.init<MODE>(args, cluster_id, num_clusters, num_m_units);
+    for (; it.valid<MODE>(args, num_m_units); it.next<MODE>(args), ++tile_iter) {
       const int n_blk = it.n_blk;
       const int m_blk = it.m_unit * CL + cta_rank;
       const int m0 = m_blk * BLOCK_M, n0 = n_blk * BN;
@@ -531,6 +579,85 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (args.prof && threadIdx.x == 128) atomicAdd(args.prof + 6, static_cast<unsigned long long>(clock64() - te0));
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         continue;
+      }
+
+      if (LN && n_blk == 0) {
+        // ---- LayerNorm transform: this warp normalises 8 of the CTA's 128 rows of the fp32 residual stream into
+        // the bf16 A panel (UMMA K-major SW128 layout, k block = 64 columns), optionally saving the normalised
+        // rows and the statistics for backward. Lane l owns columns 4l..4l+3 of each 128-column third of the row.
+        constexpr int kK = 384;
+        static_assert(kMaxPanelKBlocks * BLOCK_K == kK, "the LayerNorm-fused mode is built for D = 384");
+        const long long tt0 = args.prof ? clock64() : 0;
+        if (ln_unit > 0) mbar_wait(panel_empty, (ln_unit - 1) & 1);  // MMAs of the previous unit are done with the panel
+        ++ln_unit;
+        const long long tt1 = args.prof ? clock64() : 0;
+        float g[12], bt[12];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float4 gv = __ldg(reinterpret_cast<const float4*>(args.ln_gamma + 128 * j) + lane);
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(args.ln_beta + 128 * j) + lane);
+          g[4 * j] = gv.x; g[4 * j + 1] = gv.y; g[4 * j + 2] = gv.z; g[4 * j + 3] = gv.w;
+          bt[4 * j] = bv.x; bt[4 * j + 1] = bv.y; bt[4 * j + 2] = bv.z; bt[4 * j + 3] = bv.w;
+        }
+        const uint32_t panel_s = smem_u32(panel);
+        const int wrow0 = (warp - 4) * 8;  // first tile row of this warp
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float4 xv[4][3];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int grow = m0 + wrow0 + half * 4 + i;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              xv[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (grow < args.M)
+                xv[i][j] = __ldg(reinterpret_cast<const float4*>(args.ln_x + static_cast<long long>(grow) * args.ln_ldx + 128 * j) + lane);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int trow = wrow0 + half * 4 + i;
+            const int grow = m0 + trow;
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) sum += (xv[i][j].x + xv[i][j].y) + (xv[i][j].z + xv[i][j].w);
+            const float mean = warp_sum(sum) * (1.f / kK);
+            float var = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const float a = xv[i][j].x - mean, b = xv[i][j].y - mean, c = xv[i][j].z - mean, d = xv[i][j].w - mean;
+              var += (a * a + b * b) + (c * c + d * d);
+            }
+            const float rstd = rsqrtf(warp_sum(var) * (1.f / kK) + args.ln_eps);
+            const bool live = grow < args.M;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const float y0 = (xv[i][j].x - mean) * rstd * g[4 * j] + bt[4 * j];
+              const float y1 = (xv[i][j].y - mean) * rstd * g[4 * j + 1] + bt[4 * j + 1];
+              const float y2 = (xv[i][j].z - mean) * rstd * g[4 * j + 2] + bt[4 * j + 2];
+              const float y3 = (xv[i][j].w - mean) * rstd * g[4 * j + 3] + bt[4 * j + 3];
+              const uint32_t p0 = live ? pack_bf16x2(y0, y1) : 0u, p1 = live ? pack_bf16x2(y2, y3) : 0u;
+              // column 4 lane + 128 j -> k block 2j + (lane >= 16), 16-byte chunk (lane % 16) / 2, half (lane & 1)
+              const int kb = 2 * j + (lane >> 4);
+              const uint32_t dst = panel_s + kb * A_STAGE_BYTES + trow * 128 +
+                                   (((((lane & 15) >> 1)) ^ (trow & 7)) << 4) + (lane & 1) * 8;
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(p0), "r"(p1) : "memory");
+              if (live && args.ln_out != nullptr)
+                *reinterpret_cast<uint2*>(args.ln_out + static_cast<long long>(grow) * kK + 128 * j + 4 * lane) = make_uint2(p0, p1);
+            }
+            if (live && lane == 0 && args.ln_mean != nullptr) {
+              args.ln_mean[grow] = mean;
+              args.ln_rstd[grow] = rstd;
+            }
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy panel writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader_release(panel_full);
+        if (args.prof && threadIdx.x == 128) {
+          atomicAdd(args.prof + 5, static_cast<unsigned long long>(clock64() - tt1));  // transform proper
+          atomicAdd(args.prof + 7, static_cast<unsigned long long>(tt1 - tt0));        // waiting for the panel
+        }
       }
 
       const int c_first = (group - tile_iter) & 3;
@@ -721,7 +848,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tcgen05_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // the peer may still arrive on / read from this CTA until it is done
-  if (args.prof && threadIdx.x == 32) {
+  if (args.prof && threadIdx.x == 32 && !LN) {
     atomicAdd(args.prof + 5, static_cast<unsigned long long>(clock64() - t_entry));
     atomicAdd(args.prof + 7, 1ull);
   }
@@ -739,20 +866,20 @@ static int g_gemm_stationary = 1;  // 0 disables the B-stationary mode (develope
 static int g_gemm_wide = 1;        // 0 disables the automatic choice of 256 x 384 CTA-pair tiles
 static unsigned long long* g_gemm_prof = nullptr;
 
-template <int BN, int EPI, int CL, bool BS>
+template <int BN, int EPI, int CL, int MODE>
 static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                           const CUtensorMap& tmD2, const GemmArgs& args, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CL, BS>;
+  using Cfg = GemmCfg<BN, CL, MODE>;
   static bool configured = false;
   if (!configured) {
-    B200SSL_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, CL, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200SSL_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, CL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::kSmemBytes));
     configured = true;
   }
   const int units = ((args.num_m_blocks + CL - 1) / CL) * args.num_n_blocks * args.k_splits;
   const int max_clusters = sm_count() / CL;
   const int clusters = units < max_clusters ? units : max_clusters;
-  B200SSL_CUDA(launch_pdl(gemm_kernel<BN, EPI, CL, BS>, dim3(clusters * CL), dim3(GEMM_THREADS), Cfg::kSmemBytes, stream,
+  B200SSL_CUDA(launch_pdl(gemm_kernel<BN, EPI, CL, MODE>, dim3(clusters * CL), dim3(GEMM_THREADS), Cfg::kSmemBytes, stream,
                           CL, tmA, tmB, tmD, tmD2, args));
   return 0;
 }
@@ -764,7 +891,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   if constexpr (BN == 384) {
     // 256 x 384 CTA-pair tiles: wgrad (both store orders), plain dgrad and the fp32-residual fprop
     if constexpr (EPI == EPI_BIAS || EPI == EPI_ATOMIC_F32 || EPI == EPI_ATOMIC_F32_T || EPI == EPI_BIAS_RES_F32) {
-      if (mode >= 2) return launch_gemm_cl<BN, EPI, 2, false>(tmA, tmB, tmD, tmD2, args, stream);
+      if (mode >= 2) return launch_gemm_cl<BN, EPI, 2, 0>(tmA, tmB, tmD, tmD2, args, stream);
     }
     set_last_error("gemm: block_n 384 needs the CTA-pair mode and epilogue 0, 4, 5 or 6 (got %d)", EPI);
     return -2;
@@ -773,10 +900,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     return -2;
   } else {
     if constexpr (!is_wgrad_epi(EPI) && (BN == 192 || BN == 256)) {
-      if (mode == 3) return launch_gemm_cl<BN, EPI, 2, true>(tmA, tmB, tmD, tmD2, args, stream);
+      if (mode == 3) return launch_gemm_cl<BN, EPI, 2, 1>(tmA, tmB, tmD, tmD2, args, stream);
     }
-    if (mode >= 2) return launch_gemm_cl<BN, EPI, 2, false>(tmA, tmB, tmD, tmD2, args, stream);
-    return launch_gemm_cl<BN, EPI, 1, false>(tmA, tmB, tmD, tmD2, args, stream);
+    if (mode >= 2) return launch_gemm_cl<BN, EPI, 2, 0>(tmA, tmB, tmD, tmD2, args, stream);
+    return launch_gemm_cl<BN, EPI, 1, 0>(tmA, tmB, tmD, tmD2, args, stream);
   }
 }
 
@@ -888,6 +1015,8 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
   args.out_f32 = static_cast<float*>(D);
   args.ldd = ldd;
   args.prof = g_gemm_prof;
+  args.ln_x = nullptr; args.ln_ldx = 0; args.ln_gamma = nullptr; args.ln_beta = nullptr; args.ln_eps = 0.f;
+  args.ln_out = nullptr; args.ln_mean = nullptr; args.ln_rstd = nullptr;
 
   // CTA-pair mode needs two m blocks and, for an MN-major B, a half tile made of whole 64-column chunks
   int cluster = (g_gemm_cluster == 2 && args.num_m_blocks > 1 && (!b_mn_major || bn % 128 == 0 || bn == 384)) ? 2 : 1;
@@ -929,6 +1058,71 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
     case 192: return dispatch_epi<192>(epilogue, tmA, tmB, tmD, tmD2, args, cluster, stream);
     case 384: return dispatch_epi<384>(epilogue, tmA, tmB, tmD, tmD2, args, cluster, stream);
     default: return dispatch_epi<256>(epilogue, tmA, tmB, tmD, tmD2, args, cluster, stream);
+  }
+}
+
+// LayerNorm fused into the GEMM that consumes it (Block.norm1 -> attn.qkv, Block.norm2 -> mlp.fc1; VT.pyc@L147,151):
+//   D = epilogue( LN(x) W^T + bias ),  x fp32 [M, 384] (the residual stream), W bf16 [N, 384].
+// The epilogue warps of each CTA pair normalise 2 x 128 rows straight into bf16 A panels in the UMMA layout; every n
+// block of those rows is computed from the panel while only W streams through the smem ring. ln_out (bf16 [M, 384],
+// contiguous) / mean / rstd (fp32 [M]) are optional side outputs for backward. Epilogues 0, 1, 7.
+extern "C" int b200ssl_ln_gemm(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
+                               void* ln_out, float* mean, float* rstd, const void* W, long long ldw, void* D,
+                               long long ldd, void* D2, const float* bias, int M, int N, int K, int epilogue,
+                               void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200SSL_CHECK(K == kMaxPanelKBlocks * BLOCK_K, -2, "ln_gemm: K=%d unsupported (the fused mode is built for D = 384)", K);
+  B200SSL_CHECK(M > BLOCK_M, -2, "ln_gemm: needs more than 128 rows (CTA-pair tiles), got %d", M);
+  B200SSL_CHECK(epilogue == EPI_BIAS || epilogue == EPI_BIAS_GELU || epilogue == EPI_BIAS_GELU_FWD, -2,
+                "ln_gemm: epilogue %d unsupported (0, 1 or 7)", epilogue);
+  B200SSL_CHECK(N % 192 == 0 || N % 256 == 0, -2, "ln_gemm: N=%d must be a multiple of 192 or 256", N);
+  B200SSL_CHECK(ldx % 4 == 0 && ldw % 8 == 0 && ldd % 8 == 0, -2, "ln_gemm: ldx %% 4, ldw %% 8, ldd %% 8 must be 0");
+  B200SSL_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(D) |
+                  reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+                  reinterpret_cast<uintptr_t>(ln_out) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0,
+                -2, "ln_gemm: operands must be 16-byte aligned");
+  B200SSL_CHECK((mean == nullptr) == (rstd == nullptr), -2, "ln_gemm: mean and rstd go together");
+  if (epilogue == EPI_BIAS_GELU) B200SSL_CHECK(D2 != nullptr, -2, "ln_gemm: GELU epilogue needs D2");
+  const int bn = N % 256 == 0 ? 256 : 192;
+
+  GemmArgs args;
+  args.M = M; args.N = N; args.K = K;
+  args.a_mn = 0; args.b_mn = 0;
+  args.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  args.num_n_blocks = N / bn;
+  args.k_splits = 1;
+  args.k_blocks_per_split = kMaxPanelKBlocks;
+  args.k_blocks_total = kMaxPanelKBlocks;
+  args.bias = bias;
+  args.aux = nullptr; args.ldaux = 0;
+  args.out_f32 = nullptr;
+  args.ldd = ldd;
+  args.prof = g_gemm_prof;
+  args.ln_x = x; args.ln_ldx = ldx; args.ln_gamma = gamma; args.ln_beta = beta; args.ln_eps = eps;
+  args.ln_out = static_cast<__nv_bfloat16*>(ln_out); args.ln_mean = mean; args.ln_rstd = rstd;
+
+  CUtensorMap tmB, tmD, tmD2;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t strides[2] = {2, static_cast<uint64_t>(ldw) * 2};
+    uint32_t box[2] = {64, static_cast<uint32_t>(bn / 2)};
+    if (int rc = make_tensor_map(&tmB, W, 2, 2, dims, strides, box, 128)) return rc;
+    dims[0] = N; dims[1] = M; box[0] = 32; box[1] = 32;
+    strides[1] = static_cast<uint64_t>(ldd) * 2;
+    if (int rc = make_tensor_map(&tmD, D, 2, 2, dims, strides, box, 64)) return rc;
+    if (int rc = make_tensor_map(&tmD2, D2 ? D2 : D, 2, 2, dims, strides, box, 64)) return rc;
+  }
+  if (bn == 256) {
+    switch (epilogue) {
+      case EPI_BIAS: return launch_gemm_cl<256, EPI_BIAS, 2, 2>(tmB, tmB, tmD, tmD2, args, stream);
+      case EPI_BIAS_GELU: return launch_gemm_cl<256, EPI_BIAS_GELU, 2, 2>(tmB, tmB, tmD, tmD2, args, stream);
+      default: return launch_gemm_cl<256, EPI_BIAS_GELU_FWD, 2, 2>(tmB, tmB, tmD, tmD2, args, stream);
+    }
+  }
+  switch (epilogue) {
+    case EPI_BIAS: return launch_gemm_cl<192, EPI_BIAS, 2, 2>(tmB, tmB, tmD, tmD2, args, stream);
+    case EPI_BIAS_GELU: return launch_gemm_cl<192, EPI_BIAS_GELU, 2, 2>(tmB, tmB, tmD, tmD2, args, stream);
+    default: return launch_gemm_cl<192, EPI_BIAS_GELU_FWD, 2, 2>(tmB, tmB, tmD, tmD2, args, stream);
   }
 }
 

@@ -246,6 +246,42 @@ def layernorm_fwd(x, w, b, eps):
     return y, mean, rstd
 
 
+# The LayerNorm-fused GEMM is correct (tests/gpu_checks/ln_gemm_check.py) but measured SLOWER than the separate
+# LayerNorm kernel + B-stationary GEMM (qkv: 175 vs 135 us, fc1: 237 vs 210 us at 100,864 rows): with one 96 KB A
+# panel per CTA the in-kernel normalisation (17 k cycles per 128 rows) cannot overlap the MMAs. Off by default.
+_LN_GEMM = {"on": False}
+
+
+def ln_gemm_ok(x, w16):
+    """The LayerNorm-fused GEMM covers the fp32 residual stream of a 384-wide encoder (ViT-S) in CTA-pair tiles."""
+    N = w16.shape[0]
+    return (_LN_GEMM["on"] and x.dtype == torch.float32 and x.shape[1] == 384 and x.shape[0] > 128
+            and x.is_contiguous() and (N % 192 == 0 or N % 256 == 0))
+
+
+def ln_linear_fwd(x, ln_w, ln_b, eps, w16, bias=None, gelu=False, keep=True):
+    """y = epilogue(LN(x) @ w16^T + bias) in ONE kernel (b200ssl_ln_gemm): the normalised rows never make a round
+    trip through HBM on their way into the GEMM. Returns (y | (gelu', gelu) | (None, gelu), ln, mean, rstd); with
+    keep=False (no-grad forward) ln / mean / rstd are not produced."""
+    M, K = x.shape
+    N = w16.shape[0]
+    dev = x.device
+    ln = torch.empty(M, K, dtype=_BF16, device=dev) if keep else None
+    mean = torch.empty(M, dtype=torch.float32, device=dev) if keep else None
+    rstd = torch.empty(M, dtype=torch.float32, device=dev) if keep else None
+    y = torch.empty(M, N, dtype=_BF16, device=dev)
+    h = torch.empty(M, N, dtype=_BF16, device=dev) if gelu is True else None
+    epi = EPI_BIAS if not gelu else (EPI_BIAS_GELU if gelu is True else EPI_BIAS_GELU_FWD)
+    _call("b200ssl_ln_gemm", x.data_ptr(), x.stride(0), ln_w.data_ptr(), ln_b.data_ptr(), float(eps), _ptr(ln),
+          _ptr(mean), _ptr(rstd), w16.data_ptr(), w16.stride(0), y.data_ptr(), y.stride(0), _ptr(h), _ptr(bias),
+          M, N, K, epi, _stream())
+    if gelu is True:
+        return (y, h), ln, mean, rstd
+    if gelu:
+        return (None, y), ln, mean, rstd
+    return y, ln, mean, rstd
+
+
 def layernorm_bwd(x, dy, w, mean, rstd, dres=None, weight=None, bias=None):
     """Gradients travel in bf16: dy, dres, dx are bf16 regardless of the stream dtype of x. dgamma / dbeta
     are accumulated into the parameters' gradient sinks when registered (then returned as None)."""
@@ -399,10 +435,15 @@ class AttentionCoreFn(torch.autograd.Function):
 
 
 # ---- residual half-blocks: plain functions shared by the per-block and whole-encoder autograd nodes ----
-def attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale):
+def attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale, keep=True):
     """x + proj(attention(qkv(LN(x)))) (VT.pyc@L147,150). Returns (y, saved-for-backward)."""
-    ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
-    qkv = linear_fwd(ln, bf16_of(qkv_w), _f32(qkv_b) if qkv_b is not None else None)
+    wq16 = bf16_of(qkv_w)
+    qb32 = _f32(qkv_b) if qkv_b is not None else None
+    if ln_gemm_ok(x, wq16):
+        qkv, ln, mean, rstd = ln_linear_fwd(x, _f32(ln_w), _f32(ln_b), eps, wq16, qb32, keep=keep)
+    else:
+        ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
+        qkv = linear_fwd(ln, wq16, qb32)
     att, lse2 = attention_fwd(qkv, B, N, H, scale)
     y = linear_fwd(att, bf16_of(proj_w), _f32(proj_b) if proj_b is not None else None, residual=x)
     return y, (x, mean, rstd, ln, qkv, att, lse2)
@@ -424,8 +465,14 @@ def attn_half_bwd(dy, saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale
 
 def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, keep=True):
     """x + fc2(gelu(fc1(LN(x)))) (VT.pyc@L151). keep=False (no-grad forward): gelu' is not produced."""
-    ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
-    pre, h = linear_fwd(ln, bf16_of(w1), _f32(b1) if b1 is not None else None, gelu=True if keep else "fwd_only")
+    w116 = bf16_of(w1)
+    b132 = _f32(b1) if b1 is not None else None
+    if ln_gemm_ok(x, w116):
+        (pre, h), ln, mean, rstd = ln_linear_fwd(x, _f32(ln_w), _f32(ln_b), eps, w116, b132,
+                                                 gelu=True if keep else "fwd_only", keep=keep)
+    else:
+        ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
+        pre, h = linear_fwd(ln, w116, b132, gelu=True if keep else "fwd_only")
     y = linear_fwd(h, bf16_of(w2), _f32(b2) if b2 is not None else None, residual=x)
     return y, (x, mean, rstd, ln, pre, h)
 
@@ -497,7 +544,7 @@ class EncoderFn(torch.autograd.Function):
         x = tok
         for i in range(depth):
             ln1w, ln1b, qw, qb, pw, pb, ln2w, ln2b, w1, b1, w2, b2 = params[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS]
-            x, s1 = attn_half_fwd(x, ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale)
+            x, s1 = attn_half_fwd(x, ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale, keep=keep)
             x, s2 = mlp_half_fwd(x, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1], keep=keep)
             if keep:
                 saved.append((s1, s2))

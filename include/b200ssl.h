@@ -46,6 +46,15 @@ int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const void* B, lo
                  void* D, long long ldd, void* D2, const float* bias, const void* aux, long long ldaux,
                  int M, int N, int K, int epilogue, int split_k, int block_n, void* stream);
 
+/* LayerNorm fused into the GEMM that consumes it (Block.norm1 -> attn.qkv VT.pyc@L147,121; Block.norm2 -> mlp.fc1
+ * @L151,99): D = epilogue(LN(x) W^T + bias) with x the fp32 residual stream [M, 384], W bf16 [N, 384] K-major.
+ * ln_out (bf16 [M,384] contiguous), mean, rstd (fp32 [M]) are optional side outputs for backward (NULL: skipped,
+ * e.g. the no-grad teacher). epilogue 0 (bias), 1 (GELU' -> D, GELU -> D2) or 7 (GELU only). M > 128, K == 384,
+ * N % 192 == 0 or N % 256 == 0. */
+int b200ssl_ln_gemm(const float* x, long long ldx, const float* gamma, const float* beta, float eps, void* ln_out,
+                    float* mean, float* rstd, const void* W, long long ldw, void* D, long long ldd, void* D2,
+                    const float* bias, int M, int N, int K, int epilogue, void* stream);
+
 /* 1 = independent CTAs; 2 (default) = CTA pairs (tcgen05 cta_group::2: 256-row tiles, each CTA loads half of B). */
 int b200ssl_set_gemm_cluster(int ctas);
 /* 1 (default) = for K <= 384 keep the B tile stationary in shared memory and stream only A; 0 = always stream both. */
