@@ -25,6 +25,7 @@ SIGNATURES = {
     "b200ssl_set_gemm_cluster": [_I],
     "b200ssl_set_gemm_stationary": [_I],
     "b200ssl_set_gemm_prof": [_P],
+    "b200ssl_set_attn_prof": [_P],
     "b200ssl_set_gemm_wide": [_I],
     "b200ssl_set_pdl": [_I],
     "b200ssl_layernorm_fwd": [_P, _I, _P, _P, _P, _P, _P, _L, _I, _F, _P],

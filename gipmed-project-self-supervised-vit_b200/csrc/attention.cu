@@ -28,6 +28,7 @@ struct AttnArgs {
   float* lse2;
   const __nv_bfloat16* out;   // bwd only
   const __nv_bfloat16* dout;  // bwd only
+  unsigned long long* prof;   // developer instrumentation (null = off): per-phase cycle counters of one softmax thread
 };
 
 // valid key range [lo, hi) for tile-row r
@@ -243,8 +244,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         return (c0 >= lo && c0 + 16 <= hi) ? 1 : 2;
       };
 
+      const bool prof_on = args.prof != nullptr && gtid == 0;
+      long long tp0 = prof_on ? clock64() : 0;
+      auto lap = [&](int idx) {
+        if (prof_on) {
+          const long long now = clock64();
+          atomicAdd(args.prof + slot * 8 + idx, static_cast<unsigned long long>(now - tp0));
+          tp0 = now;
+        }
+      };
       mbar_wait(&bar_s[slot], par);
       tcgen05_fence_after();
+      lap(0);
       // ---- pass 1: row max of the raw scores over this thread's column range
       float mx = -INFINITY;
 #pragma unroll 1
@@ -270,7 +281,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         }
       }
       xchg[hf * 128 + r] = mx;
+      lap(1);
       named_bar_sync(1 + slot, 256);  // also: every thread of the group is done with pass 1
+      lap(2);
       mx = fmaxf(mx, xchg[(hf ^ 1) * 128 + r]);
       const float m2 = mx == -INFINITY ? 0.f : mx * args.scale_log2;
       // ---- pass 2: p = 2^(s*c - m) -> bf16 pairs -> written over the already-consumed S columns
@@ -314,6 +327,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       tmem_st_wait();
       tcgen05_fence_before();
       mbar_arrive(&bar_p[slot]);
+      lap(3);
       named_bar_sync(1 + slot, 256);
       sum += xchg[256 + (hf ^ 1) * 128 + r];
       if (NT == 2) sum -= static_cast<float>(args.keys_n - args.N) * ex2_approx(-m2);  // zero-padded keys
@@ -325,8 +339,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         if (b < args.B) args.lse2[(static_cast<long long>(b) * args.H + head) * args.N + n] = m2 + log2f(sum);
       }
       // ---- epilogue: O / rowsum -> bf16 -> swizzled staging (the dead Q tile) -> TMA store
+      lap(4);
       mbar_wait(&bar_o[slot], par);
       tcgen05_fence_after();
+      lap(5);
       uint32_t v[32];
       tmem_ld_32x32b_x32(trow + O_COL + hf * 32, v);
       tmem_ld_wait();
@@ -350,6 +366,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         tma_store_wait_read<0>();      // staging (and with it the whole buffer, for this group) is reusable
         mbar_arrive(&buf_free[buf]);
       }
+      lap(6);
+      if (prof_on) atomicAdd(args.prof + slot * 8 + 7, 1ull);
     }
     if (gtid == 0) tma_store_wait_all<0>();
   }
@@ -734,7 +752,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+static unsigned long long* g_attn_prof = nullptr;
+
 static int setup_args(AttnArgs& a, int B, int N, int H, float scale, int& nt, int& groups) {
+  a.prof = g_attn_prof;
   B200SSL_CHECK(N >= 1 && N <= 256, -2, "attention: sequence length %d unsupported (1..256)", N);
   a.B = B; a.N = N; a.H = H;
   nt = N <= 128 ? 1 : 2;
@@ -758,6 +779,14 @@ static int make_bnd_map(CUtensorMap* tm, const void* base, int cols, int N, int 
 }  // namespace b200ssl
 
 using namespace b200ssl;
+
+// Developer instrumentation: device buffer of 16 uint64 counters (2 slots x 8) the forward kernel's first softmax
+// thread of each slot adds to: cycles in [0] wait for S, [1] max pass, [2] barrier, [3] exp pass, [4] barrier + lse,
+// [5] wait for O, [6] epilogue + store, [7] tiles. NULL = off.
+extern "C" int b200ssl_set_attn_prof(void* counters) {
+  b200ssl::g_attn_prof = static_cast<unsigned long long*>(counters);
+  return 0;
+}
 
 extern "C" int b200ssl_attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, int head_dim,
                                      float scale, void* stream_) {

@@ -67,6 +67,8 @@ int b200ssl_set_gemm_wide(int on);
 int b200ssl_set_pdl(int on);
 /* Developer instrumentation: device buffer of 8 uint64 cycle counters the GEMM kernels accumulate into (NULL = off). */
 int b200ssl_set_gemm_prof(void* counters);
+/* Same for attention forward: 16 uint64 (2 slots x {wait S, max pass, barrier, exp pass, barrier, wait O, epilogue, tiles}). */
+int b200ssl_set_attn_prof(void* counters);
 
 /* ---- K2: LayerNorm (Block.norm1/norm2 VT.pyc@L138,142,147,151; VisionTransformer.norm @L195,252) -----
  * x is bf16 (x_f32 = 0) or the fp32 residual stream (x_f32 = 1); y bf16; mean/rstd fp32 [rows].

@@ -1,0 +1,31 @@
+"""Developer probe: where one softmax thread of the attention-forward kernel spends its cycles, per phase."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch
+
+import b200ssl
+from b200ssl import ops
+
+lib = b200ssl._lib.lib()
+names = ["wait S", "max pass", "barrier", "exp pass", "barrier+lse", "wait O", "epilogue"]
+for B, N, H in ((512, 197, 6), (2560, 37, 6)):
+    qkv = torch.randn(B * N, 3 * H * 64, device="cuda").bfloat16()
+    for _ in range(3):
+        ops.attention_fwd(qkv, B, N, H, 0.125)
+    torch.cuda.synchronize()
+    prof = torch.zeros(16, dtype=torch.int64, device="cuda")
+    lib.b200ssl_set_attn_prof(prof.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ops.attention_fwd(qkv, B, N, H, 0.125)
+    e1.record()
+    torch.cuda.synchronize()
+    lib.b200ssl_set_attn_prof(None)
+    p = prof.view(2, 8).tolist()
+    print(f"B={B} N={N} H={H}: {e0.elapsed_time(e1)*1e3:.1f} us")
+    for s in range(2):
+        n = max(p[s][7], 1)
+        tot = sum(p[s][:7])
+        print(f"  slot {s}: {tot/n:7.0f} clk/tile  " + "  ".join(f"{nm} {p[s][i]/n:6.0f}" for i, nm in enumerate(names)))

@@ -34,11 +34,14 @@ def run(rows):
     wq, wp, w1, w2 = (r(3 * D, D) * .05).bfloat16(), (r(D, D) * .05).bfloat16(), (r(H4, D) * .05).bfloat16(), (r(D, H4) * .05).bfloat16()
     bq, bp, b1, b2 = r(3 * D), r(D), r(H4), r(D)
     res = r(rows, D)
+    y32 = torch.empty(rows, D, device="cuda")
     cases = {
         "qkv fwd": (lambda: ops.linear_fwd(x, wq, bq), 2 * rows * D * 3 * D),
         "proj fwd+res32": (lambda: ops.linear_fwd(x, wp, bp, residual=res), 2 * rows * D * D),
         "fc1 fwd+gelu": (lambda: ops.linear_fwd(x, w1, b1, gelu=True), 2 * rows * D * H4),
         "fc2 fwd+res32": (lambda: ops.linear_fwd(x4, w2, b2, residual=res), 2 * rows * D * H4),
+        "fc2 fwd+res32/384": (lambda: ops.gemm(x4, w2, y32, rows, D, H4, epi=ops.EPI_BIAS_RES_F32, bias=b2, aux=res,
+                                                block_n=384), 2 * rows * D * H4),
         "proj dgrad": (lambda: ops.linear_dgrad(x, wp), 2 * rows * D * D),
         "qkv dgrad": (lambda: ops.linear_dgrad(x3, wq), 2 * rows * D * 3 * D),
         "fc2 dgrad*aux": (lambda: ops.linear_dgrad(x, w2, dgelu_of=x4), 2 * rows * D * H4),
