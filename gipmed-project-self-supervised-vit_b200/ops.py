@@ -197,6 +197,14 @@ def linear_dgrad(dy, w16, dgelu_of=None):
     """dx = dy @ w16 ; optionally multiplied in the epilogue by ``dgelu_of`` = the saved gelu'(pre)."""
     M, N = dy.shape
     K = w16.shape[1]
+    if dgelu_of is None and N >= 8192 and (M // 128) * ((K + 255) // 256) < 64:
+        # a very long reduction with too few output tiles to fill the SMs (the DINO head's last layer: 65,536
+        # prototypes, 3072 x 256 output): split K across the machine into an fp32 buffer, then round once
+        acc = torch.zeros(M, K, dtype=torch.float32, device=dy.device)
+        gemm(dy, w16, acc, M, K, N, b_mn=True, epi=EPI_ATOMIC_F32, split_k=0)
+        dx = torch.empty(M, K, dtype=_BF16, device=dy.device)
+        cast_f32_to_bf16(acc, dx)
+        return dx
     dx = torch.empty(M, K, dtype=_BF16, device=dy.device)
     if dgelu_of is not None:
         gemm(dy, w16, dx, M, K, N, b_mn=True, epi=EPI_MUL_AUX, aux=dgelu_of)

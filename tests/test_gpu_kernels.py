@@ -204,3 +204,89 @@ def test_ema_and_adamw(ops):
     # bf16 shadow written by the optimiser matches the updated weights
     w = next(model.parameters())
     assert torch.equal(ops.bf16_of(w), w.detach().bfloat16())
+
+
+@pytest.mark.parametrize("rows,N,gelu,keep", [(300, 1152, False, True), (128 * 9 + 77, 1536, True, True),
+                                              (128 * 40 + 5, 1536, "fwd_only", False)])
+def test_ln_gemm_fused(ops, rows, N, gelu, keep):
+    """LayerNorm fused into its consumer GEMM (b200ssl_ln_gemm; off by default in the model, see ops._LN_GEMM)."""
+    import torch.nn.functional as F
+    g = torch.Generator(device="cuda").manual_seed(rows + N)
+    x = torch.randn(rows, 384, device="cuda", generator=g) * 2.0 + torch.randn(rows, 1, device="cuda", generator=g)
+    gw = 1.0 + 0.1 * torch.randn(384, device="cuda", generator=g)
+    gb = 0.1 * torch.randn(384, device="cuda", generator=g)
+    w = (torch.randn(N, 384, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    out, ln, mean, rstd = ops.ln_linear_fwd(x, gw, gb, 1e-6, w, b, gelu=gelu, keep=keep)
+    ln_ref = F.layer_norm(x, (384,), gw, gb, 1e-6)
+    pre_ref = ln_ref.bfloat16().float() @ w.float().t() + b
+    if gelu:
+        assert rel(out[1], F.gelu(pre_ref)) < 1e-2
+        if gelu is True:
+            pr = pre_ref.clone().requires_grad_(True)
+            F.gelu(pr).sum().backward()
+            assert rel(out[0], pr.grad) < 1e-2
+    else:
+        assert rel(out, pre_ref) < 1e-2
+    if keep:
+        assert rel(ln, ln_ref) < 1e-2
+        assert rel(mean, x.mean(1)) < 1e-5
+        assert rel(rstd, 1.0 / torch.sqrt(x.var(1, unbiased=False) + 1e-6)) < 1e-5
+    else:
+        assert ln is None and mean is None
+
+
+def test_gemm_tile_modes_agree(ops):
+    """The same problem through every tile mode the dispatcher can pick: streamed / B-stationary pairs, single CTAs,
+    256 x 384 pair tiles. All must agree with fp32 math (and therefore with each other)."""
+    import b200ssl
+    lib = b200ssl._lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M = 128 * 23 + 9
+    x = torch.randn(M, 384, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(1152, 384, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(1152, device="cuda", generator=g)
+    ref = x.float() @ w.float().t() + b
+    try:
+        for stationary, cluster in ((1, 2), (0, 2), (0, 1)):
+            lib.b200ssl_set_gemm_stationary(stationary)
+            lib.b200ssl_set_gemm_cluster(cluster)
+            assert rel(ops.linear_fwd(x, w, b), ref) < 1e-2, (stationary, cluster)
+    finally:
+        lib.b200ssl_set_gemm_stationary(1)
+        lib.b200ssl_set_gemm_cluster(2)
+    dy = torch.randn(M, 1152, device="cuda", generator=g).bfloat16()
+    ref_dx = dy.float() @ w.float()
+    try:
+        for wide in (1, 0):
+            lib.b200ssl_set_gemm_wide(wide)
+            assert rel(ops.linear_dgrad(dy, w), ref_dx) < 1e-2, wide          # K = 1152 -> 256 x 384 tiles when wide
+            dw, db = ops.linear_wgrad(dy, x)
+            assert rel(dw, dy.float().t() @ x.float()) < 1e-3 and rel(db, dy.float().sum(0)) < 1e-3, wide
+    finally:
+        lib.b200ssl_set_gemm_wide(1)
+
+
+def test_ema_refreshes_bf16_shadows(ops):
+    """The EMA kernel rewrites the teacher's bf16 weight shadows in the same pass: the next forward must see them."""
+    import b200ssl
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(384, 384).cuda()
+    ema = b200ssl.ModelEma(lin, decay=0.5)
+    x = torch.randn(256, 384, device="cuda").bfloat16()
+    ops.linear_fwd(x, ops.bf16_of(ema.module.weight), ema.module.bias.float())   # creates the teacher's shadow
+    with torch.no_grad():
+        lin.weight.add_(1.0)
+    ema.update(lin, momentum=0.5)
+    w_now = ema.module.weight.detach()
+    assert torch.equal(ops.bf16_of(ema.module.weight), w_now.bfloat16())        # refreshed by the kernel, not stale
+    y = ops.linear_fwd(x, ops.bf16_of(ema.module.weight), ema.module.bias.float())
+    assert rel(y, x.float() @ w_now.bfloat16().float().t() + ema.module.bias.float()) < 1e-2
+
+
+def test_dgrad_long_reduction_split_k(ops):
+    """dgrad of the head's last layer: K = 65,536 prototypes reduced into a 3072 x 256 output goes through split-K."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dy = (torch.randn(1024, 16384, device="cuda", generator=g) * 0.1).bfloat16()
+    w = (torch.randn(16384, 256, device="cuda", generator=g) * 0.05).bfloat16()
+    assert rel(ops.linear_dgrad(dy, w), dy.float() @ w.float()) < 1e-2

@@ -85,6 +85,25 @@ def test_teacher_temp_schedule_and_param_groups():
     assert all(p.ndim > 1 for p in groups[0]["params"])
 
 
+def test_position_table_resize_matches_oracle():
+    """interpolate_pos_encoding applies the bicubic resize as a cached matrix; it must equal the oracle's
+    F.interpolate call (VT.pyc@L213-233, incl. the +0.1 fudge) for every crop size the step uses."""
+    import b200ssl
+    from oracle import vision_transformer as ovt
+    torch.manual_seed(0)
+    ours, ref = b200ssl.vit_tiny(), ovt.vit_tiny()
+    ref.load_state_dict(ours.state_dict())
+    for size in (96, 224, 256, 160):
+        n = (size // 16) ** 2 + 1
+        x = torch.zeros(1, n, 192)
+        a = ours.interpolate_pos_encoding(x, size, size)
+        b = ref.interpolate_pos_encoding(x, size, size)
+        assert a.shape == b.shape and torch.allclose(a, b, atol=2e-6), size
+    # gradients flow back to pos_embed through the matrix form
+    ours.interpolate_pos_encoding(torch.zeros(1, 37, 192), 96, 96).sum().backward()
+    assert ours.pos_embed.grad is not None and ours.pos_embed.grad.abs().sum() > 0
+
+
 _DDP_SCRIPT = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
