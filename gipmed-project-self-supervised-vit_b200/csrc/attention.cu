@@ -614,11 +614,21 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     }
     bool stores_pending = false;
     int gp = 0;
+    const bool prof_on = args.prof != nullptr && leader;
+    long long tp0 = prof_on ? clock64() : 0;
+    auto lap = [&](int idx) {  // developer instrumentation: cycles of the leader math thread per phase
+      if (prof_on) {
+        const long long now = clock64();
+        atomicAdd(args.prof + idx, static_cast<unsigned long long>(now - tp0));
+        tp0 = now;
+      }
+    };
 
     for (int k = 0; k < n_my; ++k) {
       const int item = item_of(k);
       const int head = item % args.H, b0 = (item / args.H) * args.G;
       float delta[NT], lse2[NT];
+      lap(7);
       {
         const float* rc = rowc + (k & 1) * (NT * 128 * 2);
         mbar_wait(&bar_rowc_full[k & 1], (k >> 1) & 1);
@@ -629,6 +639,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         }
         mbar_arrive(&bar_rowc_free[k & 1]);
       }
+      lap(0);
 
       // 128x64 fp32 accumulator at TMEM column `tcol` -> bf16 -> staging tile `stage` -> TMA store at
       // (col, row0, b0). Staging tiles are the P / dS chunk buffers, dead at the points of use, so several
@@ -663,6 +674,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         for (int t = 0; t < NT; ++t, ++gp) {
           mbar_wait(bar_sdp, gp & 1);
           tcgen05_fence_after();
+          lap(1);
           const int col0 = qc * 32;             // first key column (within the tile) of this thread
           const bool active = col0 < ku;
           uint32_t pp[16], dd[16];              // 32 columns of P and dS, packed bf16 pairs
@@ -709,6 +721,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           }
           tcgen05_fence_before();
           mbar_arrive(bar_sdp_free);
+          lap(2);
           if (gp > 0) mbar_wait(bar_mma, (gp - 1) & 1);  // previous MMAs done with sP / sdS
           if (stores_pending) {  // tiles staged in sP / sdS: let those TMA stores finish reading
             if (leader) tma_store_wait_read<0>();
@@ -727,15 +740,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           }
           fence_proxy_async_smem();
           mbar_arrive(bar_pds);
+          lap(3);
 
           if (t == NT - 1) {
             // dK_u and dV_u are complete once this pair's MMAs retire
             mbar_wait(bar_mma, gp & 1);
             tcgen05_fence_after();
+            lap(4);
             store_tile(T_DK, sP, (args.H + head) * 64, NT == 1 ? 0 : u * 128);
             store_tile(T_DV, sP + TILE_BYTES, (2 * args.H + head) * 64, NT == 1 ? 0 : u * 128);
             // the dK/dV accumulators are re-used by the next key tile: order these reads before its MMAs
             tcgen05_fence_before();
+            lap(5);
           }
         }
       }
@@ -743,6 +759,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 #pragma unroll
       for (int t = 0; t < NT; ++t) store_tile(T_DQ + t * 64, sdS + t * TILE_BYTES, head * 64, NT == 1 ? 0 : t * 128);
       tcgen05_fence_before();
+      lap(6);
+      if (prof_on) atomicAdd(args.prof + 8, 1ull);
     }
     if (leader) tma_store_wait_all<0>();
   }
@@ -782,7 +800,9 @@ using namespace b200ssl;
 
 // Developer instrumentation: device buffer of 16 uint64 counters (2 slots x 8) the forward kernel's first softmax
 // thread of each slot adds to: cycles in [0] wait for S, [1] max pass, [2] barrier, [3] exp pass, [4] barrier + lse,
-// [5] wait for O, [6] epilogue + store, [7] tiles. NULL = off.
+// [5] wait for O, [6] epilogue + store, [7] tiles. NULL = off. The backward kernel's leader math thread adds:
+// [0] wait row constants, [1] wait S/dP, [2] P/dS math, [3] wait previous MMAs + smem writes, [4] wait dK/dV MMAs,
+// [5] dK/dV stores, [6] dQ stores, [7] item turnaround, [8] items.
 extern "C" int b200ssl_set_attn_prof(void* counters) {
   b200ssl::g_attn_prof = static_cast<unsigned long long*>(counters);
   return 0;

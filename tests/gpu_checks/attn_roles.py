@@ -29,3 +29,20 @@ for B, N, H in ((512, 197, 6), (2560, 37, 6)):
         n = max(p[s][7], 1)
         tot = sum(p[s][:7])
         print(f"  slot {s}: {tot/n:7.0f} clk/tile  " + "  ".join(f"{nm} {p[s][i]/n:6.0f}" for i, nm in enumerate(names)))
+
+bnames = ["wait rowc", "wait S/dP", "math", "wait prev MMA + smem", "wait dK/dV MMA", "dK/dV stores", "dQ stores", "turnaround"]
+for B, N, H in ((512, 197, 6), (2560, 37, 6)):
+    qkv = torch.randn(B * N, 3 * H * 64, device="cuda").bfloat16()
+    dout = torch.randn(B * N, H * 64, device="cuda").bfloat16()
+    out, lse2 = ops.attention_fwd(qkv, B, N, H, 0.125)
+    for _ in range(3):
+        ops.attention_bwd(qkv, out, dout, lse2, B, N, H, 0.125)
+    torch.cuda.synchronize()
+    prof = torch.zeros(16, dtype=torch.int64, device="cuda")
+    lib.b200ssl_set_attn_prof(prof.data_ptr())
+    ops.attention_bwd(qkv, out, dout, lse2, B, N, H, 0.125)
+    torch.cuda.synchronize()
+    lib.b200ssl_set_attn_prof(None)
+    p = prof.tolist()
+    n = max(p[8], 1)
+    print(f"bwd B={B} N={N} H={H}: {sum(p[:8])/n:7.0f} clk/item  " + "  ".join(f"{nm} {p[i]/n:6.0f}" for i, nm in enumerate(bnames)))
