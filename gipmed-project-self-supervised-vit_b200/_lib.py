@@ -32,6 +32,8 @@ SIGNATURES = {
     "b200ssl_layernorm_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
     "b200ssl_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "b200ssl_attention_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "b200ssl_attention_fwd_ws": [_P, _P, _P, _I, _I, _I, _I, _F, _P, _L, _P],
+    "b200ssl_attention_fwd_workspace_bytes": [_I, _I, _I],
     "b200ssl_patchify": [_P, _P, _I, _I, _I, _I, _I, _P],
     "b200ssl_assemble_tokens": [_P, _P, _P, _P, _I, _I, _I, _P],
     "b200ssl_assemble_tokens_bwd": [_P, _P, _P, _P, _I, _I, _I, _P],
@@ -48,7 +50,7 @@ SIGNATURES = {
     "b200ssl_adamw_multi_tensor": [_P, _I, _P, _P, _F, _F, _F, _F, _P],
     "b200ssl_sumsq_multi_tensor": [_P, _I, _P, _P],
 }
-_RESTYPES = {"b200ssl_last_error": c_char_p}
+_RESTYPES = {"b200ssl_last_error": c_char_p, "b200ssl_attention_fwd_workspace_bytes": c_longlong}
 
 
 def lib():
@@ -66,7 +68,7 @@ def lib():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(h, name)  # AttributeError here == header/library mismatch: fail loudly
         fn.argtypes = argtypes
-        fn.restype = c_int
+        fn.restype = _RESTYPES.get(name, c_int)
     _lib = h
     return h
 

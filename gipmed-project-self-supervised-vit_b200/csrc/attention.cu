@@ -19,7 +19,10 @@ namespace b200ssl {
 constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
 
 struct AttnArgs {
-  int B, N, H;       // batch, tokens per sequence, heads
+  int B, N, H;       // batch, query tokens per sequence handled by this launch, heads
+  int Nk;            // key tokens handled by this launch (== N except for the block-decomposed long-sequence path)
+  int Ns;            // tokens per sequence in memory (row stride of lse2 / out / dout); == N on the main path
+  int acc_dq, acc_dkv;  // bwd, long-sequence path: add this launch's dQ / dK,dV to what is already there
   int G;             // sequences packed per 128-row tile (NT == 1), else 1
   int rows;          // valid rows per tile group: G*N (NT == 1) or N (NT == 2)
   int keys_n;        // round_up(rows, 16): MMA N extent over keys
@@ -42,7 +45,7 @@ __device__ __forceinline__ void key_range(const AttnArgs& a, int nt, int r_in_gr
   } else {
     row_valid = r_in_group < a.N;
     lo = 0;
-    hi = a.N;
+    hi = a.Nk;
   }
 }
 
@@ -64,8 +67,8 @@ constexpr int FWD_BUF_BYTES = 6 * TILE_BYTES;
 
 template <int NT>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
-attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
-                     const AttnArgs args, const int num_items) {
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV,
+                     const __grid_constant__ CUtensorMap tmO, const AttnArgs args, const int num_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -145,8 +148,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           mbar_expect_tx(&load_full[buf], 6 * TILE_BYTES);
           for (int t = 0; t < 2; ++t) {
             tma_load_3d(q_tile(buf, t), &tmQKV, &load_full[buf], cq, t * 128, b0);
-            tma_load_3d(k_tile(buf, 0) + t * TILE_BYTES, &tmQKV, &load_full[buf], ck, t * 128, b0);
-            tma_load_3d(v_tile(buf, 0) + t * TILE_BYTES, &tmQKV, &load_full[buf], cv, t * 128, b0);
+            tma_load_3d(k_tile(buf, 0) + t * TILE_BYTES, &tmKV, &load_full[buf], ck, t * 128, b0);
+            tma_load_3d(v_tile(buf, 0) + t * TILE_BYTES, &tmKV, &load_full[buf], cv, t * 128, b0);
           }
         } else {
           const int n_valid = slot_item(round, 1) >= 0 ? 2 : 1;
@@ -330,13 +333,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       lap(3);
       named_bar_sync(1 + slot, 256);
       sum += xchg[256 + (hf ^ 1) * 128 + r];
-      if (NT == 2) sum -= static_cast<float>(args.keys_n - args.N) * ex2_approx(-m2);  // zero-padded keys
+      if (NT == 2) sum -= static_cast<float>(args.keys_n - args.Nk) * ex2_approx(-m2);  // zero-padded keys
       const float inv = sum > 0.f ? 1.f / sum : 0.f;
       if (hf == 0 && row_valid) {
         const int rr = NT == 1 ? r : t * 128 + r;
         const int b = b0 + (NT == 1 ? rr / args.N : 0);
         const int n = NT == 1 ? rr % args.N : rr;
-        if (b < args.B) args.lse2[(static_cast<long long>(b) * args.H + head) * args.N + n] = m2 + log2f(sum);
+        if (b < args.B) args.lse2[(static_cast<long long>(b) * args.H + head) * args.Ns + n] = m2 + log2f(sum);
       }
       // ---- epilogue: O / rowsum -> bf16 -> swizzled staging (the dead Q tile) -> TMA store
       lap(4);
@@ -395,8 +398,9 @@ constexpr int BWD_THREADS = 128 + BWD_MATH_THREADS;
 
 template <int NT>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
-attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                     const __grid_constant__ CUtensorMap tmDQKV, const AttnArgs args, const int num_items) {
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV,
+                     const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQKV,
+                     const __grid_constant__ CUtensorMap tmDKV, const AttnArgs args, const int num_items) {
   constexpr int SETS = NT == 1 ? 2 : 1;
   constexpr int PPI = NT * NT;                    // (key tile, query tile) pairs per item
   constexpr int SET_BYTES = 4 * NT * TILE_BYTES;  // Q | dO | K | V
@@ -423,8 +427,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmDQKV);
+    tma_prefetch_desc(&tmDKV);
     mbar_init(&bar_load[0], 1);
     mbar_init(&bar_load[1], 1);
     mbar_init(bar_sdp, 1);
@@ -477,8 +483,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           mbar_expect_tx(bar, 4 * NT * TILE_BYTES);
           for (int t = 0; t < NT; ++t) {
             tma_load_3d(sQ + t * TILE_BYTES, &tmQKV, bar, cq, t * 128, b0);
-            tma_load_3d(sK + t * TILE_BYTES, &tmQKV, bar, ck, t * 128, b0);
-            tma_load_3d(sV + t * TILE_BYTES, &tmQKV, bar, cv, t * 128, b0);
+            tma_load_3d(sK + t * TILE_BYTES, &tmKV, bar, ck, t * 128, b0);
+            tma_load_3d(sV + t * TILE_BYTES, &tmKV, bar, cv, t * 128, b0);
             tma_load_3d(sdO + t * TILE_BYTES, &tmDO, bar, cq, t * 128, b0);
           }
         }
@@ -492,7 +498,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       const uint32_t idesc_kv = make_idesc_bf16(128, 64, true, true);  // dK/dV: both MN-major
       auto issue_sdp = [&](int k, int p) {
         const int u = p / NT, t = p % NT;
-        const int ku = min(128, args.keys_n - u * 128);  // keys in this key tile (multiple of 16)
+        const int ku = max(16, min(128, args.keys_n - u * 128));  // keys in this key tile (multiple of 16; an empty
+                                                                   // tile of a short key block still runs on zeros)
         const uint32_t idesc_s = make_idesc_bf16(128, ku, false, false);
         const uint32_t base = smem_u32(set_base(k));
         const uint32_t q_t = base + t * TILE_BYTES, do_t = base + (NT + t) * TILE_BYTES;
@@ -509,7 +516,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       };
       auto issue_dqkv = [&](int k, int p) {
         const int u = p / NT, t = p % NT;
-        const int ku = min(128, args.keys_n - u * 128);
+        const int ku = max(16, min(128, args.keys_n - u * 128));
         const uint32_t base = smem_u32(set_base(k));
         const uint32_t q_t = base + t * TILE_BYTES, do_t = base + (NT + t) * TILE_BYTES;
         const uint32_t k_u = base + (2 * NT + u) * TILE_BYTES;
@@ -578,7 +585,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const int n = NT == 1 ? idx % args.N : idx;
         float delta = 0.f, l2 = INFINITY;  // invalid rows: lse2 = +inf so that P = 0
         if (row_valid && b < args.B) {
-          const long long off = ((static_cast<long long>(b) * args.N + n) * args.H + head) * 64;
+          const long long off = ((static_cast<long long>(b) * args.Ns + n) * args.H + head) * 64;
           const uint4* po = reinterpret_cast<const uint4*>(args.out + off);
           const uint4* pd = reinterpret_cast<const uint4*>(args.dout + off);
 #pragma unroll
@@ -591,7 +598,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
               delta += x.x * y.x + x.y * y.y;
             }
           }
-          l2 = args.lse2[(static_cast<long long>(b) * args.H + head) * args.N + n];
+          l2 = args.lse2[(static_cast<long long>(b) * args.H + head) * args.Ns + n];
         }
         rc[idx * 2] = delta;
         rc[idx * 2 + 1] = l2;
@@ -644,7 +651,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       // 128x64 fp32 accumulator at TMEM column `tcol` -> bf16 -> staging tile `stage` -> TMA store at
       // (col, row0, b0). Staging tiles are the P / dS chunk buffers, dead at the points of use, so several
       // stores are in flight at once; `stores_pending` makes the next writer of those buffers wait.
-      auto store_tile = [&](uint32_t tcol, uint8_t* stage, int gcol, int row0) {
+      auto store_tile = [&](uint32_t tcol, uint8_t* stage, const CUtensorMap* tm, bool accumulate, int gcol, int row0) {
         uint32_t v[16];
         tmem_ld_32x32b_x16(tcol + lane_off + qc * 16, v);
         tmem_ld_wait();
@@ -661,7 +668,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         fence_proxy_async_smem();
         named_bar_sync(1, BWD_MATH_THREADS);
         if (leader) {
-          tma_store_3d(&tmDQKV, stage, gcol, row0, b0);
+          if (accumulate) tma_reduce_add_3d(tm, stage, gcol, row0, b0);
+          else tma_store_3d(tm, stage, gcol, row0, b0);
           tma_store_commit();
         }
         stores_pending = true;
@@ -669,7 +677,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 
 #pragma unroll
       for (int u = 0; u < NT; ++u) {
-        const int ku = min(128, args.keys_n - u * 128);
+        const int ku = max(16, min(128, args.keys_n - u * 128));
 #pragma unroll
         for (int t = 0; t < NT; ++t, ++gp) {
           mbar_wait(bar_sdp, gp & 1);
@@ -747,8 +755,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             mbar_wait(bar_mma, gp & 1);
             tcgen05_fence_after();
             lap(4);
-            store_tile(T_DK, sP, (args.H + head) * 64, NT == 1 ? 0 : u * 128);
-            store_tile(T_DV, sP + TILE_BYTES, (2 * args.H + head) * 64, NT == 1 ? 0 : u * 128);
+            store_tile(T_DK, sP, &tmDKV, args.acc_dkv != 0, (args.H + head) * 64, NT == 1 ? 0 : u * 128);
+            store_tile(T_DV, sP + TILE_BYTES, &tmDKV, args.acc_dkv != 0, (2 * args.H + head) * 64, NT == 1 ? 0 : u * 128);
             // the dK/dV accumulators are re-used by the next key tile: order these reads before its MMAs
             tcgen05_fence_before();
             lap(5);
@@ -757,7 +765,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       }
       // dQ tiles (complete after the last pair; bar_mma already waited on above)
 #pragma unroll
-      for (int t = 0; t < NT; ++t) store_tile(T_DQ + t * 64, sdS + t * TILE_BYTES, head * 64, NT == 1 ? 0 : t * 128);
+      for (int t = 0; t < NT; ++t)
+        store_tile(T_DQ + t * 64, sdS + t * TILE_BYTES, &tmDQKV, args.acc_dq != 0, head * 64, NT == 1 ? 0 : t * 128);
       tcgen05_fence_before();
       lap(6);
       if (prof_on) atomicAdd(args.prof + 8, 1ull);
@@ -772,26 +781,146 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 
 static unsigned long long* g_attn_prof = nullptr;
 
-static int setup_args(AttnArgs& a, int B, int N, int H, float scale, int& nt, int& groups) {
+// Nq / Nk: query and key tokens of this launch (equal, and equal to the stride Ns, on the main path).
+static int setup_args(AttnArgs& a, int B, int Nq, int Nk, int Ns, int H, float scale, bool blocked, int& nt, int& groups) {
   a.prof = g_attn_prof;
-  B200SSL_CHECK(N >= 1 && N <= 256, -2, "attention: sequence length %d unsupported (1..256)", N);
-  a.B = B; a.N = N; a.H = H;
-  nt = N <= 128 ? 1 : 2;
-  a.G = nt == 1 ? 128 / N : 1;
+  B200SSL_CHECK(Nq >= 1 && Nq <= 256 && Nk >= 1 && Nk <= 256, -2, "attention: block of %d x %d tokens unsupported (1..256)",
+                Nq, Nk);
+  a.B = B; a.N = Nq; a.Nk = Nk; a.Ns = Ns; a.H = H;
+  a.acc_dq = 0; a.acc_dkv = 0;
+  // blocks of a long sequence always take the two-tile kernels (no packing): their zero-padding rules cover any
+  // Nq, Nk <= 256, including Nq != Nk
+  nt = (!blocked && Nq <= 128) ? 1 : 2;
+  a.G = nt == 1 ? 128 / Nq : 1;
   if (a.G > B) a.G = B;
-  a.rows = nt == 1 ? a.G * N : N;
-  a.keys_n = (a.rows + 15) / 16 * 16;
+  a.rows = nt == 1 ? a.G * Nq : Nq;
+  a.keys_n = ((nt == 1 ? a.rows : Nk) + 15) / 16 * 16;
   a.scale = scale;
   a.scale_log2 = scale * 1.4426950408889634f;
   groups = (B + a.G - 1) / a.G;
   return 0;
 }
 
-static int make_bnd_map(CUtensorMap* tm, const void* base, int cols, int N, int B, int nt, int G) {
-  uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
-  uint64_t strides[3] = {2, static_cast<uint64_t>(cols) * 2, static_cast<uint64_t>(cols) * 2 * N};
-  uint32_t box[3] = {64, static_cast<uint32_t>(nt == 1 ? N : 128), static_cast<uint32_t>(nt == 1 ? G : 1)};
+// 3-D map (cols, rows of this block, B) over a [B, Ns, cols] bf16 tensor whose base already points at the block's
+// first row; TMA clips rows >= n_rows and batches >= B.
+static int make_bnd_map(CUtensorMap* tm, const void* base, int cols, int n_rows, int Ns, int B, int nt, int G) {
+  uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(n_rows), static_cast<uint64_t>(B)};
+  uint64_t strides[3] = {2, static_cast<uint64_t>(cols) * 2, static_cast<uint64_t>(cols) * 2 * Ns};
+  uint32_t box[3] = {64, static_cast<uint32_t>(nt == 1 ? n_rows : 128), static_cast<uint32_t>(nt == 1 ? G : 1)};
   return make_tensor_map(tm, base, 2, 3, dims, strides, box, 128);
+}
+
+// one launch: queries [q0, q0 + Nq) against keys [k0, k0 + Nk) of every (batch, head)
+static int attention_fwd_block(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int B, int Ns, int H, int q0, int Nq,
+                               int k0, int Nk, float scale, bool blocked, cudaStream_t stream) {
+  AttnArgs a{};
+  int nt, groups;
+  if (int rc = setup_args(a, B, Nq, Nk, Ns, H, scale, blocked, nt, groups)) return rc;
+  a.lse2 = lse2 + q0;
+  const long long row = 3LL * H * 64;
+  CUtensorMap tq, tkv, to;
+  if (int rc = make_bnd_map(&tq, qkv + q0 * row, 3 * H * 64, Nq, Ns, B, nt, a.G)) return rc;
+  if (int rc = make_bnd_map(&tkv, qkv + k0 * row, 3 * H * 64, Nk, Ns, B, nt, a.G)) return rc;
+  if (int rc = make_bnd_map(&to, out + static_cast<long long>(q0) * H * 64, H * 64, Nq, Ns, B, nt, a.G)) return rc;
+  const int num_items = groups * H;
+  const int num_rounds = nt == 2 ? num_items : (num_items + 1) / 2;
+  const int grid = num_rounds < sm_count() ? num_rounds : sm_count();
+  const int smem = 2 * FWD_BUF_BYTES + 8192 + 1024;
+  if (nt == 1) {
+    static bool cfg = false;
+    if (!cfg) {
+      B200SSL_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      cfg = true;
+    }
+    B200SSL_CUDA(launch_pdl(attention_fwd_kernel<1>, dim3(grid), dim3(FWD_THREADS), smem, stream, 1, tq, tkv, to, a, num_items));
+  } else {
+    static bool cfg = false;
+    if (!cfg) {
+      B200SSL_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      cfg = true;
+    }
+    B200SSL_CUDA(launch_pdl(attention_fwd_kernel<2>, dim3(grid), dim3(FWD_THREADS), smem, stream, 1, tq, tkv, to, a, num_items));
+  }
+  return 0;
+}
+
+static int attention_bwd_block(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse2,
+                               __nv_bfloat16* dqkv, int B, int Ns, int H, int q0, int Nq, int k0, int Nk, float scale,
+                               bool blocked, bool acc_dq, bool acc_dkv, cudaStream_t stream) {
+  AttnArgs a{};
+  int nt, groups;
+  if (int rc = setup_args(a, B, Nq, Nk, Ns, H, scale, blocked, nt, groups)) return rc;
+  a.acc_dq = acc_dq; a.acc_dkv = acc_dkv;
+  a.lse2 = const_cast<float*>(lse2) + q0;
+  a.out = out + static_cast<long long>(q0) * H * 64;
+  a.dout = dout + static_cast<long long>(q0) * H * 64;
+  const long long row = 3LL * H * 64;
+  CUtensorMap tq, tkv, tdo, tdq, tdkv;
+  if (int rc = make_bnd_map(&tq, qkv + q0 * row, 3 * H * 64, Nq, Ns, B, nt, a.G)) return rc;
+  if (int rc = make_bnd_map(&tkv, qkv + k0 * row, 3 * H * 64, Nk, Ns, B, nt, a.G)) return rc;
+  if (int rc = make_bnd_map(&tdo, a.dout, H * 64, Nq, Ns, B, nt, a.G)) return rc;
+  if (int rc = make_bnd_map(&tdq, dqkv + q0 * row, 3 * H * 64, Nq, Ns, B, nt, a.G)) return rc;
+  if (int rc = make_bnd_map(&tdkv, dqkv + k0 * row, 3 * H * 64, Nk, Ns, B, nt, a.G)) return rc;
+  const int num_items = groups * H;
+  const int grid = num_items < sm_count() ? num_items : sm_count();
+  if (nt == 1) {
+    const int smem = 12 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 2 * 128 * 2 * 4 + 256;
+    static bool cfg = false;
+    if (!cfg) {
+      B200SSL_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      cfg = true;
+    }
+    B200SSL_CUDA(launch_pdl(attention_bwd_kernel<1>, dim3(grid), dim3(BWD_THREADS), smem, stream, 1, tq, tkv, tdo, tdq, tdkv, a,
+                            num_items));
+  } else {
+    const int smem = 12 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 2 * 256 * 2 * 4 + 256;
+    static bool cfg = false;
+    if (!cfg) {
+      B200SSL_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      cfg = true;
+    }
+    B200SSL_CUDA(launch_pdl(attention_bwd_kernel<2>, dim3(grid), dim3(BWD_THREADS), smem, stream, 1, tq, tkv, tdo, tdq, tdkv, a,
+                            num_items));
+  }
+  return 0;
+}
+
+// ---- long sequences (N > 256): key / query blocks of <= 256 tokens, partial softmax results merged by lse ----
+// out[b, n, h, :] = sum_j 2^(lse_j - L) O_j[b, n, h, :],  L = log2 sum_j 2^lse_j ; one warp per (b, n, h)
+__global__ void __launch_bounds__(256)
+attention_combine_kernel(const __nv_bfloat16* __restrict__ o_part, const float* __restrict__ lse_part,
+                         __nv_bfloat16* __restrict__ out, float* __restrict__ lse2, int B, int N, int H, int nblk) {
+  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = static_cast<long long>(B) * N * H;
+  if (w >= total) return;
+  const int h = static_cast<int>(w % H);
+  const long long bn = w / H;
+  const int n = static_cast<int>(bn % N);
+  const long long b = bn / N;
+  const long long lse_idx = (b * H + h) * N + n;
+  const long long o_idx = (bn * H + h) * 64 + 2 * lane;
+  const long long o_stride = static_cast<long long>(B) * N * H * 64, l_stride = static_cast<long long>(B) * H * N;
+  float m = -INFINITY;
+  for (int j = 0; j < nblk; ++j) m = fmaxf(m, lse_part[j * l_stride + lse_idx]);
+  float den = 0.f, a0 = 0.f, a1 = 0.f;
+  for (int j = 0; j < nblk; ++j) {
+    const float wj = ex2_approx(lse_part[j * l_stride + lse_idx] - m);
+    const float2 o = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o_part + j * o_stride + o_idx));
+    den += wj;
+    a0 += wj * o.x;
+    a1 += wj * o.y;
+  }
+  const float inv = 1.f / den;
+  *reinterpret_cast<uint32_t*>(out + o_idx) = pack_bf16x2(a0 * inv, a1 * inv);
+  if (lane == 0) lse2[lse_idx] = m + log2f(den);
+}
+
+static int num_blocks_for(int N) { return (N + 255) / 256; }
+static void block_range(int N, int nblk, int i, int& start, int& len) {  // near-equal blocks
+  const int base = N / nblk, rem = N % nblk;
+  start = i * base + (i < rem ? i : rem);
+  len = base + (i < rem ? 1 : 0);
 }
 
 }  // namespace b200ssl
@@ -808,75 +937,75 @@ extern "C" int b200ssl_set_attn_prof(void* counters) {
   return 0;
 }
 
-extern "C" int b200ssl_attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, int head_dim,
-                                     float scale, void* stream_) {
+// bytes of scratch b200ssl_attention_fwd_ws needs (0 for N <= 256): per key block a partial output and lse
+extern "C" long long b200ssl_attention_fwd_workspace_bytes(int B, int N, int H) {
+  if (N <= 256) return 0;
+  const long long nblk = num_blocks_for(N);
+  return nblk * (static_cast<long long>(B) * N * H * 64 * 2 + static_cast<long long>(B) * H * N * 4);
+}
+
+extern "C" int b200ssl_attention_fwd_ws(const void* qkv_, void* out_, float* lse2, int B, int N, int H, int head_dim,
+                                        float scale, void* workspace, long long workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   B200SSL_CHECK(head_dim == 64, -2, "attention: head_dim %d unsupported (64 only)", head_dim);
-  B200SSL_CHECK(B > 0 && H > 0, -2, "attention: empty problem");
-  AttnArgs a{};
-  int nt, groups;
-  if (int rc = setup_args(a, B, N, H, scale, nt, groups)) return rc;
-  a.lse2 = lse2;
-  CUtensorMap tq, to;
-  if (int rc = make_bnd_map(&tq, qkv, 3 * H * 64, N, B, nt, a.G)) return rc;
-  if (int rc = make_bnd_map(&to, out, H * 64, N, B, nt, a.G)) return rc;
-  const int num_items = groups * H;
-  const int num_rounds = nt == 2 ? num_items : (num_items + 1) / 2;
-  const int grid = num_rounds < sm_count() ? num_rounds : sm_count();
-  const int smem = 2 * FWD_BUF_BYTES + 8192 + 1024;
-  if (nt == 1) {
-    static bool cfg = false;
-    if (!cfg) {
-      B200SSL_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      cfg = true;
+  B200SSL_CHECK(B > 0 && H > 0 && N > 0, -2, "attention: empty problem");
+  const __nv_bfloat16* qkv = static_cast<const __nv_bfloat16*>(qkv_);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_);
+  if (N <= 256) return attention_fwd_block(qkv, out, lse2, B, N, H, 0, N, 0, N, scale, false, stream);
+  B200SSL_CHECK(N <= 4096, -2, "attention: sequence length %d unsupported (1..4096)", N);
+  const long long need = b200ssl_attention_fwd_workspace_bytes(B, N, H);
+  B200SSL_CHECK(workspace != nullptr && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 127) == 0, -2,
+                "attention: N=%d needs a 128B-aligned workspace of %lld bytes (b200ssl_attention_fwd_workspace_bytes)", N, need);
+  const int nblk = num_blocks_for(N);
+  const long long o_elems = static_cast<long long>(B) * N * H * 64, l_elems = static_cast<long long>(B) * H * N;
+  __nv_bfloat16* o_part = static_cast<__nv_bfloat16*>(workspace);
+  float* l_part = reinterpret_cast<float*>(o_part + nblk * o_elems);
+  for (int j = 0; j < nblk; ++j) {
+    int k0, nk;
+    block_range(N, nblk, j, k0, nk);
+    for (int i = 0; i < nblk; ++i) {
+      int q0, nq;
+      block_range(N, nblk, i, q0, nq);
+      if (int rc = attention_fwd_block(qkv, o_part + j * o_elems, l_part + j * l_elems, B, N, H, q0, nq, k0, nk, scale, true,
+                                       stream))
+        return rc;
     }
-    B200SSL_CUDA(launch_pdl(attention_fwd_kernel<1>, dim3(grid), dim3(FWD_THREADS), smem, stream, 1, tq, to, a, num_items));
-  } else {
-    static bool cfg = false;
-    if (!cfg) {
-      B200SSL_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      cfg = true;
-    }
-    B200SSL_CUDA(launch_pdl(attention_fwd_kernel<2>, dim3(grid), dim3(FWD_THREADS), smem, stream, 1, tq, to, a, num_items));
   }
+  const long long warps = static_cast<long long>(B) * N * H;
+  attention_combine_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, stream>>>(o_part, l_part, out, lse2, B, N,
+                                                                                               H, nblk);
   B200SSL_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int b200ssl_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2,
-                                     void* dqkv, int B, int N, int H, int head_dim, float scale, void* stream_) {
+extern "C" int b200ssl_attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, int head_dim,
+                                     float scale, void* stream) {
+  return b200ssl_attention_fwd_ws(qkv, out, lse2, B, N, H, head_dim, scale, nullptr, 0, stream);
+}
+
+extern "C" int b200ssl_attention_bwd(const void* qkv_, const void* out_, const void* dout_, const float* lse2,
+                                     void* dqkv_, int B, int N, int H, int head_dim, float scale, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   B200SSL_CHECK(head_dim == 64, -2, "attention: head_dim %d unsupported (64 only)", head_dim);
-  B200SSL_CHECK(B > 0 && H > 0, -2, "attention: empty problem");
-  AttnArgs a{};
-  int nt, groups;
-  if (int rc = setup_args(a, B, N, H, scale, nt, groups)) return rc;
-  a.lse2 = const_cast<float*>(lse2);
-  a.out = static_cast<const __nv_bfloat16*>(out);
-  a.dout = static_cast<const __nv_bfloat16*>(dout);
-  CUtensorMap tq, tdo, tdq;
-  if (int rc = make_bnd_map(&tq, qkv, 3 * H * 64, N, B, nt, a.G)) return rc;
-  if (int rc = make_bnd_map(&tdo, dout, H * 64, N, B, nt, a.G)) return rc;
-  if (int rc = make_bnd_map(&tdq, dqkv, 3 * H * 64, N, B, nt, a.G)) return rc;
-  const int num_items = groups * H;
-  const int grid = num_items < sm_count() ? num_items : sm_count();
-  if (nt == 1) {
-    const int smem = 12 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 2 * 128 * 2 * 4 + 256;
-    static bool cfg = false;
-    if (!cfg) {
-      B200SSL_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      cfg = true;
+  B200SSL_CHECK(B > 0 && H > 0 && N > 0, -2, "attention: empty problem");
+  const __nv_bfloat16* qkv = static_cast<const __nv_bfloat16*>(qkv_);
+  const __nv_bfloat16* out = static_cast<const __nv_bfloat16*>(out_);
+  const __nv_bfloat16* dout = static_cast<const __nv_bfloat16*>(dout_);
+  __nv_bfloat16* dqkv = static_cast<__nv_bfloat16*>(dqkv_);
+  if (N <= 256) return attention_bwd_block(qkv, out, dout, lse2, dqkv, B, N, H, 0, N, 0, N, scale, false, false, false, stream);
+  B200SSL_CHECK(N <= 4096, -2, "attention: sequence length %d unsupported (1..4096)", N);
+  // every (query block, key block) pair is exact given the row's global lse and delta; dQ accumulates over key
+  // blocks, dK / dV over query blocks (TMA reduce-add in bf16 after the first, plain store)
+  const int nblk = num_blocks_for(N);
+  for (int i = 0; i < nblk; ++i) {
+    int q0, nq;
+    block_range(N, nblk, i, q0, nq);
+    for (int j = 0; j < nblk; ++j) {
+      int k0, nk;
+      block_range(N, nblk, j, k0, nk);
+      if (int rc = attention_bwd_block(qkv, out, dout, lse2, dqkv, B, N, H, q0, nq, k0, nk, scale, true, j > 0, i > 0, stream))
+        return rc;
     }
-    B200SSL_CUDA(launch_pdl(attention_bwd_kernel<1>, dim3(grid), dim3(BWD_THREADS), smem, stream, 1, tq, tdo, tdq, a, num_items));
-  } else {
-    const int smem = 12 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 2 * 256 * 2 * 4 + 256;
-    static bool cfg = false;
-    if (!cfg) {
-      B200SSL_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      cfg = true;
-    }
-    B200SSL_CUDA(launch_pdl(attention_bwd_kernel<2>, dim3(grid), dim3(BWD_THREADS), smem, stream, 1, tq, tdo, tdq, a, num_items));
   }
-  B200SSL_CUDA(cudaGetLastError());
   return 0;
 }

@@ -314,6 +314,14 @@ def layernorm_bwd(x, dy, w, mean, rstd, dres=None, weight=None, bias=None):
 def attention_fwd(qkv, B, N, H, scale):
     out = torch.empty(B * N, H * 64, dtype=_BF16, device=qkv.device)
     lse2 = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
+    if N > 256:
+        # long sequences (native 256^2 tiles: 257 tokens; ViT-S/8: 785): blocks of <= 256 queries x <= 256 keys
+        # through the same kernels, partial results merged by their log-sum-exp; needs scratch for the partials
+        nbytes = int(_lib.lib().b200ssl_attention_fwd_workspace_bytes(B, N, H))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
+        _call("b200ssl_attention_fwd_ws", qkv.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, N, H, 64, float(scale),
+              ws.data_ptr(), nbytes, _stream(), launches=((N + 255) // 256) ** 2 + 1)
+        return out, lse2
     _call("b200ssl_attention_fwd", qkv.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, N, H, 64, float(scale),
           _stream())
     return out, lse2
@@ -322,7 +330,7 @@ def attention_fwd(qkv, B, N, H, scale):
 def attention_bwd(qkv, out, dout, lse2, B, N, H, scale):
     dqkv = torch.empty_like(qkv)
     _call("b200ssl_attention_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse2.data_ptr(),
-          dqkv.data_ptr(), B, N, H, 64, float(scale), _stream())
+          dqkv.data_ptr(), B, N, H, 64, float(scale), _stream(), launches=((N + 255) // 256) ** 2)
     return dqkv
 
 

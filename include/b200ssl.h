@@ -87,6 +87,14 @@ int b200ssl_attention_fwd(const void* qkv, void* out, float* lse2, int B, int N,
                           float scale, void* stream);
 int b200ssl_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv,
                           int B, int N, int H, int head_dim, float scale, void* stream);
+/* Sequences longer than 256 tokens (the reference's native 256^2 tiles give 257; ViT-S/8 at 224^2 gives 785; up to
+ * 4096) are decomposed into blocks of <= 256 queries x <= 256 keys run through the same kernels: forward merges
+ * the per-key-block partial results by their log-sum-exp and needs scratch for them (query the size, pass a
+ * 128-byte aligned buffer); backward needs none (dQ accumulates over key blocks, dK/dV over query blocks through
+ * TMA reduce-add). b200ssl_attention_fwd == b200ssl_attention_fwd_ws with no workspace (N <= 256 only). */
+long long b200ssl_attention_fwd_workspace_bytes(int B, int N, int H);
+int b200ssl_attention_fwd_ws(const void* qkv, void* out, float* lse2, int B, int N, int H, int head_dim, float scale,
+                             void* workspace, long long workspace_bytes, void* stream);
 
 /* ---- K1 helpers: patch gathering and token assembly (PatchEmbed.forward VT.pyc@L167-170,
  *      prepare_tokens @L235-246). img [B,C,H,W] bf16 -> cols [B*Np, C*P*P] bf16 (then b200ssl_gemm);

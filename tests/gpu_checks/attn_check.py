@@ -11,6 +11,10 @@ h.b200ssl_last_error.restype = ctypes.c_char_p
 P, I, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 h.b200ssl_attention_fwd.argtypes = [P, P, P, I, I, I, I, F, P]
 h.b200ssl_attention_bwd.argtypes = [P, P, P, P, P, I, I, I, I, F, P]
+LL = ctypes.c_longlong
+h.b200ssl_attention_fwd_ws.argtypes = [P, P, P, I, I, I, I, F, P, LL, P]
+h.b200ssl_attention_fwd_workspace_bytes.argtypes = [I, I, I]
+h.b200ssl_attention_fwd_workspace_bytes.restype = LL
 
 
 def ck(rc):
@@ -37,7 +41,9 @@ def run(B, N, H, bench=False):
     out = torch.full((B, N, H * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
     lse2 = torch.zeros(B, H, N, device="cuda", dtype=torch.float32)
     s = torch.cuda.current_stream().cuda_stream
-    ck(h.b200ssl_attention_fwd(qkv.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, N, H, 64, scale, s))
+    nws = h.b200ssl_attention_fwd_workspace_bytes(B, N, H)
+    ws = torch.empty(max(nws, 16), dtype=torch.uint8, device="cuda")
+    ck(h.b200ssl_attention_fwd_ws(qkv.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, N, H, 64, scale, ws.data_ptr(), nws, s))
     torch.cuda.synchronize()
     qkv_ref = qkv.float().requires_grad_(True)
     o_ref, lse_ref = ref_attn(qkv_ref, B, N, H, scale)
@@ -64,7 +70,7 @@ def run(B, N, H, bench=False):
             dd = (gg[:, :, i].float() - gref[:, :, i]).abs().amax(-1)
             print(f"  {nm} err per n (b0,h0):", [round(x, 3) for x in dd[0, :, 0].cpu().tolist()[:40]])
     if bench:
-        for name, fn in (("fwd", lambda: h.b200ssl_attention_fwd(qkv.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, N, H, 64, scale, s)),
+        for name, fn in (("fwd", lambda: h.b200ssl_attention_fwd_ws(qkv.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, N, H, 64, scale, ws.data_ptr(), nws, s)),
                          ("bwd", lambda: h.b200ssl_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse2.data_ptr(), dqkv.data_ptr(), B, N, H, 64, scale, s))):
             for _ in range(3):
                 fn()
@@ -92,9 +98,14 @@ def main():
     ok &= run(64, 197, 6)     # 384 items: persistent CTAs take 2-3 items each
     ok &= run(700, 37, 6)     # 1404 packed items: ~9.5 per CTA, two operand sets in flight
     ok &= run(160, 100, 3)    # N <= 128 without packing
+    ok &= run(3, 257, 2)      # long sequences: native 256^2 tiles -> 257 tokens (2 x 2 blocks of 129 / 128)
+    ok &= run(2, 785, 3)      # ViT-S/8 at 224^2: 785 tokens (4 x 4 blocks)
+    ok &= run(40, 325, 6)     # 288^2 tiles, many items
     if "--bench" in sys.argv and ok:
         run(512, 197, 6, bench=True)
         run(2560, 37, 6, bench=True)
+        run(256, 257, 6, bench=True)
+        run(64, 785, 6, bench=True)
     print("ALL OK" if ok else "SOME FAILED")
     return 0 if ok else 1
 

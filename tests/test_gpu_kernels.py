@@ -121,10 +121,29 @@ def test_attention(ops, B, N, H):
     assert rel(dqkv, qr.grad) < 1.5e-2
 
 
-def test_attention_rejects_long_sequences(ops):
-    qkv = torch.zeros(300, 192, device="cuda", dtype=torch.bfloat16)
+@pytest.mark.parametrize("B,N,H", [(3, 257, 2), (2, 785, 3), (5, 325, 6)])
+def test_attention_long_sequences(ops, B, N, H):
+    """N > 256 (257 = the reference's native 256^2 tiles, 785 = ViT-S/8 at 224^2): block-decomposed path."""
+    g = torch.Generator(device="cuda").manual_seed(N)
+    qkv = torch.randn(B * N, 3 * H * 64, device="cuda", generator=g).bfloat16()
+    dout = torch.randn(B * N, H * 64, device="cuda", generator=g).bfloat16()
+    out, lse2 = ops.attention_fwd(qkv, B, N, H, 0.125)
+    qr = qkv.float().requires_grad_(True)
+    q, k, v = qr.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    a = (q @ k.transpose(-2, -1)) * 0.125
+    ref = (a.softmax(-1) @ v).transpose(1, 2).reshape(B * N, H * 64)
+    assert rel(out, ref) < 1e-2
+    assert rel(lse2 * math.log(2.0), torch.logsumexp(a, -1)) < 1e-4
+    ref.backward(dout.float())
+    dqkv = ops.attention_bwd(qkv, out, dout, lse2, B, N, H, 0.125)
+    assert not torch.isnan(dqkv.float()).any()
+    assert rel(dqkv, qr.grad) < 1.5e-2
+
+
+def test_attention_rejects_unsupported_lengths(ops):
+    qkv = torch.zeros(5000, 192, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="sequence length"):
-        ops.attention_fwd(qkv, 1, 300, 1, 0.125)
+        ops.attention_fwd(qkv, 1, 5000, 1, 0.125)
 
 
 @pytest.mark.parametrize("ncrops,B,K", [(2, 8, 1024), (4, 5, 4096), (12, 3, 65536)])

@@ -60,7 +60,7 @@ def test_state_dict_keys_match_oracle(libs):
                                                    "last_layer.weight_v"]
 
 
-@pytest.mark.parametrize("size,B", [(224, 4), (96, 6), (240, 2)])
+@pytest.mark.parametrize("size,B", [(224, 4), (96, 6), (240, 2), (256, 3)])   # 256: the reference's native tiles, 257 tokens
 def test_vit_forward_backward(libs, size, B):
     b200ssl, ovt, _ = libs
     ref, mine = _pair(b200ssl, ovt)
