@@ -346,3 +346,40 @@ extern "C" int b200ssl_weightnorm_bwd(const float* v, const float* g, const floa
   B200SSL_CUDA(cudaGetLastError());
   return 0;
 }
+
+// y[r, :] = x[r, :] * scale[r]   (bf16 rows, fp32 per-row scale): the branch gradient under stochastic depth
+// (drop_path VT.pyc@L66-74: the kept samples' branch is scaled by 1/keep, the dropped ones' by 0)
+namespace b200ssl {
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, uint4* __restrict__ y, long long rows,
+                  int vec_per_row) {
+  const long long total = rows * vec_per_row;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float s = __ldg(scale + i / vec_per_row);
+    const uint4 v = __ldg(x + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack_bf16x2(w[e]);
+      o[e] = pack_bf16x2(f.x * s, f.y * s);
+    }
+    y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+}  // namespace b200ssl
+
+extern "C" int b200ssl_scale_rows(const void* x, const float* scale, void* y, long long rows, int D, void* stream) {
+  B200SSL_CHECK(D % 8 == 0 && rows > 0, -2, "scale_rows: D=%d must be a multiple of 8", D);
+  B200SSL_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, -2,
+                "scale_rows: operands must be 16-byte aligned");
+  const long long total = rows * (D / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(b200ssl::sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  b200ssl::scale_rows_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), scale, static_cast<uint4*>(y), rows, D / 8);
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -45,6 +45,7 @@ struct GemmArgs {
   long long ldaux;
   float* out_f32;
   long long ldd;
+  const float* rowscale;     // EPI_BIAS_RES_F32 only (nullable): D = rowscale[row] * (acc + bias) + aux (stochastic depth)
   unsigned long long* prof;  // developer instrumentation (null = off): per-role wait / busy cycle counters
   // LayerNorm-fused mode (MODE 2): A = LN(x) is produced inside the kernel from the fp32 residual stream
   const float* ln_x;
@@ -673,6 +674,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (slab_bias && c < kChunks && lane < W) bias_r[i] = __ldg(args.bias + n0 + c * W + lane);
       }
 
+      // stochastic depth: per-row scale of the branch output (this lane's own row, and below the rows of its aux pieces)
+      const bool has_rs = EPI == EPI_BIAS_RES_F32 && args.rowscale != nullptr;
+      const float rs_own = (has_rs && row0 + lane < args.M) ? __ldg(args.rowscale + row0 + lane) : 1.f;
+
       const long long te0 = args.prof ? clock64() : 0;
       mbar_wait(&tmem_full[acc], acc_phase);
       if (args.prof && threadIdx.x == 128) atomicAdd(args.prof + 4, static_cast<unsigned long long>(clock64() - te0));
@@ -698,10 +703,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < 4; ++k) {
             uint4 a = cur[k];
             if (EPI == EPI_BIAS_RES_F32) {
-              a.x = __float_as_uint(__uint_as_float(a.x) + b4.x);
-              a.y = __float_as_uint(__uint_as_float(a.y) + b4.y);
-              a.z = __float_as_uint(__uint_as_float(a.z) + b4.z);
-              a.w = __float_as_uint(__uint_as_float(a.w) + b4.w);
+              float rk = 1.f;  // the bias belongs to the (scaled) branch, not to the residual
+              if (has_rs && row0 + k * 8 + (lane >> 2) < args.M) rk = __ldg(args.rowscale + row0 + k * 8 + (lane >> 2));
+              a.x = __float_as_uint(fmaf(rk, b4.x, __uint_as_float(a.x)));
+              a.y = __float_as_uint(fmaf(rk, b4.y, __uint_as_float(a.y)));
+              a.z = __float_as_uint(fmaf(rk, b4.z, __uint_as_float(a.z)));
+              a.w = __float_as_uint(fmaf(rk, b4.w, __uint_as_float(a.w)));
             }
             sts128(slab + sw64_offset(k * 8 + (lane >> 2), lane & 3), a);
           }
@@ -753,7 +760,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t w[4] = {a.x, a.y, a.z, a.w};
             if (kAuxF32) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) f[(4 * j + e) % W] += __uint_as_float(w[e]);
+              for (int e = 0; e < 4; ++e) f[(4 * j + e) % W] = fmaf(f[(4 * j + e) % W], rs_own, __uint_as_float(w[e]));
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -1015,6 +1022,7 @@ extern "C" int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const 
   args.out_f32 = static_cast<float*>(D);
   args.ldd = ldd;
   args.prof = g_gemm_prof;
+  args.rowscale = epilogue == EPI_BIAS_RES_F32 ? static_cast<const float*>(D2) : nullptr;
   args.ln_x = nullptr; args.ln_ldx = 0; args.ln_gamma = nullptr; args.ln_beta = nullptr; args.ln_eps = 0.f;
   args.ln_out = nullptr; args.ln_mean = nullptr; args.ln_rstd = nullptr;
 
@@ -1098,6 +1106,7 @@ extern "C" int b200ssl_ln_gemm(const float* x, long long ldx, const float* gamma
   args.out_f32 = nullptr;
   args.ldd = ldd;
   args.prof = g_gemm_prof;
+  args.rowscale = nullptr;
   args.ln_x = x; args.ln_ldx = ldx; args.ln_gamma = gamma; args.ln_beta = beta; args.ln_eps = eps;
   args.ln_out = static_cast<__nv_bfloat16*>(ln_out); args.ln_mean = mean; args.ln_rstd = rstd;
 

@@ -167,16 +167,26 @@ def gemm(A, B, D, M, N, K, *, a_mn=False, b_mn=False, epi=EPI_BIAS, D2=None, bia
           M, N, K, epi, split_k, block_n, _stream())
 
 
-def linear_fwd(x, w16, bias=None, residual=None, gelu=False):
+def scale_rows(x, rs):
+    """y[r, :] = x[r, :] * rs[r] (bf16 rows, fp32 per-row scale)."""
+    y = torch.empty_like(x)
+    _call("b200ssl_scale_rows", x.data_ptr(), rs.data_ptr(), y.data_ptr(), x.shape[0], x.shape[1], _stream())
+    return y
+
+
+def linear_fwd(x, w16, bias=None, residual=None, gelu=False, rowscale=None):
     """y = x @ w16^T (+bias) (+residual); with gelu=True returns (gelu'(pre), gelu(pre)) — the derivative is
     what backward needs, so it is saved instead of the pre-activation (one erf evaluation serves both).
     An fp32 ``residual`` selects the fp32-stream epilogue (fp32 output); bf16 residual -> bf16 output."""
     M, K = x.shape
     N = w16.shape[0]
     if residual is not None and residual.dtype == torch.float32:
+        # rowscale (fp32 [M], optional): y = residual + rowscale[row] * (x w^T + bias) -- stochastic depth
         y = torch.empty(M, N, dtype=torch.float32, device=x.device)
-        gemm(x, w16, y, M, N, K, epi=EPI_BIAS_RES_F32, bias=bias, aux=residual)
+        gemm(x, w16, y, M, N, K, epi=EPI_BIAS_RES_F32, bias=bias, aux=residual, D2=rowscale)
         return y
+    if rowscale is not None:
+        raise RuntimeError("linear_fwd: rowscale needs the fp32 residual epilogue")
     y = torch.empty(M, N, dtype=_BF16, device=x.device)
     if gelu == "fwd_only":
         # no-grad forward (teacher): gelu(pre) only, nothing saved for backward
@@ -451,7 +461,7 @@ class AttentionCoreFn(torch.autograd.Function):
 
 
 # ---- residual half-blocks: plain functions shared by the per-block and whole-encoder autograd nodes ----
-def attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale, keep=True):
+def attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale, keep=True, rs=None):
     """x + proj(attention(qkv(LN(x)))) (VT.pyc@L147,150). Returns (y, saved-for-backward)."""
     wq16 = bf16_of(qkv_w)
     qb32 = _f32(qkv_b) if qkv_b is not None else None
@@ -461,17 +471,18 @@ def attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, sca
         ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
         qkv = linear_fwd(ln, wq16, qb32)
     att, lse2 = attention_fwd(qkv, B, N, H, scale)
-    y = linear_fwd(att, bf16_of(proj_w), _f32(proj_b) if proj_b is not None else None, residual=x)
-    return y, (x, mean, rstd, ln, qkv, att, lse2)
+    y = linear_fwd(att, bf16_of(proj_w), _f32(proj_b) if proj_b is not None else None, residual=x, rowscale=rs)
+    return y, (x, mean, rstd, ln, qkv, att, lse2, rs)
 
 
 def attn_half_bwd(dy, saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale, ln_b=None, qkv_b=None,
                   proj_b=None):
     """dy: bf16 gradient of the half-block output. Returns (dx bf16, d_ln_w, d_ln_b, d_qkv_w, d_qkv_b,
     d_proj_w, d_proj_b); the residual gradient is added inside the LayerNorm-backward kernel."""
-    x, mean, rstd, ln, qkv, att, lse2 = saved
-    d_att = linear_dgrad(dy, bf16_of(proj_w))
-    d_pw, d_pb = linear_wgrad(dy, att, has_pb, proj_w, proj_b)
+    x, mean, rstd, ln, qkv, att, lse2, rs = saved
+    dyb = dy if rs is None else scale_rows(dy, rs)   # stochastic depth: the branch sees the scaled gradient
+    d_att = linear_dgrad(dyb, bf16_of(proj_w))
+    d_pw, d_pb = linear_wgrad(dyb, att, has_pb, proj_w, proj_b)
     d_qkv = attention_bwd(qkv, att, d_att, lse2, B, N, H, scale)
     d_ln = linear_dgrad(d_qkv, bf16_of(qkv_w))
     d_qw, d_qb = linear_wgrad(d_qkv, ln, has_qb, qkv_w, qkv_b)
@@ -479,7 +490,7 @@ def attn_half_bwd(dy, saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale
     return dx, d_lw, d_lb, d_qw, d_qb, d_pw, d_pb
 
 
-def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, keep=True):
+def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, keep=True, rs=None):
     """x + fc2(gelu(fc1(LN(x)))) (VT.pyc@L151). keep=False (no-grad forward): gelu' is not produced."""
     w116 = bf16_of(w1)
     b132 = _f32(b1) if b1 is not None else None
@@ -489,14 +500,15 @@ def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, keep=True):
     else:
         ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
         pre, h = linear_fwd(ln, w116, b132, gelu=True if keep else "fwd_only")
-    y = linear_fwd(h, bf16_of(w2), _f32(b2) if b2 is not None else None, residual=x)
-    return y, (x, mean, rstd, ln, pre, h)
+    y = linear_fwd(h, bf16_of(w2), _f32(b2) if b2 is not None else None, residual=x, rowscale=rs)
+    return y, (x, mean, rstd, ln, pre, h, rs)
 
 
 def mlp_half_bwd(dy, saved, ln_w, w1, w2, has_b1, has_b2, ln_b=None, b1=None, b2=None):
-    x, mean, rstd, ln, pre, h = saved
-    d_pre = linear_dgrad(dy, bf16_of(w2), dgelu_of=pre)
-    d_w2, d_b2 = linear_wgrad(dy, h, has_b2, w2, b2)
+    x, mean, rstd, ln, pre, h, rs = saved
+    dyb = dy if rs is None else scale_rows(dy, rs)
+    d_pre = linear_dgrad(dyb, bf16_of(w2), dgelu_of=pre)
+    d_w2, d_b2 = linear_wgrad(dyb, h, has_b2, w2, b2)
     d_ln = linear_dgrad(d_pre, bf16_of(w1))
     d_w1, d_b1 = linear_wgrad(d_pre, ln, has_b1, w1, b1)
     dx, d_lw, d_lb = layernorm_bwd(x, d_ln, _f32(ln_w), mean, rstd, dres=dy, weight=ln_w, bias=ln_b)
@@ -507,8 +519,8 @@ class AttnHalfFn(torch.autograd.Function):
     """First residual branch of a Block as one autograd node (standalone Block.forward path)."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale):
-        y, saved = attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale)
+    def forward(ctx, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale, rs=None):
+        y, saved = attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale, rs=rs)
         ctx.save_for_backward(*saved, ln_w, qkv_w, proj_w)
         ctx.meta = (B, N, H, scale, qkv_b is not None, proj_b is not None)
         return y
@@ -518,15 +530,15 @@ class AttnHalfFn(torch.autograd.Function):
         *saved, ln_w, qkv_w, proj_w = ctx.saved_tensors
         B, N, H, scale, has_qb, has_pb = ctx.meta
         dx, *g = attn_half_bwd(_g16(dy), saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale)
-        return (dx.to(dy.dtype), *g, None, None, None, None, None)
+        return (dx.to(dy.dtype), *g, None, None, None, None, None, None)
 
 
 class MlpHalfFn(torch.autograd.Function):
     """Second residual branch of a Block as one autograd node (standalone Block.forward path)."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, eps):
-        y, saved = mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps)
+    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, eps, rs=None):
+        y, saved = mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, rs=rs)
         ctx.save_for_backward(*saved, ln_w, w1, w2)
         ctx.meta = (b1 is not None, b2 is not None)
         return y
@@ -536,7 +548,7 @@ class MlpHalfFn(torch.autograd.Function):
         *saved, ln_w, w1, w2 = ctx.saved_tensors
         has_b1, has_b2 = ctx.meta
         dx, *g = mlp_half_bwd(_g16(dy), saved, ln_w, w1, w2, has_b1, has_b2)
-        return (dx.to(dy.dtype), *g, None)
+        return (dx.to(dy.dtype), *g, None, None)
 
 
 BLOCK_PARAMS = 12  # ln1 w,b | qkv w,b | proj w,b | ln2 w,b | fc1 w,b | fc2 w,b
@@ -553,15 +565,17 @@ class EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, tok, meta, *params):
-        B, N, H, scale, eps_list, norm_eps = meta
+        B, N, H, scale, eps_list, norm_eps = meta[:6]
+        rs_list = meta[6] if len(meta) > 6 else None   # stochastic depth: per block (rs_attn, rs_mlp) row scales or None
         depth = (len(params) - 2) // BLOCK_PARAMS
         keep = any(ctx.needs_input_grad)  # False under no_grad (teacher): nothing is retained
         saved = []
         x = tok
         for i in range(depth):
             ln1w, ln1b, qw, qb, pw, pb, ln2w, ln2b, w1, b1, w2, b2 = params[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS]
-            x, s1 = attn_half_fwd(x, ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale, keep=keep)
-            x, s2 = mlp_half_fwd(x, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1], keep=keep)
+            rs1, rs2 = rs_list[i] if rs_list is not None else (None, None)
+            x, s1 = attn_half_fwd(x, ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale, keep=keep, rs=rs1)
+            x, s2 = mlp_half_fwd(x, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1], keep=keep, rs=rs2)
             if keep:
                 saved.append((s1, s2))
         D = x.shape[1]
@@ -577,7 +591,7 @@ class EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        B, N, H, scale, eps_list, norm_eps = ctx.meta
+        B, N, H, scale, eps_list, norm_eps = ctx.meta[:6]
         params = ctx.params
         depth = (len(params) - 2) // BLOCK_PARAMS
         cls, mean, rstd = ctx.final

@@ -141,8 +141,21 @@ class Block(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=mlp_hidden_dim, act_layer=act_layer, drop=drop)
 
     def _fused_ok(self):
-        no_dp = isinstance(self.drop_path, nn.Identity) or not self.training or not self.drop_path.drop_prob
-        return no_dp and _is_plain_layernorm(self.norm1) and _is_plain_layernorm(self.norm2) and self.mlp._fusable()
+        return _is_plain_layernorm(self.norm1) and _is_plain_layernorm(self.norm2) and self.mlp._fusable()
+
+    def _drop_path_scales(self, B, N, device):
+        """Stochastic depth (VT.pyc@L66-85,150-151) for the fused path: one fp32 scale per token row and residual
+        branch -- mask[b] / keep, drawn exactly like drop_path() does (torch.rand of shape [B,1,1], attention branch
+        first) so that a seeded run matches the reference -- or (None, None) when the block drops nothing."""
+        dp = self.drop_path
+        if isinstance(dp, nn.Identity) or not self.training or not dp.drop_prob:
+            return None, None
+        keep = 1.0 - dp.drop_prob
+        out = []
+        for _ in range(2):
+            mask = (keep + torch.rand((B, 1, 1), dtype=torch.float32, device=device)).floor_()
+            out.append((mask.view(B) / keep).repeat_interleave(N).contiguous())
+        return out[0], out[1]
 
     def _param_list(self):
         a, m = self.attn, self.mlp
@@ -154,13 +167,14 @@ class Block(nn.Module):
         a = self.attn
         a._check(x2.shape[1])
         if not self._fused_ok():
-            raise NotImplementedError("b200ssl Block: stochastic depth / custom norm or activation layers are not "
-                                      "on the accelerated path (SURVEY.md §8f)")
+            raise NotImplementedError("b200ssl Block: custom norm or activation layers are not on the accelerated "
+                                      "path (SURVEY.md §8f)")
+        rs1, rs2 = self._drop_path_scales(B, N, x2.device)
         x2 = ops.AttnHalfFn.apply(x2, self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.proj.weight,
-                                  a.proj.bias, self.norm1.eps, B, N, a.num_heads, a.scale)
+                                  a.proj.bias, self.norm1.eps, B, N, a.num_heads, a.scale, rs1)
         m = self.mlp
         return ops.MlpHalfFn.apply(x2, self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight,
-                                   m.fc2.bias, self.norm2.eps)
+                                   m.fc2.bias, self.norm2.eps, rs2)
 
     def forward(self, x, return_attention=False):
         ops.require_cuda(x, "Block")
@@ -289,14 +303,17 @@ class VisionTransformer(nn.Module):
         blk0 = self.blocks[0]
         blk0.attn._check(tok.shape[1])
         if not (all(b._fused_ok() for b in self.blocks) and _is_plain_layernorm(self.norm)):
-            raise NotImplementedError("b200ssl VisionTransformer: stochastic depth / custom norm or activation "
-                                      "layers are not on the accelerated path (SURVEY.md §8f)")
+            raise NotImplementedError("b200ssl VisionTransformer: custom norm or activation layers are not on the "
+                                      "accelerated path (SURVEY.md §8f)")
         params = []
         for b in self.blocks:
             params += b._param_list()
         params += [self.norm.weight, self.norm.bias]
+        rs_list = [b._drop_path_scales(B, N, tok.device) for b in self.blocks]
+        if all(r[0] is None for r in rs_list):
+            rs_list = None
         meta = (B, N, blk0.attn.num_heads, blk0.attn.scale, [(b.norm1.eps, b.norm2.eps) for b in self.blocks],
-                self.norm.eps)
+                self.norm.eps, rs_list)
         # the reference normalises every token then keeps row 0 (@L252-253); only CLS rows are normalised here
         cls = ops.EncoderFn.apply(tok, meta, *params)
         return cls.to(x.dtype)

@@ -35,7 +35,8 @@ int b200ssl_device_check(void);
  *   a_mn_major / b_mn_major: 0 = operand stored [M|N, K] row-major (K-major), 1 = stored [K, M|N].
  *   epilogue: 0 D=acc+bias | 1 D=gelu'(acc+bias), D2=gelu(acc+bias) (exact erf) | 2 D=acc+bias+aux(bf16)
  *             3 D=acc*aux(bf16) | 4 D(fp32)+=acc split-K atomics, and bias (if non-null) is the OUTPUT
- *             db[M] += column sums of A (wgrad bias gradient) | 5 D(fp32)=acc+bias+aux(fp32) (residual stream)
+ *             db[M] += column sums of A (wgrad bias gradient) | 5 D(fp32)=acc+bias+aux(fp32) (residual stream; with
+ *             D2 != NULL, D2 is a fp32 per-row scale s[M] and D = s[row]*(acc+bias)+aux: stochastic depth)
  *             6 like 4 but stored TRANSPOSED: D(fp32)[n, m] += acc[m, n] (ldd >= M) and bias is the OUTPUT
  *             db[N] += column sums of B (wgrad of a layer with more inputs than outputs; needs block_n 384)
  *             7 D=gelu(acc+bias) only (no-grad forward, e.g. the teacher: nothing saved for backward)
@@ -109,6 +110,8 @@ int b200ssl_assemble_tokens_bwd(const void* dx, void* dy, float* dpos, float* dc
 /* out[c] (+)= sum_r x[r,c]; bf16 in, fp32 out (accumulate != 0 keeps the previous content). */
 int b200ssl_colsum(const void* x, long long ldx, float* out, long long rows, int ncols, int accumulate,
                    void* stream);
+/* y[r,:] = x[r,:] * scale[r] (bf16 rows, fp32 scale[rows]): the branch gradient under stochastic depth. */
+int b200ssl_scale_rows(const void* x, const float* scale, void* y, long long rows, int D, void* stream);
 int b200ssl_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 /* F.normalize(dim=-1, p=2, eps) (DINOHead.forward VT.pyc@L328): y = x / max(||x||, eps). */
 int b200ssl_l2norm_fwd(const void* x, void* y, float* norm, long long rows, int D, float eps, void* stream);

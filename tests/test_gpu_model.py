@@ -82,6 +82,33 @@ def test_vit_forward_backward(libs, size, B):
     assert not bad, bad
 
 
+def test_stochastic_depth_matches_oracle(libs):
+    """drop_path_rate > 0 in training mode (DINO trains the ViT-S student with 0.1; VT.pyc@L66-85,150-151): with the
+    same seed the fused path draws the same per-sample masks as the reference's DropPath modules."""
+    b200ssl, ovt, _ = libs
+    ref, mine = _pair(b200ssl, ovt, drop_path_rate=0.3)
+    ref.train()
+    mine.train()
+    x = torch.randn(24, 3, 96, 96, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9))
+    torch.manual_seed(1234)
+    out_ref = ref(x)
+    torch.manual_seed(1234)
+    out = mine(x.bfloat16())
+    assert rel(out, out_ref) < 1e-2
+    w = torch.randn_like(out_ref)
+    (out_ref * w).sum().backward()
+    (out.float() * w).sum().backward()
+    bad = [(n, cos(q.grad, p.grad)) for (n, p), (_, q) in zip(ref.named_parameters(), mine.named_parameters())
+           if cos(q.grad, p.grad) < 0.999]
+    assert not bad, bad
+    # the masks really dropped something: a different seed gives a different output
+    torch.manual_seed(99)
+    assert rel(mine(x.bfloat16()), out_ref) > 1e-2
+    # and eval mode is deterministic / mask free
+    mine.eval(), ref.eval()
+    assert rel(mine(x.bfloat16()), ref(x)) < 1e-2
+
+
 def test_vit_utilities(libs):
     b200ssl, ovt, _ = libs
     ref, mine = _pair(b200ssl, ovt)
