@@ -82,6 +82,41 @@ def test_vit_forward_backward(libs, size, B):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("name,size,B,kw", [("vit_small", 224, 3, {}),                   # BASELINE configs[1]
+                                            ("vit_base", 224, 2, {}),                    # configs[3]: D = 768, 12 heads
+                                            ("vit_small", 224, 2, {"patch_size": 8}),    # configs[4]: 785 tokens
+                                            ("vit_small", 96, 5, {"patch_size": 8})])    # ... and its 145-token crops
+def test_other_baseline_configs_forward_backward(libs, name, size, B, kw):
+    b200ssl, ovt, _ = libs
+    ref, mine = _pair(b200ssl, ovt, name=name, **kw)
+    g = torch.Generator(device="cuda").manual_seed(size + B)
+    x = torch.randn(B, 3, size, size, device="cuda", generator=g)
+    out_ref = ref(x)
+    out = mine(x.bfloat16())
+    assert out.shape == out_ref.shape
+    assert rel(out, out_ref) < 1e-2
+    w = torch.randn_like(out_ref)
+    (out_ref * w).sum().backward()
+    (out.float() * w).sum().backward()
+    bad = [(n, cos(q.grad, p.grad)) for (n, p), (_, q) in zip(ref.named_parameters(), mine.named_parameters())
+           if cos(q.grad, p.grad) < 0.999]
+    assert not bad, bad
+
+
+def test_frozen_encoder_embedding(libs):
+    """configs[4], second half: forward-only embedding of tiles under no_grad (the --extract_features flow,
+    train.py:530-533) -- nothing is saved for backward, outputs match the oracle."""
+    b200ssl, ovt, _ = libs
+    ref, mine = _pair(b200ssl, ovt, name="vit_small", patch_size=8)
+    ref.eval(), mine.eval()
+    x = torch.randn(6, 3, 224, 224, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    with torch.no_grad():
+        feats = mine(x.bfloat16())
+        feats_ref = ref(x)
+    assert feats.shape == (6, 384) and not feats.requires_grad
+    assert rel(feats, feats_ref) < 1e-2
+
+
 def test_stochastic_depth_matches_oracle(libs):
     """drop_path_rate > 0 in training mode (DINO trains the ViT-S student with 0.1; VT.pyc@L66-85,150-151): with the
     same seed the fused path draws the same per-sample masks as the reference's DropPath modules."""
