@@ -117,6 +117,20 @@ def test_frozen_encoder_embedding(libs):
     assert rel(feats, feats_ref) < 1e-2
 
 
+def test_embed_tiles_pipeline(libs):
+    """b200ssl.embed_tiles: host tiles -> pinned double-buffered H2D -> frozen encoder -> host features."""
+    b200ssl, ovt, _ = libs
+    ref, mine = _pair(b200ssl, ovt, name="vit_tiny")
+    tiles = torch.randn(37, 3, 224, 224, generator=torch.Generator().manual_seed(4))
+    feats = b200ssl.embed_tiles(mine, tiles, batch_size=16)          # 3 batches, ragged tail
+    assert feats.shape == (37, 192) and feats.dtype == torch.float32 and not feats.is_cuda
+    ref.eval()
+    with torch.no_grad():
+        feats_ref = ref(tiles.cuda()).cpu()
+    assert rel(feats, feats_ref) < 1e-2
+    assert rel(b200ssl.embed_tiles(mine, tiles.cuda(), batch_size=64), feats_ref) < 1e-2   # device-resident input
+
+
 def test_stochastic_depth_matches_oracle(libs):
     """drop_path_rate > 0 in training mode (DINO trains the ViT-S student with 0.1; VT.pyc@L66-85,150-151): with the
     same seed the fused path draws the same per-sample masks as the reference's DropPath modules."""

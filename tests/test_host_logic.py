@@ -104,6 +104,34 @@ def test_position_table_resize_matches_oracle():
     assert ours.pos_embed.grad is not None and ours.pos_embed.grad.abs().sum() > 0
 
 
+def test_feature_file_formats(tmp_path):
+    """The two on-disk formats of the frozen-encoder embedding flow, read back the way the reference reads them
+    (train.py:1203,1282 for <slide>_features.pt; datasets.py:1043-1092 for the MIL inference pickles)."""
+    import pickle
+    import numpy as np
+    import b200ssl
+    feats = torch.randn(5, 384)
+    arr = b200ssl.save_slide_features(str(tmp_path / "s_features.pt"), feats)
+    back = torch.load(str(tmp_path / "s_features.pt"), weights_only=False)
+    assert back.shape == (6, 384) and (back[0] == 0).all() and np.allclose(back[1:], feats.numpy())
+    assert np.array_equal(arr, back)
+    per_slide = [torch.randn(3, 384), torch.randn(7, 384)]
+    b200ssl.pack_mil_inference_file(str(tmp_path / "inf.data"), ["a.mrxs", "b.mrxs"], per_slide, targets=[1, 0])
+    with open(tmp_path / "inf.data", "rb") as fh:
+        data = pickle.load(fh)
+    assert len(data) == 6
+    labels, targets, scores, patch_scores, slide_names, features = data
+    assert features.shape == (2, 1, 7, 384) and patch_scores.shape == (2, 7) and list(slide_names) == ["a.mrxs", "b.mrxs"]
+    # the reference finds the tile count of a slide as the first NaN of feature 0 (datasets.py:1088-1092)
+    for i, m in enumerate(per_slide):
+        nan_idx = np.argwhere(np.isnan(features[i, :, :, 0])).tolist()
+        first_nan = nan_idx[0][1] if nan_idx else features.shape[2]
+        assert first_nan == m.shape[0] and np.allclose(features[i, 0, :first_nan], m.numpy())
+    data8 = b200ssl.pack_mil_inference_file(str(tmp_path / "inf8.data"), ["a.mrxs"], per_slide[:1], targets=[1],
+                                            tile_locations=[[(0, 0), (256, 0), (0, 256)]])
+    assert len(data8) == 8 and data8[7].shape == (1, 3, 2)
+
+
 _DDP_SCRIPT = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
