@@ -9,7 +9,8 @@ There is no CPU, PyTorch-math or Triton fallback: ops raise if the library or an
 """
 from . import _lib, ops  # noqa: F401
 from .dino import (DINOLoss, FusedAdamW, GradBucketDataParallel, GraphedDinoStep, ModelEma,  # noqa: F401
-                   MultiCropWrapper, cosine_momentum, dino_step, param_groups_wd)
+                   MultiCropWrapper, apply_schedules, cancel_gradients_last_layer, cosine_momentum,
+                   cosine_scheduler, dino_step, param_groups_wd)
 from .features import embed_tiles, pack_mil_inference_file, save_slide_features  # noqa: F401
 from .vision_transformer import (Attention, Block, DINOHead, DropPath, Mlp, PatchEmbed,  # noqa: F401
                                  VisionTransformer, drop_path, trunc_normal_, vit_base, vit_small, vit_tiny)

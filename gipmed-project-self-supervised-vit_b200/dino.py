@@ -120,6 +120,37 @@ def cosine_momentum(it: int, total_iters: int, base: float = 0.996, final: float
     return final - (final - base) * (math.cos(math.pi * it / max(total_iters, 1)) + 1) / 2
 
 
+def cosine_scheduler(base_value, final_value, epochs, niter_per_ep, warmup_epochs=0, start_warmup_value=0.0):
+    """Per-iteration cosine schedule with linear warm-up (learning rate, weight decay and teacher momentum in DINO
+    training; the reference builds its LR schedule with timm's ``create_scheduler_v2``, train.py:883-898). The fused
+    optimiser reads lr / weight_decay from its param groups before every step -- also under CUDA-graph replay."""
+    warmup_iters = int(warmup_epochs * niter_per_ep)
+    warm = np.linspace(start_warmup_value, base_value, warmup_iters) if warmup_iters > 0 else np.array([])
+    iters = np.arange(epochs * niter_per_ep - warmup_iters)
+    sched = final_value + 0.5 * (base_value - final_value) * (1 + np.cos(np.pi * iters / max(len(iters), 1)))
+    out = np.concatenate((warm, sched))
+    assert len(out) == epochs * niter_per_ep
+    return out
+
+
+def apply_schedules(optimizer, it, lr_schedule=None, wd_schedule=None):
+    """Write iteration ``it`` of the schedules into the param groups (weight decay only where it is non-zero)."""
+    for group in optimizer.param_groups:
+        if lr_schedule is not None:
+            group["lr"] = float(lr_schedule[it])
+        if wd_schedule is not None and group.get("weight_decay", 0.0) > 0:
+            group["weight_decay"] = float(wd_schedule[it])
+
+
+def cancel_gradients_last_layer(epoch, model, freeze_last_layer, optimizer):
+    """DINO's first-epoch stabiliser: the prototype layer is not updated while ``epoch < freeze_last_layer``.
+    Upstream sets ``p.grad = None`` so the optimiser skips those tensors (no step, no decay, moments untouched);
+    gradients live in persistent flat buckets here, so the same effect is obtained by excluding the tensors from
+    the fused optimiser's chunk tables (``FusedAdamW.set_frozen``). Call once per epoch, before the step."""
+    frozen = [p for n, p in model.named_parameters() if "last_layer" in n] if epoch < freeze_last_layer else []
+    optimizer.set_frozen(frozen)
+
+
 # ------------------------------------------------------------------------------------------------
 # chunk tables for the multi-tensor kernels
 # ------------------------------------------------------------------------------------------------
@@ -250,9 +281,20 @@ class FusedAdamW(torch.optim.Optimizer):
         self._gnorm = None
         self._hyper_dev = self._hyper_host = None
         self.last_grad_norm_sq = None
+        self._frozen = frozenset()   # ids of parameters the step skips entirely (set_frozen)
+        self.table_version = 0       # bumped whenever the chunk tables change shape (captured graphs must follow)
+
+    def set_frozen(self, params):
+        """Parameters to leave completely untouched by ``step`` (no update, no decay, no moment update, not part
+        of the clipping norm) until the set changes again."""
+        new = frozenset(id(p) for p in params)
+        if new != self._frozen:
+            self._frozen = new
+            self._tables.clear()
+            self.table_version += 1
 
     def _table(self, gi, group):
-        params = [p for p in group["params"] if p.grad is not None]
+        params = [p for p in group["params"] if p.grad is not None and id(p) not in self._frozen]
         key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params)
         ent = self._tables.get(gi)
         if ent is not None and ent["key"] == key:
@@ -282,7 +324,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def _entries(self):
         ents = []
         for gi, group in enumerate(self.param_groups):
-            if any(p.grad is not None for p in group["params"]):
+            if any(p.grad is not None and id(p) not in self._frozen for p in group["params"]):
                 ents.append((gi, group, self._table(gi, group)))
         return ents
 
@@ -591,6 +633,7 @@ class GraphedDinoStep:
         self._multi = False
         self._pending_static = None
         self._temp = None
+        self._opt_version = -1
         self.loss = self.student_out = self.teacher_out = None
 
     def _set_defer(self, flag):
@@ -641,6 +684,7 @@ class GraphedDinoStep:
                 _step_update(self.student, self.teacher, self.loss_fn, self.opt, self.clip_grad, ents)
             self._set_defer(False)   # the flags only matter while capturing; eager steps stay self-contained
         self._temp = float(self.loss_fn.teacher_temp_schedule[epoch])
+        self._opt_version = self.opt.table_version
 
     def load(self, crops, non_blocking=True):
         """Copy a batch of crops into the graph's static input buffers (same stream as the replay)."""
@@ -651,7 +695,8 @@ class GraphedDinoStep:
     def __call__(self, crops=None, epoch=0, momentum=0.996):
         if crops is not None:
             self.load(crops)
-        if self._graph is None or float(self.loss_fn.teacher_temp_schedule[epoch]) != self._temp:
+        if (self._graph is None or float(self.loss_fn.teacher_temp_schedule[epoch]) != self._temp
+                or self.opt.table_version != self._opt_version):
             self._capture(epoch, momentum)      # the capture itself executes nothing: fall through to replay
         _step_prepare(self.student, self.teacher, self.opt, momentum)
         self._graph.replay()

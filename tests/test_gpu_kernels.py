@@ -309,3 +309,25 @@ def test_dgrad_long_reduction_split_k(ops):
     dy = (torch.randn(1024, 16384, device="cuda", generator=g) * 0.1).bfloat16()
     w = (torch.randn(16384, 256, device="cuda", generator=g) * 0.05).bfloat16()
     assert rel(ops.linear_dgrad(dy, w), dy.float() @ w.float()) < 1e-2
+
+
+def test_frozen_last_layer_is_skipped(ops):
+    """cancel_gradients_last_layer: while frozen, the prototype layer is untouched by the fused optimiser (no step,
+    no decay) and excluded from the clipping norm; everything else steps; unfreezing resumes it."""
+    import b200ssl
+    torch.manual_seed(1)
+    model = torch.nn.ModuleDict({"mlp": torch.nn.Linear(64, 64), "last_layer": torch.nn.Linear(64, 128, bias=False)}).cuda()
+    opt = b200ssl.FusedAdamW(b200ssl.param_groups_wd(model, 0.04), lr=1e-2)
+    for p in model.parameters():
+        p.grad = torch.randn_like(p)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    b200ssl.cancel_gradients_last_layer(0, model, 1, opt)
+    opt.step(max_grad_norm=3.0)
+    gn_frozen = opt.last_grad_norm_sq.item()
+    assert torch.equal(model["last_layer"].weight, before["last_layer.weight"])
+    assert not torch.equal(model["mlp"].weight, before["mlp.weight"])
+    expect = sum((p.grad.float() ** 2).sum().item() for n, p in model.named_parameters() if "last_layer" not in n)
+    assert abs(gn_frozen - expect) / expect < 1e-4
+    b200ssl.cancel_gradients_last_layer(1, model, 1, opt)
+    opt.step(max_grad_norm=3.0)
+    assert not torch.equal(model["last_layer"].weight, before["last_layer.weight"])

@@ -104,6 +104,19 @@ def test_position_table_resize_matches_oracle():
     assert ours.pos_embed.grad is not None and ours.pos_embed.grad.abs().sum() > 0
 
 
+def test_cosine_scheduler_and_apply():
+    import b200ssl
+    lr = b200ssl.cosine_scheduler(1e-3, 1e-6, epochs=10, niter_per_ep=7, warmup_epochs=2)
+    assert len(lr) == 70 and lr[0] == 0.0 and abs(lr[14] - 1e-3) < 1e-12 and abs(lr[-1] - 1e-6) < 1e-5
+    assert all(lr[i] <= lr[i + 1] for i in range(13)) and all(lr[i] >= lr[i + 1] for i in range(14, 69))
+    wd = b200ssl.cosine_scheduler(0.04, 0.4, epochs=10, niter_per_ep=7)
+    model = torch.nn.Linear(4, 4)
+    opt = torch.optim.AdamW(b200ssl.param_groups_wd(model, 0.04), lr=1.0)
+    b200ssl.apply_schedules(opt, 20, lr, wd)
+    assert opt.param_groups[0]["lr"] == float(lr[20]) and opt.param_groups[0]["weight_decay"] == float(wd[20])
+    assert opt.param_groups[1]["weight_decay"] == 0.0          # biases / norms stay undecayed
+
+
 def test_feature_file_formats(tmp_path):
     """The two on-disk formats of the frozen-encoder embedding flow, read back the way the reference reads them
     (train.py:1203,1282 for <slide>_features.pt; datasets.py:1043-1092 for the MIL inference pickles)."""
