@@ -106,7 +106,7 @@ class MultiCropWrapper(nn.Module):
         bounds = [i + 1 for i in range(len(sizes)) if i + 1 == len(sizes) or sizes[i + 1] != sizes[i]]
         start, outs = 0, []
         for end in bounds:
-            group = x[start] if end - start == 1 else torch.cat(list(x[start:end]))
+            group = x[start] if end - start == 1 else _cat_or_view(list(x[start:end]))
             out = self.backbone(group)
             if isinstance(out, tuple):
                 out = out[0]
@@ -114,6 +114,39 @@ class MultiCropWrapper(nn.Module):
             start = end
         feats = outs[0] if len(outs) == 1 else torch.cat(outs)
         return self.head(feats)
+
+
+def _cat_or_view(tensors):
+    """torch.cat along dim 0 -- or, when the crops already lie back to back in one allocation (GraphedDinoStep's
+    static inputs, ``alloc_crop_buffers``), a zero-copy view of that memory."""
+    t0 = tensors[0]
+    adjacent = all(t.is_contiguous() and t.dtype == t0.dtype and t.shape == t0.shape and not t.requires_grad
+                   and t.untyped_storage().data_ptr() == t0.untyped_storage().data_ptr() for t in tensors)
+    if adjacent:
+        for a, b in zip(tensors[:-1], tensors[1:]):
+            if b.storage_offset() != a.storage_offset() + a.numel():
+                adjacent = False
+                break
+    if not adjacent:
+        return torch.cat(tensors)
+    return torch.as_strided(t0, (len(tensors) * t0.shape[0],) + tuple(t0.shape[1:]), t0.stride(), t0.storage_offset())
+
+
+def alloc_crop_buffers(example_crops):
+    """Device buffers shaped like ``example_crops`` in which consecutive crops of equal resolution share one
+    allocation, so the multi-crop wrapper can feed each resolution group to the backbone without a concatenation
+    copy. Returns the list of per-crop views."""
+    out, i = [], 0
+    while i < len(example_crops):
+        j = i
+        while j + 1 < len(example_crops) and example_crops[j + 1].shape == example_crops[i].shape \
+                and example_crops[j + 1].dtype == example_crops[i].dtype:
+            j += 1
+        c = example_crops[i]
+        block = torch.empty((j - i + 1,) + tuple(c.shape), dtype=c.dtype, device=c.device)
+        out += [block[k] for k in range(j - i + 1)]
+        i = j + 1
+    return out
 
 
 def cosine_momentum(it: int, total_iters: int, base: float = 0.996, final: float = 1.0) -> float:
@@ -625,7 +658,7 @@ class GraphedDinoStep:
             raise TypeError("GraphedDinoStep needs b200ssl.FusedAdamW (device-resident step scalars)")
         self.student, self.teacher, self.loss_fn, self.opt = student, teacher_ema, loss_fn, optimizer
         self.clip_grad = clip_grad
-        self.static_crops = [torch.empty_like(c) for c in example_crops]
+        self.static_crops = alloc_crop_buffers(example_crops)   # equal-resolution crops back to back: no cat copy
         for dst, src in zip(self.static_crops, example_crops):
             dst.copy_(src)
         self._warmup = warmup

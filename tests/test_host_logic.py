@@ -104,6 +104,26 @@ def test_position_table_resize_matches_oracle():
     assert ours.pos_embed.grad is not None and ours.pos_embed.grad.abs().sum() > 0
 
 
+def test_crop_buffers_group_without_copy():
+    """alloc_crop_buffers lays equal-resolution crops back to back; the multi-crop wrapper then views each group
+    instead of concatenating it, and falls back to torch.cat for ordinary (separate) tensors."""
+    from b200ssl import dino
+    ex = [torch.zeros(4, 3, 8, 8) for _ in range(2)] + [torch.zeros(4, 3, 4, 4) for _ in range(3)]
+    bufs = dino.alloc_crop_buffers(ex)
+    assert [tuple(b.shape) for b in bufs] == [tuple(e.shape) for e in ex]
+    for i, b in enumerate(bufs):
+        b.fill_(float(i))
+    g = dino._cat_or_view(bufs[:2])
+    assert g.shape == (8, 3, 8, 8) and g.data_ptr() == bufs[0].data_ptr()          # a view, not a copy
+    assert torch.equal(g, torch.cat(bufs[:2]))
+    l = dino._cat_or_view(bufs[2:])
+    assert l.shape == (12, 3, 4, 4) and l.data_ptr() == bufs[2].data_ptr() and torch.equal(l, torch.cat(bufs[2:]))
+    sep = [torch.randn(4, 3, 4, 4) for _ in range(3)]
+    c = dino._cat_or_view(sep)
+    assert torch.equal(c, torch.cat(sep)) and c.data_ptr() != sep[0].data_ptr()
+    assert torch.equal(dino._cat_or_view([bufs[3], bufs[2]]), torch.cat([bufs[3], bufs[2]]))   # wrong order -> cat
+
+
 def test_cosine_scheduler_and_apply():
     import b200ssl
     lr = b200ssl.cosine_scheduler(1e-3, 1e-6, epochs=10, niter_per_ep=7, warmup_epochs=2)
