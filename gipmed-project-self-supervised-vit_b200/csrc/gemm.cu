@@ -75,7 +75,7 @@ constexpr int kMaxPanelKBlocks = 6;  // B-stationary mode: the whole K extent (<
 // A only. MODE 2 (LayerNorm-fused, A-stationary): the epilogue warps normalise 128 rows of the fp32 residual stream
 // straight into a bf16 A panel in the UMMA layout, every n block of those rows is computed from it, the ring
 // carries B only.
-template <int BN, int CL, int MODE = 0>
+template <int BN, int CL, int MODE = 0, bool WG = false>
 struct GemmCfg {
   static constexpr bool BS = MODE == 1;
   static constexpr bool LN = MODE == 2;
@@ -84,7 +84,9 @@ struct GemmCfg {
   // B-stationary: B lives in a panel of kMaxPanelKBlocks k-blocks loaded once; the ring carries A only
   static constexpr int kPanelBytes = BS ? kMaxPanelKBlocks * kBStageBytes : LN ? kMaxPanelKBlocks * A_STAGE_BYTES : 0;
   static constexpr int kStageBytes = BS ? A_STAGE_BYTES : LN ? kBStageBytes : A_STAGE_BYTES + kBStageBytes;
-  static constexpr int kStagingBytes = NUM_EPI_GROUPS * STAGING_BYTES;
+  // split-K wgrad (WG) stores straight from registers (warp-shuffle transpose + coalesced reds): no epilogue
+  // staging, so its long K loop gets one or two more pipeline stages
+  static constexpr int kStagingBytes = WG ? 0 : NUM_EPI_GROUPS * STAGING_BYTES;
   // as many stages as fit: the operand feed is latency bound (bytes in flight per SM / ~1 us L2 latency),
   // so depth matters more than anything else; pair mode gets 5-6 stages where single-CTA mode gets 3-4
   static constexpr int kStagesFit = (kSmemBudget - kStagingBytes - kPanelBytes) / kStageBytes;
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
             const GemmArgs args) {
-  using Cfg = GemmCfg<BN, CL, MODE>;
+  using Cfg = GemmCfg<BN, CL, MODE, is_wgrad_epi(EPI)>;
   constexpr bool BS = MODE == 1;
   constexpr bool LN = MODE == 2;
   constexpr int kStages = Cfg::kStages;
@@ -177,7 +179,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* panel = smem + kStages * Cfg::kStageBytes;  // BS: the stationary B tile, kMaxPanelKBlocks k-blocks
   uint8_t* staging = panel + Cfg::kPanelBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + NUM_EPI_GROUPS * STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;                 // [kStages]
   uint64_t* empty_bar = bars + kStages;      // [kStages]
   uint64_t* tmem_full = bars + 2 * kStages;  // [2]
@@ -553,22 +555,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (!kT) {
             // row-major store: a lane owns a ROW, so reds straight from its registers touch 32 cache lines per
-            // instruction (measured 3x slower than the mainloop could hide). Transpose the 32 x 32 fp32 chunk
-            // through the warp's two slabs (4 KB, 16-byte pieces XOR-swizzled by row) and issue one coalesced
-            // 128-byte red per row instead.
-            __syncwarp();
+            // instruction (measured 3x slower than the mainloop could hide). Transpose the 32 x 32 fp32 chunk inside
+            // the warp with butterfly shuffles (no shared memory: the smem all goes to pipeline stages) so that lane
+            // c holds COLUMN c of every row, and issue one coalesced 128-byte red per row.
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              sts128(slab_base + lane * 128 + ((j ^ (lane & 7)) << 4), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-            __syncwarp();
+            for (int sft = 16; sft >= 1; sft >>= 1) {
+              const bool upper = (lane & sft) != 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if ((i & sft) == 0) {
+                  // lanes with bit `sft` clear keep v[i] and receive the partner's v[i] into v[i + sft];
+                  // lanes with the bit set keep v[i + sft] and receive the partner's v[i + sft] into v[i]
+                  const uint32_t send = upper ? v[i] : v[i + sft];
+                  const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, sft);
+                  if (upper) v[i] = recv;
+                  else v[i + sft] = recv;
+                }
+              }
+            }
+            // now v[r] = element (row r, column lane) of the chunk
             float* dst = args.out_f32 + static_cast<long long>(row0) * args.ldd + n0 + c * 32 + lane;
             const int rows_here = min(32, args.M - row0);
-            for (int r = 0; r < rows_here; ++r) {
-              uint32_t x;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x) : "r"(slab_base + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4) : "memory");
-              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + static_cast<long long>(r) * args.ldd), "f"(__uint_as_float(x))
-                           : "memory");
-            }
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (r < rows_here)
+                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + static_cast<long long>(r) * args.ldd),
+                             "f"(__uint_as_float(v[r]))
+                             : "memory");
           }
         }
         tcgen05_fence_before();
@@ -876,7 +889,7 @@ static unsigned long long* g_gemm_prof = nullptr;
 template <int BN, int EPI, int CL, int MODE>
 static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                           const CUtensorMap& tmD2, const GemmArgs& args, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CL, MODE>;
+  using Cfg = GemmCfg<BN, CL, MODE, is_wgrad_epi(EPI)>;
   static bool configured = false;
   if (!configured) {
     B200SSL_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, CL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -40,3 +40,11 @@ for bn in (256, 192, 128):
 for rep in range(2):
     for name, fn in cases:
         print(f"{name:28s} {timeit(fn):7.1f} us")
+
+# proj wgrad (384 x 384 output, K = rows): single-CTA 128x192 split-K vs the 256x384 pair tile
+dy3 = r(rows, D).bfloat16()
+dw = torch.zeros(D, D, device="cuda")
+db = torch.zeros(D, device="cuda")
+for bn in (192, 384, 128):
+    t = timeit(lambda bn=bn: ops.gemm(dy3, x, dw, D, D, rows, a_mn=True, b_mn=True, epi=ops.EPI_ATOMIC_F32, split_k=0, bias=db, block_n=bn))
+    print(f"proj wgrad bn={bn:3d}          {t:7.1f} us")
