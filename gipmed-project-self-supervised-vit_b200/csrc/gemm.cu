@@ -702,6 +702,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int c = c_first + NUM_EPI_GROUPS * i;
         if (c >= kChunks) break;
         const int col0 = n0 + c * W;
+        const bool lap_on = args.prof != nullptr && threadIdx.x == 128;
+        long long lap_t = lap_on ? clock64() : 0;
+        auto lap = [&](int idx) {  // developer instrumentation: cycles of the first epilogue thread per chunk phase
+          if (lap_on) {
+            const long long now = clock64();
+            atomicAdd(args.prof + 8 + idx, static_cast<unsigned long long>(now - lap_t));
+            lap_t = now;
+          }
+        };
         uint32_t v[W];
         if constexpr (W == 32) tmem_ld_32x32b_x32(lane_taddr + static_cast<uint32_t>(acc * BN + c * W), v);
         else tmem_ld_32x32b_x16(lane_taddr + static_cast<uint32_t>(acc * BN + c * W), v);
@@ -710,6 +719,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint32_t slab = slab_base + (ring & 1) * SLAB_BYTES;
         if (lane == 0) tma_store_wait_read<1>();  // the store that last read this slab has drained
         __syncwarp();
+        lap(0);
         // park this chunk's aux set in the slab (coalesced mapping) and refill the registers two chunks ahead
         auto stage_and_refill = [&](uint4 (&cur)[4]) {
 #pragma unroll
@@ -740,6 +750,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           stage_aux();  // while the TMEM load is in flight
         }
         tmem_ld_wait();
+        lap(1);
         if (c + NUM_EPI_GROUPS >= kChunks) {
           // last TMEM read of this tile by this warp: hand the accumulator stage back (to the leader's MMA)
           tcgen05_fence_before();
@@ -790,6 +801,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           // each lane re-uses only its own row below, so no further warp sync is needed before the writes
         }
+        lap(2);
         const bool rows_ok = row0 < args.M;
         if (EPI == EPI_BIAS_RES_F32) {
 #pragma unroll
@@ -797,13 +809,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             sts128(slab + sw64_offset(lane, j),
                    make_uint4(__float_as_uint(f[(4 * j) % W]), __float_as_uint(f[(4 * j + 1) % W]),
                               __float_as_uint(f[(4 * j + 2) % W]), __float_as_uint(f[(4 * j + 3) % W])));
+          lap(3);
           fence_proxy_async_smem();
           __syncwarp();
+          lap(4);
           if (lane == 0 && rows_ok) {
             tma_store_2d_s(&tmD, slab, col0, row0);
             tma_store_commit();
           }
           ++ring;
+          lap(5);
+          if (lap_on) atomicAdd(args.prof + 15, 1ull);
           continue;
         }
         if (EPI == EPI_BIAS_GELU_FWD) {
@@ -827,13 +843,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           sts128(slab + sw64_offset(lane, j),
                  make_uint4(pack_bf16x2(f[(8 * j) % W], f[(8 * j + 1) % W]), pack_bf16x2(f[(8 * j + 2) % W], f[(8 * j + 3) % W]),
                             pack_bf16x2(f[(8 * j + 4) % W], f[(8 * j + 5) % W]), pack_bf16x2(f[(8 * j + 6) % W], f[(8 * j + 7) % W])));
+        lap(3);
         fence_proxy_async_smem();
         __syncwarp();
+        lap(4);
         if (lane == 0 && rows_ok) {
           tma_store_2d_s(&tmD, slab, col0, row0);
           tma_store_commit();
         }
         ++ring;
+        lap(5);
+        if (lap_on) atomicAdd(args.prof + 15, 1ull);
         if (EPI == EPI_BIAS_GELU) {
           slab = slab_base + (ring & 1) * SLAB_BYTES;
           if (lane == 0) tma_store_wait_read<1>();
@@ -1155,7 +1175,9 @@ extern "C" int b200ssl_set_gemm_cluster(int ctas) {
   return 0;
 }
 
-// Developer instrumentation: device buffer of 8 uint64 counters the GEMM kernels add to (null = off):
+// Developer instrumentation: device buffer of 16 uint64 counters the GEMM kernels add to (null = off); [8..13] are
+// per-chunk phases of the first epilogue thread (wait for a free slab, TMEM load, bias/aux combine, pack + st.shared,
+// proxy fence, TMA store issue) and [15] the number of chunks it processed:
 // [0] MMA-issuer cycles waiting for operand stages, [1] waiting for a free accumulator, [2] MMA-issuer loop cycles,
 // [3] number of issuing CTAs, [4] cycles the first epilogue warp waited for accumulators.
 extern "C" int b200ssl_set_gemm_prof(void* counters) {

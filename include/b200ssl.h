@@ -66,7 +66,7 @@ int b200ssl_set_gemm_wide(int on);
  * scheduling, mbarrier + TMEM allocation, descriptor prefetch) overlaps the tail of its predecessor in the stream and
  * it waits (griddepcontrol.wait) before its first global-memory access. 0 = plain stream order. */
 int b200ssl_set_pdl(int on);
-/* Developer instrumentation: device buffer of 8 uint64 cycle counters the GEMM kernels accumulate into (NULL = off). */
+/* Developer instrumentation: device buffer of 16 uint64 cycle counters the GEMM kernels accumulate into (NULL = off). */
 int b200ssl_set_gemm_prof(void* counters);
 /* Same for attention forward: 16 uint64 (2 slots x {wait S, max pass, barrier, exp pass, barrier, wait O, epilogue, tiles}). */
 int b200ssl_set_attn_prof(void* counters);

@@ -30,7 +30,7 @@ cases = {
     "fc1 wgrad": lambda: ops.linear_wgrad(x4, x),
     "fc2 wgrad": lambda: ops.linear_wgrad(x, x4),
 }
-prof = torch.zeros(8, dtype=torch.int64, device="cuda")
+prof = torch.zeros(16, dtype=torch.int64, device="cuda")
 for name, fn in cases.items():
     for _ in range(3):
         fn()

@@ -12,7 +12,7 @@ lib = b200ssl._lib.lib()
 rows = 100864
 x = torch.randn(rows, 384, device="cuda")
 gw, gb = torch.ones(384, device="cuda"), torch.zeros(384, device="cuda")
-prof = torch.zeros(8, dtype=torch.int64, device="cuda")
+prof = torch.zeros(16, dtype=torch.int64, device="cuda")
 for name, N, gelu in (("qkv", 1152, False), ("fc1", 1536, True)):
     w = (torch.randn(N, 384, device="cuda") * 0.05).bfloat16()
     b = torch.randn(N, device="cuda")
