@@ -7,7 +7,8 @@ schedule, and the full step (§3.3) that occupies the reference's call slots
 ``output = model(input)`` / ``loss = loss_fn(output, target)`` / ``model_ema.update(model)``
 (train.py:1045, :1053, :1081).  Semantics follow Caron et al. 2021, Alg. 1.
 
-PARITY UNPINNED: nothing in /root/reference implements or tests these (see vision_transformer.py).
+PARITY UNPINNED for this file: nothing in /root/reference implements or tests these pieces (the encoder and
+head they wrap ARE pinned to the reference's own outputs, see vision_transformer.py).
 """
 from __future__ import annotations
 

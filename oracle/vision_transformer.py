@@ -5,11 +5,13 @@ line-level spec recovered from the reference's orphaned bytecode
 ``/root/reference/nn_encoder_arch/__pycache__/vision_transformer.cpython-37.pyc`` (SURVEY.md §0.2,
 §8a rows E1-E11 and H1; ``VT.pyc@Lnn`` = original source line nn).
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or runnable source for this path
-(CPython-3.7 bytecode only, timm absent), so this restatement cannot be checked against outputs of
-the reference itself.  What *is* pinned: the symbol table, signatures, defaults and constants of
-every function, extracted from the bytecode by ``tests/golden/make_vt_pyc_spec.py`` and compared
-in ``tests/test_oracle_structure.py``.
+PARITY PINNED: the reference ships this path only as CPython-3.7 bytecode and has no tests or golden
+vectors of its own, but ``tests/golden/py37vm.py`` executes that bytecode unmodified on this container's
+torch; ``tests/golden/make_vt_goldens.py`` records its outputs (``tests/golden/vt_goldens.pt``) and
+``tests/test_oracle_golden.py`` checks this file against them: initial weights per seed, forward,
+position-table interpolation, attention maps, intermediate layers, stochastic depth and all gradients are
+bit-identical to the reference when run side by side (<= 2e-5 against the committed fixture on another
+host). Signatures / defaults / constants are additionally pinned by ``tests/test_oracle_structure.py``.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / reference arm may
 import this package.

@@ -60,6 +60,40 @@ def test_state_dict_keys_match_oracle(libs):
                                                    "last_layer.weight_v"]
 
 
+def test_cuda_path_matches_reference_golden(libs):
+    """The CUDA path against outputs of the REFERENCE ITSELF (not of the oracle): tests/golden/vt_goldens.pt["hot"]
+    was produced by executing the reference's CPython-3.7 bytecode (tests/golden/make_vt_goldens.py). ViT-S/16 +
+    DINOHead on two 224x224 and three 96x96 tiles; weights are re-drawn from the same seed (their fingerprints are
+    checked against the reference in tests/test_oracle_golden.py). bf16 tolerances of the north star."""
+    import os
+    import sys
+    import warnings
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_vt_goldens as mk
+    b200ssl, _, _ = libs
+    gold = torch.load(os.path.join(here, "golden", "vt_goldens.pt"), weights_only=False)["hot"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        backbone, head = mk.hot_modules(b200ssl)
+    backbone, head = backbone.cuda().train(), head.cuda().train()
+    xg, xl, w = (t.cuda() for t in mk.hot_inputs())
+    feats = torch.cat((backbone(xg.bfloat16()), backbone(xl.bfloat16())))
+    logits = head(feats)
+    assert rel(feats.cpu(), gold["features"]) < 1e-2, rel(feats.cpu(), gold["features"])
+    assert rel(logits.cpu(), gold["logits"]) < 1e-2, rel(logits.cpu(), gold["logits"])
+    (logits.float() * w).sum().backward()
+    grads = {"backbone." + k: p.grad for k, p in backbone.named_parameters() if p.grad is not None}
+    grads.update({"head." + k: p.grad for k, p in head.named_parameters() if p.grad is not None})
+    low = []
+    for k, ref in gold["grads"].items():
+        g = grads[k][:8] if k in mk.HOT_GRAD_ROWS else grads[k]
+        c = cos(g.cpu(), ref)
+        if c < 0.999:
+            low.append((k, round(c, 5)))
+    assert not low, low
+
+
 @pytest.mark.parametrize("size,B", [(224, 4), (96, 6), (240, 2), (256, 3)])   # 256: the reference's native tiles, 257 tokens
 def test_vit_forward_backward(libs, size, B):
     b200ssl, ovt, _ = libs
