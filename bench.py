@@ -152,6 +152,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=4, help="images per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-merge-crops", action="store_true",
+                    help="one backbone pass per crop resolution instead of one pass over the packed rows (A/B switch)")
     ap.add_argument("--pdl", action="store_true", help="enable programmatic dependent launch (A/B switch; off by default)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying "
                     "the captured CUDA graph of the step")
@@ -194,6 +196,8 @@ def main():
     from b200ssl import ops
     if args.pdl:
         b200ssl._lib.lib().b200ssl_set_pdl(1)
+    if args.no_merge_crops:
+        b200ssl.dino.MERGE_CROP_GROUPS["on"] = False
 
     torch.manual_seed(0)
     D = MODELS[args.model]["D"]

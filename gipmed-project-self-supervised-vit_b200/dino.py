@@ -104,16 +104,26 @@ class MultiCropWrapper(nn.Module):
             x = [x]
         sizes = [int(inp.shape[-1]) for inp in x]
         bounds = [i + 1 for i in range(len(sizes)) if i + 1 == len(sizes) or sizes[i + 1] != sizes[i]]
-        start, outs = 0, []
+        start, groups = 0, []
         for end in bounds:
-            group = x[start] if end - start == 1 else _cat_or_view(list(x[start:end]))
+            groups.append(x[start] if end - start == 1 else _cat_or_view(list(x[start:end])))
+            start = end
+        if len(groups) > 1 and MERGE_CROP_GROUPS["on"] and hasattr(self.backbone, "forward_multi"):
+            # all resolutions in one pass over the packed token rows (VisionTransformer.forward_multi)
+            return self.head(self.backbone.forward_multi(groups))
+        outs = []
+        for group in groups:
             out = self.backbone(group)
             if isinstance(out, tuple):
                 out = out[0]
             outs.append(out)
-            start = end
         feats = outs[0] if len(outs) == 1 else torch.cat(outs)
         return self.head(feats)
+
+
+# Run the crop groups of different resolution through the backbone in ONE pass (packed token rows) instead of one
+# pass per resolution. Same results; off only for A/B measurements (bench.py --no-merge-crops).
+MERGE_CROP_GROUPS = {"on": True}
 
 
 def _cat_or_view(tensors):

@@ -321,8 +321,20 @@ def layernorm_bwd(x, dy, w, mean, rstd, dres=None, weight=None, bias=None):
     return dx, ret[0], ret[1]
 
 
-def attention_fwd(qkv, B, N, H, scale):
-    out = torch.empty(B * N, H * 64, dtype=_BF16, device=qkv.device)
+def segments(B, N):
+    """[(B_i, N_i, first_row_i)] of a packed token stream. ``B`` / ``N`` are ints (one crop group) or equally long
+    tuples: several groups of different sequence length stored back to back (global crops, then local crops), so
+    that every row-wise kernel (LayerNorm, the GEMMs) runs ONCE over all rows and only attention is per group."""
+    if not isinstance(B, (tuple, list)):
+        return [(int(B), int(N), 0)]
+    out, r0 = [], 0
+    for b, n in zip(B, N):
+        out.append((int(b), int(n), r0))
+        r0 += int(b) * int(n)
+    return out
+
+
+def _attention_fwd_one(qkv, out, B, N, H, scale):
     lse2 = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
     if N > 256:
         # long sequences (native 256^2 tiles: 257 tokens; ViT-S/8: 785): blocks of <= 256 queries x <= 256 keys
@@ -331,16 +343,28 @@ def attention_fwd(qkv, B, N, H, scale):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
         _call("b200ssl_attention_fwd_ws", qkv.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, N, H, 64, float(scale),
               ws.data_ptr(), nbytes, _stream(), launches=((N + 255) // 256) ** 2 + 1)
-        return out, lse2
+        return lse2
     _call("b200ssl_attention_fwd", qkv.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, N, H, 64, float(scale),
           _stream())
-    return out, lse2
+    return lse2
+
+
+def attention_fwd(qkv, B, N, H, scale):
+    """-> (out [rows, H*64] bf16, lse2): lse2 is one [B, H, N] tensor, or a tuple of them for several groups."""
+    out = torch.empty(qkv.shape[0], H * 64, dtype=_BF16, device=qkv.device)
+    segs = segments(B, N)
+    lses = tuple(_attention_fwd_one(qkv[r0:r0 + b * n], out[r0:r0 + b * n], b, n, H, scale) for b, n, r0 in segs)
+    return out, (lses if isinstance(B, (tuple, list)) else lses[0])
 
 
 def attention_bwd(qkv, out, dout, lse2, B, N, H, scale):
     dqkv = torch.empty_like(qkv)
-    _call("b200ssl_attention_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse2.data_ptr(),
-          dqkv.data_ptr(), B, N, H, 64, float(scale), _stream(), launches=((N + 255) // 256) ** 2)
+    lses = lse2 if isinstance(B, (tuple, list)) else (lse2,)
+    for (b, n, r0), lse in zip(segments(B, N), lses):
+        r1 = r0 + b * n
+        _call("b200ssl_attention_bwd", qkv[r0:r1].data_ptr(), out[r0:r1].data_ptr(), dout[r0:r1].data_ptr(),
+              lse.data_ptr(), dqkv[r0:r1].data_ptr(), b, n, H, 64, float(scale), _stream(),
+              launches=((n + 255) // 256) ** 2)
     return dqkv
 
 
@@ -561,7 +585,9 @@ class EncoderFn(torch.autograd.Function):
 
     apply(tokens[B*N, D] fp32, meta, *params) with params = depth * BLOCK_PARAMS tensors (None for absent
     biases) followed by (norm_w, norm_b); meta = (B, N, H, scale, [eps1, eps2] per block, norm_eps).
-    Returns the normalised CLS embedding [B, D] bf16."""
+    B and N may be tuples (``segments``): several crop groups of different resolution packed back to back run
+    through every row-wise kernel in one launch; only attention is launched per group.
+    Returns the normalised CLS embedding [sum(B), D] bf16."""
 
     @staticmethod
     def forward(ctx, tok, meta, *params):
@@ -579,7 +605,9 @@ class EncoderFn(torch.autograd.Function):
             if keep:
                 saved.append((s1, s2))
         D = x.shape[1]
-        cls = x.view(B, N, D)[:, 0].contiguous()
+        segs = segments(B, N)
+        cls = [x[r0:r0 + b * n].view(b, n, D)[:, 0] for b, n, r0 in segs]
+        cls = cls[0].contiguous() if len(cls) == 1 else torch.cat(cls)
         norm_w, norm_b = params[-2], params[-1]
         out, mean, rstd = layernorm_fwd(cls, _f32(norm_w), _f32(norm_b), norm_eps)
         if keep:
@@ -598,9 +626,12 @@ class EncoderFn(torch.autograd.Function):
         d_cls, d_nw, d_nb = layernorm_bwd(cls, _g16(dout), _f32(params[-2]), mean, rstd, weight=params[-2],
                                           bias=params[-1])
         D = cls.shape[1]
-        dx = torch.zeros(B, N, D, dtype=_BF16, device=cls.device)
-        dx[:, 0] = d_cls
-        dx = dx.view(B * N, D)
+        segs = segments(B, N)
+        dx = torch.zeros(sum(b * n for b, n, _ in segs), D, dtype=_BF16, device=cls.device)
+        b0 = 0
+        for b, n, r0 in segs:
+            dx[r0:r0 + b * n].view(b, n, D)[:, 0] = d_cls[b0:b0 + b]
+            b0 += b
         grads = [None] * len(params)
         for i in range(depth - 1, -1, -1):
             ln1w, ln1b, qw, qb, pw, pb, ln2w, ln2b, w1, b1, w2, b2 = params[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS]
@@ -653,6 +684,60 @@ class TokensFn(torch.autograd.Function):
         dw, db = linear_wgrad(dy, cols, has_bias, proj_w, ctx.proj_b)
         return None, (dw.view(proj_w.shape) if dw is not None else None), db, dcls.view(cls_shape), \
             dpos.view(pos_shape), None
+
+
+class MultiTokensFn(torch.autograd.Function):
+    """prepare_tokens for several crop groups of different resolution in one node: per-group patch gather into one
+    column buffer, ONE patch-embed GEMM over all patches, per-group CLS / position assembly into one packed fp32
+    token stream (group after group). apply(patch, n, proj_w, proj_b, cls_token, img_1..img_n, pos_1..pos_n)."""
+
+    @staticmethod
+    def forward(ctx, patch, n, proj_w, proj_b, cls_token, *rest):
+        imgs, poss = rest[:n], rest[n:]
+        D = proj_w.shape[0]
+        dims = []
+        for img in imgs:
+            B, C, H, W = img.shape
+            dims.append((B, (H // patch) * (W // patch), C, H, W))
+        Kp = dims[0][2] * patch * patch
+        dev = imgs[0].device
+        cols = torch.empty(sum(B * Np for B, Np, *_ in dims), Kp, dtype=_BF16, device=dev)
+        c0 = 0
+        for img, (B, Np, C, H, W) in zip(imgs, dims):
+            _call("b200ssl_patchify", img.data_ptr(), cols[c0:c0 + B * Np].data_ptr(), B, C, H, W, patch, _stream())
+            c0 += B * Np
+        y = linear_fwd(cols, bf16_of(proj_w).view(D, Kp), _f32(proj_b) if proj_b is not None else None)
+        x = torch.empty(sum(B * (Np + 1) for B, Np, *_ in dims), D, dtype=torch.float32, device=dev)
+        c0 = r0 = 0
+        for pos, (B, Np, *_) in zip(poss, dims):
+            _call("b200ssl_assemble_tokens", y[c0:c0 + B * Np].data_ptr(), _f32(cls_token).data_ptr(),
+                  _f32(pos).data_ptr(), x[r0:r0 + B * (Np + 1)].data_ptr(), B, Np, D, _stream())
+            c0 += B * Np
+            r0 += B * (Np + 1)
+        ctx.save_for_backward(cols, proj_w)
+        ctx.proj_b = proj_b
+        ctx.meta = (n, dims, D, proj_b is not None, cls_token.shape, [p.shape for p in poss])
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        cols, proj_w = ctx.saved_tensors
+        n, dims, D, has_bias, cls_shape, pos_shapes = ctx.meta
+        dx = _g16(dx)
+        dy = torch.empty(cols.shape[0], D, dtype=_BF16, device=dx.device)
+        dcls = torch.empty(n, D, dtype=torch.float32, device=dx.device)
+        dposs = []
+        c0 = r0 = 0
+        for i, (B, Np, *_) in enumerate(dims):
+            dpos = torch.empty(Np + 1, D, dtype=torch.float32, device=dx.device)
+            _call("b200ssl_assemble_tokens_bwd", dx[r0:r0 + B * (Np + 1)].data_ptr(), dy[c0:c0 + B * Np].data_ptr(),
+                  dpos.data_ptr(), dcls[i].data_ptr(), B, Np, D, _stream(), launches=2)
+            dposs.append(dpos.view(pos_shapes[i]))
+            c0 += B * Np
+            r0 += B * (Np + 1)
+        dw, db = linear_wgrad(dy, cols, has_bias, proj_w, ctx.proj_b)
+        return (None, None, (dw.view(proj_w.shape) if dw is not None else None), db, dcls.sum(0).view(cls_shape),
+                *([None] * n), *dposs)
 
 
 class L2NormFn(torch.autograd.Function):

@@ -238,6 +238,44 @@ def _build_step(b200ssl, ovt, odino, out_dim, ncrops):
     return ref_student, student, ref_teacher, teacher, ref_loss, loss
 
 
+@pytest.mark.parametrize("drop_path", [0.0, 0.2])
+def test_merged_crop_groups_match_per_group_passes(libs, drop_path):
+    """MultiCropWrapper runs global and local crops through the backbone in ONE pass over the packed token rows
+    (VisionTransformer.forward_multi). Per row the arithmetic is the same as in one pass per resolution: logits are
+    identical, weight gradients differ only by the summation order of their split-K reductions; stochastic-depth
+    masks are drawn in the same order."""
+    b200ssl, ovt, _ = libs
+    from b200ssl import dino as pdino
+    torch.manual_seed(0)
+    student = b200ssl.MultiCropWrapper(b200ssl.vit_tiny(drop_path_rate=drop_path),
+                                       b200ssl.DINOHead(192, 1024, hidden_dim=256, bottleneck_dim=64)).cuda().train()
+    with torch.no_grad():
+        for p in student.parameters():
+            if p.ndim == 1:
+                p.add_(torch.randn_like(p) * 0.02)
+    g = torch.Generator(device="cuda").manual_seed(77)
+    crops = [torch.randn(4, 3, 224, 224, device="cuda", generator=g).bfloat16() for _ in range(2)] + \
+            [torch.randn(4, 3, 96, 96, device="cuda", generator=g).bfloat16() for _ in range(3)]
+    w = torch.randn(20, 1024, device="cuda", generator=g)
+    res = {}
+    try:
+        for merged in (False, True):
+            pdino.MERGE_CROP_GROUPS["on"] = merged
+            student.zero_grad(set_to_none=True)
+            torch.manual_seed(4321)
+            out = student(crops)
+            (out.float() * w).sum().backward()
+            res[merged] = (out.float().clone(), {n: p.grad.clone() for n, p in student.named_parameters()
+                                                 if p.grad is not None})
+    finally:
+        pdino.MERGE_CROP_GROUPS["on"] = True
+    assert res[True][0].shape == (20, 1024)
+    assert torch.equal(res[True][0], res[False][0]), rel(res[True][0], res[False][0])
+    assert sorted(res[True][1]) == sorted(res[False][1])
+    for n, gm in res[True][1].items():
+        assert rel(gm, res[False][1][n]) < 2e-3 and cos(gm, res[False][1][n]) > 0.99999, (n, rel(gm, res[False][1][n]))
+
+
 def test_dino_step_matches_oracle(libs):
     """Config-1 style step (ViT-Tiny, 2 global + 2 local crops) — loss, logits, gradients, centre, EMA."""
     b200ssl, ovt, odino = libs

@@ -124,6 +124,14 @@ def test_crop_buffers_group_without_copy():
     assert torch.equal(dino._cat_or_view([bufs[3], bufs[2]]), torch.cat([bufs[3], bufs[2]]))   # wrong order -> cat
 
 
+def test_packed_row_segments():
+    """ops.segments: row ranges of crop groups packed back to back (the merged multi-crop pass)."""
+    from b200ssl import ops
+    assert ops.segments(4, 197) == [(4, 197, 0)]
+    assert ops.segments((512, 2560), (197, 37)) == [(512, 197, 0), (2560, 37, 512 * 197)]
+    assert ops.segments([2, 3, 1], [5, 7, 11]) == [(2, 5, 0), (3, 7, 10), (1, 11, 31)]
+
+
 def test_cosine_scheduler_and_apply():
     import b200ssl
     lr = b200ssl.cosine_scheduler(1e-3, 1e-6, epochs=10, niter_per_ep=7, warmup_epochs=2)
