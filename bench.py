@@ -152,6 +152,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=4, help="images per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-teacher-stream", action="store_true",
+                    help="teacher forward on the main stream instead of a second captured stream (A/B switch)")
     ap.add_argument("--no-merge-crops", action="store_true",
                     help="one backbone pass per crop resolution instead of one pass over the packed rows (A/B switch)")
     ap.add_argument("--pdl", action="store_true", help="enable programmatic dependent launch (A/B switch; off by default)")
@@ -196,6 +198,8 @@ def main():
     from b200ssl import ops
     if args.pdl:
         b200ssl._lib.lib().b200ssl_set_pdl(1)
+    if args.no_teacher_stream:
+        b200ssl.dino.TEACHER_STREAM["on"] = False
     if args.no_merge_crops:
         b200ssl.dino.MERGE_CROP_GROUPS["on"] = False
 

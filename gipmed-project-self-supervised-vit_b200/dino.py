@@ -580,11 +580,35 @@ def _step_prepare(student, teacher_ema, optimizer, momentum):
     return ents
 
 
+# Measured on B200 (bench.py, same box, alternating): 54.59 / 54.78 ms per step without, 54.19 / 53.88 ms with.
+TEACHER_STREAM = {"on": True}
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def _step_compute(student, teacher_ema, loss_fn, optimizer, crops, epoch):
     """Forward (teacher + student), loss, backward. Kernel launches (and, unless deferred, NCCL calls) only."""
-    with torch.no_grad():
-        teacher_out = teacher_ema.module(list(crops[:2]))
-    student_out = student(list(crops))
+    if TEACHER_STREAM["on"]:
+        # teacher forward on a second stream (a parallel branch of the captured graph): it is independent of the
+        # student forward until the loss, so its CTAs can fill the tails of the student's persistent kernels
+        main = torch.cuda.current_stream()
+        side = _side_stream(main.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side), torch.no_grad():
+            teacher_out = teacher_ema.module(list(crops[:2]))
+        student_out = student(list(crops))
+        main.wait_stream(side)
+        teacher_out.record_stream(main)
+    else:
+        with torch.no_grad():
+            teacher_out = teacher_ema.module(list(crops[:2]))
+        student_out = student(list(crops))
     loss = loss_fn(student_out, teacher_out, epoch)
     ddp = student if isinstance(student, GradBucketDataParallel) else None
     if ddp is not None:
