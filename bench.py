@@ -336,12 +336,12 @@ def main():
     # like `achieved` (family total per step / launches per step)
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_step_summary_v4.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1_step_summary_v5.json")) as f:
             summ = json.load(f)
         gk = [k for k in summ["kernels"] if k["kernel"].startswith("gemm_kernel")]
         n_l = sum(k["launches_per_step"] for k in gk)
         traffic = sum(k["dram_read_mb_per_step"] + k["dram_write_mb_per_step"] for k in gk) * 1e6 / max(n_l, 1)
-        traffic_src = ("profiles/r1_step_summary_v4.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the "
+        traffic_src = ("profiles/r1_step_summary_v5.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the "
                        f"{n_l:.0f} gemm_kernel launches of one step, divided by the launch count")
     except Exception:
         pass

@@ -238,8 +238,8 @@ def _build_step(b200ssl, ovt, odino, out_dim, ncrops):
     return ref_student, student, ref_teacher, teacher, ref_loss, loss
 
 
-@pytest.mark.parametrize("drop_path", [0.0, 0.2])
-def test_merged_crop_groups_match_per_group_passes(libs, drop_path):
+@pytest.mark.parametrize("drop_path,patch", [(0.0, 16), (0.2, 16), (0.0, 8)])   # patch 8: 785 + 145 tokens (long-sequence attention)
+def test_merged_crop_groups_match_per_group_passes(libs, drop_path, patch):
     """MultiCropWrapper runs global and local crops through the backbone in ONE pass over the packed token rows
     (VisionTransformer.forward_multi). Per row the arithmetic is the same as in one pass per resolution: logits are
     identical, weight gradients differ only by the summation order of their split-K reductions; stochastic-depth
@@ -247,7 +247,7 @@ def test_merged_crop_groups_match_per_group_passes(libs, drop_path):
     b200ssl, ovt, _ = libs
     from b200ssl import dino as pdino
     torch.manual_seed(0)
-    student = b200ssl.MultiCropWrapper(b200ssl.vit_tiny(drop_path_rate=drop_path),
+    student = b200ssl.MultiCropWrapper(b200ssl.vit_tiny(patch_size=patch, drop_path_rate=drop_path),
                                        b200ssl.DINOHead(192, 1024, hidden_dim=256, bottleneck_dim=64)).cuda().train()
     with torch.no_grad():
         for p in student.parameters():
