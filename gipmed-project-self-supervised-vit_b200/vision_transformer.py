@@ -282,8 +282,8 @@ class VisionTransformer(nn.Module):
             shape = (1, npatch + 1, self.embed_dim)
         return self.interpolate_pos_encoding(_Shape, w, h)[0]
 
-    def _tokens(self, x):
-        """prepare_tokens on the packed layout: returns ([B*N, D] bf16, B, N)."""
+    def _tokens(self, x, relay=None):
+        """prepare_tokens on the packed layout: returns ([B*N, D] fp32 stream, B, N)."""
         ops.require_cuda(x, "VisionTransformer")
         if self.training and self.pos_drop.p > 0:
             raise NotImplementedError("drop_rate > 0 is not on the b200ssl hot path (reference default 0)")
@@ -291,14 +291,14 @@ class VisionTransformer(nn.Module):
         P = self.patch_embed.patch_size
         pos = self._pos_table(w, h)
         tok = ops.TokensFn.apply(x.to(torch.bfloat16).contiguous(), self.patch_embed.proj.weight,
-                                 self.patch_embed.proj.bias, self.cls_token, pos, P)
+                                 self.patch_embed.proj.bias, self.cls_token, pos, P, relay)
         return tok, B, (w // P) * (h // P) + 1
 
     def prepare_tokens(self, x):
         tok, B, N = self._tokens(x)
         return tok.view(B, N, -1).to(x.dtype)
 
-    def _encode(self, tok, B, N, rs_list):
+    def _encode(self, tok, B, N, rs_list, relay=None):
         """All blocks + the final norm on the CLS rows as one autograd node. ``B`` / ``N`` are ints, or tuples when
         ``tok`` packs several crop groups (``forward_multi``)."""
         blk0 = self.blocks[0]
@@ -313,14 +313,15 @@ class VisionTransformer(nn.Module):
         if all(r[0] is None for r in rs_list):
             rs_list = None
         meta = (B, N, blk0.attn.num_heads, blk0.attn.scale, [(b.norm1.eps, b.norm2.eps) for b in self.blocks],
-                self.norm.eps, rs_list)
+                self.norm.eps, rs_list, relay)
         # the reference normalises every token then keeps row 0 (@L252-253); only CLS rows are normalised here
         return ops.EncoderFn.apply(tok, meta, *params)
 
     def forward(self, x):
-        tok, B, N = self._tokens(x)
+        relay = ops.GradRelay()   # the token stream is private to this call: its gradient travels in bf16
+        tok, B, N = self._tokens(x, relay)
         rs_list = [b._drop_path_scales(B, N, tok.device) for b in self.blocks]
-        return self._encode(tok, B, N, rs_list).to(x.dtype)
+        return self._encode(tok, B, N, rs_list, relay).to(x.dtype)
 
     def forward_multi(self, xs):
         """``torch.cat([self(x) for x in xs])`` for image batches of DIFFERENT resolution (the multi-crop student:
@@ -339,7 +340,8 @@ class VisionTransformer(nn.Module):
             raise NotImplementedError("drop_rate > 0 is not on the b200ssl hot path (reference default 0)")
         P = self.patch_embed.patch_size
         poss = [self._pos_table(x.shape[2], x.shape[3]) for x in xs]
-        tok = ops.MultiTokensFn.apply(P, len(xs), self.patch_embed.proj.weight, self.patch_embed.proj.bias,
+        relay = ops.GradRelay()
+        tok = ops.MultiTokensFn.apply(P, len(xs), relay, self.patch_embed.proj.weight, self.patch_embed.proj.bias,
                                       self.cls_token, *[x.to(torch.bfloat16).contiguous() for x in xs], *poss)
         Bs = tuple(int(x.shape[0]) for x in xs)
         Ns = tuple((x.shape[2] // P) * (x.shape[3] // P) + 1 for x in xs)
@@ -349,7 +351,7 @@ class VisionTransformer(nn.Module):
             pair = tuple(None if per_group[0][i][j] is None else torch.cat([g[i][j] for g in per_group])
                          for j in range(2))
             rs_list.append(pair)
-        return self._encode(tok, Bs, Ns, rs_list).to(xs[0].dtype)
+        return self._encode(tok, Bs, Ns, rs_list, relay).to(xs[0].dtype)
 
     def get_last_selfattention(self, x):
         tok, B, N = self._tokens(x)
