@@ -327,8 +327,13 @@ def main():
         gemm_events.append((e0, e1))
 
     ops.gemm = timed_gemm
+    # one stream for the instrumented step: with the teacher forward running concurrently on its own stream the
+    # event-bracketed durations of overlapping kernels would each include the other's share of the machine
+    teacher_branch = b200ssl.dino.TEACHER_STREAM["on"]
+    b200ssl.dino.TEACHER_STREAM["on"] = False
     eager_step(crops, total_steps)
     torch.cuda.synchronize()
+    b200ssl.dino.TEACHER_STREAM["on"] = teacher_branch
     ops.gemm = real_gemm
     gemm_ms = sum(a.elapsed_time(b) for a, b in gemm_events)
     gemm_tflops = gemm_f * B / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
