@@ -539,8 +539,9 @@ def attn_half_bwd(dy, saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale
     return dx, d_lw, d_lb, d_qw, d_qb, d_pw, d_pb
 
 
-def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, keep=True, rs=None):
-    """x + fc2(gelu(fc1(LN(x)))) (VT.pyc@L151). keep=False (no-grad forward): gelu' is not produced."""
+def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, keep=True, rs=None, need_out=True):
+    """x + fc2(gelu(fc1(LN(x)))) (VT.pyc@L151). keep=False (no-grad forward): gelu' is not produced.
+    need_out=False (activation recompute in backward): the fc2 GEMM is skipped, only the saved tensors are rebuilt."""
     w116 = bf16_of(w1)
     b132 = _f32(b1) if b1 is not None else None
     if ln_gemm_ok(x, w116):
@@ -549,7 +550,7 @@ def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, keep=True, rs=None):
     else:
         ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
         pre, h = linear_fwd(ln, w116, b132, gelu=True if keep else "fwd_only")
-    y = linear_fwd(h, bf16_of(w2), _f32(b2) if b2 is not None else None, residual=x, rowscale=rs)
+    y = linear_fwd(h, bf16_of(w2), _f32(b2) if b2 is not None else None, residual=x, rowscale=rs) if need_out else None
     return y, (x, mean, rstd, ln, pre, h, rs)
 
 
@@ -620,14 +621,21 @@ class EncoderFn(torch.autograd.Function):
         rs_list = meta[6] if len(meta) > 6 else None   # stochastic depth: per block (rs_attn, rs_mlp) row scales or None
         depth = (len(params) - 2) // BLOCK_PARAMS
         keep = any(ctx.needs_input_grad)  # False under no_grad (teacher): nothing is retained
+        # activation recompute (the reference's --grad-checkpointing, train.py:146,509-510): keep only every block's
+        # input (the fp32 stream) and rebuild the block's activations in backward
+        recompute = keep and len(meta) > 8 and bool(meta[8])
         saved = []
         x = tok
         for i in range(depth):
             ln1w, ln1b, qw, qb, pw, pb, ln2w, ln2b, w1, b1, w2, b2 = params[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS]
             rs1, rs2 = rs_list[i] if rs_list is not None else (None, None)
-            x, s1 = attn_half_fwd(x, ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale, keep=keep, rs=rs1)
-            x, s2 = mlp_half_fwd(x, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1], keep=keep, rs=rs2)
-            if keep:
+            x_in = x
+            x, s1 = attn_half_fwd(x, ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale,
+                                  keep=keep and not recompute, rs=rs1)
+            x, s2 = mlp_half_fwd(x, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1], keep=keep and not recompute, rs=rs2)
+            if recompute:
+                saved.append(x_in)
+            elif keep:
                 saved.append((s1, s2))
         D = x.shape[1]
         segs = segments(B, N)
@@ -660,7 +668,12 @@ class EncoderFn(torch.autograd.Function):
         grads = [None] * len(params)
         for i in range(depth - 1, -1, -1):
             ln1w, ln1b, qw, qb, pw, pb, ln2w, ln2b, w1, b1, w2, b2 = params[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS]
-            s1, s2 = ctx.saved[i]
+            if torch.is_tensor(ctx.saved[i]):   # activation recompute: rebuild this block's saved tensors from its input
+                rs1, rs2 = ctx.meta[6][i] if ctx.meta[6] is not None else (None, None)
+                x1, s1 = attn_half_fwd(ctx.saved[i], ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale, rs=rs1)
+                _, s2 = mlp_half_fwd(x1, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1], rs=rs2, need_out=False)
+            else:
+                s1, s2 = ctx.saved[i]
             dx, g_l2w, g_l2b, g_w1, g_b1, g_w2, g_b2 = mlp_half_bwd(dx, s2, ln2w, w1, w2, b1 is not None, b2 is not None,
                                                                     ln2b, b1, b2)
             dx, g_l1w, g_l1b, g_qw, g_qb, g_pw, g_pb = attn_half_bwd(dx, s1, ln1w, qw, pw, qb is not None,

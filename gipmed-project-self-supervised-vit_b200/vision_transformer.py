@@ -298,6 +298,12 @@ class VisionTransformer(nn.Module):
         tok, B, N = self._tokens(x)
         return tok.view(B, N, -1).to(x.dtype)
 
+    def set_grad_checkpointing(self, enable=True):
+        """timm's API behind the reference's ``--grad-checkpointing`` (train.py:146,509-510): keep only each block's
+        input in the forward and recompute the block's activations in backward (≈ 1/3 more forward work, the per-block
+        activation memory drops from ~23 to 4 bytes per token feature)."""
+        self.grad_checkpointing = bool(enable)
+
     def _encode(self, tok, B, N, rs_list, relay=None):
         """All blocks + the final norm on the CLS rows as one autograd node. ``B`` / ``N`` are ints, or tuples when
         ``tok`` packs several crop groups (``forward_multi``)."""
@@ -313,7 +319,7 @@ class VisionTransformer(nn.Module):
         if all(r[0] is None for r in rs_list):
             rs_list = None
         meta = (B, N, blk0.attn.num_heads, blk0.attn.scale, [(b.norm1.eps, b.norm2.eps) for b in self.blocks],
-                self.norm.eps, rs_list, relay)
+                self.norm.eps, rs_list, relay, getattr(self, "grad_checkpointing", False))
         # the reference normalises every token then keeps row 0 (@L252-253); only CLS rows are normalised here
         return ops.EncoderFn.apply(tok, meta, *params)
 

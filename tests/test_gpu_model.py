@@ -276,6 +276,34 @@ def test_merged_crop_groups_match_per_group_passes(libs, drop_path, patch):
         assert rel(gm, res[False][1][n]) < 2e-3 and cos(gm, res[False][1][n]) > 0.99999, (n, rel(gm, res[False][1][n]))
 
 
+def test_grad_checkpointing_recomputes_the_same_gradients(libs):
+    """set_grad_checkpointing (the reference's --grad-checkpointing, train.py:146,509-510): same outputs, same
+    gradients (recomputed activations are bit-identical; split-K reductions differ by summation order only), less
+    activation memory held between forward and backward."""
+    b200ssl, ovt, _ = libs
+    _, mine = _pair(b200ssl, ovt, drop_path_rate=0.1)
+    mine.train()
+    x = torch.randn(16, 3, 224, 224, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)).bfloat16()
+    w = torch.randn(16, 192, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    res = {}
+    for ck in (False, True):
+        mine.set_grad_checkpointing(ck)
+        mine.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        torch.manual_seed(99)
+        out = mine(x)
+        held = torch.cuda.memory_allocated() - base
+        (out.float() * w).sum().backward()
+        res[ck] = (out.float().clone(), {n: p.grad.clone() for n, p in mine.named_parameters()}, held)
+    mine.set_grad_checkpointing(False)
+    assert torch.equal(res[True][0], res[False][0])
+    for n, g in res[True][1].items():
+        assert rel(g, res[False][1][n]) < 2e-3 and cos(g, res[False][1][n]) > 0.99999, n
+    assert res[True][2] < 0.35 * res[False][2], (res[True][2], res[False][2])
+
+
 def test_dino_step_matches_oracle(libs):
     """Config-1 style step (ViT-Tiny, 2 global + 2 local crops) — loss, logits, gradients, centre, EMA."""
     b200ssl, ovt, odino = libs
