@@ -28,6 +28,7 @@ SIGNATURES = {
     "b200ssl_set_attn_prof": [_P],
     "b200ssl_set_gemm_wide": [_I],
     "b200ssl_set_pdl": [_I],
+    "b200ssl_set_ln_bwd_staged": [_I],
     "b200ssl_layernorm_fwd": [_P, _I, _P, _P, _P, _P, _P, _L, _I, _F, _P],
     "b200ssl_layernorm_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
     "b200ssl_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P],

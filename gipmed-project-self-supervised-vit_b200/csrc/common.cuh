@@ -355,6 +355,15 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* tm
       : "memory");
 }
 // arrive on the leader CTA's copy of `bar` (local arrive when executed by the leader itself)
+// 1-D bulk copy global -> shared (TMA engine, no tensor map): bytes % 16 == 0, both addresses 16-byte aligned;
+// completion is signalled on the mbarrier as transaction bytes
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_smem_addr(bar)) : "memory");
 }

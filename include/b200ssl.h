@@ -66,6 +66,9 @@ int b200ssl_set_gemm_wide(int on);
  * scheduling, mbarrier + TMEM allocation, descriptor prefetch) overlaps the tail of its predecessor in the stream and
  * it waits (griddepcontrol.wait) before its first global-memory access. 0 = plain stream order. */
 int b200ssl_set_pdl(int on);
+/* Developer A/B switch: LayerNorm backward with rows staged through shared memory by bulk copies (1, default) or the
+ * register-resident version (0). */
+int b200ssl_set_ln_bwd_staged(int on);
 /* Developer instrumentation: device buffer of 16 uint64 cycle counters the GEMM kernels accumulate into (NULL = off). */
 int b200ssl_set_gemm_prof(void* counters);
 /* Same for attention forward: 16 uint64 (2 slots x {wait S, max pass, barrier, exp pass, barrier, wait O, epilogue, tiles}). */
