@@ -372,7 +372,7 @@ static int launch_ln_fwd(const void* x, int x_f32, const float* w, const float* 
   constexpr int RPW = 32 / LPR;
   const long long warps_needed = (rows + RPW - 1) / RPW;
   long long blocks = (warps_needed + 7) / 8;
-  const long long cap = static_cast<long long>(sm_count()) * 8;
+  const long long cap = static_cast<long long>(sm_count()) * 4;  // exactly the four resident blocks per SM: one wave (41.9 -> 39.8 us at 100,864 rows vs 8 per SM)
   if (blocks > cap) blocks = cap;
   if (x_f32)
     B200SSL_CUDA(launch_pdl(ln_fwd_kernel<LPR, CPL, float>, dim3(static_cast<int>(blocks)), dim3(256), 0, s, 1,
