@@ -16,6 +16,8 @@ gradient clipping + AdamW, teacher EMA. Prints ONE JSON line on rank 0 (contract
 `cpu_baseline`: the PyTorch oracle (oracle/) timed on the host cores on a bounded sample of the workload.
 `--impl reference`: the reference's CPU path for this step == the oracle restatement (the reference's own
                sources for the path are Python-3.7 bytecode + un-vendored timm), all host threads.
+               The restatement's encoder and head are bit-identical to that bytecode executed by
+               tests/golden/py37vm.py (tests/test_oracle_golden.py); /root/reference itself does not exist on the GPU box.
 """
 import argparse
 import json
@@ -177,7 +179,8 @@ def main():
         warm = 1 if args.warmup > 0 else 0
         ips, dt, threads = run_cpu_oracle(args.model, args.out_dim, n_local, args.cpu_batch, steps, warm)
         sample = (f"{steps} timed step(s) after {warm} warm-up of the same step at batch {args.cpu_batch} "
-                  f"(all {2 + n_local} crops), fp32, PyTorch oracle restatement on {threads} host threads")
+                  f"(all {2 + n_local} crops), fp32, PyTorch oracle restatement (encoder + head bit-identical to the "
+                  f"reference's bytecode, tests/test_oracle_golden.py) on {threads} host threads")
         line = {"impl": "reference", "metric": "SSL train images/sec (ViT-S/16 DINO multi-crop)", "value": ips,
                 "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
