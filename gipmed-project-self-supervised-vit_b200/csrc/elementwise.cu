@@ -10,49 +10,52 @@ namespace b200ssl {
 
 // img [B,C,H,W] bf16 -> A [B*(H/P)*(W/P), C*P*P] bf16, K index = (c, i, j) as in Conv2d weight.flatten(1).
 // One thread moves one 16-byte piece (8 pixels of one patch row).
+// IdxT = unsigned (whenever the piece count fits 32 bits: 64-bit div / mod per 16-byte piece made the kernel issue
+// bound) or long long.
+template <typename IdxT>
 __global__ void patchify_kernel(const __nv_bfloat16* __restrict__ img, __nv_bfloat16* __restrict__ out, int B,
                                 int C, int H, int W, int P) {
-  const int pw = W / P, ph = H / P;
-  const int pieces_per_prow = P / 8;
-  const long long total = static_cast<long long>(B) * C * H * (W / 8);
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const IdxT pw = W / P, ph = H / P, w8 = W / 8, uH = H, uC = C, uP = P;
+  const IdxT total = static_cast<IdxT>(B) * uC * uH * w8;
+  const IdxT stride = static_cast<IdxT>(gridDim.x) * blockDim.x;
+  const long long row_elems = static_cast<long long>(C) * P * P;
+  for (IdxT idx = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
     // idx enumerates the image in memory order so global reads are fully coalesced
-    const int x8 = static_cast<int>(idx % (W / 8));
-    long long r = idx / (W / 8);
-    const int y = static_cast<int>(r % H);
-    r /= H;
-    const int c = static_cast<int>(r % C);
-    const int b = static_cast<int>(r / C);
-    const int px = (x8 * 8) / P, j = (x8 * 8) % P;
-    const int py = y / P, i = y % P;
+    const IdxT x8 = idx % w8;
+    IdxT r = idx / w8;
+    const IdxT y = r % uH;
+    r /= uH;
+    const IdxT c = r % uC;
+    const IdxT b = r / uC;
+    const IdxT px = (x8 * 8) / uP, j = (x8 * 8) % uP;
+    const IdxT py = y / uP, i = y % uP;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(img) + idx);
-    const long long row = (static_cast<long long>(b) * ph + py) * pw + px;
-    const long long col = (static_cast<long long>(c) * P + i) * P + j;
-    *reinterpret_cast<uint4*>(out + row * (static_cast<long long>(C) * P * P) + col) = v;
-    (void)pieces_per_prow;
+    const long long row = static_cast<long long>((b * ph + py) * pw + px);
+    const long long col = static_cast<long long>((c * uP + i) * uP + j);
+    *reinterpret_cast<uint4*>(out + row * row_elems + col) = v;
   }
 }
 
 // x[b,0,:] = cls + pos[0] ; x[b,1+p,:] = y[b*Np+p,:] + pos[1+p]   (pos, cls fp32; y bf16; x = fp32 stream)
+template <typename IdxT>
 __global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ cls,
                                        const float* __restrict__ pos, float* __restrict__ x, int B, int Np,
                                        int D) {
-  const int N = Np + 1;
-  const int d8 = D / 8;
-  const long long total = static_cast<long long>(B) * N * d8;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c8 = static_cast<int>(idx % d8);
-    const long long rn = idx / d8;
-    const int n = static_cast<int>(rn % N);
-    const long long b = rn / N;
+  const IdxT N = Np + 1;
+  const IdxT d8 = D / 8;
+  const IdxT total = static_cast<IdxT>(B) * N * d8;
+  const IdxT stride = static_cast<IdxT>(gridDim.x) * blockDim.x;
+  for (IdxT idx = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const IdxT c8 = idx % d8;
+    const IdxT rn = idx / d8;
+    const IdxT n = rn % N;
+    const IdxT b = rn / N;
     float v[8];
     if (n == 0) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = __ldg(cls + c8 * 8 + e);
     } else {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(y + (b * Np + n - 1) * D) + c8);
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(y + static_cast<long long>(b * Np + n - 1) * D) + c8);
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -61,12 +64,11 @@ __global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ y, cons
         v[2 * e + 1] = f.y;
       }
     }
-    const float* pp = pos + static_cast<long long>(n) * D + c8 * 8;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] += __ldg(pp + e);
-    float4* px = reinterpret_cast<float4*>(x + rn * D) + 2 * c8;
-    px[0] = make_float4(v[0], v[1], v[2], v[3]);
-    px[1] = make_float4(v[4], v[5], v[6], v[7]);
+    const float4* pp = reinterpret_cast<const float4*>(pos + static_cast<long long>(n) * D + c8 * 8);
+    const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+    float4* px = reinterpret_cast<float4*>(x + static_cast<long long>(rn) * D) + 2 * c8;
+    px[0] = make_float4(v[0] + p0.x, v[1] + p0.y, v[2] + p0.z, v[3] + p0.w);
+    px[1] = make_float4(v[4] + p1.x, v[5] + p1.y, v[6] + p1.z, v[7] + p1.w);
   }
 }
 
@@ -250,8 +252,12 @@ using namespace b200ssl;
 extern "C" int b200ssl_patchify(const void* img, void* out, int B, int C, int H, int W, int P, void* stream) {
   B200SSL_CHECK(P % 8 == 0 && H % P == 0 && W % P == 0, -2, "patchify: H=%d W=%d must divide by P=%d (P %% 8 == 0)", H, W, P);
   const long long total = static_cast<long long>(B) * C * H * (W / 8);
-  patchify_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(img), static_cast<__nv_bfloat16*>(out), B, C, H, W, P);
+  if (total < (1ll << 31))
+    patchify_kernel<unsigned><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(img), static_cast<__nv_bfloat16*>(out), B, C, H, W, P);
+  else
+    patchify_kernel<long long><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(img), static_cast<__nv_bfloat16*>(out), B, C, H, W, P);
   B200SSL_CUDA(cudaGetLastError());
   return 0;
 }
@@ -260,8 +266,12 @@ extern "C" int b200ssl_assemble_tokens(const void* y, const float* cls, const fl
                                        int D, void* stream) {
   B200SSL_CHECK(D % 8 == 0, -2, "assemble_tokens: D=%d must be a multiple of 8", D);
   const long long total = static_cast<long long>(B) * (Np + 1) * (D / 8);
-  assemble_tokens_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(y), cls, pos, static_cast<float*>(x), B, Np, D);
+  if (total < (1ll << 31))
+    assemble_tokens_kernel<unsigned><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(y), cls, pos, static_cast<float*>(x), B, Np, D);
+  else
+    assemble_tokens_kernel<long long><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(y), cls, pos, static_cast<float*>(x), B, Np, D);
   B200SSL_CUDA(cudaGetLastError());
   return 0;
 }
