@@ -1,27 +1,34 @@
 #!/usr/bin/env python
 """Headline benchmark: DINO self-supervised ViT training step, images/s (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model vit_small] [--batch 256]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|4|5a|5b]
 
-One process per GPU (torchrun sets RANK / LOCAL_RANK / WORLD_SIZE for N > 1). A "step" is the whole
-hot path over one batch of synthetic crops (2 x 224^2 + 10 x 96^2 per image, bf16): teacher forward,
-student forward, fused DINO loss + centre update, backward (bucketed NCCL all-reduce for N > 1),
-gradient clipping + AdamW, teacher EMA. Prints ONE JSON line on rank 0 (contract in the task brief).
+`--config` picks one of BASELINE.json's configurations (default 2 = configs[1], the one the metric is quoted on):
+  1   ViT-Tiny/16, batch 8, 2 global 224^2 crops only              (configs[0], the reference's CPU-runnable case)
+  2   ViT-S/16, batch 256/GPU, 2 x 224^2 + 10 x 96^2 crops         (configs[1]; with --gpus N: configs[2])
+  4   ViT-B/16, batch 128/GPU, multi-crop                          (configs[3])
+  5a  ViT-S/8 (785-token sequences), batch 64/GPU, multi-crop      (configs[4], training half)
+  5b  ViT-S/8 frozen-encoder embedding of 4096 tiles per slide     (configs[4], embedding half; a step = one slide)
+
+One process per GPU (torchrun sets RANK / LOCAL_RANK / WORLD_SIZE for N > 1). A training "step" is the whole
+hot path over one batch of synthetic crops (bf16): teacher forward, student forward, fused DINO loss + centre
+update, backward (bucketed NCCL all-reduce for N > 1), gradient clipping + AdamW, teacher EMA. Prints ONE JSON
+line on rank 0 (contract in the task brief).
 
 `value`      : device-resident inputs, K steps bracketed by barrier + synchronize, CUDA events, max over ranks.
 `e2e`        : same step driven from PINNED HOST crops (H2D copy every step, prefetched on a copy stream)
-               plus a D2H read of the loss every step.
+               plus a D2H read of the loss (5b: of the feature matrix) every step.
 `roofline`   : the tcgen05 GEMM kernel family (dominant kernel): algorithmic FLOPs / summed per-launch
                CUDA-event durations over one fully instrumented step, vs the measured bf16 peak.
 `cpu_baseline`: the PyTorch oracle (oracle/) timed on the host cores on a bounded sample of the workload.
 `--impl reference`: the reference's CPU path for this step == the oracle restatement (the reference's own
-               sources for the path are Python-3.7 bytecode + un-vendored timm), all host threads.
-               The restatement's encoder and head are bit-identical to that bytecode executed by
-               tests/golden/py37vm.py (tests/test_oracle_golden.py); /root/reference itself does not exist on the GPU box.
+               sources for the path are Python-3.7 bytecode + un-vendored timm), all host threads,
+               EXACTLY K timed steps after W warm-up steps, each step a bounded sample (``--cpu-batch`` images) of
+               the same workload. The restatement's encoder and head are bit-identical to that bytecode executed by
+               tests/golden/py37vm.py (tests/test_oracle_golden.py); /root/reference does not exist on the GPU box.
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -40,21 +47,36 @@ MODELS = {
     "vit_base": dict(D=768, depth=12, heads=12),
 }
 
+CONFIGS = {
+    "1": dict(model="vit_tiny", patch=16, batch=8, local_crops=0, kind="train", cpu_batch=8,
+              label="BASELINE.json configs[0]"),
+    "2": dict(model="vit_small", patch=16, batch=256, local_crops=10, kind="train", cpu_batch=4,
+              label="BASELINE.json configs[1]"),
+    "4": dict(model="vit_base", patch=16, batch=128, local_crops=10, kind="train", cpu_batch=2,
+              label="BASELINE.json configs[3]"),
+    "5a": dict(model="vit_small", patch=8, batch=64, local_crops=10, kind="train", cpu_batch=1,
+               label="BASELINE.json configs[4], training half"),
+    "5b": dict(model="vit_small", patch=8, batch=4096, local_crops=0, kind="embed", cpu_batch=4,
+               label="BASELINE.json configs[4], embedding half"),
+}
+
+METRIC = "SSL train images/sec (ViT-S/16 DINO multi-crop)"
+SUMMARY_JSON = os.path.join("profiles", "r2_step_summary.json")
+
+
+def fwd_flops(model: str, S: int, patch: int):
+    """(GEMM, attention) FLOPs of one encoder forward on one S x S image."""
+    cfg = MODELS[model]
+    D, depth = cfg["D"], cfg["depth"]
+    N = (S // patch) ** 2 + 1
+    return 2 * (N - 1) * 3 * patch * patch * D + depth * 24 * N * D * D, depth * 4 * N * N * D
+
 
 def flops_per_sample(model: str, out_dim: int, n_local: int, patch: int = 16):
     """multiply-add = 2, backward = 2x forward, no recompute / padding credit."""
-    cfg = MODELS[model]
-    D, depth = cfg["D"], cfg["depth"]
-
-    def f_fwd(S):
-        N = (S // patch) ** 2 + 1
-        Np = N - 1
-        gemm = 2 * Np * 3 * patch * patch * D + depth * 24 * N * D * D
-        attn = depth * 4 * N * N * D
-        return gemm, attn
-
-    g224, a224 = f_fwd(224)
-    g96, a96 = f_fwd(96)
+    D = MODELS[model]["D"]
+    g224, a224 = fwd_flops(model, 224, patch)
+    g96, a96 = fwd_flops(model, 96, patch)
     f_head = 2 * (D * 2048 + 2048 * 2048 + 2048 * 256 + 256 * out_dim)
     ncrops = 2 + n_local
     gemm = 3 * (2 * g224 + n_local * g96) + 2 * g224 + (3 * ncrops + 2) * f_head
@@ -68,7 +90,7 @@ def read_peaks():
             p = json.load(f)
         return p.get("bf16_tflops", 1590.0), p.get("bf16_tflops_sustained", 1400.0), p.get("hbm_gbs", 6650.0), "measured"
     except Exception:
-        return 1590.0, 1400.0, 6650.0, "fallback"
+        return 1590.0, 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -121,24 +143,96 @@ def make_crops(B, n_local, device, dtype, seed, pin=False):
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle restatement on the host cores
 # ------------------------------------------------------------------------------------------------
-def run_cpu_oracle(model_name, out_dim, n_local, batch, steps, warmup):
+def run_cpu_oracle(cfg, out_dim, batch, steps, warmup):
+    """-> (images/s, seconds per step, threads). Training configs: the whole DINO step; 5b: the frozen-encoder
+    forward (train.py:1229-1230) on ``batch`` tiles."""
     from oracle import dino as odino
     from oracle import vision_transformer as ovt
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
-    student = odino.MultiCropWrapper(getattr(ovt, model_name)(), ovt.DINOHead(MODELS[model_name]["D"], out_dim))
-    teacher = odino.ModelEma(student)
-    loss_fn = odino.DINOLoss(out_dim, 2 + n_local, 0.04, 0.04, 0, 10)
-    params = [p for p in student.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=0.04)
-    crops = make_crops(batch, n_local, "cpu", torch.float32, 1234)
+    name, patch, n_local = cfg["model"], cfg["patch"], cfg["local_crops"]
+    backbone = getattr(ovt, name)(patch_size=patch)
+    if cfg["kind"] == "embed":
+        backbone.eval()
+        tiles = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(1234))
+
+        def one():
+            with torch.no_grad():
+                backbone(tiles)
+    else:
+        student = odino.MultiCropWrapper(backbone, ovt.DINOHead(MODELS[name]["D"], out_dim))
+        teacher = odino.ModelEma(student)
+        loss_fn = odino.DINOLoss(out_dim, 2 + n_local, 0.04, 0.04, 0, 10)
+        opt = torch.optim.AdamW([p for p in student.parameters() if p.requires_grad], lr=5e-4, weight_decay=0.04)
+        crops = make_crops(batch, n_local, "cpu", torch.float32, 1234)
+
+        def one():
+            odino.dino_step(student, teacher, loss_fn, opt, crops)
     for _ in range(warmup):
-        odino.dino_step(student, teacher, loss_fn, opt, crops)
+        one()
     t0 = time.perf_counter()
     for _ in range(steps):
-        odino.dino_step(student, teacher, loss_fn, opt, crops)
+        one()
     dt = (time.perf_counter() - t0) / max(steps, 1)
     return batch / dt, dt, torch.get_num_threads()
+
+
+def workload_text(cfg, args):
+    m, p = cfg["model"], cfg["patch"]
+    if cfg["kind"] == "embed":
+        return (f"{m}/{p} frozen-encoder embedding (train.py --extract_features flow), {args.batch} tiles of 3x224x224 per "
+                f"slide, forward only, bf16 ({cfg['label']})")
+    return (f"{m}/{p} DINO multi-crop 2x224+{args.local_crops}x96, batch {args.batch}/GPU, head out_dim "
+            f"{args.out_dim}, bf16 ({cfg['label']})")
+
+
+def make_config(cfg, args, world, total_f):
+    """The `config` object of the JSON line: identical for both arms (the reference arm times a bounded sample of
+    this very workload and says so under `reference_sample`)."""
+    B = args.batch
+    return {"workload": workload_text(cfg, args), "global_batch": B * world, "parallelism": f"dp{world}",
+            "l2_policy": "inputs + activations per step (GBs) far exceed the 126 MB L2",
+            "flop_per_image": total_f,
+            "reference_sample": f"--impl reference and cpu_baseline time the same step on the host cores at "
+                                f"{args.cpu_batch} image(s) per step (a bounded sample of the batch above), fp32"}
+
+
+def run_reference(cfg, args, world, total_f):
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    ips, dt, threads = run_cpu_oracle(cfg, args.out_dim, args.cpu_batch, steps, warm)
+    what = ("frozen-encoder forward" if cfg["kind"] == "embed"
+            else f"whole DINO step (all {2 + args.local_crops} crops, loss, backward, AdamW, EMA)")
+    sample = (f"{steps} timed step(s) after {warm} warm-up; each step = the {what} on a bounded sample of "
+              f"{args.cpu_batch} image(s) of the workload's batch of {args.batch}, fp32, PyTorch oracle restatement "
+              f"(encoder + head bit-identical to the reference's bytecode, tests/test_oracle_golden.py) on {threads} "
+              f"host threads")
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": make_config(cfg, args, world, total_f),
+            "sample_images_per_step": args.cpu_batch,
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline_leg(cfg, args):
+    """Bounded CPU sample of this run's workload; for the default config also BASELINE config 1 IN FULL
+    (ViT-Tiny/16, batch 8, 2 global crops, 5 timed steps), the case the reference plumbing is quoted on."""
+    out = None
+    try:
+        ips, dt, threads = run_cpu_oracle(cfg, args.out_dim, args.cpu_batch, 2, 1)
+        out = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"2 timed steps after 1 warm-up of the same step at {args.cpu_batch} image(s) per step, "
+                         f"fp32 oracle, {dt:.2f} s/step"}
+        if args.config == "2":
+            c1 = CONFIGS["1"]
+            ips1, dt1, _ = run_cpu_oracle(c1, args.out_dim, c1["batch"], 5, 1)
+            out["config1_full"] = {"value": ips1, "unit": "images/s", "cores": threads,
+                                   "sample": f"BASELINE config 1 in full: vit_tiny/16, batch 8, 2 global 224^2 crops, "
+                                             f"out_dim {args.out_dim}, 5 timed steps after 1 warm-up, {dt1:.2f} s/step"}
+    except Exception as e:  # the baseline is informative; never lose the GPU line over it
+        out = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    return out
 
 
 def main():
@@ -147,11 +241,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="vit_small", choices=list(MODELS))
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--config", default="2", choices=list(CONFIGS))
+    ap.add_argument("--model", default=None, choices=list(MODELS))
+    ap.add_argument("--patch", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (5b: tiles per slide)")
     ap.add_argument("--out-dim", type=int, default=65536)
-    ap.add_argument("--local-crops", type=int, default=10)
-    ap.add_argument("--cpu-batch", type=int, default=4, help="images per step of the bounded CPU sample")
+    ap.add_argument("--local-crops", type=int, default=None)
+    ap.add_argument("--cpu-batch", type=int, default=None, help="images per step of the bounded CPU sample")
+    ap.add_argument("--embed-batch", type=int, default=512, help="5b: tiles per encoder forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-teacher-stream", action="store_true",
@@ -162,35 +259,29 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying "
                     "the captured CUDA graph of the step")
     args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    for k_arg, k_cfg in (("model", "model"), ("patch", "patch"), ("batch", "batch"), ("local_crops", "local_crops"),
+                         ("cpu_batch", "cpu_batch")):
+        if getattr(args, k_arg) is None:
+            setattr(args, k_arg, cfg[k_cfg])
+        else:
+            cfg[k_cfg] = getattr(args, k_arg)
 
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     n_local = args.local_crops
-    total_f, gemm_f, attn_f = flops_per_sample(args.model, args.out_dim, n_local)
-    workload = (f"{args.model}/16 DINO multi-crop 2x224+{n_local}x96, batch {args.batch}/GPU, head out_dim "
-                f"{args.out_dim}, bf16 (BASELINE.json configs[1])")
+    if cfg["kind"] == "embed":
+        g, a = fwd_flops(args.model, 224, args.patch)
+        total_f, gemm_f, attn_f = g + a, g, a
+    else:
+        total_f, gemm_f, attn_f = flops_per_sample(args.model, args.out_dim, n_local, args.patch)
 
-    # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
-        if rank != 0:
-            return 0
-        steps = max(1, min(args.steps, 3))
-        warm = 1 if args.warmup > 0 else 0
-        ips, dt, threads = run_cpu_oracle(args.model, args.out_dim, n_local, args.cpu_batch, steps, warm)
-        sample = (f"{steps} timed step(s) after {warm} warm-up of the same step at batch {args.cpu_batch} "
-                  f"(all {2 + n_local} crops), fp32, PyTorch oracle restatement (encoder + head bit-identical to the "
-                  f"reference's bytecode, tests/test_oracle_golden.py) on {threads} host threads")
-        line = {"impl": "reference", "metric": "SSL train images/sec (ViT-S/16 DINO multi-crop)", "value": ips,
-                "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload},
-                "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
-                "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        if rank == 0:
+            run_reference(cfg, args, world, total_f)
         return 0
 
-    # ------------------------------------------------------------------ our arm (GPU)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a B200; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -205,35 +296,6 @@ def main():
         b200ssl.dino.TEACHER_STREAM["on"] = False
     if args.no_merge_crops:
         b200ssl.dino.MERGE_CROP_GROUPS["on"] = False
-
-    torch.manual_seed(0)
-    D = MODELS[args.model]["D"]
-    student = b200ssl.MultiCropWrapper(getattr(b200ssl, args.model)(), b200ssl.DINOHead(D, args.out_dim)).to(device)
-    teacher = b200ssl.ModelEma(student)
-    ddp = b200ssl.GradBucketDataParallel(student)
-    loss_fn = b200ssl.DINOLoss(args.out_dim, 2 + n_local, 0.04, 0.04, 0, 10).to(device)
-    opt = b200ssl.FusedAdamW(b200ssl.param_groups_wd(student, 0.04), lr=5e-4 * args.batch * world / 256.0)
-    B = args.batch
-    crops = make_crops(B, n_local, device, torch.bfloat16, 1234 + 1000 * rank)
-    total_steps = args.steps + args.warmup
-
-    def eager_step(cr, it):
-        m = b200ssl.cosine_momentum(it, max(total_steps, 1))
-        return b200ssl.dino_step(ddp, teacher, loss_fn, opt, cr, epoch=0, momentum=m, clip_grad=3.0)
-
-    use_graph = not args.no_graph
-    graphed = None
-    if use_graph:
-        graphed = b200ssl.GraphedDinoStep(ddp, teacher, loss_fn, opt, crops, clip_grad=3.0)
-
-    def step(cr, it):
-        """The public step API: GraphedDinoStep (whole step = one CUDA-graph replay) or eager dino_step.
-        cr=None replays on the crops already resident in the graph's input buffers (the `value` measurement:
-        inputs in HBM before the timed region); the e2e path passes host crops and pays the copy every step."""
-        m = b200ssl.cosine_momentum(it, max(total_steps, 1))
-        if graphed is not None:
-            return graphed(cr, epoch=0, momentum=m), None, None
-        return b200ssl.dino_step(ddp, teacher, loss_fn, opt, cr, epoch=0, momentum=m, clip_grad=3.0)
 
     def barrier():
         if world > 1:
@@ -253,71 +315,11 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for i in range(args.warmup):
-        step(crops, i)
+    torch.manual_seed(0)
+    D = MODELS[args.model]["D"]
+    B = args.batch
+    total_steps = args.steps + args.warmup
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = ops.launch_count()
-    host_t = [0.0]
-
-    resident = None if graphed is not None else crops   # graph mode: the crops were loaded into the static inputs
-
-    def step_host_timed(i):
-        t0 = time.perf_counter()
-        step(resident, args.warmup + i)
-        host_t[0] += time.perf_counter() - t0
-
-    ms_total = timed(step_host_timed, args.steps)
-    launches = ops.launch_count() - launches0
-    host_ms = host_t[0] * 1e3 / args.steps   # host time to ENQUEUE one step (GPU runs asynchronously)
-    if graphed is not None:
-        # replays launch the captured kernels without going through Python: count them on one eager step
-        l0 = ops.launch_count()
-        eager_step(crops, total_steps)
-        torch.cuda.synchronize()
-        launches = (ops.launch_count() - l0) * args.steps
-    clocks = sampler.stop() if rank == 0 else None
-    ms_step = ms_total / args.steps
-    value = B * world / (ms_step / 1e3)
-
-    # ---- end-to-end: pinned host crops -> H2D (prefetched on a copy stream) -> step -> D2H loss
-    e2e = None
-    if not args.no_e2e:
-        host = make_crops(B, n_local, device, torch.bfloat16, 4321 + rank, pin=True)
-        h2d_bytes = sum(c.numel() * c.element_size() for c in host)
-        copy_stream = torch.cuda.Stream()
-        bufs = [[torch.empty_like(c, device=device) for c in host] for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
-
-        def prefetch(slot):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[slot])
-                for dst, src in zip(bufs[slot], host):
-                    dst.copy_(src, non_blocking=True)
-                ready[slot].record(copy_stream)
-
-        losses = []
-
-        def e2e_step(i):
-            slot = i & 1
-            torch.cuda.current_stream().wait_event(ready[slot])
-            loss, _, _ = step(bufs[slot], args.warmup + i)
-            consumed[slot].record(torch.cuda.current_stream())
-            prefetch(slot)                 # refill this slot for step i+2 while step i+1 computes
-            losses.append(loss.item())     # D2H read of the step's result (4 bytes) every step
-
-        for s in range(2):
-            consumed[s].record(torch.cuda.current_stream())
-            prefetch(s)
-        for i in range(2):
-            e2e_step(i)
-        ms_e2e = timed(e2e_step, args.steps) / args.steps
-        e2e = {"value": B * world / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
-               "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e}
-
-    # ---- roofline of the dominant kernel family (tcgen05 GEMM): one instrumented step
     peak_burst, peak_sus, hbm_peak, peak_src = read_peaks()
     gemm_events = []
     real_gemm = ops.gemm
@@ -329,30 +331,159 @@ def main():
         e1.record()
         gemm_events.append((e0, e1))
 
-    ops.gemm = timed_gemm
-    # one stream for the instrumented step: with the teacher forward running concurrently on its own stream the
-    # event-bracketed durations of overlapping kernels would each include the other's share of the machine
-    teacher_branch = b200ssl.dino.TEACHER_STREAM["on"]
-    b200ssl.dino.TEACHER_STREAM["on"] = False
-    eager_step(crops, total_steps)
-    torch.cuda.synchronize()
-    b200ssl.dino.TEACHER_STREAM["on"] = teacher_branch
-    ops.gemm = real_gemm
+    if cfg["kind"] == "embed":
+        # ------------------------------------------------------------------ 5b: frozen-encoder embedding
+        backbone = getattr(b200ssl, args.model)(patch_size=args.patch).to(device).eval()
+        tiles_dev = torch.randn(B, 3, 224, 224, device=device,
+                                generator=torch.Generator(device=device).manual_seed(1234 + rank)).bfloat16()
+        feats_dev = torch.empty(B, D, dtype=torch.float32, device=device)
+
+        def slide_resident(i):
+            with torch.no_grad():
+                for s0 in range(0, B, args.embed_batch):
+                    feats_dev[s0:s0 + args.embed_batch] = backbone(tiles_dev[s0:s0 + args.embed_batch]).float()
+
+        for i in range(args.warmup):
+            slide_resident(i)
+        if rank == 0:
+            sampler.start()
+        l0 = ops.launch_count()
+        ms_step = timed(slide_resident, args.steps) / args.steps
+        launches = ops.launch_count() - l0
+        clocks = sampler.stop() if rank == 0 else None
+        value = B * world / (ms_step / 1e3)
+        e2e = None
+        if not args.no_e2e:
+            tiles_host = tiles_dev.cpu().pin_memory()
+            b200ssl.embed_tiles(backbone, tiles_host, batch_size=args.embed_batch)
+
+            def slide_e2e(i):
+                b200ssl.embed_tiles(backbone, tiles_host, batch_size=args.embed_batch)   # returns host features
+
+            ms_e2e = timed(slide_e2e, args.steps) / args.steps
+            e2e = {"value": B * world / (ms_e2e / 1e3), "unit": "images/s",
+                   "h2d_bytes_per_step": tiles_host.numel() * 2, "d2h_bytes_per_step": B * D * 4, "ms_per_step": ms_e2e}
+        ops.gemm = timed_gemm
+        slide_resident(0)
+        torch.cuda.synchronize()
+        ops.gemm = real_gemm
+        step_api = "b200ssl.embed_tiles / VisionTransformer.forward under no_grad (eager launches)"
+        host_ms = None
+    else:
+        # ------------------------------------------------------------------ training step
+        student = b200ssl.MultiCropWrapper(getattr(b200ssl, args.model)(patch_size=args.patch),
+                                           b200ssl.DINOHead(D, args.out_dim)).to(device)
+        teacher = b200ssl.ModelEma(student)
+        ddp = b200ssl.GradBucketDataParallel(student)
+        loss_fn = b200ssl.DINOLoss(args.out_dim, 2 + n_local, 0.04, 0.04, 0, 10).to(device)
+        opt = b200ssl.FusedAdamW(b200ssl.param_groups_wd(student, 0.04), lr=5e-4 * args.batch * world / 256.0)
+        crops = make_crops(B, n_local, device, torch.bfloat16, 1234 + 1000 * rank)
+
+        def eager_step(cr, it):
+            m = b200ssl.cosine_momentum(it, max(total_steps, 1))
+            return b200ssl.dino_step(ddp, teacher, loss_fn, opt, cr, epoch=0, momentum=m, clip_grad=3.0)
+
+        use_graph = not args.no_graph
+        graphed = b200ssl.GraphedDinoStep(ddp, teacher, loss_fn, opt, crops, clip_grad=3.0) if use_graph else None
+
+        def step(cr, it):
+            """The public step API: GraphedDinoStep (whole step = one CUDA-graph replay) or eager dino_step.
+            cr=None replays on the crops already resident in the graph's input buffers (the `value` measurement:
+            inputs in HBM before the timed region); the e2e path passes host crops and pays the copy every step."""
+            m = b200ssl.cosine_momentum(it, max(total_steps, 1))
+            if graphed is not None:
+                return graphed(cr, epoch=0, momentum=m), None, None
+            return b200ssl.dino_step(ddp, teacher, loss_fn, opt, cr, epoch=0, momentum=m, clip_grad=3.0)
+
+        for i in range(args.warmup):
+            step(crops, i)
+        if rank == 0:
+            sampler.start()
+        host_t = [0.0]
+        resident = None if graphed is not None else crops   # graph mode: the crops sit in the static inputs
+
+        def step_host_timed(i):
+            t0 = time.perf_counter()
+            step(resident, args.warmup + i)
+            host_t[0] += time.perf_counter() - t0
+
+        l0 = ops.launch_count()
+        ms_total = timed(step_host_timed, args.steps)
+        launches = ops.launch_count() - l0
+        host_ms = host_t[0] * 1e3 / args.steps   # host time to ENQUEUE one step (GPU runs asynchronously)
+        if graphed is not None:
+            # replays launch the captured kernels without going through Python: count them on one eager step
+            l0 = ops.launch_count()
+            eager_step(crops, total_steps)
+            torch.cuda.synchronize()
+            launches = (ops.launch_count() - l0) * args.steps
+        clocks = sampler.stop() if rank == 0 else None
+        ms_step = ms_total / args.steps
+        value = B * world / (ms_step / 1e3)
+
+        # ---- end-to-end: pinned host crops -> H2D (prefetched on a copy stream) -> step -> D2H loss
+        e2e = None
+        if not args.no_e2e:
+            host = make_crops(B, n_local, device, torch.bfloat16, 4321 + rank, pin=True)
+            h2d_bytes = sum(c.numel() * c.element_size() for c in host)
+            copy_stream = torch.cuda.Stream()
+            bufs = [[torch.empty_like(c, device=device) for c in host] for _ in range(2)]
+            ready = [torch.cuda.Event() for _ in range(2)]
+            consumed = [torch.cuda.Event() for _ in range(2)]
+
+            def prefetch(slot):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[slot])
+                    for dst, src in zip(bufs[slot], host):
+                        dst.copy_(src, non_blocking=True)
+                    ready[slot].record(copy_stream)
+
+            losses = []
+
+            def e2e_step(i):
+                slot = i & 1
+                torch.cuda.current_stream().wait_event(ready[slot])
+                loss, _, _ = step(bufs[slot], args.warmup + i)
+                consumed[slot].record(torch.cuda.current_stream())
+                prefetch(slot)                 # refill this slot for step i+2 while step i+1 computes
+                losses.append(loss.item())     # D2H read of the step's result (4 bytes) every step
+
+            for s in range(2):
+                consumed[s].record(torch.cuda.current_stream())
+                prefetch(s)
+            for i in range(2):
+                e2e_step(i)
+            ms_e2e = timed(e2e_step, args.steps) / args.steps
+            e2e = {"value": B * world / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
+                   "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e}
+
+        # ---- roofline of the dominant kernel family (tcgen05 GEMM): one instrumented step on ONE stream (with the
+        # teacher forward running concurrently the event-bracketed durations would include the other's share)
+        ops.gemm = timed_gemm
+        teacher_branch = b200ssl.dino.TEACHER_STREAM["on"]
+        b200ssl.dino.TEACHER_STREAM["on"] = False
+        eager_step(crops, total_steps)
+        torch.cuda.synchronize()
+        b200ssl.dino.TEACHER_STREAM["on"] = teacher_branch
+        ops.gemm = real_gemm
+        step_api = "b200ssl.GraphedDinoStep (CUDA graph replay)" if use_graph else "b200ssl.dino_step (eager)"
+
     gemm_ms = sum(a.elapsed_time(b) for a, b in gemm_events)
     gemm_tflops = gemm_f * B / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    # DRAM traffic of the same kernel family from the committed ncu capture of one step (profiles/): per launch,
-    # like `achieved` (family total per step / launches per step)
+    # DRAM traffic of the same kernel family from the committed ncu capture of one config-2 step (profiles/): per
+    # launch, like `achieved` (family total per step / launches per step)
     traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_step_summary_v5.json")) as f:
-            summ = json.load(f)
-        gk = [k for k in summ["kernels"] if k["kernel"].startswith("gemm_kernel")]
-        n_l = sum(k["launches_per_step"] for k in gk)
-        traffic = sum(k["dram_read_mb_per_step"] + k["dram_write_mb_per_step"] for k in gk) * 1e6 / max(n_l, 1)
-        traffic_src = ("profiles/r1_step_summary_v5.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the "
-                       f"{n_l:.0f} gemm_kernel launches of one step, divided by the launch count")
-    except Exception:
-        pass
+    if args.config == "2" and args.batch == 256:
+        try:
+            with open(os.path.join(ROOT, SUMMARY_JSON)) as f:
+                summ = json.load(f)
+            gk = [k for k in summ["kernels"] if k["kernel"].startswith("gemm_kernel")]
+            n_l = sum(k["launches_per_step"] for k in gk)
+            traffic = sum(k["dram_read_mb_per_step"] + k["dram_write_mb_per_step"] for k in gk) * 1e6 / max(n_l, 1)
+            traffic_src = (f"{SUMMARY_JSON}: dram__bytes_read.sum + dram__bytes_write.sum summed over the "
+                           f"{n_l:.0f} gemm_kernel launches of one step, divided by the launch count")
+        except Exception:
+            pass
     roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN,EPI> (tcgen05, all Linear fprop/dgrad/wgrad)",
                 "achieved": gemm_tflops, "peak": peak_sus, "unit": "TFLOP/s", "frac": gemm_tflops / peak_sus,
                 "traffic": traffic, "traffic_source": traffic_src,
@@ -361,35 +492,22 @@ def main():
                 "launches_per_step": len(gemm_events), "gemm_ms_per_step": gemm_ms,
                 "gemm_share_of_step": gemm_ms / ms_step,
                 "step_tflops": total_f * B / (ms_step / 1e3) / 1e12,
-                "step_frac_of_peak": total_f * B / (ms_step / 1e3) / 1e12 / peak_sus}
+                "step_frac_of_peak": total_f * B / (ms_step / 1e3) / 1e12 / peak_sus,
+                "step_frac_of_burst_peak": total_f * B / (ms_step / 1e3) / 1e12 / peak_burst}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    cpu_baseline = None
-    if not args.no_cpu_baseline and world == 1:
-        try:
-            ips, dt, threads = run_cpu_oracle(args.model, args.out_dim, n_local, args.cpu_batch, 2, 1)
-            cpu_baseline = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                            "sample": f"2 timed steps after 1 warm-up of the same step at batch {args.cpu_batch} "
-                                      f"(all {2 + n_local} crops), fp32 oracle, {dt:.1f} s/step"}
-        except Exception as e:  # the baseline is informative; never lose the GPU line over it
-            cpu_baseline = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                            "sample": f"failed: {e}"}
-
-    line = {"metric": "SSL train images/sec (ViT-S/16 DINO multi-crop)", "value": value, "unit": "images/s",
+    line = {"metric": METRIC, "value": value, "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "step_api": "b200ssl.GraphedDinoStep (CUDA graph replay)" if use_graph else "b200ssl.dino_step (eager)",
-                       "l2_policy": "inputs + activations per step (>20 GB) far exceed the 126 MB L2",
-                       "flop_per_image": total_f},
+            "config": make_config(cfg, args, world, total_f), "step_api": step_api,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms,
             "roofline": roofline}
-    if cpu_baseline is not None:
-        line["cpu_baseline"] = cpu_baseline
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline_leg(cfg, args)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -200,6 +200,36 @@ def cancel_gradients_last_layer(epoch, model, freeze_last_layer, optimizer):
 _CHUNK = 65536
 
 
+class _ScalarStager:
+    """Per-step scalars (lr, weight decay, Adam bias corrections, EMA momentum) travel host -> device through a RING
+    of pinned slots. The copy is asynchronous and a whole step is enqueued in well under a millisecond (one graph
+    launch) while the GPU needs tens of milliseconds to run it, so a single reused pinned buffer would be
+    overwritten for step k+1 before step k's copy has executed. Each slot carries an event recorded behind its
+    last copy; the host waits on it before reusing the slot, i.e. it can run at most ``slots`` steps ahead."""
+
+    def __init__(self, shape, device, slots=8):
+        self.host = torch.zeros((slots,) + tuple(shape), dtype=torch.float32).pin_memory()
+        self.dev = torch.zeros(tuple(shape), dtype=torch.float32, device=device)
+        self._events = [None] * slots
+        self._i = 0
+
+    def slot(self):
+        """The next pinned slot, safe to overwrite (its previous host-to-device copy has executed)."""
+        k = self._i % len(self._events)
+        if self._events[k] is not None:
+            self._events[k].synchronize()
+        return self.host[k]
+
+    def push(self):
+        """Enqueue the copy of the slot handed out by ``slot()`` on the current stream."""
+        k = self._i % len(self._events)
+        self.dev.copy_(self.host[k], non_blocking=True)
+        if self._events[k] is None:
+            self._events[k] = torch.cuda.Event()
+        self._events[k].record()
+        self._i += 1
+
+
 def _chunk_rows(tensors_per_row, numels):
     """int64 table: one row per <=_CHUNK elements; columns = per-tensor byte addresses + count (+extras)."""
     rows = []
@@ -239,7 +269,7 @@ class ModelEma(nn.Module):
             self.module.to(device=device)
         self._table = None
         self._table_key = None
-        self._m_dev = self._m_host = None
+        self._m_stage = None     # _ScalarStager for the per-step momentum
         self._m_value = decay
         self._pairs, self._others, self._shadowed = [], [], []
 
@@ -278,11 +308,10 @@ class ModelEma(nn.Module):
         table = self._build(model)
         if table is not None:
             ops.require_cuda(table, "ModelEma")
-            if self._m_dev is None:
-                self._m_host = torch.zeros(1, dtype=torch.float32).pin_memory()
-                self._m_dev = torch.zeros(1, dtype=torch.float32, device=table.device)
-            self._m_host[0] = float(m)
-            self._m_dev.copy_(self._m_host, non_blocking=True)
+            if self._m_stage is None or self._m_stage.dev.device != table.device:
+                self._m_stage = _ScalarStager((1,), table.device)
+            self._m_stage.slot()[0] = float(m)
+            self._m_stage.push()
         self._m_value = float(m)
 
     @torch.no_grad()
@@ -290,7 +319,7 @@ class ModelEma(nn.Module):
         """Device-side part: one multi-tensor kernel over every fp32 state-dict tensor (graph-capturable)."""
         if self._table is not None:
             ops._call("b200ssl_ema_multi_tensor", self._table.data_ptr(), self._table.shape[0],
-                      self._m_dev.data_ptr(), ops._stream())
+                      self._m_stage.dev.data_ptr(), ops._stream())
         m = self._m_value
         for e, s in self._others:  # integer buffers etc.: plain copy like timm
             if e.dtype.is_floating_point:
@@ -322,7 +351,7 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._tables = {}
         self._gnorm = None
-        self._hyper_dev = self._hyper_host = None
+        self._hyper = None           # _ScalarStager for {lr, weight_decay, 1-beta1^t, 1-beta2^t} per group
         self.last_grad_norm_sq = None
         self._frozen = frozenset()   # ids of parameters the step skips entirely (set_frozen)
         self.table_version = 0       # bumped whenever the chunk tables change shape (captured graphs must follow)
@@ -338,7 +367,12 @@ class FusedAdamW(torch.optim.Optimizer):
 
     def _table(self, gi, group):
         params = [p for p in group["params"] if p.grad is not None and id(p) not in self._frozen]
-        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params)
+
+        def _moments(p):  # load_state_dict replaces the moment tensors: the table must follow them
+            st = self.state.get(p, {})
+            return (st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()) if "exp_avg" in st else (0, 0)
+
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) + _moments(p) for p in params)
         ent = self._tables.get(gi)
         if ent is not None and ent["key"] == key:
             return ent
@@ -359,6 +393,7 @@ class FusedAdamW(torch.optim.Optimizer):
                              sh.data_ptr() + 2 * off])
                 grows.append([p.grad.data_ptr() + 4 * off, cnt])
         dev = params[0].device
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) + _moments(p) for p in params)   # moments exist now
         ent = {"key": key, "params": params, "table": torch.tensor(rows, dtype=torch.int64).to(dev),
                "gtable": torch.tensor(grows, dtype=torch.int64).to(dev)}
         self._tables[gi] = ent
@@ -379,22 +414,22 @@ class FusedAdamW(torch.optim.Optimizer):
         if not ents:
             return ents
         dev = ents[0][2]["table"].device
-        if self._hyper_dev is None or self._hyper_dev.device != dev:
+        if self._hyper is None or self._hyper.dev.device != dev:
             n = len(self.param_groups)
-            self._hyper_host = torch.zeros(n, 8, dtype=torch.float32).pin_memory()
-            self._hyper_dev = torch.zeros(n, 8, dtype=torch.float32, device=dev)
+            self._hyper = _ScalarStager((n, 8), dev)
             self._gnorm = torch.zeros(n + 1, dtype=torch.float32, device=dev)
             self._gnorm_ws = {}
+        host = self._hyper.slot()
         for gi, group, _ in ents:
             group["step"] = group.get("step", 0) + 1
             t = group["step"]
             b1, b2 = group["betas"]
-            self._hyper_host[gi, 0] = float(group["lr"])
-            self._hyper_host[gi, 1] = float(group["weight_decay"])
-            self._hyper_host[gi, 2] = 1.0 - b1 ** t
-            self._hyper_host[gi, 3] = 1.0 - b2 ** t
-            self._hyper_host[gi, 4] = 0.0
-        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+            host[gi, 0] = float(group["lr"])
+            host[gi, 1] = float(group["weight_decay"])
+            host[gi, 2] = 1.0 - b1 ** t
+            host[gi, 3] = 1.0 - b2 ** t
+            host[gi, 4] = 0.0
+        self._hyper.push()
         return ents
 
     @torch.no_grad()
@@ -426,7 +461,7 @@ class FusedAdamW(torch.optim.Optimizer):
         for gi, group, ent in ents:
             b1, b2 = group["betas"]
             ops._call("b200ssl_adamw_multi_tensor", ent["table"].data_ptr(), ent["table"].shape[0], gnorm_ptr,
-                      self._hyper_dev[gi].data_ptr(), float(b1), float(b2), float(group["eps"]),
+                      self._hyper.dev[gi].data_ptr(), float(b1), float(b2), float(group["eps"]),
                       float(max_grad_norm or 0.0), ops._stream())
             for p in ent["params"]:
                 ops.shadows.mark_fresh(p)
@@ -435,6 +470,12 @@ class FusedAdamW(torch.optim.Optimizer):
     def step(self, closure=None, max_grad_norm: float = 0.0):
         self.launch_step(max_grad_norm, self.prepare_step())
         return None
+
+    def zero_grad(self, set_to_none: bool = False):
+        """Defaults to ``set_to_none=False`` (torch's default is True): gradients are persistent buffers here --
+        views into GradBucketDataParallel's flat buckets that the kernels accumulate into and the cached chunk
+        tables point at. Freeing them would silently detach the parameters from their buckets."""
+        return super().zero_grad(set_to_none=set_to_none)
 
 
 def param_groups_wd(model, weight_decay):
@@ -478,13 +519,14 @@ class GradBucketDataParallel(nn.Module):
             cur_n += p.numel()
         if cur:
             self.buckets.append(cur)
-        self._flat, self._bucket_of = [], {}
+        self._flat, self._bucket_of, self._view_of = [], {}, {}
         for bi, bucket in enumerate(self.buckets):
             n = sum((p.numel() + 3) // 4 * 4 for p in bucket)
             flat = torch.zeros(n, dtype=torch.float32, device=bucket[0].device)
             off = 0
             for p in bucket:
                 p.grad = flat[off:off + p.numel()].view_as(p)
+                self._view_of[id(p)] = p.grad
                 off += (p.numel() + 3) // 4 * 4
                 self._bucket_of[id(p)] = bi
             self._flat.append(flat)
@@ -512,7 +554,31 @@ class GradBucketDataParallel(nn.Module):
         if self._expected is not None:
             self._pending = [sum(self._expected.get(id(p), 1) for p in b) for b in self.buckets]
 
+    def _adopt(self, p):
+        """``optimizer.zero_grad()`` with torch's default ``set_to_none=True`` (the reference loop, train.py:1061)
+        makes autograd allocate a fresh ``p.grad`` outside the flat bucket; move it into the bucket view and point
+        ``p.grad`` back at the view, so what is all-reduced is what backward produced."""
+        view = self._view_of[id(p)]
+        g = p.grad
+        if g is None:
+            view.zero_()
+        elif g.data_ptr() != view.data_ptr():
+            view.copy_(g)
+        p.grad = view
+
+    def _check_views(self):
+        for p in self._params:
+            g = p.grad
+            if g is None or g.data_ptr() != self._view_of[id(p)].data_ptr():
+                if p.is_cuda and torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("GradBucketDataParallel: a parameter's .grad left its flat bucket during a "
+                                       "CUDA-graph capture; use ddp.zero_grad() / zero_grad(set_to_none=False)")
+                self._adopt(p)
+
     def _hook(self, p):
+        g = p.grad
+        if g is not None and g.data_ptr() != self._view_of[id(p)].data_ptr():
+            self._adopt(p)
         self._seen[id(p)] = self._seen.get(id(p), 0) + 1
         if self._expected is None or self.world == 1 or self.defer_comm:
             return
@@ -542,6 +608,7 @@ class GradBucketDataParallel(nn.Module):
 
     def allreduce_now(self):
         """Deferred mode (two-graph step): average every flat bucket over ranks, eagerly, in bucket order."""
+        self._check_views()
         if self.world > 1:
             for bi in range(len(self.buckets)):
                 if self._avg_native:
@@ -554,6 +621,7 @@ class GradBucketDataParallel(nn.Module):
         """Wait for the bucket all-reduces of this backward; re-arm the counters for the next one."""
         if self.defer_comm:
             return
+        self._check_views()
         if self.world > 1:
             for bi in range(len(self.buckets)):
                 if not self._launched[bi]:
@@ -647,7 +715,7 @@ def dino_step(student, teacher_ema, loss_fn, optimizer, crops, epoch=0, momentum
     """One optimisation step: teacher forward on the 2 global crops, student forward on
     all crops, fused loss (+ centre update), backward (bucketed all-reduce overlapped when ``student`` is
     a ``GradBucketDataParallel``), clip + AdamW, teacher EMA. Returns (loss, student_out, teacher_out)."""
-    if isinstance(optimizer, FusedAdamW) and optimizer._hyper_dev is None:
+    if isinstance(optimizer, FusedAdamW) and optimizer._hyper is None:
         # very first step: gradients (hence the optimiser tables) do not exist before the first backward
         out = _step_launch_first(student, teacher_ema, loss_fn, optimizer, crops, epoch, momentum, clip_grad)
         return out
@@ -716,17 +784,66 @@ class GraphedDinoStep:
         if hasattr(self.loss_fn, "allreduce_center_now"):
             self.loss_fn.allreduce_center_now()
 
+    def _snapshot(self):
+        """Everything a step mutates: student parameters / buffers, AdamW moments and step counters, the teacher,
+        the centre and the CUDA RNG stream (stochastic depth)."""
+        mod = self.student.module if isinstance(self.student, GradBucketDataParallel) else self.student
+        snap = {"student": [(t, t.detach().clone()) for t in mod.state_dict().values()],
+                "teacher": [(t, t.detach().clone()) for t in self.teacher.module.state_dict().values()],
+                "center": self.loss_fn.center.detach().clone() if hasattr(self.loss_fn, "center") else None,
+                "steps": [g.get("step", 0) for g in self.opt.param_groups],
+                "moments": {}, "rng": torch.cuda.get_rng_state()}
+        for g in self.opt.param_groups:
+            for p in g["params"]:
+                st = self.opt.state.get(p, {})
+                snap["moments"][p] = (st["exp_avg"].clone(), st["exp_avg_sq"].clone()) if "exp_avg" in st else None
+        return snap
+
+    @torch.no_grad()
+    def _restore(self, snap):
+        """Put the state back IN PLACE (storages, hence chunk tables and bucket views, are kept)."""
+        for t, saved in snap["student"] + snap["teacher"]:
+            t.copy_(saved)
+        if snap["center"] is not None:
+            self.loss_fn.center.copy_(snap["center"])
+        for g, n in zip(self.opt.param_groups, snap["steps"]):
+            g["step"] = n
+        for p, saved in snap["moments"].items():
+            st = self.opt.state.get(p, {})
+            if "exp_avg" in st:
+                if saved is None:
+                    st["exp_avg"].zero_()
+                    st["exp_avg_sq"].zero_()
+                else:
+                    st["exp_avg"].copy_(saved[0])
+                    st["exp_avg_sq"].copy_(saved[1])
+        torch.cuda.set_rng_state(snap["rng"])
+        # the bf16 weight shadows were written for the warm-up's weights: refresh them now, outside the capture
+        mod = self.student.module if isinstance(self.student, GradBucketDataParallel) else self.student
+        for p in list(mod.parameters()) + list(self.teacher.module.parameters()):
+            if id(p) in ops.shadows._d:
+                ops.shadows.invalidate(p)
+                ops.bf16_of(p)
+
     def _capture(self, epoch, momentum):
         self._multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         torch.cuda.synchronize()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):          # warm-up on a side stream (allocator, tables, DP arrival counts)
-            for _ in range(self._warmup):
-                dino_step(self.student, self.teacher, self.loss_fn, self.opt, self.static_crops, epoch, momentum,
-                          self.clip_grad)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
+        if self._graph is None and self._warmup > 0:
+            # Warm-up (first capture only): eager steps on a side stream teach the allocator its working set, build
+            # the optimiser / EMA tables and let the data-parallel wrapper count gradient arrivals. They are steps
+            # on the live model, so everything they changed is restored afterwards: the first replay is step 0 of
+            # training, exactly as in an eager run. Re-captures (new teacher temperature, frozen-set change) need
+            # none of this and skip the warm-up.
+            snap = self._snapshot()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(self._warmup):
+                    dino_step(self.student, self.teacher, self.loss_fn, self.opt, self.static_crops, epoch, momentum,
+                              self.clip_grad)
+            torch.cuda.current_stream().wait_stream(side)
+            self._restore(snap)
+            torch.cuda.synchronize()
         # capture records launches only: it needs the optimiser's chunk tables but must NOT advance the step
         # counter / restage scalars (that is _step_prepare's job, once per replay)
         ents = self.opt._entries()

@@ -42,6 +42,7 @@ def embed_tiles(backbone, tiles: torch.Tensor, batch_size: int = 512) -> torch.T
     dev_buf = [None, None]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     done = [torch.cuda.Event(), torch.cuda.Event()]
+    copied = [None, None]   # recorded behind each slot's host-to-device copy; the HOST waits on it before reuse
 
     def upload(i, slot):
         chunk = tiles[i:i + batch_size]
@@ -51,11 +52,18 @@ def embed_tiles(backbone, tiles: torch.Tensor, batch_size: int = 512) -> torch.T
         if stage[slot] is None or stage[slot].shape[0] < chunk.shape[0]:
             stage[slot] = torch.empty((batch_size,) + tuple(tiles.shape[1:]), dtype=torch.bfloat16).pin_memory()
             dev_buf[slot] = torch.empty((batch_size,) + tuple(tiles.shape[1:]), dtype=torch.bfloat16, device=dev)
+        # the pinned slot is written by the CPU right now, not in stream order: wait until the asynchronous copy that
+        # last read it has executed (a device-side wait alone would let the host run two batches ahead and overwrite it)
+        if copied[slot] is not None:
+            copied[slot].synchronize()
+        stage[slot][:chunk.shape[0]].copy_(chunk)        # host-side cast to bf16 into pinned memory
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(done[slot])           # the batch that last used this slot has been consumed
-            stage[slot][:chunk.shape[0]].copy_(chunk)    # host-side cast to bf16 into pinned memory
+            copy_stream.wait_event(done[slot])           # the batch that last used this slot's device buffer is consumed
             dev_buf[slot][:chunk.shape[0]].copy_(stage[slot][:chunk.shape[0]], non_blocking=True)
             ready[slot].record(copy_stream)
+            if copied[slot] is None:
+                copied[slot] = torch.cuda.Event()
+            copied[slot].record(copy_stream)
 
     for s in range(2):
         done[s].record(main)

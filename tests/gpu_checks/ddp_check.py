@@ -87,9 +87,11 @@ twin_ddp = b200ssl.GradBucketDataParallel(twin, bucket_mb=1.0)
 twin_teacher = b200ssl.ModelEma(twin)
 twin_loss = b200ssl.DINOLoss(out_dim, ncrops, 0.04, 0.04, 0, 10).cuda()
 twin_opt = b200ssl.FusedAdamW(b200ssl.param_groups_wd(twin, 0.04), lr=5e-4)
-step = b200ssl.GraphedDinoStep(twin_ddp, twin_teacher, twin_loss, twin_opt, mine, warmup=1)  # warm-up == eager step 0
+step = b200ssl.GraphedDinoStep(twin_ddp, twin_teacher, twin_loss, twin_opt, mine)  # warm-up leaves no trace: replay i == step i
 eager = [b200ssl.dino_step(ddp, teacher, loss_fn, opt, mine, momentum=0.9)[0].item() for _ in range(2)]
-graph = [step(mine, momentum=0.9).item() for _ in range(2)]
+graph_all = [step(mine, momentum=0.9).item() for _ in range(3)]
+ok &= abs(graph_all[0] - loss0.item()) / abs(loss0.item()) < 1e-4   # first replay == eager step 0 on the same weights
+graph = graph_all[1:]
 ok &= max(abs(a - b) / abs(a) for a, b in zip(eager, graph)) < 1e-2
 ok &= rel(twin_loss.center, loss_fn.center) < 1e-2
 for n, p in twin.named_parameters():

@@ -102,6 +102,47 @@ def test_layernorm(ops, D, dtype):
     assert rel(db, br.grad) < 1e-3
 
 
+def _check_attention_grad(dqkv, ref):
+    """Gradients are gated by COSINE in the north star (>= 0.999 per tensor); forward outputs by norm-wise relative
+    error (<= 1e-2). dQ/dK/dV are required to reach cosine >= 0.9999 -- ten times closer to 1 than the gate. The
+    norm-wise error of a bf16 attention backward on unit-variance random inputs is bounded below by its operand
+    roundings (P and dS enter the second-stage MMAs as bf16, 2^-9 each, and the result is stored as bf16): the same
+    arithmetic done by torch (fp32 softmax, P / dS rounded to bf16, fp32 accumulation) lands at 1.0e-2 ... 1.2e-2, so
+    the relative bound stays at 1.5e-2 here and is reported, not silently widened."""
+    a, b = dqkv.float().flatten(), ref.float().flatten()
+    c = (torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)).item()
+    assert c > 0.9999, c
+    assert rel(dqkv, ref) < 1.5e-2, rel(dqkv, ref)
+
+
+def test_attention_grad_error_is_at_the_bf16_operand_floor(ops):
+    """Measures the floor named in _check_attention_grad: torch math with the SAME operand roundings as the kernel
+    (P, dS -> bf16; outputs -> bf16) against full fp32; the kernel must be within 25 % of it."""
+    B, N, H, scale = 4, 197, 6, 0.125
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv = torch.randn(B * N, 3 * H * 64, device="cuda", generator=g).bfloat16()
+    dout = torch.randn(B * N, H * 64, device="cuda", generator=g).bfloat16()
+    out, lse2 = ops.attention_fwd(qkv, B, N, H, scale)
+    dqkv = ops.attention_bwd(qkv, out, dout, lse2, B, N, H, scale)
+    qr = qkv.float().requires_grad_(True)
+    q, k, v = qr.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    p = ((q @ k.transpose(-2, -1)) * scale).softmax(-1)
+    o = (p @ v)
+    o.transpose(1, 2).reshape(B * N, H * 64).backward(dout.float())
+    with torch.no_grad():
+        do = dout.float().view(B, N, H, 64).permute(0, 2, 1, 3)
+        r16 = lambda t: t.bfloat16().float()
+        p16 = r16(p)
+        dv = p16.transpose(-2, -1) @ do
+        dp = do @ v.transpose(-2, -1)
+        delta = (do * r16(o)).sum(-1, keepdim=True)
+        ds16 = r16(p * (dp - delta) * scale)
+        dq, dk = ds16 @ k, ds16.transpose(-2, -1) @ q
+        floor = torch.stack((dq, dk, dv)).permute(1, 3, 0, 2, 4).reshape(B * N, 3 * H * 64).bfloat16()
+    e_floor, e_kernel = rel(floor, qr.grad), rel(dqkv, qr.grad)
+    assert e_kernel < 1.25 * e_floor + 1e-3, (e_kernel, e_floor)
+
+
 @pytest.mark.parametrize("B,N,H", [(2, 197, 6), (7, 37, 3), (3, 64, 2), (5, 100, 1), (2, 256, 2), (1, 1, 1)])
 def test_attention(ops, B, N, H):
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -118,7 +159,7 @@ def test_attention(ops, B, N, H):
     ref.backward(dout.float())
     dqkv = ops.attention_bwd(qkv, out, dout, lse2, B, N, H, scale)
     assert not torch.isnan(dqkv.float()).any()
-    assert rel(dqkv, qr.grad) < 1.5e-2
+    _check_attention_grad(dqkv, qr.grad)
 
 
 @pytest.mark.parametrize("B,N,H", [(3, 257, 2), (2, 785, 3), (5, 325, 6)])
@@ -137,7 +178,7 @@ def test_attention_long_sequences(ops, B, N, H):
     ref.backward(dout.float())
     dqkv = ops.attention_bwd(qkv, out, dout, lse2, B, N, H, 0.125)
     assert not torch.isnan(dqkv.float()).any()
-    assert rel(dqkv, qr.grad) < 1.5e-2
+    _check_attention_grad(dqkv, qr.grad)
 
 
 def test_attention_rejects_unsupported_lengths(ops):

@@ -2,8 +2,9 @@
 (oracle/ — fp32, TF32 off) on identical weights, inputs and seeds.
 
 Tolerances (north_star, bf16 path): loss and logits norm-wise relative error <= 1e-2; per-parameter
-gradient cosine similarity >= 0.999 (relaxed to 0.995 for tensors whose gradient is numerically tiny,
-stated at the assertion); EMA / centre relative error <= 1e-2.
+gradient cosine similarity >= 0.999; EMA / centre relative error <= 1e-2. Multi-step tests re-synchronise the
+weights / optimiser state from the oracle before every step, so each step is judged at the same gate on
+identical inputs (two trajectories that each took an Adam step are no longer "the same inputs").
 """
 import copy
 
@@ -304,42 +305,156 @@ def test_grad_checkpointing_recomputes_the_same_gradients(libs):
     assert res[True][2] < 0.35 * res[False][2], (res[True][2], res[False][2])
 
 
+def _sync_from_oracle(ref_student, student, ref_teacher, teacher, ref_loss, loss_fn, ref_opt, opt):
+    """Copy the oracle's state (weights, teacher, centre, AdamW moments and step count) into the CUDA path."""
+    with torch.no_grad():
+        for (_, p), (_, q) in zip(ref_student.state_dict().items(), student.state_dict().items()):
+            q.copy_(p)
+        for (_, p), (_, q) in zip(ref_teacher.module.state_dict().items(), teacher.module.state_dict().items()):
+            q.copy_(p)
+        loss_fn.finish_center_update()
+        loss_fn.center.copy_(ref_loss.center)
+        for gr, gm in zip(ref_opt.param_groups, opt.param_groups):
+            for pr, pm in zip(gr["params"], gm["params"]):
+                if pr in ref_opt.state and "exp_avg" in opt.state.get(pm, {}):
+                    opt.state[pm]["exp_avg"].copy_(ref_opt.state[pr]["exp_avg"])
+                    opt.state[pm]["exp_avg_sq"].copy_(ref_opt.state[pr]["exp_avg_sq"])
+                    gm["step"] = int(ref_opt.state[pr]["step"].item())
+
+
+def _check_step(tag, student, grads_ref, l, l_ref, s, s_ref, t, t_ref, loss_fn, ref_loss, teacher, ref_teacher):
+    assert abs(l.item() - l_ref.item()) / abs(l_ref.item()) < 1e-2, (tag, l.item(), l_ref.item())
+    assert rel(s, s_ref) < 1e-2 and rel(t, t_ref) < 1e-2, (tag, rel(s, s_ref), rel(t, t_ref))
+    loss_fn.finish_center_update()
+    assert rel(loss_fn.center, ref_loss.center) < 1e-2, tag
+    low = []
+    for n, p in student.named_parameters():
+        if p.grad is None:
+            assert n not in grads_ref or n.endswith("weight_g"), n
+            continue
+        c = cos(p.grad, grads_ref[n])
+        if c < 0.999:
+            low.append((n, round(c, 5)))
+    assert not low, (tag, low)
+    for (n, p), (_, q) in zip(ref_teacher.module.named_parameters(), teacher.module.named_parameters()):
+        assert rel(q, p) < 1e-2, (tag, n)
+
+
 def test_dino_step_matches_oracle(libs):
-    """Config-1 style step (ViT-Tiny, 2 global + 2 local crops) — loss, logits, gradients, centre, EMA."""
+    """Config-1 style step (ViT-Tiny, 2 global + 2 local crops) — loss, logits, EVERY gradient, centre, EMA at the
+    north-star gate, for three consecutive steps. Before each step the CUDA path takes over the oracle's weights,
+    teacher, centre and AdamW state, so every step compares the two implementations on identical inputs (Adam's
+    sign-like update turns bf16 noise on near-zero gradients into +-lr per weight, which is a property of the
+    optimiser, not an error of the kernels; the fused optimiser is checked exactly in test_ema_and_adamw)."""
     b200ssl, ovt, odino = libs
     out_dim, ncrops, B = 2048, 4, 4
     ref_student, student, ref_teacher, teacher, ref_loss, loss_fn = _build_step(b200ssl, ovt, odino, out_dim, ncrops)
-    g = torch.Generator(device="cuda").manual_seed(1234)
-    crops = [torch.randn(B, 3, 224, 224, device="cuda", generator=g) for _ in range(2)] + \
-            [torch.randn(B, 3, 96, 96, device="cuda", generator=g) for _ in range(ncrops - 2)]
     ref_opt = torch.optim.AdamW(b200ssl.param_groups_wd(ref_student, 0.04), lr=5e-4)
     opt = b200ssl.FusedAdamW(b200ssl.param_groups_wd(student, 0.04), lr=5e-4)
-    for step in range(2):
+    for step in range(3):
+        g = torch.Generator(device="cuda").manual_seed(1234 + step)
+        crops = [torch.randn(B, 3, 224, 224, device="cuda", generator=g) for _ in range(2)] + \
+                [torch.randn(B, 3, 96, 96, device="cuda", generator=g) for _ in range(ncrops - 2)]
+        if step > 0:
+            _sync_from_oracle(ref_student, student, ref_teacher, teacher, ref_loss, loss_fn, ref_opt, opt)
         l_ref, s_ref, t_ref = odino.dino_step(ref_student, ref_teacher, ref_loss, ref_opt, crops, momentum=0.9)
         grads_ref = {n: p.grad.clone() for n, p in ref_student.named_parameters() if p.grad is not None}
         l, s, t = b200ssl.dino_step(student, teacher, loss_fn, opt, [c.bfloat16() for c in crops], momentum=0.9)
-        # step 0: identical weights -> north-star bf16 tolerance (1e-2). step 1 runs on weights that already
-        # went through one AdamW update: Adam's sign-like step turns bf16 noise on near-zero gradients into
-        # +-lr differences per weight, so logits are only required to stay within 3e-2 there (the fused
-        # optimiser itself is checked exactly in test_ema_and_adamw).
-        tol = 1e-2 if step == 0 else 3e-2
-        assert abs(l.item() - l_ref.item()) / abs(l_ref.item()) < 1e-2, (step, l.item(), l_ref.item())
-        assert rel(s, s_ref) < tol and rel(t, t_ref) < tol, (step, rel(s, s_ref), rel(t, t_ref))
-        loss_fn.finish_center_update()
-        assert rel(loss_fn.center, ref_loss.center) < 1e-2
-        low = []
-        for n, p in student.named_parameters():
-            if p.grad is None:
-                assert n not in grads_ref or n.endswith("weight_g"), n
-                continue
-            c = cos(p.grad, grads_ref[n])
-            if c < 0.999:
-                low.append((n, round(c, 5)))
-        # clipping + accumulated bf16 rounding: allow 0.995 on at most a few tiny-gradient tensors
-        if step == 0:
-            assert all(c >= 0.995 for _, c in low) and len(low) <= 6, low
-        for (n, p), (_, q) in zip(ref_teacher.module.named_parameters(), teacher.module.named_parameters()):
-            assert rel(q, p) < 1e-2, n
+        _check_step(f"step {step}", student, grads_ref, l, l_ref, s, s_ref, t, t_ref, loss_fn, ref_loss, teacher,
+                    ref_teacher)
+
+
+@pytest.mark.parametrize("mode", ["eager", "graph"])
+def test_full_step_at_bench_shape(libs, mode):
+    """The step bench.py times (BASELINE configs[1]: ViT-S/16, 2 x 224^2 + 10 x 96^2 crops, head out_dim 65,536,
+    the packed multi-crop pass, the split-K head dgrad) at batch 8, against the fp32 oracle: loss, logits, centre,
+    teacher EMA and all 157 parameter gradients, through eager ``dino_step`` and through ``GraphedDinoStep``
+    (whose first replay must be training step 0: the capture warm-up leaves no trace)."""
+    b200ssl, ovt, odino = libs
+    out_dim, ncrops, B = 65536, 12, 8
+    torch.manual_seed(0)
+    ref = odino.MultiCropWrapper(ovt.vit_small(), ovt.DINOHead(384, out_dim)).cuda()
+    with torch.no_grad():
+        for p in ref.parameters():
+            if p.ndim == 1:
+                p.add_(torch.randn_like(p) * 0.02)
+    mine = b200ssl.MultiCropWrapper(b200ssl.vit_small(), b200ssl.DINOHead(384, out_dim)).cuda()
+    mine.load_state_dict(ref.state_dict())
+    ref_t, mine_t = odino.ModelEma(ref), b200ssl.ModelEma(mine)
+    ref_l = odino.DINOLoss(out_dim, ncrops, 0.04, 0.04, 0, 10).cuda()
+    mine_l = b200ssl.DINOLoss(out_dim, ncrops, 0.04, 0.04, 0, 10).cuda()
+    ref_o = torch.optim.AdamW(b200ssl.param_groups_wd(ref, 0.04), lr=5e-4)
+    mine_o = b200ssl.FusedAdamW(b200ssl.param_groups_wd(mine, 0.04), lr=5e-4)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    crops = [torch.randn(B, 3, 224, 224, device="cuda", generator=g) for _ in range(2)] + \
+            [torch.randn(B, 3, 96, 96, device="cuda", generator=g) for _ in range(ncrops - 2)]
+    l_ref, s_ref, t_ref = odino.dino_step(ref, ref_t, ref_l, ref_o, crops, momentum=0.9)
+    grads_ref = {n: p.grad.clone() for n, p in ref.named_parameters() if p.grad is not None}
+    c16 = [c.bfloat16() for c in crops]
+    if mode == "eager":
+        l, s, t = b200ssl.dino_step(mine, mine_t, mine_l, mine_o, c16, momentum=0.9)
+    else:
+        step = b200ssl.GraphedDinoStep(b200ssl.GradBucketDataParallel(mine), mine_t, mine_l, mine_o, c16)
+        l = step(c16, momentum=0.9)
+        s, t = step.student_out, step.teacher_out
+    assert sum(1 for p in mine.parameters() if p.grad is not None) == len(grads_ref) == 157
+    _check_step(mode, mine, grads_ref, l, l_ref, s, s_ref, t, t_ref, mine_l, ref_l, mine_t, ref_t)
+
+
+def test_graphed_steps_enqueued_without_sync_match_synced_steps(libs):
+    """Per-step scalars (lr, weight decay, Adam bias corrections, EMA momentum) reach the device through a ring of
+    pinned slots: eight graph replays enqueued back to back with NO host sync in between, under a changing lr /
+    weight-decay / momentum schedule, must produce the same parameters as the same eight steps with a device
+    synchronise after each (a single reused pinned buffer would hand every queued step the last-written values)."""
+    b200ssl, ovt, odino = libs
+    out_dim, ncrops, B, steps = 1024, 4, 4, 8
+    g = torch.Generator(device="cuda").manual_seed(5)
+    crops = [torch.randn(B, 3, 224, 224, device="cuda", generator=g).bfloat16() for _ in range(2)] + \
+            [torch.randn(B, 3, 96, 96, device="cuda", generator=g).bfloat16() for _ in range(ncrops - 2)]
+    lrs = [1e-3 * (i + 1) for i in range(steps)]
+    wds = [0.04 + 0.05 * i for i in range(steps)]
+    moms = [0.5 + 0.05 * i for i in range(steps)]
+    finals = {}
+    for sync in (True, False):
+        torch.manual_seed(0)
+        mod = b200ssl.MultiCropWrapper(b200ssl.vit_tiny(), b200ssl.DINOHead(192, out_dim, hidden_dim=256,
+                                                                             bottleneck_dim=64)).cuda()
+        teacher = b200ssl.ModelEma(mod)
+        loss_fn = b200ssl.DINOLoss(out_dim, ncrops, 0.04, 0.04, 0, 10).cuda()
+        opt = b200ssl.FusedAdamW(b200ssl.param_groups_wd(mod, 0.04), lr=1e-3)
+        step = b200ssl.GraphedDinoStep(b200ssl.GradBucketDataParallel(mod), teacher, loss_fn, opt, crops)
+        step(crops, momentum=moms[0])          # capture + step 0
+        torch.cuda.synchronize()
+        for i in range(1, steps):
+            b200ssl.apply_schedules(opt, i, lrs, wds)
+            step(None, momentum=moms[i])
+            if sync:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        finals[sync] = (torch.cat([p.detach().flatten() for p in mod.parameters()]),
+                        torch.cat([p.detach().flatten() for p in teacher.module.parameters()]))
+    # Reading the LAST-written scalars in every queued step (lr 8e-3 throughout instead of 1e-3 ... 8e-3, momentum
+    # 0.85 throughout) moves every weight by several lr: relative distance O(1) for the student, > 0.1 for the
+    # teacher. Correct staging leaves only the run-to-run noise of fp32 atomics amplified by Adam (< 1e-2).
+    assert rel(finals[False][0], finals[True][0]) < 2e-2, rel(finals[False][0], finals[True][0])
+    assert rel(finals[False][1], finals[True][1]) < 2e-2, rel(finals[False][1], finals[True][1])
+
+
+def test_ddp_two_ranks(libs):
+    """Data parallelism on real GPUs (skipped below 2): spawns 2 ranks of tests/gpu_checks/ddp_check.py -- replicas
+    bit-identical after eager and graphed steps, all-reduced gradients / centre equal to a single-process step on
+    the concatenated batch, overlapped eager == graphed."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29653",
+                        os.path.join(here, "gpu_checks", "ddp_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("-> OK") == 2, r.stdout[-3000:]
 
 
 def test_dino_step_bf16_autocast_oracle_agrees(libs):
@@ -399,7 +514,9 @@ def test_grad_sinks_and_graphed_step_match_eager(libs):
     teacher = b200ssl.ModelEma(graphed_mod)
     loss_fn = b200ssl.DINOLoss(out_dim, ncrops, 0.04, 0.04, 0, 10).cuda()
     opt = b200ssl.FusedAdamW(b200ssl.param_groups_wd(graphed_mod, 0.04), lr=5e-4)
-    step = b200ssl.GraphedDinoStep(graphed_ddp, teacher, loss_fn, opt, crops, warmup=1)
-    # the capture warm-up ran 1 eager step; replays continue from there
-    glosses = [step(crops, momentum=0.99).item() for _ in range(3)]
-    assert max(abs(a - b) / abs(a) for a, b in zip(runs["wrapped"][0][1:], glosses)) < 1e-2, (runs["wrapped"][0], glosses)
+    step = b200ssl.GraphedDinoStep(graphed_ddp, teacher, loss_fn, opt, crops)
+    # the capture warm-up leaves no trace (weights, moments, step counters, teacher and centre are restored):
+    # replay i IS training step i of the eager run
+    glosses = [step(crops, momentum=0.99).item() for _ in range(4)]
+    assert abs(glosses[0] - runs["wrapped"][0][0]) / abs(glosses[0]) < 1e-5, (runs["wrapped"][0], glosses)
+    assert max(abs(a - b) / abs(a) for a, b in zip(runs["wrapped"][0], glosses)) < 1e-2, (runs["wrapped"][0], glosses)
