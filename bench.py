@@ -255,6 +255,10 @@ def main():
                     help="teacher forward on the main stream instead of a second captured stream (A/B switch)")
     ap.add_argument("--no-merge-crops", action="store_true",
                     help="one backbone pass per crop resolution instead of one pass over the packed rows (A/B switch)")
+    ap.add_argument("--no-nccl-graph", action="store_true", help="N > 1: keep the NCCL all-reduces out of the step "
+                    "graph (compute graph -> eager all-reduces -> update graph; A/B switch)")
+    ap.add_argument("--ncu-step", action="store_true", help="profiling aid: after the warm-up run ONE steady-state eager "
+                    "step between cudaProfilerStart/Stop and exit (use with ncu --profile-from-start off)")
     ap.add_argument("--pdl", action="store_true", help="enable programmatic dependent launch (A/B switch; off by default)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying "
                     "the captured CUDA graph of the step")
@@ -296,6 +300,8 @@ def main():
         b200ssl.dino.TEACHER_STREAM["on"] = False
     if args.no_merge_crops:
         b200ssl.dino.MERGE_CROP_GROUPS["on"] = False
+    if args.no_nccl_graph:
+        b200ssl.dino.NCCL_IN_GRAPH["on"] = False
 
     def barrier():
         if world > 1:
@@ -383,6 +389,16 @@ def main():
             m = b200ssl.cosine_momentum(it, max(total_steps, 1))
             return b200ssl.dino_step(ddp, teacher, loss_fn, opt, cr, epoch=0, momentum=m, clip_grad=3.0)
 
+        if args.ncu_step:
+            for i in range(max(args.warmup, 2)):
+                eager_step(crops, i)
+            torch.cuda.synchronize()
+            b200ssl.dino.TEACHER_STREAM["on"] = False     # one stream: serialised per-kernel times
+            torch.cuda.cudart().cudaProfilerStart()
+            eager_step(crops, args.warmup)
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStop()
+            return 0
         use_graph = not args.no_graph
         graphed = b200ssl.GraphedDinoStep(ddp, teacher, loss_fn, opt, crops, clip_grad=3.0) if use_graph else None
 
@@ -467,6 +483,9 @@ def main():
         b200ssl.dino.TEACHER_STREAM["on"] = teacher_branch
         ops.gemm = real_gemm
         step_api = "b200ssl.GraphedDinoStep (CUDA graph replay)" if use_graph else "b200ssl.dino_step (eager)"
+        if world > 1:
+            step_api += "; " + (graphed.comm_mode if graphed is not None else
+                                "nccl bucket all-reduces launched from backward hooks (overlapped)")
 
     gemm_ms = sum(a.elapsed_time(b) for a, b in gemm_events)
     gemm_tflops = gemm_f * B / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0

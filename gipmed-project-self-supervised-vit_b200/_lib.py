@@ -44,7 +44,14 @@ SIGNATURES = {
     "b200ssl_l2norm_fwd": [_P, _P, _P, _L, _I, _F, _P],
     "b200ssl_l2norm_bwd": [_P, _P, _P, _P, _L, _I, _F, _P],
     "b200ssl_weightnorm_fwd": [_P, _P, _P, _P, _L, _I, _P],
-    "b200ssl_weightnorm_bwd": [_P, _P, _P, _P, _P, _P, _L, _I, _P],
+    "b200ssl_weightnorm_bwd": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
+    "b200ssl_bn_gelu_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _F, _I, _I, _P],
+    "b200ssl_bn_gelu_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
+    "b200ssl_zero_bytes": [_P, _L, _P],
+    "b200ssl_copy_bytes": [_P, _P, _L, _P],
+    "b200ssl_copy_rows": [_P, _L, _P, _L, _L, _I, _P],
+    "b200ssl_add_f32": [_P, _P, _L, _P],
+    "b200ssl_pos_interp": [_P, _P, _P, _I, _I, _I, _I, _P],
     "b200ssl_dino_loss_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P],
     "b200ssl_dino_loss_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P],
     "b200ssl_center_update": [_P, _P, _I, _L, _F, _P],

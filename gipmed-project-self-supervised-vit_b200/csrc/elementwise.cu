@@ -214,7 +214,8 @@ __global__ void weightnorm_fwd_kernel(const float* __restrict__ v, const float* 
 // dg[r] = <dw, v>/||v|| ; dv = g/||v|| * dw - g*<dw,v>/||v||^3 * v
 __global__ void weightnorm_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
                                       const float* __restrict__ norm, const float* __restrict__ dw,
-                                      float* __restrict__ dv, float* __restrict__ dg, long long rows, int D) {
+                                      float* __restrict__ dv, float* __restrict__ dg, long long rows, int D,
+                                      int accumulate) {
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -231,10 +232,14 @@ __global__ void weightnorm_bwd_kernel(const float* __restrict__ v, const float* 
   for (int i = lane * 4; i < D; i += 128) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(v + row * D + i));
     const float4 b = __ldg(reinterpret_cast<const float4*>(dw + row * D + i));
-    *reinterpret_cast<float4*>(dv + row * D + i) =
-        make_float4(c1 * b.x - c2 * a.x, c1 * b.y - c2 * a.y, c1 * b.z - c2 * a.z, c1 * b.w - c2 * a.w);
+    float4 o = make_float4(c1 * b.x - c2 * a.x, c1 * b.y - c2 * a.y, c1 * b.z - c2 * a.z, c1 * b.w - c2 * a.w);
+    if (accumulate) {  // gradient sink: dv is the parameter's .grad (zeroed at the start of the step)
+      const float4 p = *reinterpret_cast<const float4*>(dv + row * D + i);
+      o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+    }
+    *reinterpret_cast<float4*>(dv + row * D + i) = o;
   }
-  if (dg && lane == 0) dg[row] = dot / nrm;
+  if (dg && lane == 0) dg[row] = (accumulate ? dg[row] : 0.f) + dot / nrm;
 }
 
 static int grid_for(long long work_items, int threads) {
@@ -348,11 +353,11 @@ extern "C" int b200ssl_weightnorm_fwd(const float* v, const float* g, void* w, f
 }
 
 extern "C" int b200ssl_weightnorm_bwd(const float* v, const float* g, const float* norm, const float* dw, float* dv,
-                                      float* dg, long long rows, int D, void* stream) {
+                                      float* dg, long long rows, int D, int accumulate, void* stream) {
   B200SSL_CHECK(D % 4 == 0, -2, "weightnorm: D must be a multiple of 4");
   const long long threads = rows * 32;
   weightnorm_bwd_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      v, g, norm, dw, dv, dg, rows, D);
+      v, g, norm, dw, dv, dg, rows, D, accumulate);
   B200SSL_CUDA(cudaGetLastError());
   return 0;
 }
@@ -390,6 +395,129 @@ extern "C" int b200ssl_scale_rows(const void* x, const float* scale, void* y, lo
   if (blocks > cap) blocks = cap;
   b200ssl::scale_rows_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), scale, static_cast<uint4*>(y), rows, D / 8);
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plumbing that used to be PyTorch glue inside the captured step (torch.zeros / clone / slicing + cat / indexed
+// assignment / tiny matmuls): memset and copy nodes, a strided row copy, an fp32 accumulate and the position-table
+// resize as a fixed linear map.
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200ssl_zero_bytes(void* p, long long nbytes, void* stream) {
+  if (nbytes <= 0) return 0;
+  B200SSL_CUDA(cudaMemsetAsync(p, 0, static_cast<size_t>(nbytes), static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int b200ssl_copy_bytes(void* dst, const void* src, long long nbytes, void* stream) {
+  if (nbytes <= 0) return 0;
+  B200SSL_CUDA(cudaMemcpyAsync(dst, src, static_cast<size_t>(nbytes), cudaMemcpyDeviceToDevice,
+                               static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+namespace b200ssl {
+// dst[r * dst_stride + :] = src[r * src_stride + :] in 16-byte pieces (strides counted in 16-byte units)
+__global__ void __launch_bounds__(256)
+copy_rows_kernel(const uint4* __restrict__ src, long long src_stride, uint4* __restrict__ dst, long long dst_stride,
+                 long long rows, int vec_per_row) {
+  const long long total = rows * vec_per_row;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int c = static_cast<int>(i - r * vec_per_row);
+    dst[r * dst_stride + c] = __ldg(src + r * src_stride + c);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+add_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] += __ldg(src + i);
+}
+
+// Position-table resize (VisionTransformer.interpolate_pos_encoding, VT.pyc@L213-233) as the fixed linear map it is:
+//   forward : out[0, :] = pos[0, :] ;  out[1 + i, :] = sum_j mat[i, j] * pos[1 + j, :]          (mat [Mo, Ki], fp32)
+//   backward: dpos[0, :] += dout[0, :] ;  dpos[1 + j, :] += sum_i mat[i, j] * dout[1 + i, :]
+// one thread per output element; Mo, Ki <= a few hundred, D <= 768: microseconds.
+__global__ void __launch_bounds__(128)
+pos_interp_fwd_kernel(const float* __restrict__ mat, const float* __restrict__ pos, float* __restrict__ out, int Mo,
+                      int Ki, int D) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;  // output row, 0 = class position
+  if (d >= D) return;
+  if (i == 0) {
+    out[d] = __ldg(pos + d);
+    return;
+  }
+  const float* m = mat + static_cast<long long>(i - 1) * Ki;
+  // four independent accumulators, unrolled: the loop is a chain of dependent L2 loads otherwise (40 us measured)
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int j = 0;
+#pragma unroll 4
+  for (; j + 4 <= Ki; j += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      acc[u] = fmaf(__ldg(m + j + u), __ldg(pos + static_cast<long long>(1 + j + u) * D + d), acc[u]);
+  }
+  for (; j < Ki; ++j) acc[0] = fmaf(__ldg(m + j), __ldg(pos + static_cast<long long>(1 + j) * D + d), acc[0]);
+  out[static_cast<long long>(i) * D + d] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
+__global__ void __launch_bounds__(128)
+pos_interp_bwd_kernel(const float* __restrict__ mat, const float* __restrict__ dout, float* __restrict__ dpos, int Mo,
+                      int Ki, int D) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;  // input row, 0 = class position
+  if (d >= D) return;
+  if (j == 0) {
+    dpos[d] += __ldg(dout + d);
+    return;
+  }
+  float acc = 0.f;
+  for (int i = 0; i < Mo; ++i)
+    acc = fmaf(__ldg(mat + static_cast<long long>(i) * Ki + (j - 1)), __ldg(dout + static_cast<long long>(1 + i) * D + d), acc);
+  dpos[static_cast<long long>(j) * D + d] += acc;
+}
+}  // namespace b200ssl
+
+// rows x row_bytes from a strided source to a strided destination (gather of the CLS rows, scatter of their gradient)
+extern "C" int b200ssl_copy_rows(const void* src, long long src_stride_bytes, void* dst, long long dst_stride_bytes,
+                                 long long rows, int row_bytes, void* stream) {
+  if (rows <= 0) return 0;
+  B200SSL_CHECK(row_bytes > 0 && row_bytes % 16 == 0 && src_stride_bytes % 16 == 0 && dst_stride_bytes % 16 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0,
+                -2, "copy_rows: pointers, strides and row size must be multiples of 16 bytes");
+  const long long total = rows * (row_bytes / 16);
+  b200ssl::copy_rows_kernel<<<b200ssl::grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(src), src_stride_bytes / 16, static_cast<uint4*>(dst), dst_stride_bytes / 16, rows,
+      row_bytes / 16);
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// dst[i] += src[i], fp32
+extern "C" int b200ssl_add_f32(float* dst, const float* src, long long n, void* stream) {
+  if (n <= 0) return 0;
+  b200ssl::add_f32_kernel<<<b200ssl::grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, src, n);
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// transpose = 0: out[1 + Mo, D] = resize(pos[1 + Ki, D]); transpose = 1: pos (as dpos) += resize^T(out (as dout))
+extern "C" int b200ssl_pos_interp(const float* mat, const float* in, float* out, int Mo, int Ki, int D, int transpose,
+                                  void* stream) {
+  B200SSL_CHECK(Mo > 0 && Ki > 0 && D > 0, -2, "pos_interp: empty problem");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!transpose) {
+    dim3 grid((D + 127) / 128, Mo + 1);
+    b200ssl::pos_interp_fwd_kernel<<<grid, 128, 0, s>>>(mat, in, out, Mo, Ki, D);
+  } else {
+    dim3 grid((D + 127) / 128, Ki + 1);
+    b200ssl::pos_interp_bwd_kernel<<<grid, 128, 0, s>>>(mat, in, out, Mo, Ki, D);
+  }
   B200SSL_CUDA(cudaGetLastError());
   return 0;
 }

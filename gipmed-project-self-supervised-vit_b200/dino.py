@@ -350,9 +350,9 @@ class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.04):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._tables = {}
-        self._gnorm = None
         self._hyper = None           # _ScalarStager for {lr, weight_decay, 1-beta1^t, 1-beta2^t} per group
         self.last_grad_norm_sq = None
+        self._gall = None            # (key, concatenated gradient chunk table of all groups, workspace)
         self._frozen = frozenset()   # ids of parameters the step skips entirely (set_frozen)
         self.table_version = 0       # bumped whenever the chunk tables change shape (captured graphs must follow)
 
@@ -363,6 +363,7 @@ class FusedAdamW(torch.optim.Optimizer):
         if new != self._frozen:
             self._frozen = new
             self._tables.clear()
+            self._gall = None
             self.table_version += 1
 
     def _table(self, gi, group):
@@ -404,7 +405,16 @@ class FusedAdamW(torch.optim.Optimizer):
         for gi, group in enumerate(self.param_groups):
             if any(p.grad is not None and id(p) not in self._frozen for p in group["params"]):
                 ents.append((gi, group, self._table(gi, group)))
+        if ents:
+            self._grad_table_all(ents)   # built here (host side, never inside a graph capture)
         return ents
+
+    def _grad_table_all(self, ents):
+        gkey = tuple(id(ent["gtable"]) for _, _, ent in ents)
+        if self._gall is None or self._gall[0] != gkey:
+            gt = torch.cat([ent["gtable"] for _, _, ent in ents]) if len(ents) > 1 else ents[0][2]["gtable"]
+            self._gall = (gkey, gt, torch.zeros(gt.shape[0] + 1, dtype=torch.float32, device=gt.device))
+        return self._gall
 
     def prepare_step(self):
         """Host-side part of a step: advance the step counters and stage {lr, weight_decay, 1-beta1^t,
@@ -417,8 +427,6 @@ class FusedAdamW(torch.optim.Optimizer):
         if self._hyper is None or self._hyper.dev.device != dev:
             n = len(self.param_groups)
             self._hyper = _ScalarStager((n, 8), dev)
-            self._gnorm = torch.zeros(n + 1, dtype=torch.float32, device=dev)
-            self._gnorm_ws = {}
         host = self._hyper.slot()
         for gi, group, _ in ents:
             group["step"] = group.get("step", 0) + 1
@@ -440,22 +448,10 @@ class FusedAdamW(torch.optim.Optimizer):
             return
         gnorm_ptr = None
         if max_grad_norm and max_grad_norm > 0:
-            parts = []
-            for gi, _, ent in ents:
-                n_rows = ent["gtable"].shape[0]
-                ws = self._gnorm_ws.get(gi)
-                if ws is None or ws.numel() < n_rows + 1:
-                    ws = self._gnorm_ws[gi] = torch.zeros(n_rows + 1, dtype=torch.float32, device=self._gnorm.device)
-                ops._call("b200ssl_sumsq_multi_tensor", ent["gtable"].data_ptr(), n_rows, ws.data_ptr(),
-                          ops._stream(), launches=2)
-                parts.append(ws[0:1])
-            if len(parts) == 1:
-                total = parts[0]
-            else:
-                total = self._gnorm[0:1]
-                torch.add(parts[0], parts[1], out=total)
-                for extra in parts[2:]:
-                    total.add_(extra)
+            # ONE sum-of-squares pass over the gradients of all groups (a concatenated chunk table): the global norm
+            _, gt, ws = self._grad_table_all(ents)
+            ops._call("b200ssl_sumsq_multi_tensor", gt.data_ptr(), gt.shape[0], ws.data_ptr(), ops._stream(), launches=2)
+            total = ws[0:1]
             self.last_grad_norm_sq = total
             gnorm_ptr = total.data_ptr()
         for gi, group, ent in ents:
@@ -520,9 +516,13 @@ class GradBucketDataParallel(nn.Module):
         if cur:
             self.buckets.append(cur)
         self._flat, self._bucket_of, self._view_of = [], {}, {}
-        for bi, bucket in enumerate(self.buckets):
-            n = sum((p.numel() + 3) // 4 * 4 for p in bucket)
-            flat = torch.zeros(n, dtype=torch.float32, device=bucket[0].device)
+        sizes = [sum((p.numel() + 3) // 4 * 4 for p in bucket) for bucket in self.buckets]
+        # all buckets are slices of ONE allocation: zeroing the gradients is a single memset node per step
+        self._all = torch.zeros(sum(sizes), dtype=torch.float32, device=params[0].device)
+        start = 0
+        for bi, (bucket, n) in enumerate(zip(self.buckets, sizes)):
+            flat = self._all[start:start + n]
+            start += n
             off = 0
             for p in bucket:
                 p.grad = flat[off:off + p.numel()].view_as(p)
@@ -597,14 +597,15 @@ class GradBucketDataParallel(nn.Module):
         self._handles.append(dist.all_reduce(self._flat[bi], op=op, group=self.pg, async_op=True))
 
     def zero_grad(self, set_to_none: bool = False):
-        """Zero the flat buckets (gradients stay views into them)."""
-        for flat, bucket in zip(self._flat, self.buckets):
-            flat.zero_()
-            off = 0
-            for p in bucket:
-                if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + 4 * off:
-                    p.grad = flat[off:off + p.numel()].view_as(p)
-                off += (p.numel() + 3) // 4 * 4
+        """Zero the flat buckets (gradients stay views into them): one memset over the single allocation."""
+        if self._all.is_cuda:
+            ops._call("b200ssl_zero_bytes", self._all.data_ptr(), self._all.numel() * 4, ops._stream(), launches=0)
+        else:
+            self._all.zero_()
+        for p in self._params:
+            view = self._view_of[id(p)]
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                p.grad = view
 
     def allreduce_now(self):
         """Deferred mode (two-graph step): average every flat bucket over ranks, eagerly, in bucket order."""
@@ -650,6 +651,9 @@ def _step_prepare(student, teacher_ema, optimizer, momentum):
 
 # Measured on B200 (bench.py, same box, alternating): 54.59 / 54.78 ms per step without, 54.19 / 53.88 ms with.
 TEACHER_STREAM = {"on": True}
+# N > 1: capture the NCCL all-reduces inside the step graph (overlapped with backward). Off = the two-graph step with
+# eager, serial all-reduces in between (round-1 behaviour; kept as the automatic fallback and for A/B runs).
+NCCL_IN_GRAPH = {"on": True}
 _SIDE_STREAMS = {}
 
 
@@ -766,6 +770,7 @@ class GraphedDinoStep:
         self._warmup = warmup
         self._graph = self._graph_update = None
         self._multi = False
+        self.comm_mode = None
         self._pending_static = None
         self._temp = None
         self._opt_version = -1
@@ -847,14 +852,36 @@ class GraphedDinoStep:
         # capture records launches only: it needs the optimiser's chunk tables but must NOT advance the step
         # counter / restage scalars (that is _step_prepare's job, once per replay)
         ents = self.opt._entries()
-        if not self._multi:
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
-                self.loss, self.student_out, self.teacher_out = _step_launch(
-                    self.student, self.teacher, self.loss_fn, self.opt, self.static_crops, epoch, self.clip_grad, ents)
-        else:
-            # NCCL stays out of the graphs: compute graph -> eager all-reduces (176 MB of gradients + the
-            # 256 KB centre, well under a millisecond on NVLink) -> update graph
+        self._graph_update = None
+        if not self._multi or NCCL_IN_GRAPH["on"]:
+            # ONE graph for the whole step. With several ranks the NCCL calls are captured too: every gradient
+            # bucket's all-reduce is issued (async, on NCCL's own stream = a forked branch of the graph) by the
+            # arrival hook of its last gradient, i.e. it overlaps the rest of backward exactly as in the eager step
+            # (reference: NativeDDP's bucketed, overlapped all-reduce, train.py:634); the centre all-reduce forks off
+            # right after the loss forward and is joined after the optimiser. Nothing runs between replays.
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.loss, self.student_out, self.teacher_out = _step_launch(
+                        self.student, self.teacher, self.loss_fn, self.opt, self.static_crops, epoch, self.clip_grad,
+                        ents)
+                self._graph = g
+                self.comm_mode = "nccl all-reduces captured in the step graph, overlapped with backward" \
+                    if self._multi else "single rank"
+            except Exception as e:  # pragma: no cover - depends on the NCCL / driver combination
+                if not self._multi:
+                    raise
+                import warnings
+                warnings.warn(f"capturing the NCCL collectives in the step graph failed ({e!r}); falling back to "
+                              "compute graph -> eager all-reduces -> update graph")
+                NCCL_IN_GRAPH["on"] = False
+                if isinstance(self.student, GradBucketDataParallel):
+                    self.student._handles = []
+                    self.student._arm()
+                self.loss_fn._pending = None
+                torch.cuda.synchronize()
+        if self._multi and not NCCL_IN_GRAPH["on"]:
+            # fallback: NCCL stays out of the graphs: compute graph -> eager all-reduces -> update graph
             self._set_defer(True)
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
@@ -867,6 +894,7 @@ class GraphedDinoStep:
             with torch.cuda.graph(self._graph_update, pool=self._graph.pool()):
                 _step_update(self.student, self.teacher, self.loss_fn, self.opt, self.clip_grad, ents)
             self._set_defer(False)   # the flags only matter while capturing; eager steps stay self-contained
+            self.comm_mode = "eager nccl all-reduces between a compute graph and an update graph (not overlapped)"
         self._temp = float(self.loss_fn.teacher_temp_schedule[epoch])
         self._opt_version = self.opt.table_version
 
@@ -884,7 +912,7 @@ class GraphedDinoStep:
             self._capture(epoch, momentum)      # the capture itself executes nothing: fall through to replay
         _step_prepare(self.student, self.teacher, self.opt, momentum)
         self._graph.replay()
-        if self._multi:
+        if self._graph_update is not None:
             self.loss_fn._pending = self._pending_static   # the compute graph refilled this buffer
             self._comm()
             self._graph_update.replay()

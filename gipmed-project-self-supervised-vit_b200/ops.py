@@ -160,6 +160,52 @@ def cast_f32_to_bf16(src: torch.Tensor, dst: torch.Tensor):
     _call("b200ssl_cast_f32_to_bf16", src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
 
 
+def zeros(shape, dtype, device):
+    """torch.empty + one memset node on the current stream (instead of a PyTorch fill kernel)."""
+    t = torch.empty(shape, dtype=dtype, device=device)
+    _call("b200ssl_zero_bytes", t.data_ptr(), t.numel() * t.element_size(), _stream(), launches=0)
+    return t
+
+
+def clone(t):
+    out = torch.empty_like(t, memory_format=torch.contiguous_format)
+    _call("b200ssl_copy_bytes", out.data_ptr(), t.contiguous().data_ptr(), t.numel() * t.element_size(), _stream(),
+          launches=0)
+    return out
+
+
+def copy_rows(src, src_stride_bytes, dst, dst_stride_bytes, rows, row_bytes):
+    """dst[r * dst_stride ...] = src[r * src_stride ...] for r < rows (src / dst: tensors giving the base pointers)."""
+    _call("b200ssl_copy_rows", src.data_ptr(), src_stride_bytes, dst.data_ptr(), dst_stride_bytes, rows, row_bytes,
+          _stream())
+
+
+def add_f32(dst, src):
+    _call("b200ssl_add_f32", dst.data_ptr(), src.data_ptr(), dst.numel(), _stream())
+
+
+def pos_table(pos_embed32, mat):
+    """[1 + Mo, D] fp32 position table for one resolution: the stored table itself (mat None) or its bicubic
+    resize applied as the cached linear map ``mat`` [Mo, Ki] (VT.pyc@L213-233)."""
+    if mat is None:
+        return pos_embed32
+    Mo, Ki = mat.shape
+    D = pos_embed32.shape[1]
+    out = torch.empty(Mo + 1, D, dtype=torch.float32, device=pos_embed32.device)
+    _call("b200ssl_pos_interp", mat.data_ptr(), pos_embed32.data_ptr(), out.data_ptr(), Mo, Ki, D, 0, _stream())
+    return out
+
+
+def pos_table_bwd(dtable, mat, dpos_embed):
+    """dpos_embed (fp32 [1 + Ki, D]) += resize^T(dtable)."""
+    if mat is None:
+        add_f32(dpos_embed, dtable)
+    else:
+        Mo, Ki = mat.shape
+        _call("b200ssl_pos_interp", mat.data_ptr(), dtable.data_ptr(), dpos_embed.data_ptr(), Mo, Ki,
+              dtable.shape[1], 1, _stream())
+
+
 def gemm(A, B, D, M, N, K, *, a_mn=False, b_mn=False, epi=EPI_BIAS, D2=None, bias=None, aux=None, split_k=1,
          block_n=0):
     _call("b200ssl_gemm", A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn),
@@ -210,7 +256,7 @@ def linear_dgrad(dy, w16, dgelu_of=None):
     if dgelu_of is None and N >= 8192 and (M // 128) * ((K + 255) // 256) < 64:
         # a very long reduction with too few output tiles to fill the SMs (the DINO head's last layer: 65,536
         # prototypes, 3072 x 256 output): split K across the machine into an fp32 buffer, then round once
-        acc = torch.zeros(M, K, dtype=torch.float32, device=dy.device)
+        acc = zeros((M, K), torch.float32, dy.device)
         gemm(dy, w16, acc, M, K, N, b_mn=True, epi=EPI_ATOMIC_F32, split_k=0)
         dx = torch.empty(M, K, dtype=_BF16, device=dy.device)
         cast_f32_to_bf16(acc, dx)
@@ -246,7 +292,7 @@ def linear_wgrad(dy, x, need_bias=True, weight=None, bias=None):
         if b_sink is not None:
             _sunk(bias)
         return None, None
-    buf = torch.zeros(N * K + (N if need_bias else 0), dtype=torch.float32, device=dy.device)
+    buf = zeros((N * K + (N if need_bias else 0),), torch.float32, dy.device)
     dw = buf[:N * K].view(N, K)
     db = buf[N * K:] if need_bias else None
     run(dw, db)
@@ -309,7 +355,7 @@ def layernorm_bwd(x, dy, w, mean, rstd, dres=None, weight=None, bias=None):
     if w_sink is not None and b_sink is not None:
         dw, db, ret = w_sink, b_sink, (None, None)
     else:
-        dwb = torch.zeros(2, D, dtype=torch.float32, device=x.device)
+        dwb = zeros((2, D), torch.float32, x.device)
         dw, db = dwb[0], dwb[1]
         ret = (dw, db)
     _call("b200ssl_layernorm_bwd", x.data_ptr(), int(x.dtype == torch.float32), dy.data_ptr(), w.data_ptr(),
@@ -639,8 +685,12 @@ class EncoderFn(torch.autograd.Function):
                 saved.append((s1, s2))
         D = x.shape[1]
         segs = segments(B, N)
-        cls = [x[r0:r0 + b * n].view(b, n, D)[:, 0] for b, n, r0 in segs]
-        cls = cls[0].contiguous() if len(cls) == 1 else torch.cat(cls)
+        # x[:, 0] of every group gathered by one strided row copy each (VT.pyc@L253)
+        cls = torch.empty(sum(b for b, _, _ in segs), D, dtype=x.dtype, device=x.device)
+        es, b0 = x.element_size(), 0
+        for b, n, r0 in segs:
+            copy_rows(x[r0], n * D * es, cls[b0], D * es, b, D * es)
+            b0 += b
         norm_w, norm_b = params[-2], params[-1]
         out, mean, rstd = layernorm_fwd(cls, _f32(norm_w), _f32(norm_b), norm_eps)
         if keep:
@@ -660,10 +710,10 @@ class EncoderFn(torch.autograd.Function):
                                           bias=params[-1])
         D = cls.shape[1]
         segs = segments(B, N)
-        dx = torch.zeros(sum(b * n for b, n, _ in segs), D, dtype=_BF16, device=cls.device)
+        dx = zeros((sum(b * n for b, n, _ in segs), D), _BF16, cls.device)
         b0 = 0
         for b, n, r0 in segs:
-            dx[r0:r0 + b * n].view(b, n, D)[:, 0] = d_cls[b0:b0 + b]
+            copy_rows(d_cls[b0], D * 2, dx[r0], n * D * 2, b, D * 2)   # only the CLS rows carry gradient
             b0 += b
         grads = [None] * len(params)
         for i in range(depth - 1, -1, -1):
@@ -692,13 +742,40 @@ class EncoderFn(torch.autograd.Function):
         return (d_tok, None, *grads)
 
 
+def _tokens_param_grads(cls_token, pos_embed, dcls_parts, dtables, mats):
+    """Gradients of cls_token / pos_embed from the per-group token-table gradients. With registered gradient sinks
+    the contributions are accumulated straight into ``.grad`` (and None is returned for autograd); otherwise into
+    fresh zero-filled buffers. No PyTorch kernels either way."""
+    D = dtables[0].shape[1]
+    out = []
+    for param, parts in ((cls_token, dcls_parts), (pos_embed, None)):
+        if param is None or not param.requires_grad:
+            out.append(None)
+            continue
+        sink = _sink(param)
+        buf = sink if sink is not None else zeros(tuple(param.shape), torch.float32, dtables[0].device)
+        flat = buf.view(-1, D)
+        if parts is not None:
+            for d in parts:
+                add_f32(flat[0], d)
+        else:
+            for dt, mat in zip(dtables, mats):
+                pos_table_bwd(dt, mat, flat)
+        if sink is not None:
+            _sunk(param)
+            out.append(None)
+        else:
+            out.append(buf if param.dtype == torch.float32 else buf.to(param.dtype))
+    return out[0], out[1]
+
+
 class TokensFn(torch.autograd.Function):
     """prepare_tokens (VT.pyc@L235-246): patch-embed conv as GEMM, prepend CLS, add position table.
-    img [B,C,H,W] bf16 -> tokens [B*(Np+1), D] bf16. ``pos`` is the (already interpolated) fp32 table
-    [Np+1, D]; its gradient flows back to pos_embed through the caller's interpolation graph."""
+    img [B,C,H,W] bf16 -> tokens [B*(Np+1), D] fp32. ``pos_embed`` is the stored table [1, 1+Ki, D]; ``mat`` (None at
+    the native resolution) the cached linear map of its bicubic resize, applied here forward and transposed backward."""
 
     @staticmethod
-    def forward(ctx, img, proj_w, proj_b, cls_token, pos, patch, relay=None):
+    def forward(ctx, img, proj_w, proj_b, cls_token, pos_embed, patch, relay=None, mat=None):
         ctx.relay = relay
         B, C, H, W = img.shape
         Np = (H // patch) * (W // patch)
@@ -709,38 +786,41 @@ class TokensFn(torch.autograd.Function):
         w16 = bf16_of(proj_w).view(D, Kp)
         y = linear_fwd(cols, w16, _f32(proj_b) if proj_b is not None else None)
         x = torch.empty(B * (Np + 1), D, dtype=torch.float32, device=img.device)
-        _call("b200ssl_assemble_tokens", y.data_ptr(), _f32(cls_token).data_ptr(), _f32(pos).data_ptr(),
+        table = pos_table(_f32(pos_embed).view(-1, D), mat)
+        if table.shape[0] != Np + 1:
+            raise RuntimeError(f"position table has {table.shape[0]} rows, the image needs {Np + 1}")
+        _call("b200ssl_assemble_tokens", y.data_ptr(), _f32(cls_token).data_ptr(), table.data_ptr(),
               x.data_ptr(), B, Np, D, _stream())
         ctx.save_for_backward(cols, proj_w)
-        ctx.proj_b = proj_b
-        ctx.meta = (B, Np, D, proj_b is not None, cls_token.shape, pos.shape)
+        ctx.params = (proj_b, cls_token, pos_embed, mat)
+        ctx.meta = (B, Np, D, proj_b is not None)
         return x
 
     @staticmethod
     def backward(ctx, dx):
         cols, proj_w = ctx.saved_tensors
-        B, Np, D, has_bias, cls_shape, pos_shape = ctx.meta
+        proj_b, cls_token, pos_embed, mat = ctx.params
+        B, Np, D, has_bias = ctx.meta
         dx = ctx.relay.take(dx) if ctx.relay is not None else _g16(dx)
         dy = torch.empty(B * Np, D, dtype=_BF16, device=dx.device)
-        dpos = torch.empty(Np + 1, D, dtype=torch.float32, device=dx.device)
+        dtab = torch.empty(Np + 1, D, dtype=torch.float32, device=dx.device)
         dcls = torch.empty(D, dtype=torch.float32, device=dx.device)
-        _call("b200ssl_assemble_tokens_bwd", dx.data_ptr(), dy.data_ptr(), dpos.data_ptr(), dcls.data_ptr(), B, Np,
-              D, _stream(), launches=2)
-        dw, db = linear_wgrad(dy, cols, has_bias, proj_w, ctx.proj_b)
-        return None, (dw.view(proj_w.shape) if dw is not None else None), db, dcls.view(cls_shape), \
-            dpos.view(pos_shape), None, None
+        _call("b200ssl_assemble_tokens_bwd", dx.data_ptr(), dy.data_ptr(), dtab.data_ptr(), dcls.data_ptr(), B, Np,
+              D, _stream(), launches=1)
+        dw, db = linear_wgrad(dy, cols, has_bias, proj_w, proj_b)
+        g_cls, g_pos = _tokens_param_grads(cls_token, pos_embed, [dcls], [dtab], [mat])
+        return None, (dw.view(proj_w.shape) if dw is not None else None), db, g_cls, g_pos, None, None, None
 
 
 class MultiTokensFn(torch.autograd.Function):
     """prepare_tokens for several crop groups of different resolution in one node: per-group patch gather into one
     column buffer, ONE patch-embed GEMM over all patches, per-group CLS / position assembly into one packed fp32
-    token stream (group after group). apply(patch, n, relay, proj_w, proj_b, cls_token, img_1..img_n, pos_1..pos_n);
-    ``relay`` is a GradRelay or None."""
+    token stream (group after group). apply(patch, n, relay, mats, proj_w, proj_b, cls_token, pos_embed, img_1..img_n);
+    ``relay`` is a GradRelay or None, ``mats`` the per-group resize maps (None = native resolution)."""
 
     @staticmethod
-    def forward(ctx, patch, n, relay, proj_w, proj_b, cls_token, *rest):
+    def forward(ctx, patch, n, relay, mats, proj_w, proj_b, cls_token, pos_embed, *imgs):
         ctx.relay = relay
-        imgs, poss = rest[:n], rest[n:]
         D = proj_w.shape[0]
         dims = []
         for img in imgs:
@@ -755,36 +835,42 @@ class MultiTokensFn(torch.autograd.Function):
             c0 += B * Np
         y = linear_fwd(cols, bf16_of(proj_w).view(D, Kp), _f32(proj_b) if proj_b is not None else None)
         x = torch.empty(sum(B * (Np + 1) for B, Np, *_ in dims), D, dtype=torch.float32, device=dev)
+        pos32, cls32 = _f32(pos_embed).view(-1, D), _f32(cls_token)
         c0 = r0 = 0
-        for pos, (B, Np, *_) in zip(poss, dims):
-            _call("b200ssl_assemble_tokens", y[c0:c0 + B * Np].data_ptr(), _f32(cls_token).data_ptr(),
-                  _f32(pos).data_ptr(), x[r0:r0 + B * (Np + 1)].data_ptr(), B, Np, D, _stream())
+        for mat, (B, Np, *_) in zip(mats, dims):
+            table = pos_table(pos32, mat)
+            if table.shape[0] != Np + 1:
+                raise RuntimeError(f"position table has {table.shape[0]} rows, the crop needs {Np + 1}")
+            _call("b200ssl_assemble_tokens", y[c0:c0 + B * Np].data_ptr(), cls32.data_ptr(), table.data_ptr(),
+                  x[r0:r0 + B * (Np + 1)].data_ptr(), B, Np, D, _stream())
             c0 += B * Np
             r0 += B * (Np + 1)
         ctx.save_for_backward(cols, proj_w)
-        ctx.proj_b = proj_b
-        ctx.meta = (n, dims, D, proj_b is not None, cls_token.shape, [p.shape for p in poss])
+        ctx.params = (proj_b, cls_token, pos_embed, mats)
+        ctx.meta = (n, dims, D, proj_b is not None)
         return x
 
     @staticmethod
     def backward(ctx, dx):
         cols, proj_w = ctx.saved_tensors
-        n, dims, D, has_bias, cls_shape, pos_shapes = ctx.meta
+        proj_b, cls_token, pos_embed, mats = ctx.params
+        n, dims, D, has_bias = ctx.meta
         dx = ctx.relay.take(dx) if ctx.relay is not None else _g16(dx)
         dy = torch.empty(cols.shape[0], D, dtype=_BF16, device=dx.device)
         dcls = torch.empty(n, D, dtype=torch.float32, device=dx.device)
-        dposs = []
+        dtabs = []
         c0 = r0 = 0
         for i, (B, Np, *_) in enumerate(dims):
-            dpos = torch.empty(Np + 1, D, dtype=torch.float32, device=dx.device)
+            dtab = torch.empty(Np + 1, D, dtype=torch.float32, device=dx.device)
             _call("b200ssl_assemble_tokens_bwd", dx[r0:r0 + B * (Np + 1)].data_ptr(), dy[c0:c0 + B * Np].data_ptr(),
-                  dpos.data_ptr(), dcls[i].data_ptr(), B, Np, D, _stream(), launches=2)
-            dposs.append(dpos.view(pos_shapes[i]))
+                  dtab.data_ptr(), dcls[i].data_ptr(), B, Np, D, _stream(), launches=1)
+            dtabs.append(dtab)
             c0 += B * Np
             r0 += B * (Np + 1)
-        dw, db = linear_wgrad(dy, cols, has_bias, proj_w, ctx.proj_b)
-        return (None, None, None, (dw.view(proj_w.shape) if dw is not None else None), db, dcls.sum(0).view(cls_shape),
-                *([None] * n), *dposs)
+        dw, db = linear_wgrad(dy, cols, has_bias, proj_w, proj_b)
+        g_cls, g_pos = _tokens_param_grads(cls_token, pos_embed, [dcls[i] for i in range(n)], dtabs, mats)
+        return (None, None, None, None, (dw.view(proj_w.shape) if dw is not None else None), db, g_cls, g_pos,
+                *([None] * n))
 
 
 class L2NormFn(torch.autograd.Function):
@@ -835,14 +921,73 @@ class WeightNormLinearFn(torch.autograd.Function):
             dw, _ = linear_wgrad(dy, x, need_bias=False)
             v32 = _f32(weight_v)
             g32 = _f32(weight_g).view(-1) if weight_g is not None else None
-            dv = torch.empty_like(v32)
             want_g = weight_g is not None and ctx.needs_input_grad[2]
-            dg = torch.empty(v32.shape[0], dtype=torch.float32, device=x.device) if want_g else None
+            v_sink = _sink(weight_v) if ctx.needs_input_grad[1] else None
+            g_sink = _sink(weight_g) if want_g else None
+            # with gradient sinks the result is added straight into .grad (no autograd accumulation kernel)
+            sunk = v_sink is not None and (not want_g or g_sink is not None)
+            dv = v_sink if sunk else torch.empty_like(v32)
+            dg = (g_sink.view(-1) if sunk else torch.empty(v32.shape[0], dtype=torch.float32, device=x.device)) \
+                if want_g else None
             _call("b200ssl_weightnorm_bwd", v32.data_ptr(), _ptr(g32), norm.data_ptr(), dw.data_ptr(),
-                  dv.data_ptr(), _ptr(dg), v32.shape[0], v32.shape[1], _stream())
-            if dg is not None:
+                  dv.data_ptr(), _ptr(dg), v32.shape[0], v32.shape[1], int(sunk), _stream())
+            if sunk:
+                _sunk(weight_v)
+                if want_g:
+                    _sunk(weight_g)
+                dv = dg = None
+            elif dg is not None:
                 dg = dg.view(weight_g.shape)
         return dx, dv, dg
+
+
+class BatchNormGeluFn(torch.autograd.Function):
+    """gelu(BatchNorm1d(x)) for DINOHead(use_bn=True) (VT.pyc@L304-305,309-310): batch statistics in training mode
+    (running statistics and num_batches_tracked updated in place, torch semantics), running statistics in eval."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, num_batches, momentum, eps, training, gelu=True):
+        rows, C = x.shape
+        use_batch = bool(training or running_mean is None)
+        h = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        if momentum is None:
+            # nn.BatchNorm1d(momentum=None): cumulative moving average, factor 1 / num_batches_tracked (after increment)
+            raise NotImplementedError("BatchNorm1d(momentum=None) is not on the b200ssl path")
+        w32 = _f32(weight) if weight is not None else None
+        b32 = _f32(bias) if bias is not None else None
+        _call("b200ssl_bn_gelu_fwd", x.data_ptr(), _ptr(w32), _ptr(b32), _ptr(running_mean), _ptr(running_var),
+              _ptr(num_batches) if use_batch and training else None, h.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+              rows, C, float(momentum), float(eps), int(use_batch), int(gelu), _stream())
+        ctx.save_for_backward(x, mean, invstd)
+        ctx.params = (weight, bias)
+        ctx.flags = (use_batch, gelu)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, mean, invstd = ctx.saved_tensors
+        weight, bias = ctx.params
+        use_batch, gelu = ctx.flags
+        rows, C = x.shape
+        dx = torch.empty_like(x)
+        w_sink, b_sink = _sink(weight), _sink(bias)
+        sunk = weight is not None and bias is not None and w_sink is not None and b_sink is not None
+        if sunk:
+            dw, db = w_sink, b_sink
+        else:
+            dwb = zeros((2, C), torch.float32, x.device)
+            dw, db = dwb[0], dwb[1]
+        _call("b200ssl_bn_gelu_bwd", x.data_ptr(), _g16(dh).data_ptr(), _ptr(_f32(weight) if weight is not None else None),
+              _ptr(_f32(bias) if bias is not None else None), mean.data_ptr(), invstd.data_ptr(), dx.data_ptr(),
+              dw.data_ptr(), db.data_ptr(), rows, C, int(use_batch), int(gelu), _stream())
+        if sunk:
+            _sunk(weight)
+            _sunk(bias)
+            dw = db = None
+        return (dx, dw if weight is not None else None, db if bias is not None else None, None, None, None, None, None,
+                None, None)
 
 
 class DinoLossFn(torch.autograd.Function):
@@ -858,7 +1003,7 @@ class DinoLossFn(torch.autograd.Function):
         _call("b200ssl_dino_loss_fwd", student.data_ptr(), teacher.data_ptr(), center.data_ptr(), loss.data_ptr(),
               s_lse.data_ptr(), t_lse.data_ptr(), B, ncrops, K, float(student_temp), float(teacher_temp), _stream(),
               launches=2)
-        ctx.save_for_backward(student, teacher, center.clone(), s_lse, t_lse)
+        ctx.save_for_backward(student, teacher, clone(center), s_lse, t_lse)   # the centre moves before backward runs
         ctx.meta = (B, ncrops, K, float(student_temp), float(teacher_temp))
         return loss.view(())
 

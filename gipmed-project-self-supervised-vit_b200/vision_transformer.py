@@ -256,14 +256,29 @@ class VisionTransformer(nn.Module):
         w0 = w // self.patch_embed.patch_size
         h0 = h // self.patch_embed.patch_size
         w0, h0 = w0 + 0.1, h0 + 0.1
-        side = int(math.sqrt(N))
-        # The resize is a fixed linear map of the table, so it is applied as a cached [Np_out, Np_in] matrix
-        # (built once per resolution by pushing the identity through the very same F.interpolate call) --
-        # one tiny matmul per step and direction instead of the slow bicubic kernels (0.5 ms per step).
+        # The resize is a fixed linear map of the table: applied as a cached [Np_out, Np_in] matrix (_pos_matrix).
+        # This public method keeps plain differentiable torch ops; the training path applies the same matrix with
+        # its own kernel (ops.pos_table).
+        mat = self._pos_matrix(w, h)
+        patch_pos_embed = torch.matmul(mat, patch_pos_embed[0].to(torch.float32)).to(patch_pos_embed.dtype).unsqueeze(0)
+        return torch.cat((class_pos_embed.unsqueeze(0), patch_pos_embed), dim=1)
+
+    def _pos_matrix(self, w, h):
+        """The resize of ``interpolate_pos_encoding`` for a w x h input as a cached [Np_out, Np_in] fp32 matrix, or None
+        at the native resolution (``npatch == N and w == h``, VT.pyc@L216-217). Built once per resolution by pushing
+        the identity through the very same ``F.interpolate(scale_factor=..., mode='bicubic')`` call (incl. the +0.1
+        fudge and the output-size assertion, @L225-231); the hot path applies it with b200ssl_pos_interp."""
+        P = self.patch_embed.patch_size
+        npatch = (w // P) * (h // P)
+        N = self.pos_embed.shape[1] - 1
+        if npatch == N and w == h:
+            return None
         key = (w, h, N, str(self.pos_embed.device))
         cache = self.__dict__.setdefault("_interp_cache", {})
         mat = cache.get(key)
         if mat is None:
+            w0, h0 = w // P + 0.1, h // P + 0.1
+            side = int(math.sqrt(N))
             with torch.no_grad():
                 eye = torch.eye(N, device=self.pos_embed.device, dtype=torch.float32)
                 out = F.interpolate(eye.reshape(1, side, side, N).permute(0, 3, 1, 2),
@@ -271,16 +286,7 @@ class VisionTransformer(nn.Module):
                 assert int(w0) == out.shape[-2] and int(h0) == out.shape[-1]
                 mat = out.permute(0, 2, 3, 1).reshape(-1, N).contiguous()   # [Np_out, Np_in]
             cache[key] = mat
-        patch_pos_embed = torch.matmul(mat, patch_pos_embed[0].to(torch.float32)).to(patch_pos_embed.dtype).unsqueeze(0)
-        return torch.cat((class_pos_embed.unsqueeze(0), patch_pos_embed), dim=1)
-
-    def _pos_table(self, w, h):
-        P = self.patch_embed.patch_size
-        npatch = (w // P) * (h // P)
-
-        class _Shape:  # interpolate_pos_encoding only reads x.shape
-            shape = (1, npatch + 1, self.embed_dim)
-        return self.interpolate_pos_encoding(_Shape, w, h)[0]
+        return mat
 
     def _tokens(self, x, relay=None):
         """prepare_tokens on the packed layout: returns ([B*N, D] fp32 stream, B, N)."""
@@ -289,9 +295,9 @@ class VisionTransformer(nn.Module):
             raise NotImplementedError("drop_rate > 0 is not on the b200ssl hot path (reference default 0)")
         B, nc, w, h = x.shape
         P = self.patch_embed.patch_size
-        pos = self._pos_table(w, h)
         tok = ops.TokensFn.apply(x.to(torch.bfloat16).contiguous(), self.patch_embed.proj.weight,
-                                 self.patch_embed.proj.bias, self.cls_token, pos, P, relay)
+                                 self.patch_embed.proj.bias, self.cls_token, self.pos_embed, P, relay,
+                                 self._pos_matrix(w, h))
         return tok, B, (w // P) * (h // P) + 1
 
     def prepare_tokens(self, x):
@@ -345,10 +351,11 @@ class VisionTransformer(nn.Module):
         if self.training and self.pos_drop.p > 0:
             raise NotImplementedError("drop_rate > 0 is not on the b200ssl hot path (reference default 0)")
         P = self.patch_embed.patch_size
-        poss = [self._pos_table(x.shape[2], x.shape[3]) for x in xs]
+        mats = tuple(self._pos_matrix(x.shape[2], x.shape[3]) for x in xs)
         relay = ops.GradRelay()
-        tok = ops.MultiTokensFn.apply(P, len(xs), relay, self.patch_embed.proj.weight, self.patch_embed.proj.bias,
-                                      self.cls_token, *[x.to(torch.bfloat16).contiguous() for x in xs], *poss)
+        tok = ops.MultiTokensFn.apply(P, len(xs), relay, mats, self.patch_embed.proj.weight,
+                                      self.patch_embed.proj.bias, self.cls_token, self.pos_embed,
+                                      *[x.to(torch.bfloat16).contiguous() for x in xs])
         Bs = tuple(int(x.shape[0]) for x in xs)
         Ns = tuple((x.shape[2] // P) * (x.shape[3] // P) + 1 for x in xs)
         per_group = [[b._drop_path_scales(B, N, tok.device) for b in self.blocks] for B, N in zip(Bs, Ns)]
@@ -428,15 +435,29 @@ class DINOHead(nn.Module):
 
     def forward(self, x):
         ops.require_cuda(x, "DINOHead")
-        if self.use_bn:
-            raise NotImplementedError("DINOHead(use_bn=True) is not on the b200ssl hot path (reference default False)")
         dtype = x.dtype
         x2 = ops.to_bf16_2d(x)
-        linears = [self.mlp] if isinstance(self.mlp, nn.Linear) else [m for m in self.mlp if isinstance(m, nn.Linear)]
-        wb = []
-        for lin in linears:
-            wb += [lin.weight, lin.bias]
-        x2 = ops.MlpChainFn.apply(x2, None, *wb)
+        if self.use_bn and not isinstance(self.mlp, nn.Linear):
+            # Linear -> BatchNorm1d -> GELU per hidden layer (VT.pyc@L304-305,309-310): plain GEMM, then ONE kernel for
+            # the batch statistics, the normalisation and the GELU
+            mods = list(self.mlp)
+            i = 0
+            while i < len(mods):
+                lin = mods[i]
+                x2 = ops.LinearFn.apply(x2, lin.weight, lin.bias, None)
+                i += 1
+                if i < len(mods) and isinstance(mods[i], nn.BatchNorm1d):
+                    bn = mods[i]
+                    x2 = ops.BatchNormGeluFn.apply(x2, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                                   bn.num_batches_tracked, bn.momentum, bn.eps,
+                                                   bn.training or not bn.track_running_stats, True)
+                    i += 2   # the GELU that follows is fused
+        else:
+            linears = [self.mlp] if isinstance(self.mlp, nn.Linear) else [m for m in self.mlp if isinstance(m, nn.Linear)]
+            wb = []
+            for lin in linears:
+                wb += [lin.weight, lin.bias]
+            x2 = ops.MlpChainFn.apply(x2, None, *wb)
         x2 = ops.L2NormFn.apply(x2, 1e-12)
         ll = self.last_layer
         y = ops.WeightNormLinearFn.apply(x2, ll.weight_v, ll.weight_g)

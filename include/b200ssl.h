@@ -123,8 +123,36 @@ int b200ssl_l2norm_bwd(const void* y, const void* dy, const float* norm, void* d
 /* weight_norm(Linear) rows (VT.pyc@L315-318): w(bf16) = g * v / ||v||; g nullable (= 1). */
 int b200ssl_weightnorm_fwd(const float* v, const float* g, void* w, float* norm, long long rows, int D,
                            void* stream);
+/* accumulate != 0: dv / dg are ADDED to (they are the parameters' persistent .grad buffers), else overwritten. */
 int b200ssl_weightnorm_bwd(const float* v, const float* g, const float* norm, const float* dw, float* dv,
-                           float* dg, long long rows, int D, void* stream);
+                           float* dg, long long rows, int D, int accumulate, void* stream);
+
+/* ---- BatchNorm1d (+ fused exact-erf GELU) for DINOHead(use_bn=True) (VT.pyc@L304-305,309-310) ----------------
+ * x, h, dh, dx bf16 [rows, C]; w, b (nullable), running_mean / running_var, save_mean / save_invstd fp32 [C];
+ * num_batches: int64 device scalar (nullable). training != 0: batch statistics (biased variance for the output,
+ * unbiased for running_var, torch.nn.BatchNorm1d); training == 0: running statistics. dw / db are ACCUMULATED. */
+int b200ssl_bn_gelu_fwd(const void* x, const float* w, const float* b, float* running_mean, float* running_var,
+                        long long* num_batches, void* h, float* save_mean, float* save_invstd, long long rows, int C,
+                        float momentum, float eps, int training, int apply_gelu, void* stream);
+int b200ssl_bn_gelu_bwd(const void* x, const void* dh, const float* w, const float* b, const float* save_mean,
+                        const float* save_invstd, void* dx, float* dw, float* db, long long rows, int C, int training,
+                        int apply_gelu, void* stream);
+
+/* ---- step plumbing (memset / copy nodes and three tiny kernels that replace PyTorch glue inside the captured
+ *      step: torch.zeros, clone, x[:, 0] slicing + cat (VT.pyc@L253), its indexed-assignment backward, the
+ *      accumulation of cls_token / pos_embed gradients and the position-table resize (VT.pyc@L213-233)). */
+int b200ssl_zero_bytes(void* p, long long nbytes, void* stream);
+int b200ssl_copy_bytes(void* dst, const void* src, long long nbytes, void* stream);
+/* dst[r*dst_stride .. +row_bytes) = src[r*src_stride .. +row_bytes), r < rows; everything in multiples of 16 bytes. */
+int b200ssl_copy_rows(const void* src, long long src_stride_bytes, void* dst, long long dst_stride_bytes,
+                      long long rows, int row_bytes, void* stream);
+/* dst[i] += src[i], fp32. */
+int b200ssl_add_f32(float* dst, const float* src, long long n, void* stream);
+/* interpolate_pos_encoding as the fixed linear map mat [Mo, Ki] (fp32; the bicubic weights incl. the +0.1 fudge):
+ * transpose = 0: out[0]=in[0], out[1+i] = sum_j mat[i,j] in[1+j]   (in = pos_embed [1+Ki, D], out [1+Mo, D])
+ * transpose = 1: out[0]+=in[0], out[1+j] += sum_i mat[i,j] in[1+i] (in = d(table) [1+Mo, D], out = d(pos_embed)). */
+int b200ssl_pos_interp(const float* mat, const float* in, float* out, int Mo, int Ki, int D, int transpose,
+                       void* stream);
 
 /* ---- K7: DINO loss (not in the reference; call slot train.py:1053 loss_fn(output, target)) -----------
  * student [ncrops*B, K], teacher [2*B, K] bf16, crop-major rows; center fp32 [K]; loss fp32 [1];

@@ -216,6 +216,51 @@ def test_vit_utilities(libs):
         assert rel(mine.blocks[0](t), ref.blocks[0](t_ref)) < 1e-2
 
 
+def test_dino_head_with_batchnorm(libs):
+    """DINOHead(use_bn=True) (VT.pyc@L304-305,309-310): Linear -> BatchNorm1d -> GELU per hidden layer. Training mode
+    (batch statistics; running statistics and num_batches_tracked updated like torch), gradients of every parameter
+    incl. the BatchNorm affine pair, then eval mode on the updated running statistics (the teacher's mode)."""
+    b200ssl, ovt, _ = libs
+    torch.manual_seed(0)
+    ref = ovt.DINOHead(192, 1024, use_bn=True, hidden_dim=256, bottleneck_dim=64).cuda().train()
+    with torch.no_grad():
+        for p in ref.parameters():
+            if p.ndim == 1:
+                p.add_(torch.randn_like(p) * 0.1)
+    mine = b200ssl.DINOHead(192, 1024, use_bn=True, hidden_dim=256, bottleneck_dim=64).cuda().train()
+    mine.load_state_dict(ref.state_dict())
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    x = torch.randn(48, 192, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    for it in range(2):
+        out_ref, out = ref(x), mine(x.bfloat16())
+        assert rel(out, out_ref) < 1e-2, rel(out, out_ref)
+        w = torch.randn_like(out_ref)
+        ref.zero_grad(), mine.zero_grad()
+        (out_ref * w).sum().backward()
+        (out.float() * w).sum().backward()
+        bad = []
+        for (n, p), (_, q) in zip(ref.named_parameters(), mine.named_parameters()):
+            if p.grad is None:
+                continue
+            if n in ("mlp.0.bias", "mlp.3.bias"):
+                # the bias of a Linear that feeds a BatchNorm has an exactly-zero gradient (the batch mean is
+                # subtracted again): both sides hold rounding noise only, a cosine is meaningless -- require "tiny"
+                wn = dict(mine.named_parameters())[n.replace("bias", "weight")].grad.norm()
+                assert q.grad.norm() < 2e-2 * wn and p.grad.norm() < 1e-3 * wn, (n, q.grad.norm(), p.grad.norm(), wn)
+                continue
+            if cos(q.grad, p.grad) < 0.999:
+                bad.append((n, cos(q.grad, p.grad)))
+        assert not bad, bad
+    for (n, a), (_, b) in zip(ref.named_buffers(), mine.named_buffers()):
+        if a.dtype.is_floating_point:
+            assert rel(b, a) < 1e-2, n
+        else:
+            assert torch.equal(a, b), n          # num_batches_tracked == 2
+    ref.eval(), mine.eval()
+    with torch.no_grad():
+        assert rel(mine(x.bfloat16()), ref(x)) < 1e-2
+
+
 def test_cpu_input_fails_loudly(libs):
     b200ssl, _, _ = libs
     m = b200ssl.vit_tiny()
