@@ -514,9 +514,21 @@ def main():
                 "step_frac_of_peak": total_f * B / (ms_step / 1e3) / 1e12 / peak_sus,
                 "step_frac_of_burst_peak": total_f * B / (ms_step / 1e3) / 1e12 / peak_burst}
 
-    if rank != 0:
+    def shutdown():
+        """N > 1: drop the captured step graph BEFORE the process group (NCCL does not let go of a communicator that a
+        live CUDA graph still references: destroy_process_group would hang), then leave without running the
+        interpreter's teardown (which would destroy the communicator in an arbitrary order)."""
         if world > 1:
-            dist.destroy_process_group()
+            if cfg["kind"] != "embed" and graphed is not None:
+                graphed.release()
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        shutdown()
         return 0
 
     line = {"metric": METRIC, "value": value, "unit": "images/s",
@@ -527,9 +539,8 @@ def main():
             "roofline": roofline}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_leg(cfg, args)
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    shutdown()
     return 0
 
 

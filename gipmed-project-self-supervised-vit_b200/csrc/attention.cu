@@ -525,13 +525,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         for (int j = 0; j < ku / 16; ++j)
           umma_bf16_ss(T_DQ + t * 64, make_smem_desc_sw128(ds0 + (j >> 2) * TILE_BYTES + (j & 3) * 32, 16, 1024),
                        make_smem_desc_sw128(k_u + j * 2048, 8192, 1024), idesc_q, (u > 0 || j > 0));
-        // dV_u (+)= P^T[128 keys, 128 q] . dO_t[128 q, 64] ; dK_u (+)= dS^T . Q_t
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
+        // dV_u (+)= P^T[128 keys, 128 q] . dO_t[128 q, 64] ; dK_u (+)= dS^T . Q_t. The reduction runs over the query rows
+        // of tile t: rows past the sequence end hold P = dS = 0 (lse2 = +inf), so only the live 16-row steps are issued
+        const int qsteps = (min(128, (NT == 1 ? args.rows : args.N) - t * 128) + 15) >> 4;
+        for (int j = 0; j < qsteps; ++j)
           umma_bf16_ss(T_DV, make_smem_desc_sw128(p0 + j * 2048, TILE_BYTES, 1024),
                        make_smem_desc_sw128(do_t + j * 2048, 8192, 1024), idesc_kv, (t > 0 || j > 0));
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < qsteps; ++j)
           umma_bf16_ss(T_DK, make_smem_desc_sw128(ds0 + j * 2048, TILE_BYTES, 1024),
                        make_smem_desc_sw128(q_t + j * 2048, 8192, 1024), idesc_kv, (t > 0 || j > 0));
         umma_commit(bar_mma);
@@ -779,6 +779,368 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------
+// forward, streaming variant: any sequence length > 128; key / value blocks of 128 tokens streamed through smem
+// ------------------------------------------------------------------------------------------------
+// One 128-row query tile per CTA at a time (persistent over (sequence, head, query tile) items, query tile fastest so
+// that the CTAs running at the same time share K / V in L2). The keys are walked in blocks of 128 with an online
+// softmax. Two softmax TEAMS of 128 threads (one thread per query row, no cross-thread reductions) take the even and
+// the odd key blocks; each keeps its own running (max, sum, O) and the two are merged once per item through shared
+// memory (split-softmax merge). TMEM: three S buffers of 128 columns (P, bf16, overwrites the consumed columns of its
+// own S buffer and is the A operand of P.V) + one 64-column O buffer per team. The MMA issuer keeps S three blocks
+// ahead of P.V -- across item boundaries -- so a team never waits for scores, and P.V of block j writes a FRESH
+// accumulator that the team folds into its registers (O_acc = O_acc * alpha + O_j) while it is already working on
+// block j + 2: no TMEM read-modify-write, no correction warps, nothing on the softmax's critical path but exp2.
+//   warp 0 : TMA producer (Q double-buffered per item; K ring, V ring)      warp 1 : tcgen05.mma issuer
+//   warp 2 : TMEM allocation                                                  warps 4-7 / 8-11 : teams A / B
+constexpr int FS_THREADS = 10 * 32;
+constexpr int FS_KSTAGES = 4;
+constexpr int FS_VSTAGES = 4;
+constexpr int FS_SCRATCH_BYTES = 66 * 128 * 4;  // team B -> team A: O[64], max, sum per row, column-major
+constexpr int FS_SMEM_BYTES = (2 + FS_KSTAGES + FS_VSTAGES) * TILE_BYTES + FS_SCRATCH_BYTES + 512 /*barriers*/ + 1024 /*align*/;
+
+__global__ void __launch_bounds__(FS_THREADS, 1)
+attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
+                            const AttnArgs args, const int num_items, const int nqt, const int nkb) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                                   // [2] tiles
+  uint8_t* sK = sQ + 2 * TILE_BYTES;                    // [FS_KSTAGES]
+  uint8_t* sV = sK + FS_KSTAGES * TILE_BYTES;           // [FS_VSTAGES]
+  float* scratch = reinterpret_cast<float*>(sV + FS_VSTAGES * TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(scratch) + FS_SCRATCH_BYTES);
+  uint64_t* q_full = bars;                  // [2]
+  uint64_t* q_free = bars + 2;              // [2] the item's output store has been read out of the (dead) Q tile
+  uint64_t* k_full = bars + 4;              // [FS_KSTAGES]
+  uint64_t* k_free = k_full + FS_KSTAGES;   // [FS_KSTAGES] S = Q K^T of the block retired
+  uint64_t* v_full = k_free + FS_KSTAGES;   // [FS_VSTAGES]
+  uint64_t* v_free = v_full + FS_VSTAGES;   // [FS_VSTAGES] P V of the block retired
+  uint64_t* s_ready = v_free + FS_VSTAGES;  // [3] per S buffer
+  uint64_t* p_ready = s_ready + 3;          // [3] per S buffer: the team wrote P (and holds the previous O in registers)
+  uint64_t* o_ready = p_ready + 3;          // [2] per team
+  uint64_t* b_done = o_ready + 2;           // team B's partial result of an item is in the scratch
+  uint64_t* scratch_free = b_done + 1;      // team A has read it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(scratch_free + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_my = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  auto item_of = [&](int k) { return static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x); };
+  auto keys_of = [&](int j) { return min(128, args.N - 128 * j); };           // real keys in block j
+  auto keys_n_of = [&](int j) { return (keys_of(j) + 15) & ~15; };            // MMA extent (TMA zero-fills the rest)
+
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_free[i], 1);
+      mbar_init(&o_ready[i], 1);
+    }
+    for (int i = 0; i < FS_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_free[i], 1); }
+    for (int i = 0; i < FS_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_free[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&s_ready[i], 1); mbar_init(&p_ready[i], 128); }
+    mbar_init(b_done, 128);
+    mbar_init(scratch_free, 128);
+    fence_barrier_init();
+  }
+  if (warp == 9) {
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int g = 0;
+      for (int k = 0; k < n_my; ++k) {
+        const int item = item_of(k);
+        const int qt = item % nqt, bh = item / nqt;
+        const int head = bh % args.H, b = bh / args.H;
+        mbar_wait(&q_free[k & 1], ((k >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[k & 1], TILE_BYTES);
+        tma_load_3d(sQ + (k & 1) * TILE_BYTES, &tmQKV, &q_full[k & 1], head * 64, qt * 128, b);
+        for (int j = 0; j < nkb; ++j, ++g) {
+          const int ks = g % FS_KSTAGES, vs = g % FS_VSTAGES;
+          mbar_wait(&k_free[ks], ((g / FS_KSTAGES) & 1) ^ 1);
+          mbar_expect_tx(&k_full[ks], TILE_BYTES);
+          tma_load_3d(sK + ks * TILE_BYTES, &tmQKV, &k_full[ks], (args.H + head) * 64, j * 128, b);
+          mbar_wait(&v_free[vs], ((g / FS_VSTAGES) & 1) ^ 1);
+          mbar_expect_tx(&v_full[vs], TILE_BYTES);
+          tma_load_3d(sV + vs * TILE_BYTES, &tmQKV, &v_full[vs], (2 * args.H + head) * 64, j * 128, b);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
+      const int total = n_my * nkb;
+      int gs = 0, gp = 0;        // blocks whose S / P.V have been issued
+      int ks_item = 0, ks_j = 0; // (item, block) of gs
+      int kp_j = 0;              // block of gp within its item
+      while (gp < total) {
+        while (gs < total && gs < gp + 3) {
+          // S(gs) overwrites S buffer gs % 3 = the P of block gs - 3, whose P.V was issued before (in-order pipe)
+          if (ks_j == 0) mbar_wait(&q_full[ks_item & 1], (ks_item >> 1) & 1);
+          const int ks = gs % FS_KSTAGES;
+          mbar_wait(&k_full[ks], (gs / FS_KSTAGES) & 1);
+          tcgen05_fence_after();
+          const uint32_t idesc_s = make_idesc_bf16(128, keys_n_of(ks_j), false, false);
+          const uint32_t a0 = smem_u32(sQ + (ks_item & 1) * TILE_BYTES), b0 = smem_u32(sK + ks * TILE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ss(tmem_base + (gs % 3) * 128, make_smem_desc_sw128(a0 + kk * 32, 16, 1024),
+                         make_smem_desc_sw128(b0 + kk * 32, 16, 1024), idesc_s, kk > 0);
+          umma_commit(&k_free[ks]);
+          umma_commit(&s_ready[gs % 3]);
+          ++gs;
+          if (++ks_j == nkb) { ks_j = 0; ++ks_item; }
+        }
+        const int team = kp_j & 1, vs = gp % FS_VSTAGES;
+        mbar_wait(&p_ready[gp % 3], (gp / 3) & 1);
+        mbar_wait(&v_full[vs], (gp / FS_VSTAGES) & 1);
+        tcgen05_fence_after();
+        const uint32_t v0 = smem_u32(sV + vs * TILE_BYTES);
+        const int ksteps = keys_n_of(kp_j) / 16;
+        for (int s = 0; s < ksteps; ++s)
+          umma_bf16_ts(tmem_base + 384 + team * 64, tmem_base + (gp % 3) * 128 + 8 * s,
+                       make_smem_desc_sw128(v0 + s * 2048, 8192, 1024), idesc_o, s > 0);
+        umma_commit(&v_free[vs]);
+        umma_commit(&o_ready[team]);
+        ++gp;
+        if (++kp_j == nkb) kp_j = 0;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax teams
+    const int team = warp >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t o_addr = tmem_base + lane_off + 384 + team * 64;
+    float o_acc[64];
+    float m_run = -INFINITY, l_run = 0.f, alpha_pend = 0.f;
+    bool pend = false;
+    int pend_k = 0;          // item the pending O (and the accumulators) belong to
+    bool pend_valid = false; // ... and whether this warp had live rows in it
+    uint32_t npv = 0, nfin = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+    // developer instrumentation (args.prof, 8 counters per team): cycles of the team's first thread in
+    // [0] wait for S, [1] max pass, [2] wait for O, [3] fold O, [4] finalize, [5] exp pass, [6] blocks, [7] whole loop
+    const bool prof_on = args.prof != nullptr && (threadIdx.x & 127) == 0;
+    long long tp0 = prof_on ? clock64() : 0;
+    const long long tp_begin = tp0;
+    auto lap = [&](int idx) {
+      if (prof_on) {
+        const long long now = clock64();
+        atomicAdd(args.prof + team * 8 + idx, static_cast<unsigned long long>(now - tp0));
+        tp0 = now;
+      }
+    };
+
+    // fold the P.V result of this team's previous block into the register accumulator
+    auto resolve = [&]() {
+      lap(1);
+      mbar_wait(&o_ready[team], npv & 1);
+      ++npv;
+      tcgen05_fence_after();
+      lap(2);
+      if (pend_valid) {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32b_x32(o_addr, va);
+        tmem_ld_32x32b_x32(o_addr + 32, vb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], alpha_pend, __uint_as_float(va[i]));
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[32 + i] = fmaf(o_acc[32 + i], alpha_pend, __uint_as_float(vb[i]));
+      }
+      pend = false;
+      lap(3);
+    };
+    // an item is complete for this team: B parks its partial result, A merges, normalises and stores
+    auto finalize = [&]() {
+      const int item = item_of(pend_k);
+      const int qt = item % nqt, bh = item / nqt;
+      const int head = bh % args.H, b = bh / args.H;
+      if (team == 1) {
+        mbar_wait(scratch_free, (nfin & 1) ^ 1);
+        if (pend_valid) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) scratch[i * 128 + r] = o_acc[i];
+          scratch[64 * 128 + r] = m_run;
+          scratch[65 * 128 + r] = l_run;
+        }
+        mbar_arrive(b_done);
+      } else {
+        mbar_wait(b_done, nfin & 1);
+        uint8_t* stg = sQ + (pend_k & 1) * TILE_BYTES;  // every S = Q K^T of the item has retired: Q is dead
+        if (pend_valid) {
+          const float mb = scratch[64 * 128 + r], lb = scratch[65 * 128 + r];
+          const float m = fmaxf(m_run, mb);
+          const float wa = ex2_approx(m_run - m), wb = ex2_approx(mb - m);
+          const float l = l_run * wa + lb * wb;
+          const float inv = l > 0.f ? 1.f / l : 0.f;
+          const float sa = wa * inv, sb = wb * inv;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = o_acc[8 * c + e] * sa + scratch[(8 * c + e) * 128 + r] * sb;
+            uint4 pk;
+            pk.x = pack_bf16x2(o[0], o[1]);
+            pk.y = pack_bf16x2(o[2], o[3]);
+            pk.z = pack_bf16x2(o[4], o[5]);
+            pk.w = pack_bf16x2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(stg + sw128_offset(r, c)) = pk;
+          }
+          const int n = qt * 128 + r;
+          if (n < args.N) args.lse2[(static_cast<long long>(b) * args.H + head) * args.Ns + n] = m + log2f(l);
+        }
+        mbar_arrive(scratch_free);
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (warp == 0 && lane == 0) {
+          tma_store_3d(&tmO, stg, head * 64, qt * 128, b);
+          tma_store_commit();
+          tma_store_wait_read<0>();
+          mbar_arrive(&q_free[pend_k & 1]);
+        }
+      }
+      ++nfin;
+      lap(4);
+    };
+
+    for (int k = 0; k < n_my; ++k) {
+      const int item = item_of(k);
+      const int qt = item % nqt;
+      const bool warp_valid = qt * 128 + q * 32 < args.N;  // rows >= N: scores of zero-filled queries, never stored
+      for (int j = team; j < nkb; j += 2) {
+        const int g = k * nkb + j, buf = g % 3;
+        const bool first = j == team;
+        const int kn = keys_n_of(j);
+        const int n32 = kn >> 5;              // full 32-column groups; a 16-column tail only in the last block
+        const bool tail16 = (kn & 16) != 0;
+        const uint32_t s_addr = tmem_base + lane_off + buf * 128;
+        lap(5);
+        mbar_wait(&s_ready[buf], (g / 3) & 1);
+        tcgen05_fence_after();
+        lap(0);
+        // ---- pass 1: row max of the raw scores (zero-filled pad keys score exactly 0: harmless in the max). The
+        // thread owns the whole row, so the only latency to hide is the TMEM load's: two 32-column loads in flight
+        float mx = -INFINITY;
+        auto max32 = [&](const uint32_t (&v)[32]) {
+          float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+          float m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+          for (int i = 4; i < 32; i += 4) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+          }
+          mx = fmaxf(mx, fmaxf(m0, m1));
+        };
+        if (warp_valid) {
+          uint32_t va[32], vb[32];
+          for (int c = 0; c < n32; c += 2) {
+            tmem_ld_32x32b_x32(s_addr + c * 32, va);
+            if (c + 1 < n32) tmem_ld_32x32b_x32(s_addr + (c + 1) * 32, vb);
+            tmem_ld_wait();
+            max32(va);
+            if (c + 1 < n32) max32(vb);
+          }
+          if (tail16) {
+            uint32_t t[16];
+            tmem_ld_32x32b_x16(s_addr + n32 * 32, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(t[i]));
+          }
+        }
+        // ---- the P.V result of this team's previous block is certainly there by now: fold it in; at an item
+        // boundary that completes the previous item
+        if (pend) {
+          resolve();
+          if (first) finalize();
+        }
+        lap(1);
+        if (first) {
+          m_run = -INFINITY;
+          l_run = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+        }
+        // ---- pass 2: p = 2^(s * c - m) -> bf16 pairs over the consumed columns of the same S buffer; the next 32
+        // columns are requested before the current ones go through exp2
+        if (warp_valid) {
+          const float m_new = fmaxf(m_run, mx * args.scale_log2);
+          const float alpha = m_run == -INFINITY ? 0.f : ex2_approx(m_run - m_new);
+          float sum0 = 0.f, sum1 = 0.f;
+          auto exp16 = [&](const uint32_t (&v)[16], uint32_t col) {   // 16 scores -> 8 packed columns of P at `col`
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), args.scale_log2, -m_new));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), args.scale_log2, -m_new));
+              sum0 += p0;
+              sum1 += p1;
+              pk[i] = pack_bf16x2(p0, p1);
+            }
+            tmem_st_32x32b_x8(col, pk);
+          };
+          const int nch = kn >> 4;
+          uint32_t wa[16], wb[16];
+          tmem_ld_32x32b_x16(s_addr, wa);
+          for (int c = 0; c < nch; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < nch) tmem_ld_32x32b_x16(s_addr + (c + 1) * 16, wb);
+            exp16(wa, s_addr + c * 8);
+            if (c + 1 < nch) {
+              tmem_ld_wait();
+              if (c + 2 < nch) tmem_ld_32x32b_x16(s_addr + (c + 2) * 16, wa);
+              exp16(wb, s_addr + (c + 1) * 8);
+            }
+          }
+          float sum = sum0 + sum1;
+          sum -= static_cast<float>(kn - keys_of(j)) * ex2_approx(-m_new);  // the zero-filled pad keys of the last block
+          l_run = fmaf(l_run, alpha, sum);
+          m_run = m_new;
+          alpha_pend = alpha;
+          tmem_st_wait();
+        }
+        tcgen05_fence_before();
+        mbar_arrive(&p_ready[buf]);
+        pend = true;
+        pend_k = k;
+        pend_valid = warp_valid;
+        if (prof_on) atomicAdd(args.prof + team * 8 + 6, 1ull);
+      }
+    }
+    lap(5);
+    if (pend) {
+      resolve();
+      finalize();
+    }
+    if (prof_on) atomicAdd(args.prof + team * 8 + 7, static_cast<unsigned long long>(clock64() - tp_begin));
+    if (warp == 0 && lane == 0) tma_store_wait_all<0>();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
+}
+
+// forward kernel choice: 0 = streaming kernel for N > 256 only (two-tile kernel for 129..256), 1 = streaming kernel for
+// every N > 128, -1 = never (N > 256 falls back to the block decomposition with an lse merge; developer A/B)
+static int g_attn_stream = 0;
+
 static unsigned long long* g_attn_prof = nullptr;
 
 // Nq / Nk: query and key tokens of this launch (equal, and equal to the stride Ns, on the main path).
@@ -841,6 +1203,33 @@ static int attention_fwd_block(const __nv_bfloat16* qkv, __nv_bfloat16* out, flo
     }
     B200SSL_CUDA(launch_pdl(attention_fwd_kernel<2>, dim3(grid), dim3(FWD_THREADS), smem, stream, 1, tq, tkv, to, a, num_items));
   }
+  return 0;
+}
+
+// streaming forward (any N > 128): one launch for the whole sequence, no workspace
+static int attention_fwd_stream(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int B, int N, int H, float scale,
+                                cudaStream_t stream) {
+  AttnArgs a{};
+  a.prof = g_attn_prof;
+  a.B = B; a.N = N; a.Nk = N; a.Ns = N; a.H = H;
+  a.G = 1; a.rows = N; a.keys_n = 0;
+  a.scale = scale;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.lse2 = lse2;
+  CUtensorMap tq, to;
+  if (int rc = make_bnd_map(&tq, qkv, 3 * H * 64, N, N, B, 2, 1)) return rc;
+  if (int rc = make_bnd_map(&to, out, H * 64, N, N, B, 2, 1)) return rc;
+  const int nqt = (N + 127) / 128, nkb = (N + 127) / 128;
+  const long long items = static_cast<long long>(B) * H * nqt;
+  B200SSL_CHECK(items * nkb < (1LL << 30), -2, "attention: problem too large for the streaming forward (B*H*tiles = %lld)", items);
+  const int grid = items < sm_count() ? static_cast<int>(items) : sm_count();
+  static bool cfg = false;
+  if (!cfg) {
+    B200SSL_CUDA(cudaFuncSetAttribute(attention_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES));
+    cfg = true;
+  }
+  B200SSL_CUDA(launch_pdl(attention_fwd_stream_kernel, dim3(grid), dim3(FS_THREADS), FS_SMEM_BYTES, stream, 1, tq, to, a,
+                          static_cast<int>(items), nqt, nkb));
   return 0;
 }
 
@@ -938,8 +1327,14 @@ extern "C" int b200ssl_set_attn_prof(void* counters) {
 }
 
 // bytes of scratch b200ssl_attention_fwd_ws needs (0 for N <= 256): per key block a partial output and lse
+extern "C" int b200ssl_set_attn_stream(int mode) {
+  B200SSL_CHECK(mode >= -1 && mode <= 1, -2, "attention stream mode must be -1, 0 or 1");
+  b200ssl::g_attn_stream = mode;
+  return 0;
+}
+
 extern "C" long long b200ssl_attention_fwd_workspace_bytes(int B, int N, int H) {
-  if (N <= 256) return 0;
+  if (N <= 256 || b200ssl::g_attn_stream >= 0) return 0;
   const long long nblk = num_blocks_for(N);
   return nblk * (static_cast<long long>(B) * N * H * 64 * 2 + static_cast<long long>(B) * H * N * 4);
 }
@@ -951,6 +1346,10 @@ extern "C" int b200ssl_attention_fwd_ws(const void* qkv_, void* out_, float* lse
   B200SSL_CHECK(B > 0 && H > 0 && N > 0, -2, "attention: empty problem");
   const __nv_bfloat16* qkv = static_cast<const __nv_bfloat16*>(qkv_);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_);
+  if (N > 128 && (g_attn_stream == 1 || (g_attn_stream == 0 && N > 256))) {
+    B200SSL_CHECK(N <= 65536, -2, "attention: sequence length %d unsupported (1..65536)", N);
+    return attention_fwd_stream(qkv, out, lse2, B, N, H, scale, stream);
+  }
   if (N <= 256) return attention_fwd_block(qkv, out, lse2, B, N, H, 0, N, 0, N, scale, false, stream);
   B200SSL_CHECK(N <= 4096, -2, "attention: sequence length %d unsupported (1..4096)", N);
   const long long need = b200ssl_attention_fwd_workspace_bytes(B, N, H);

@@ -898,6 +898,16 @@ class GraphedDinoStep:
         self._temp = float(self.loss_fn.teacher_temp_schedule[epoch])
         self._opt_version = self.opt.table_version
 
+    def release(self):
+        """Drop the captured graphs (their outputs stay valid tensors). MUST run before
+        ``dist.destroy_process_group()`` when the step was captured with NCCL collectives inside: NCCL keeps a
+        communicator alive -- and ``ncclCommDestroy`` waits -- for as long as a CUDA graph holding its kernels exists
+        (measured: the process hangs in destroy_process_group otherwise)."""
+        torch.cuda.synchronize()
+        self._graph = self._graph_update = None
+        self._pending_static = None
+        torch.cuda.synchronize()
+
     def load(self, crops, non_blocking=True):
         """Copy a batch of crops into the graph's static input buffers (same stream as the replay)."""
         for dst, src in zip(self.static_crops, crops):

@@ -383,13 +383,14 @@ def segments(B, N):
 def _attention_fwd_one(qkv, out, B, N, H, scale):
     lse2 = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
     if N > 256:
-        # long sequences (native 256^2 tiles: 257 tokens; ViT-S/8: 785): blocks of <= 256 queries x <= 256 keys
-        # through the same kernels, partial results merged by their log-sum-exp; needs scratch for the partials
+        # long sequences (native 256^2 tiles: 257 tokens; ViT-S/8: 785): the streaming kernel (one launch, no scratch);
+        # only the developer A/B mode b200ssl_set_attn_stream(-1) takes the block decomposition and needs scratch
         nbytes = int(_lib.lib().b200ssl_attention_fwd_workspace_bytes(B, N, H))
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
-        _call("b200ssl_attention_fwd_ws", qkv.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, N, H, 64, float(scale),
-              ws.data_ptr(), nbytes, _stream(), launches=((N + 255) // 256) ** 2 + 1)
-        return lse2
+        if nbytes > 0:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
+            _call("b200ssl_attention_fwd_ws", qkv.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, N, H, 64,
+                  float(scale), ws.data_ptr(), nbytes, _stream(), launches=((N + 255) // 256) ** 2 + 1)
+            return lse2
     _call("b200ssl_attention_fwd", qkv.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, N, H, 64, float(scale),
           _stream())
     return lse2

@@ -86,16 +86,21 @@ int b200ssl_layernorm_bwd(const void* x, int x_f32, const void* dy, const float*
 
 /* ---- K4: fused attention (Attention.forward VT.pyc@L119-131) --------------------------------------
  * qkv [B,N,3,H,64] bf16 (the QKV GEMM output as is), out/dout [B,N,H,64] bf16, lse2 [B,H,N] fp32
- * (log2-sum-exp of the scaled scores), dqkv like qkv. head_dim must be 64, 1 <= N <= 256. */
+ * (log2-sum-exp of the scaled scores), dqkv like qkv. head_dim must be 64. */
 int b200ssl_attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, int head_dim,
                           float scale, void* stream);
 int b200ssl_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv,
                           int B, int N, int H, int head_dim, float scale, void* stream);
-/* Sequences longer than 256 tokens (the reference's native 256^2 tiles give 257; ViT-S/8 at 224^2 gives 785; up to
- * 4096) are decomposed into blocks of <= 256 queries x <= 256 keys run through the same kernels: forward merges
- * the per-key-block partial results by their log-sum-exp and needs scratch for them (query the size, pass a
- * 128-byte aligned buffer); backward needs none (dQ accumulates over key blocks, dK/dV over query blocks through
- * TMA reduce-add). b200ssl_attention_fwd == b200ssl_attention_fwd_ws with no workspace (N <= 256 only). */
+/* Forward for sequences of more than 128 tokens has a STREAMING kernel (one 128-row query tile per CTA, key / value
+ * blocks of 128 tokens streamed through shared memory, online softmax, two softmax teams on alternating key blocks,
+ * no workspace): the default for N > 256 (the reference's native 256^2 tiles give 257 tokens; ViT-S/8 at 224^2 gives
+ * 785; up to 65536). b200ssl_set_attn_stream: 0 (default) = streaming kernel for N > 256, 1 = for every N > 128,
+ * -1 = never (developer A/B: N > 256 then runs as blocks of <= 256 queries x <= 256 keys through the two-tile
+ * kernel, partial results merged by their log-sum-exp in a caller-provided scratch buffer, N <= 4096).
+ * Backward for N > 256 runs block pairs through the two-tile backward kernel (dQ accumulates over key blocks, dK/dV
+ * over query blocks through TMA reduce-add; N <= 4096). b200ssl_attention_fwd == b200ssl_attention_fwd_ws with no
+ * workspace; b200ssl_attention_fwd_workspace_bytes returns 0 whenever none is needed. */
+int b200ssl_set_attn_stream(int mode);
 long long b200ssl_attention_fwd_workspace_bytes(int B, int N, int H);
 int b200ssl_attention_fwd_ws(const void* qkv, void* out, float* lse2, int B, int N, int H, int head_dim, float scale,
                              void* workspace, long long workspace_bytes, void* stream);

@@ -88,6 +88,9 @@ def run(B, N, H, bench=False):
 
 def main():
     ok = True
+    if "--stream" in sys.argv:   # forward kernel choice for N > 128: -1 block decomposition, 0 default, 1 always streaming
+        h.b200ssl_set_attn_stream.argtypes = [I]
+        ck(h.b200ssl_set_attn_stream(int(sys.argv[sys.argv.index("--stream") + 1])))
     ok &= run(2, 128, 1)
     ok &= run(3, 64, 2)
     ok &= run(7, 37, 3)
@@ -101,6 +104,9 @@ def main():
     ok &= run(3, 257, 2)      # long sequences: native 256^2 tiles -> 257 tokens (2 x 2 blocks of 129 / 128)
     ok &= run(2, 785, 3)      # ViT-S/8 at 224^2: 785 tokens (4 x 4 blocks)
     ok &= run(40, 325, 6)     # 288^2 tiles, many items
+    ok &= run(2, 129, 1)      # one key past the first block
+    ok &= run(1, 1025, 2)     # ViT-S/8 at 256^2: 9 key blocks, the last of one key
+    ok &= run(300, 200, 2)    # many items per CTA on the streaming path (mode 1)
     if "--bench" in sys.argv and ok:
         run(512, 197, 6, bench=True)
         run(2560, 37, 6, bench=True)

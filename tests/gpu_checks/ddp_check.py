@@ -110,5 +110,12 @@ ok &= max(abs(a - b) / abs(b) for a, b in zip(graph_g, ref_more)) < 1e-2
 print(f"rank {rank}: loss {loss0.item():.5f} (global ref {l_ref.item():.5f}) worst grad cos {worst:.6f} "
       f"center rel {rel(center, ref_center):.2e} | steps 1-2 global loss: ref {ref_more} eager {eager_g} graph {graph_g} "
       f"-> {'OK' if ok else 'FAIL'}")
-dist.destroy_process_group()
-sys.exit(0 if ok else 1)
+# the captured step holds NCCL kernels: release it before the communicator goes away (destroy_process_group hangs
+# otherwise), then leave without the interpreter's teardown
+step.release()
+del step
+torch.cuda.synchronize()
+dist.barrier()
+sys.stdout.flush()
+sys.stderr.flush()
+os._exit(0 if ok else 1)

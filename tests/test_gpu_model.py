@@ -497,7 +497,7 @@ def test_ddp_two_ranks(libs):
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29653",
-                        os.path.join(here, "gpu_checks", "ddp_check.py")], capture_output=True, text=True, timeout=600)
+                        os.path.join(here, "gpu_checks", "ddp_check.py")], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("-> OK") == 2, r.stdout[-3000:]
 
