@@ -784,25 +784,26 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 // ------------------------------------------------------------------------------------------------
 // One 128-row query tile per CTA at a time (persistent over (sequence, head, query tile) items, query tile fastest so
 // that the CTAs running at the same time share K / V in L2). The keys are walked in blocks of 128 with an online
-// softmax. Two softmax TEAMS of 256 threads (two threads per query row, each owning half of the block's key columns
-// and half of the 64 output columns) take the even and the odd key blocks; each team keeps its own running
-// (max, sum, O) and the two are merged once per item through shared memory (split-softmax merge). TMEM: three S
-// buffers of 128 columns (P, bf16, overwrites consumed columns of its own S buffer and is the A operand of P.V) + one
-// 64-column O buffer per team. The MMA issuer keeps S three blocks ahead of P.V -- across item boundaries -- so a team
-// never waits for scores, and P.V of block j writes a FRESH accumulator that the team folds into its registers
-// (O_acc = O_acc * alpha + O_j) while it is already working on block j + 2: no TMEM read-modify-write, no correction
-// warps; per block the only cross-thread step is the exchange of the two half-row maxima (one named barrier).
-//   warps 0-7 / 8-15 : teams A / B (warp w: TMEM lane quarter w & 3, column half (w >> 2) & 1)
-//   warp 16 : TMA producer (Q double-buffered per item; K ring, V ring)      warp 17 : tcgen05.mma issuer (+ TMEM)
-constexpr int FS_THREADS = 18 * 32;
+// softmax. Two softmax TEAMS of 128 threads (one thread per query row, no cross-thread reductions) take the even and
+// the odd key blocks; each keeps its own running (max, sum, O) and the two are merged once per item through shared
+// memory (split-softmax merge). TMEM: three S buffers of 128 columns (P, bf16, overwrites the consumed columns of its
+// own S buffer and is the A operand of P.V) + one 64-column O buffer per team. The MMA issuer keeps S three blocks
+// ahead of P.V -- across item boundaries -- so a team never waits for scores, and P.V of block j writes a FRESH
+// accumulator that the team folds into its registers (O_acc = O_acc * alpha + O_j) while it is already working on
+// block j + 2: no TMEM read-modify-write, no correction warps, nothing on the softmax's critical path but exp2.
+//   warps 0-3 / 4-7 : teams A / B      warp 8 : TMA producer (Q double-buffered per item; K ring, V ring)
+//   warp 9 : tcgen05.mma issuer (+ TMEM allocation)
+// Measured alternatives (profiles/README.md, round 2): two threads per row per team (16 softmax warps, one named
+// barrier per block for the half-row maxima): same speed -- the teams lock in phase (both in their exp2 pass, then
+// both out of it), the MUFU pipe idles ~60 % either way; ONE team of 16 warps with the next block's max pass riding
+// inside the exp pass: 234 us (every step of the per-block chain is exposed); exp2 passes taking turns: 236 us.
+constexpr int FS_THREADS = 10 * 32;
+constexpr bool FS_EXP_TURNS = false;  // measured: exp2 passes taking turns in block order 201 -> 236 us at N = 785 (one warp per scheduler cannot fill the MUFU pipe alone)
 constexpr int FS_KSTAGES = 4;
 constexpr int FS_VSTAGES = 4;
-constexpr int FS_SCRATCH_BYTES = 69 * 128 * 4;  // column-major [69][128]: team B's O[64], max, sum[2]; team A's own sum[2]
-constexpr int FS_XCHG_BYTES = 2 * 2 * 2 * 128 * 4;  // [team][parity][half][row] half-row maxima
-constexpr int FS_SMEM_BYTES = (2 + FS_KSTAGES + FS_VSTAGES) * TILE_BYTES + FS_SCRATCH_BYTES + FS_XCHG_BYTES + 512 /*barriers*/ +
-                              1024 /*align*/;
+constexpr int FS_SCRATCH_BYTES = 66 * 128 * 4;  // team B -> team A: O[64], max, sum per row, column-major
+constexpr int FS_SMEM_BYTES = (2 + FS_KSTAGES + FS_VSTAGES) * TILE_BYTES + FS_SCRATCH_BYTES + 512 /*barriers*/ + 1024 /*align*/;
 
-template <bool PROF>
 __global__ void __launch_bounds__(FS_THREADS, 1)
 attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                             const AttnArgs args, const int num_items, const int nqt, const int nkb) {
@@ -813,8 +814,7 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
   uint8_t* sK = sQ + 2 * TILE_BYTES;                    // [FS_KSTAGES]
   uint8_t* sV = sK + FS_KSTAGES * TILE_BYTES;           // [FS_VSTAGES]
   float* scratch = reinterpret_cast<float*>(sV + FS_VSTAGES * TILE_BYTES);
-  float* xchg_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + FS_SCRATCH_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg_all) + FS_XCHG_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(scratch) + FS_SCRATCH_BYTES);
   uint64_t* q_full = bars;                  // [2]
   uint64_t* q_free = bars + 2;              // [2] the item's output store has been read out of the (dead) Q tile
   uint64_t* k_full = bars + 4;              // [FS_KSTAGES]
@@ -826,7 +826,8 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
   uint64_t* o_ready = p_ready + 3;          // [2] per team
   uint64_t* b_done = o_ready + 2;           // team B's partial result of an item is in the scratch
   uint64_t* scratch_free = b_done + 1;      // team A has read it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(scratch_free + 1);
+  uint64_t* exp_turn = scratch_free + 1;    // the exp2 pass of block g is over (one phase per block, in block order)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(exp_turn + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_my = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -834,22 +835,23 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
   auto keys_of = [&](int j) { return min(128, args.N - 128 * j); };           // real keys in block j
   auto keys_n_of = [&](int j) { return (keys_of(j) + 15) & ~15; };            // MMA extent (TMA zero-fills the rest)
 
-  if (warp == 17) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tmQKV);
-      tma_prefetch_desc(&tmO);
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&q_full[i], 1);
-        mbar_init(&q_free[i], 1);
-        mbar_init(&o_ready[i], 1);
-      }
-      for (int i = 0; i < FS_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_free[i], 1); }
-      for (int i = 0; i < FS_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_free[i], 1); }
-      for (int i = 0; i < 3; ++i) { mbar_init(&s_ready[i], 1); mbar_init(&p_ready[i], 256); }
-      mbar_init(b_done, 256);
-      mbar_init(scratch_free, 256);
-      fence_barrier_init();
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_free[i], 1);
+      mbar_init(&o_ready[i], 1);
     }
+    for (int i = 0; i < FS_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_free[i], 1); }
+    for (int i = 0; i < FS_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_free[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&s_ready[i], 1); mbar_init(&p_ready[i], 128); }
+    mbar_init(b_done, 128);
+    mbar_init(scratch_free, 128);
+    mbar_init(exp_turn, 128);
+    fence_barrier_init();
+  }
+  if (warp == 9) {
     __syncwarp();
     tmem_alloc<512>(tmem_slot);
   }
@@ -860,7 +862,7 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
   pdl_launch_dependents();
   pdl_wait();
 
-  if (warp == 16) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int g = 0;
@@ -882,7 +884,7 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
         }
       }
     }
-  } else if (warp == 17) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
@@ -914,10 +916,8 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
         tcgen05_fence_after();
         const uint32_t v0 = smem_u32(sV + vs * TILE_BYTES);
         const int ksteps = keys_n_of(kp_j) / 16;
-        const int ch0 = (ksteps + 1) / 2;  // P column map of the two column halves (see the teams below)
         for (int s = 0; s < ksteps; ++s)
-          umma_bf16_ts(tmem_base + 384 + team * 64,
-                       tmem_base + (gp % 3) * 128 + (s < ch0 ? 8 * s : 16 * ch0 + 8 * (s - ch0)),
+          umma_bf16_ts(tmem_base + 384 + team * 64, tmem_base + (gp % 3) * 128 + 8 * s,
                        make_smem_desc_sw128(v0 + s * 2048, 8192, 1024), idesc_o, s > 0);
         umma_commit(&v_free[vs]);
         umma_commit(&o_ready[team]);
@@ -927,36 +927,33 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
     }
   } else {
     // ------------------------------------------------------------------ softmax teams
-    const int team = warp >> 3;
+    const int team = warp >> 2;
     const int q = warp & 3;
-    const int hf = (warp >> 2) & 1;  // which half of the block's key columns / of the output columns
-    const int r = q * 32 + lane;     // query row within the tile == TMEM lane
-    const int ttid = threadIdx.x & 255;
+    const int r = q * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t o_addr = tmem_base + lane_off + 384 + team * 64 + hf * 32;
-    float* xchg = xchg_all + team * 512;
-    float o_acc[32];
-    float m_run = -INFINITY, l_run = 0.f, alpha_pend = 0.f;  // l_run: this thread's column half only
+    const uint32_t o_addr = tmem_base + lane_off + 384 + team * 64;
+    float o_acc[64];
+    float m_run = -INFINITY, l_run = 0.f, alpha_pend = 0.f;
     bool pend = false;
     int pend_k = 0;          // item the pending O (and the accumulators) belong to
     bool pend_valid = false; // ... and whether this warp had live rows in it
-    uint32_t npv = 0, nfin = 0, nblk = 0;
+    uint32_t npv = 0, nfin = 0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
+    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
     // developer instrumentation (args.prof, 8 counters per team): cycles of the team's first thread in
-    // [0] wait for S, [1] max pass + exchange, [2] wait for O, [3] fold O, [4] finalize, [5] exp pass, [6] blocks, [7] loop
-    const bool prof_on = PROF && args.prof != nullptr && ttid == 0;
+    // [0] wait for S, [1] max pass, [2] wait for O, [3] fold O, [4] finalize, [5] exp pass, [6] blocks, [7] whole loop
+    const bool prof_on = args.prof != nullptr && (threadIdx.x & 127) == 0;
     long long tp0 = prof_on ? clock64() : 0;
     const long long tp_begin = tp0;
     auto lap = [&](int idx) {
-      if (PROF && prof_on) {
+      if (prof_on) {
         const long long now = clock64();
         atomicAdd(args.prof + team * 8 + idx, static_cast<unsigned long long>(now - tp0));
         tp0 = now;
       }
     };
 
-    // fold the P.V result of this team's previous block into the register accumulator (own 32 output columns)
+    // fold the P.V result of this team's previous block into the register accumulator
     auto resolve = [&]() {
       lap(1);
       mbar_wait(&o_ready[team], npv & 1);
@@ -964,11 +961,14 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
       tcgen05_fence_after();
       lap(2);
       if (pend_valid) {
-        uint32_t va[32];
+        uint32_t va[32], vb[32];
         tmem_ld_32x32b_x32(o_addr, va);
+        tmem_ld_32x32b_x32(o_addr + 32, vb);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], alpha_pend, __uint_as_float(va[i]));
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[32 + i] = fmaf(o_acc[32 + i], alpha_pend, __uint_as_float(vb[i]));
       }
       pend = false;
       lap(3);
@@ -982,43 +982,40 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
         mbar_wait(scratch_free, (nfin & 1) ^ 1);
         if (pend_valid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) scratch[(hf * 32 + i) * 128 + r] = o_acc[i];
-          if (hf == 0) scratch[64 * 128 + r] = m_run;
-          scratch[(65 + hf) * 128 + r] = l_run;
+          for (int i = 0; i < 64; ++i) scratch[i * 128 + r] = o_acc[i];
+          scratch[64 * 128 + r] = m_run;
+          scratch[65 * 128 + r] = l_run;
         }
         mbar_arrive(b_done);
       } else {
-        scratch[(67 + hf) * 128 + r] = l_run;   // team A's own half-row sums
         mbar_wait(b_done, nfin & 1);
-        named_bar_sync(1, 256);                 // ... visible to the row's other thread
         uint8_t* stg = sQ + (pend_k & 1) * TILE_BYTES;  // every S = Q K^T of the item has retired: Q is dead
         if (pend_valid) {
-          const float mb = scratch[64 * 128 + r], lb = scratch[65 * 128 + r] + scratch[66 * 128 + r];
-          const float la = l_run + scratch[(67 + (hf ^ 1)) * 128 + r];
+          const float mb = scratch[64 * 128 + r], lb = scratch[65 * 128 + r];
           const float m = fmaxf(m_run, mb);
           const float wa = ex2_approx(m_run - m), wb = ex2_approx(mb - m);
-          const float l = la * wa + lb * wb;
+          const float l = l_run * wa + lb * wb;
           const float inv = l > 0.f ? 1.f / l : 0.f;
           const float sa = wa * inv, sb = wb * inv;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 8; ++c) {
             float o[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = o_acc[8 * c + e] * sa + scratch[(hf * 32 + 8 * c + e) * 128 + r] * sb;
+            for (int e = 0; e < 8; ++e) o[e] = o_acc[8 * c + e] * sa + scratch[(8 * c + e) * 128 + r] * sb;
             uint4 pk;
             pk.x = pack_bf16x2(o[0], o[1]);
             pk.y = pack_bf16x2(o[2], o[3]);
             pk.z = pack_bf16x2(o[4], o[5]);
             pk.w = pack_bf16x2(o[6], o[7]);
-            *reinterpret_cast<uint4*>(stg + sw128_offset(r, hf * 4 + c)) = pk;
+            *reinterpret_cast<uint4*>(stg + sw128_offset(r, c)) = pk;
           }
           const int n = qt * 128 + r;
-          if (hf == 0 && n < args.N) args.lse2[(static_cast<long long>(b) * args.H + head) * args.Ns + n] = m + log2f(l);
+          if (n < args.N) args.lse2[(static_cast<long long>(b) * args.H + head) * args.Ns + n] = m + log2f(l);
         }
         mbar_arrive(scratch_free);
         fence_proxy_async_smem();
-        named_bar_sync(1, 256);
-        if (ttid == 0) {
+        named_bar_sync(1, 128);
+        if (warp == 0 && lane == 0) {
           tma_store_3d(&tmO, stg, head * 64, qt * 128, b);
           tma_store_commit();
           tma_store_wait_read<0>();
@@ -1033,50 +1030,47 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
       const int item = item_of(k);
       const int qt = item % nqt;
       const bool warp_valid = qt * 128 + q * 32 < args.N;  // rows >= N: scores of zero-filled queries, never stored
-      for (int j = team; j < nkb; j += 2, ++nblk) {
+      for (int j = team; j < nkb; j += 2) {
         const int g = k * nkb + j, buf = g % 3;
         const bool first = j == team;
-        const int kn = keys_n_of(j), nch = kn >> 4;
-        const int ch0 = (nch + 1) / 2;              // half 0 owns key chunks [0, ch0), half 1 owns [ch0, nch)
-        const int c_begin = hf == 0 ? 0 : ch0, c_end = hf == 0 ? ch0 : nch;
+        const int kn = keys_n_of(j);
+        const int n32 = kn >> 5;              // full 32-column groups; a 16-column tail only in the last block
+        const bool tail16 = (kn & 16) != 0;
         const uint32_t s_addr = tmem_base + lane_off + buf * 128;
-        // P (bf16 pairs, 8 columns per 16-key chunk) goes into the thread's OWN S columns, behind its read pointer:
-        // half 0 -> columns [0, 8 ch0), half 1 -> columns [16 ch0, ...). The MMA issuer uses the same map.
-        const uint32_t p_base = s_addr + (hf == 0 ? 0 : 16 * ch0) - 8 * c_begin;
         lap(5);
         mbar_wait(&s_ready[buf], (g / 3) & 1);
         tcgen05_fence_after();
         lap(0);
-        // ---- pass 1: max of the raw scores over this thread's columns (zero-filled pad keys score exactly 0)
+        // ---- pass 1: row max of the raw scores (zero-filled pad keys score exactly 0: harmless in the max). The
+        // thread owns the whole row, so the only latency to hide is the TMEM load's: two 32-column loads in flight
         float mx = -INFINITY;
-        uint32_t wa[16], wb[16];
-        auto max16 = [&](const uint32_t (&v)[16]) {
+        auto max32 = [&](const uint32_t (&v)[32]) {
           float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
           float m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
 #pragma unroll
-          for (int i = 4; i < 16; i += 4) {
+          for (int i = 4; i < 32; i += 4) {
             m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
             m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
           }
           mx = fmaxf(mx, fmaxf(m0, m1));
         };
-        if (warp_valid && c_begin < c_end) {
-          tmem_ld_32x32b_x16(s_addr + c_begin * 16, wa);
-          for (int c = c_begin; c < c_end; c += 2) {
-            if (c + 1 < c_end) tmem_ld_32x32b_x16(s_addr + (c + 1) * 16, wb);
+        if (warp_valid) {
+          uint32_t va[32], vb[32];
+          for (int c = 0; c < n32; c += 2) {
+            tmem_ld_32x32b_x32(s_addr + c * 32, va);
+            if (c + 1 < n32) tmem_ld_32x32b_x32(s_addr + (c + 1) * 32, vb);
             tmem_ld_wait();
-            max16(wa);
-            if (c + 1 < c_end) {
-              max16(wb);
-              if (c + 2 < c_end) tmem_ld_32x32b_x16(s_addr + (c + 2) * 16, wa);
-            }
+            max32(va);
+            if (c + 1 < n32) max32(vb);
+          }
+          if (tail16) {
+            uint32_t t[16];
+            tmem_ld_32x32b_x16(s_addr + n32 * 32, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(t[i]));
           }
         }
-        float* xc = xchg + (nblk & 1) * 256;   // double-buffered: the row's other thread may be one block ahead
-        xc[hf * 128 + r] = mx;
-        if (team == 0) named_bar_sync(2, 256);
-        else named_bar_sync(3, 256);
-        mx = fmaxf(mx, xc[(hf ^ 1) * 128 + r]);
         // ---- the P.V result of this team's previous block is certainly there by now: fold it in; at an item
         // boundary that completes the previous item
         if (pend) {
@@ -1088,9 +1082,13 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
           m_run = -INFINITY;
           l_run = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
+          for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
         }
-        // ---- pass 2: p = 2^(s * c - m) -> bf16 pairs over the consumed columns of the same S buffer
+        // ---- pass 2: p = 2^(s * c - m) -> bf16 pairs over the consumed columns of the same S buffer. The exp2 passes
+        // take turns in block order: the MUFU pipe is what both teams compete for, and two passes running side by side
+        // at half speed lock the teams in phase (both then sit in their MUFU-free phases together, the pipe idle)
+        if (FS_EXP_TURNS && g > 0) mbar_wait(exp_turn, (g - 1) & 1);
+        lap(1);
         if (warp_valid) {
           const float m_new = fmaxf(m_run, mx * args.scale_log2);
           const float alpha = m_run == -INFINITY ? 0.f : ex2_approx(m_run - m_new);
@@ -1107,32 +1105,35 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
             }
             tmem_st_32x32b_x8(col, pk);
           };
-          if (c_begin < c_end) {
-            tmem_ld_32x32b_x16(s_addr + c_begin * 16, wa);
-            for (int c = c_begin; c < c_end; c += 2) {
+          const int nch = kn >> 4;
+          uint32_t wa[16], wb[16];
+          tmem_ld_32x32b_x16(s_addr, wa);
+          for (int c = 0; c < nch; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < nch) tmem_ld_32x32b_x16(s_addr + (c + 1) * 16, wb);
+            exp16(wa, s_addr + c * 8);
+            if (c + 1 < nch) {
               tmem_ld_wait();
-              if (c + 1 < c_end) tmem_ld_32x32b_x16(s_addr + (c + 1) * 16, wb);
-              exp16(wa, p_base + c * 8);
-              if (c + 1 < c_end) {
-                tmem_ld_wait();
-                if (c + 2 < c_end) tmem_ld_32x32b_x16(s_addr + (c + 2) * 16, wa);
-                exp16(wb, p_base + (c + 1) * 8);
-              }
+              if (c + 2 < nch) tmem_ld_32x32b_x16(s_addr + (c + 2) * 16, wa);
+              exp16(wb, s_addr + (c + 1) * 8);
             }
           }
           float sum = sum0 + sum1;
-          if (hf == 0) sum -= static_cast<float>(kn - keys_of(j)) * ex2_approx(-m_new);  // zero-filled pad keys (last block)
+          sum -= static_cast<float>(kn - keys_of(j)) * ex2_approx(-m_new);  // the zero-filled pad keys of the last block
           l_run = fmaf(l_run, alpha, sum);
           m_run = m_new;
           alpha_pend = alpha;
+          if (FS_EXP_TURNS) mbar_arrive(exp_turn);
           tmem_st_wait();
+        } else if (FS_EXP_TURNS) {
+          mbar_arrive(exp_turn);
         }
         tcgen05_fence_before();
         mbar_arrive(&p_ready[buf]);
         pend = true;
         pend_k = k;
         pend_valid = warp_valid;
-        if (PROF && prof_on) atomicAdd(args.prof + team * 8 + 6, 1ull);
+        if (prof_on) atomicAdd(args.prof + team * 8 + 6, 1ull);
       }
     }
     lap(5);
@@ -1140,13 +1141,13 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
       resolve();
       finalize();
     }
-    if (PROF && prof_on) atomicAdd(args.prof + team * 8 + 7, static_cast<unsigned long long>(clock64() - tp_begin));
-    if (ttid == 0 && team == 0) tma_store_wait_all<0>();
+    if (prof_on) atomicAdd(args.prof + team * 8 + 7, static_cast<unsigned long long>(clock64() - tp_begin));
+    if (warp == 0 && lane == 0) tma_store_wait_all<0>();
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 17) tmem_dealloc<512>(tmem_base);
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
 
 static unsigned long long* g_attn_prof = nullptr;
@@ -1236,16 +1237,11 @@ static int attention_fwd_stream(const __nv_bfloat16* qkv, __nv_bfloat16* out, fl
   const int grid = items < sm_count() ? static_cast<int>(items) : sm_count();
   static bool cfg = false;
   if (!cfg) {
-    B200SSL_CUDA(cudaFuncSetAttribute(attention_fwd_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES));
-    B200SSL_CUDA(cudaFuncSetAttribute(attention_fwd_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES));
+    B200SSL_CUDA(cudaFuncSetAttribute(attention_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES));
     cfg = true;
   }
-  if (a.prof != nullptr)
-    B200SSL_CUDA(launch_pdl(attention_fwd_stream_kernel<true>, dim3(grid), dim3(FS_THREADS), FS_SMEM_BYTES, stream, 1, tq, to, a,
-                            static_cast<int>(items), nqt, nkb));
-  else
-    B200SSL_CUDA(launch_pdl(attention_fwd_stream_kernel<false>, dim3(grid), dim3(FS_THREADS), FS_SMEM_BYTES, stream, 1, tq, to, a,
-                            static_cast<int>(items), nqt, nkb));
+  B200SSL_CUDA(launch_pdl(attention_fwd_stream_kernel, dim3(grid), dim3(FS_THREADS), FS_SMEM_BYTES, stream, 1, tq, to, a,
+                          static_cast<int>(items), nqt, nkb));
   return 0;
 }
 

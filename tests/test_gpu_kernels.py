@@ -182,9 +182,36 @@ def test_attention_long_sequences(ops, B, N, H):
 
 
 def test_attention_rejects_unsupported_lengths(ops):
-    qkv = torch.zeros(5000, 192, device="cuda", dtype=torch.bfloat16)
+    """The streaming forward takes up to 65,536 tokens; the block-pair backward up to 4,096. Beyond: a loud error."""
+    qkv = torch.zeros(70000, 192, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="sequence length"):
-        ops.attention_fwd(qkv, 1, 5000, 1, 0.125)
+        ops.attention_fwd(qkv, 1, 70000, 1, 0.125)
+    qkv = torch.zeros(5000, 192, device="cuda", dtype=torch.bfloat16)
+    out, lse2 = ops.attention_fwd(qkv, 1, 5000, 1, 0.125)      # zeros: uniform attention over zero values
+    torch.cuda.synchronize()
+    assert float(out.float().abs().max()) == 0.0
+    assert abs(float(lse2[0, 0, 0]) - math.log2(5000.0)) < 1e-3
+    with pytest.raises(RuntimeError, match="sequence length"):
+        ops.attention_bwd(qkv, out, torch.zeros_like(out), lse2, 1, 5000, 1, 0.125)
+
+
+@pytest.mark.parametrize("mode", [1, -1])
+def test_attention_forward_kernel_choices_agree(ops, mode):
+    """b200ssl_set_attn_stream: the streaming kernel on a 197-token sequence (mode 1) and the block decomposition on a
+    325-token one (mode -1) give the same result as the default choices (two-tile kernel / streaming kernel)."""
+    from b200ssl import _lib
+    B, H = 5, 3
+    N = 197 if mode == 1 else 325
+    g = torch.Generator(device="cuda").manual_seed(17)
+    qkv = torch.randn(B * N, 3 * H * 64, device="cuda", generator=g).bfloat16()
+    ref, lse_ref = ops.attention_fwd(qkv, B, N, H, 0.125)
+    try:
+        assert _lib.lib().b200ssl_set_attn_stream(mode) == 0
+        out, lse = ops.attention_fwd(qkv, B, N, H, 0.125)
+    finally:
+        _lib.lib().b200ssl_set_attn_stream(0)
+    assert rel(out, ref) < 4e-3
+    assert rel(lse, lse_ref) < 1e-5
 
 
 @pytest.mark.parametrize("ncrops,B,K", [(2, 8, 1024), (4, 5, 4096), (12, 3, 65536)])
