@@ -8,6 +8,7 @@ The compute path is the in-tree C-ABI library ``libb200ssl.so`` (hand-written CU
 There is no CPU, PyTorch-math or Triton fallback: ops raise if the library or an sm_100 GPU is missing.
 """
 from . import _lib, ops  # noqa: F401
+from .augment import MultiCropAugment  # noqa: F401
 from .dino import (DINOLoss, FusedAdamW, GradBucketDataParallel, GraphedDinoStep, ModelEma,  # noqa: F401
                    MultiCropWrapper, apply_schedules, cancel_gradients_last_layer, cosine_momentum,
                    cosine_scheduler, dino_step, param_groups_wd)

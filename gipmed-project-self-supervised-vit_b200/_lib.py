@@ -36,6 +36,7 @@ SIGNATURES = {
     "b200ssl_attention_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "b200ssl_attention_fwd_ws": [_P, _P, _P, _I, _I, _I, _I, _F, _P, _L, _P],
     "b200ssl_attention_fwd_workspace_bytes": [_I, _I, _I],
+    "b200ssl_multicrop_augment": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "b200ssl_patchify": [_P, _P, _I, _I, _I, _I, _I, _P],
     "b200ssl_assemble_tokens": [_P, _P, _P, _P, _I, _I, _I, _P],
     "b200ssl_assemble_tokens_bwd": [_P, _P, _P, _P, _I, _I, _I, _P],

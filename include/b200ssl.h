@@ -105,6 +105,21 @@ long long b200ssl_attention_fwd_workspace_bytes(int B, int N, int H);
 int b200ssl_attention_fwd_ws(const void* qkv, void* out, float* lse2, int B, int N, int H, int head_dim, float scale,
                              void* workspace, long long workspace_bytes, void* stream);
 
+/* ---- §8f-3: multi-crop tile augmentation (replaces the per-tile host pipeline of datasets.py:498-502 /
+ *      transformations.py:103-208 and adds the DINO multi-crop geometry). One CTA per source tile: the uint8
+ *      256 x 256 x 3 tile (HWC, RGB) is staged in shared memory once and every crop is produced from it.
+ *      tiles uint8 [B,256,256,3]; params [B, n_global + n_local, 16] 32-bit words per (tile, crop):
+ *        {top, left, h, w (int32 crop box), flags (bit 0 hflip, bit 1 vflip, bits 2-3 rot90 k, bits 4-11 the order of
+ *         brightness(0) / contrast(1) / saturation(2) / hue(3) as 4 x 2 bits, bit 12 colour jitter on),
+ *         brightness, contrast, saturation, hue (float factors, torchvision semantics), noise sigma (float),
+ *         noise seed (uint32), 5 reserved};
+ *      out_global bf16 [n_global,B,3,Sg,Sg], out_local bf16 [n_local,B,3,Sl,Sl] (crop-major); mean / std: HOST
+ *      pointers to the 3 channel statistics of Normalize (transformations.py:104-116). Bilinear resize with
+ *      align_corners = false and no antialiasing; GaussianBlur(3, sigma <= 0.1) is the identity to 2e-22 and skipped. */
+int b200ssl_multicrop_augment(const void* tiles, const void* params, void* out_global, void* out_local, int B,
+                              int n_global, int n_local, int size_global, int size_local, const float* mean,
+                              const float* std, void* stream);
+
 /* ---- K1 helpers: patch gathering and token assembly (PatchEmbed.forward VT.pyc@L167-170,
  *      prepare_tokens @L235-246). img [B,C,H,W] bf16 -> cols [B*Np, C*P*P] bf16 (then b200ssl_gemm);
  *      x(fp32)[b,0]=cls+pos[0], x[b,1+p]=y[b*Np+p]+pos[1+p]; bwd: dy=dx[:,1:], dpos=sum_b dx, dcls=dpos[0]. */

@@ -1,0 +1,142 @@
+"""Multi-crop tile augmentation: oracle self-checks on the CPU, kernel parity on the GPU.
+
+Reference operators: transformations.py:103-208 (define_transformations), applied per tile at datasets.py:498-502."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import b200ssl  # noqa: E402
+from b200ssl import augment as aug  # noqa: E402
+from oracle import augment as oaug  # noqa: E402
+
+
+def _tiles(B, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    # smooth structure + texture, in the colour range of H&E tiles (bright, low saturation)
+    base = torch.rand(B, 16, 16, 3, generator=g).permute(0, 3, 1, 2)
+    img = torch.nn.functional.interpolate(base, size=(256, 256), mode="bicubic", align_corners=False).clamp(0, 1)
+    img = 0.55 + 0.45 * img + 0.04 * torch.randn(B, 3, 256, 256, generator=g)
+    return (img.clamp(0, 1) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+
+
+def test_sampler_produces_valid_tables():
+    a = b200ssl.MultiCropAugment("pcbnfrs", color_param=0.1)
+    p = a.sample_params(64, torch.Generator().manual_seed(1))
+    assert p.shape == (64, 12, aug.PARAM_WORDS) and p.dtype == torch.int32
+    top, left, h, w = (p[..., i].long() for i in range(4))
+    assert (h >= 1).all() and (w >= 1).all() and (top >= 0).all() and (left >= 0).all()
+    assert (top + h <= 256).all() and (left + w <= 256).all()
+    area = (h * w).float() / 65536
+    assert area[:, :2].min() > 0.4 / 1.2 ** 2 * 0.9 and area[:, 2:].max() < 0.4 * 1.1      # scale ranges (with the zoom)
+    fp = p.view(torch.float32)
+    assert ((fp[..., 5] >= 0.9) & (fp[..., 5] <= 1.1)).all() and ((fp[..., 6] >= 0.8) & (fp[..., 6] <= 1.2)).all()
+    assert (fp[..., 8].abs() <= 0.1).all() and ((fp[..., 9] >= 0) & (fp[..., 9] <= 0.05)).all()
+    order = torch.stack([(p[..., 4] >> (4 + 2 * s)) & 3 for s in range(4)], -1)
+    assert (order.sort(-1).values == torch.arange(4, dtype=torch.int32)).all()              # a permutation per crop
+    assert ((p[..., 4] >> 12) & 1).all()
+    none = b200ssl.MultiCropAugment("none").sample_params(4, torch.Generator().manual_seed(1))
+    assert (none[..., 4] == 0).all() and (none.view(torch.float32)[..., 9] == 0).all()
+    with pytest.raises(ValueError):
+        b200ssl.MultiCropAugment("no_such_type")
+
+
+def test_normalisation_tables_match_the_reference_constants():
+    # transformations.py:104-116
+    assert aug.MEAN["Ron"] == [0.8998, 0.8253, 0.9357] and aug.STD["Ron"] == [0.1125, 0.1751, 0.0787]
+    assert aug.MEAN["Imagenet"] == [0.485, 0.456, 0.406] and aug.STD["Imagenet"] == [0.229, 0.224, 0.225]
+    assert abs(aug.MEAN["TCGA"][0] - 58.2069073 / 255) < 1e-12 and aug.MEAN["Amir"] == aug.MEAN["Ron"][::-1]
+
+
+def test_oracle_counter_based_noise_is_standard_normal():
+    n = oaug.normal_of(12345, torch.arange(400000))
+    assert abs(float(n.mean())) < 5e-3 and abs(float(n.std()) - 1.0) < 5e-3
+    assert torch.equal(n[:100], oaug.normal_of(12345, torch.arange(100)))                   # a pure function of (seed, index)
+    assert not torch.equal(n[:100], oaug.normal_of(12346, torch.arange(100)))
+
+
+def test_oracle_matches_torchvision_pipeline_in_the_reference_operator_order():
+    """augment_one applies geometry first and the colour operators after it; the reference order is colour, flips,
+    rotation (transformations.py:153-160). Same function: every colour operator is pointwise except contrast, whose
+    mean grey level is invariant under flips and rotations."""
+    tiles = _tiles(3)
+    a = b200ssl.MultiCropAugment("pcbnfrs", color_param=0.1)
+    p = a.sample_params(3, torch.Generator().manual_seed(2))
+    p.view(torch.float32)[..., 9] = 0.0           # the noise is defined on the output frame: excluded from this comparison
+    mean, std = aug.MEAN["Ron"], aug.STD["Ron"]
+    for b in range(3):
+        for c in (0, 1, 2, 5, 11):
+            size = 224 if c < 2 else 96
+            x = oaug.augment_one(tiles[b], p[b, c], size, mean, std)
+            y = oaug.reference_style_pipeline(tiles[b], p[b, c], size, mean, std)
+            assert x.shape == (3, size, size)
+            assert float((x - y).abs().max()) < 1e-4, (b, c, float((x - y).abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ttype", ["pcbnfrs", "cbnfr", "flip", "none"])
+def test_kernel_matches_oracle(ttype):
+    dev = torch.device("cuda")
+    B = 5
+    tiles = _tiles(B, seed=3)
+    a = b200ssl.MultiCropAugment(ttype, color_param=0.1)
+    p = a.sample_params(B, torch.Generator().manual_seed(4))
+    crops = a(tiles.to(dev), params=p)
+    torch.cuda.synchronize()
+    ref = oaug.multicrop_augment(tiles, p, 2, 10, 224, 96, aug.MEAN["Ron"], aug.STD["Ron"])
+    assert len(crops) == 12
+    for c, (x, y) in enumerate(zip(crops, ref)):
+        assert x.dtype == torch.bfloat16 and tuple(x.shape) == tuple(y.shape)
+        x = x.float().cpu()
+        rel = float((x - y).norm() / y.norm())
+        assert rel < 1e-2, (ttype, c, rel)                                   # bf16 output: 2^-9 per element
+        # beyond the bf16 rounding of the output nothing may differ: compare against the oracle rounded the same way
+        exact = float((x - y.bfloat16().float()).abs().max())
+        assert exact < 0.08, (ttype, c, exact)                               # <= a few bf16 ulps at |x| <= 8
+    # crop-major layout: equal-size crops are views of one allocation, back to back (no concatenation copy downstream)
+    assert crops[1].data_ptr() == crops[0].data_ptr() + crops[0].numel() * 2
+    assert crops[3].data_ptr() == crops[2].data_ptr() + crops[2].numel() * 2
+
+
+@pytest.mark.gpu
+def test_identity_parameters_reproduce_the_tile():
+    """Whole-tile box at the tile's own size, no operators: the output is the normalised tile, exactly (bf16-rounded)."""
+    dev = torch.device("cuda")
+    tiles = _tiles(2, seed=5)
+    a = b200ssl.MultiCropAugment("none", global_size=256, local_size=256, n_global=1, n_local=1)
+    p = torch.zeros(2, 2, aug.PARAM_WORDS, dtype=torch.int32)
+    p[..., 2] = 256
+    p[..., 3] = 256
+    p.view(torch.float32)[..., 5:8] = 1.0
+    out = a(tiles.to(dev), params=p)
+    m = torch.tensor(aug.MEAN["Ron"]).view(1, 3, 1, 1)
+    s = torch.tensor(aug.STD["Ron"]).view(1, 3, 1, 1)
+    want = ((tiles.permute(0, 3, 1, 2).float() / 255 - m) / s)
+    for x in out:
+        assert float((x.float().cpu() - want.bfloat16().float()).abs().max()) <= 0.0625   # one bf16 ulp at |x| in [4, 8)
+        assert float((x.float().cpu() - want).norm() / want.norm()) < 4e-3
+
+
+@pytest.mark.gpu
+def test_augment_feeds_the_training_step():
+    """uint8 tiles -> MultiCropAugment -> MultiCropWrapper forward: the crops arrive in the layout the packed
+    multi-crop pass consumes (global crops back to back, local crops back to back)."""
+    dev = torch.device("cuda")
+    tiles = _tiles(4, seed=6).to(dev)
+    a = b200ssl.MultiCropAugment("pcbnfrs")
+    crops = a(tiles, generator=torch.Generator().manual_seed(7))
+    model = b200ssl.MultiCropWrapper(b200ssl.vit_tiny(), b200ssl.DINOHead(192, 512, hidden_dim=128, bottleneck_dim=64)).to(dev)
+    with torch.no_grad():
+        out = model(crops)
+    assert tuple(out.shape) == (12 * 4, 512) and torch.isfinite(out.float()).all()
+
+
+@pytest.mark.gpu
+def test_augment_rejects_bad_input():
+    a = b200ssl.MultiCropAugment()
+    with pytest.raises(RuntimeError, match="CUDA|cuda"):
+        a(_tiles(1))
+    with pytest.raises(RuntimeError, match="uint8"):
+        a(torch.zeros(1, 256, 256, 3, device="cuda"))
