@@ -257,6 +257,10 @@ def main():
                     help="one backbone pass per crop resolution instead of one pass over the packed rows (A/B switch)")
     ap.add_argument("--no-nccl-graph", action="store_true", help="N > 1: keep the NCCL all-reduces out of the step "
                     "graph (compute graph -> eager all-reduces -> update graph; A/B switch)")
+    ap.add_argument("--bucket-mb", type=float, default=None, help="N > 1: gradient bucket size in MiB (default: the "
+                    "wrapper's; a huge value = ONE all-reduce after the last gradient)")
+    ap.add_argument("--grad-compress", default=None, choices=["none", "bf16"], help="N > 1: gradient buckets travel as "
+                    "bf16 (cast, all-reduce, cast back) instead of fp32")
     ap.add_argument("--ncu-step", action="store_true", help="profiling aid: after the warm-up run ONE steady-state eager "
                     "step between cudaProfilerStart/Stop and exit (use with ncu --profile-from-start off)")
     ap.add_argument("--pdl", action="store_true", help="enable programmatic dependent launch (A/B switch; off by default)")
@@ -380,7 +384,12 @@ def main():
         student = b200ssl.MultiCropWrapper(getattr(b200ssl, args.model)(patch_size=args.patch),
                                            b200ssl.DINOHead(D, args.out_dim)).to(device)
         teacher = b200ssl.ModelEma(student)
-        ddp = b200ssl.GradBucketDataParallel(student)
+        ddp_kw = {}
+        if args.bucket_mb is not None:
+            ddp_kw["bucket_mb"] = args.bucket_mb
+        if args.grad_compress is not None:
+            ddp_kw["compress"] = args.grad_compress
+        ddp = b200ssl.GradBucketDataParallel(student, **ddp_kw)
         loss_fn = b200ssl.DINOLoss(args.out_dim, 2 + n_local, 0.04, 0.04, 0, 10).to(device)
         opt = b200ssl.FusedAdamW(b200ssl.param_groups_wd(student, 0.04), lr=5e-4 * args.batch * world / 256.0)
         crops = make_crops(B, n_local, device, torch.bfloat16, 1234 + 1000 * rank)
@@ -486,6 +495,7 @@ def main():
         if world > 1:
             step_api += "; " + (graphed.comm_mode if graphed is not None else
                                 "nccl bucket all-reduces launched from backward hooks (overlapped)")
+            step_api += f"; {len(ddp.buckets)} gradient bucket(s), {'bf16' if ddp.compress else 'fp32'} on the wire"
 
     gemm_ms = sum(a.elapsed_time(b) for a, b in gemm_events)
     gemm_tflops = gemm_f * B / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
@@ -526,6 +536,15 @@ def main():
             sys.stdout.flush()
             sys.stderr.flush()
             os._exit(0)
+
+    # N > 1: the timed value is the max over ranks, and the ranks run in lock-step through the all-reduces, so the
+    # slowest GPU of the box sets the pace. Each rank's own GEMM time (event-bracketed launches of its instrumented
+    # step, untouched by the collectives) shows how far the 8 power-capped GPUs of one box are apart.
+    if world > 1:
+        mine = torch.tensor([gemm_ms], device=device)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        roofline["rank_gemm_ms_per_step"] = [round(float(t.item()), 3) for t in allr]
 
     if rank != 0:
         shutdown()

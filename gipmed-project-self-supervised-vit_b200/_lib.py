@@ -42,6 +42,7 @@ SIGNATURES = {
     "b200ssl_assemble_tokens_bwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "b200ssl_colsum": [_P, _L, _P, _L, _I, _I, _P],
     "b200ssl_cast_f32_to_bf16": [_P, _P, _L, _P],
+    "b200ssl_cast_bf16_to_f32": [_P, _P, _L, _P],
     "b200ssl_scale_rows": [_P, _P, _P, _L, _I, _P],
     "b200ssl_l2norm_fwd": [_P, _P, _P, _L, _I, _F, _P],
     "b200ssl_l2norm_bwd": [_P, _P, _P, _P, _L, _I, _F, _P],

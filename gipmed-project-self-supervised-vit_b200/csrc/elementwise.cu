@@ -143,6 +143,18 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
     dst[i] = __float2bfloat16(src[i]);
 }
 
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long n4 = n / 4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(src) + i);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    reinterpret_cast<float4*>(dst)[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+  for (long long i = n4 * 4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __bfloat162float(src[i]);
+}
+
 // y = x / max(||x||_2, eps) per row (F.normalize, eps 1e-12). One warp per row.
 __global__ void l2norm_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                   float* __restrict__ norm_out, long long rows, int D, float eps) {
@@ -318,6 +330,15 @@ extern "C" int b200ssl_cast_f32_to_bf16(const float* src, void* dst, long long n
                 "cast: pointers must be 16B/8B aligned");
   cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, static_cast<__nv_bfloat16*>(dst), n);
+  B200SSL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200ssl_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream) {
+  B200SSL_CHECK((reinterpret_cast<uintptr_t>(src) & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, -2,
+                "cast: pointers must be 8B/16B aligned");
+  cast_bf16_f32_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), dst, n);
   B200SSL_CUDA(cudaGetLastError());
   return 0;
 }

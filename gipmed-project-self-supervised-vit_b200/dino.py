@@ -497,10 +497,15 @@ class GradBucketDataParallel(nn.Module):
     ``finish()`` (called by ``dino_step`` before the optimiser) waits for the outstanding handles.
     The first backward runs without overlap to learn the per-parameter contribution counts."""
 
-    def __init__(self, module, bucket_mb: float = 25.0, process_group=None):
+    def __init__(self, module, bucket_mb: float = 25.0, process_group=None, compress: str | None = None):
         super().__init__()
         self.module = module
         self.pg = process_group
+        # compress="bf16": every bucket travels as bf16 (cast -> all-reduce -> cast back into the fp32 bucket): half
+        # the bytes on the wire (88 MB instead of 176 MB for ViT-S + head); the optimiser still sees fp32 gradients
+        if compress not in (None, "none", "bf16"):
+            raise ValueError(f"unknown gradient compression {compress!r}")
+        self.compress = "bf16" if compress == "bf16" else None
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self._avg_native = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
         params = [p for p in module.parameters() if p.requires_grad]
@@ -519,9 +524,14 @@ class GradBucketDataParallel(nn.Module):
         sizes = [sum((p.numel() + 3) // 4 * 4 for p in bucket) for bucket in self.buckets]
         # all buckets are slices of ONE allocation: zeroing the gradients is a single memset node per step
         self._all = torch.zeros(sum(sizes), dtype=torch.float32, device=params[0].device)
+        self._all16 = torch.zeros(sum(sizes), dtype=torch.bfloat16, device=params[0].device) \
+            if self.compress and self.world > 1 else None
+        self._flat16 = []
         start = 0
         for bi, (bucket, n) in enumerate(zip(self.buckets, sizes)):
             flat = self._all[start:start + n]
+            if self._all16 is not None:
+                self._flat16.append(self._all16[start:start + n])
             start += n
             off = 0
             for p in bucket:
@@ -587,6 +597,25 @@ class GradBucketDataParallel(nn.Module):
         if self._pending[bi] == 0 and not self._launched[bi]:
             self._launch(bi)
 
+    def _wire(self, bi):
+        """The tensor that goes on the wire for bucket bi (the bf16 copy under compression, filled here)."""
+        if self._all16 is None:
+            return self._flat[bi]
+        if self._flat[bi].is_cuda:
+            ops.cast_f32_to_bf16(self._flat[bi], self._flat16[bi])
+        else:
+            self._flat16[bi].copy_(self._flat[bi])
+        return self._flat16[bi]
+
+    def _unwire(self, bi):
+        """After the all-reduce: bring a compressed bucket back into its fp32 home."""
+        if self._all16 is None:
+            return
+        if self._flat[bi].is_cuda:
+            ops.cast_bf16_to_f32(self._flat16[bi], self._flat[bi])
+        else:
+            self._flat[bi].copy_(self._flat16[bi])
+
     def _launch(self, bi):
         self._launched[bi] = True
         if self._avg_native:
@@ -594,7 +623,7 @@ class GradBucketDataParallel(nn.Module):
         else:  # gloo (CPU tests) has no AVG: pre-scale, then SUM
             op = dist.ReduceOp.SUM
             self._flat[bi].div_(self.world)
-        self._handles.append(dist.all_reduce(self._flat[bi], op=op, group=self.pg, async_op=True))
+        self._handles.append((bi, dist.all_reduce(self._wire(bi), op=op, group=self.pg, async_op=True)))
 
     def zero_grad(self, set_to_none: bool = False):
         """Zero the flat buckets (gradients stay views into them): one memset over the single allocation."""
@@ -613,10 +642,11 @@ class GradBucketDataParallel(nn.Module):
         if self.world > 1:
             for bi in range(len(self.buckets)):
                 if self._avg_native:
-                    dist.all_reduce(self._flat[bi], op=dist.ReduceOp.AVG, group=self.pg)
+                    dist.all_reduce(self._wire(bi), op=dist.ReduceOp.AVG, group=self.pg)
                 else:
                     self._flat[bi].div_(self.world)
-                    dist.all_reduce(self._flat[bi], op=dist.ReduceOp.SUM, group=self.pg)
+                    dist.all_reduce(self._wire(bi), op=dist.ReduceOp.SUM, group=self.pg)
+                self._unwire(bi)
 
     def finish(self):
         """Wait for the bucket all-reduces of this backward; re-arm the counters for the next one."""
@@ -627,8 +657,9 @@ class GradBucketDataParallel(nn.Module):
             for bi in range(len(self.buckets)):
                 if not self._launched[bi]:
                     self._launch(bi)
-            for h in self._handles:
+            for bi, h in self._handles:
                 h.wait()
+                self._unwire(bi)
         self._handles = []
         if self._expected is None:
             self._expected = dict(self._seen)

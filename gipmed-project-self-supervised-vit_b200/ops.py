@@ -160,6 +160,10 @@ def cast_f32_to_bf16(src: torch.Tensor, dst: torch.Tensor):
     _call("b200ssl_cast_f32_to_bf16", src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
 
 
+def cast_bf16_to_f32(src: torch.Tensor, dst: torch.Tensor):
+    _call("b200ssl_cast_bf16_to_f32", src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
+
+
 def zeros(shape, dtype, device):
     """torch.empty + one memset node on the current stream (instead of a PyTorch fill kernel)."""
     t = torch.empty(shape, dtype=dtype, device=device)

@@ -136,6 +136,8 @@ int b200ssl_colsum(const void* x, long long ldx, float* out, long long rows, int
 /* y[r,:] = x[r,:] * scale[r] (bf16 rows, fp32 scale[rows]): the branch gradient under stochastic depth. */
 int b200ssl_scale_rows(const void* x, const float* scale, void* y, long long rows, int D, void* stream);
 int b200ssl_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+/* the reverse (bf16 gradient buckets back into the fp32 buckets after a compressed all-reduce) */
+int b200ssl_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream);
 /* F.normalize(dim=-1, p=2, eps) (DINOHead.forward VT.pyc@L328): y = x / max(||x||, eps). */
 int b200ssl_l2norm_fwd(const void* x, void* y, float* norm, long long rows, int D, float eps, void* stream);
 int b200ssl_l2norm_bwd(const void* y, const void* dy, const float* norm, void* dx, long long rows, int D,

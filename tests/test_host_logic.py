@@ -181,8 +181,10 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
 torch.manual_seed(1234 + rank)                      # different init per rank: the wrapper must broadcast rank 0
 model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 8))
-ddp = b200ssl.GradBucketDataParallel(model, bucket_mb=0.001)   # tiny buckets -> several all-reduces
+compress = sys.argv[2] if len(sys.argv) > 2 else None
+ddp = b200ssl.GradBucketDataParallel(model, bucket_mb=0.001, compress=compress)   # tiny buckets -> several all-reduces
 assert len(ddp.buckets) > 1
+tol = 1e-5 if compress is None else 2e-2            # bf16 on the wire: 2^-9 relative per element
 ref = [p.detach().clone() for p in model.parameters()]
 gathered = [torch.zeros_like(ref[0]) for _ in range(world)]
 dist.all_gather(gathered, ref[0])
@@ -204,19 +206,25 @@ for step in range(3):                               # step 0 learns the arrival 
         for t, p in zip(total, local.parameters()):
             t += p.grad / world
     for t, p in zip(total, model.parameters()):
-        assert torch.allclose(p.grad, t, atol=1e-5), (step, (p.grad - t).abs().max())
+        assert torch.allclose(p.grad, t, atol=tol, rtol=tol), (step, (p.grad - t).abs().max())
+        others = [torch.zeros_like(p.grad) for _ in range(world)]
+        dist.all_gather(others, p.grad.contiguous())
+        assert all(torch.equal(o, others[0]) for o in others), "replicas hold different gradients"
         assert p.grad.data_ptr() != 0 and p.grad.is_contiguous()
 dist.destroy_process_group()
 print("ok", rank)
 '''
 
 
-def test_grad_bucket_data_parallel_gloo_world2(tmp_path):
+@pytest.mark.parametrize("compress", [None, "bf16"])
+def test_grad_bucket_data_parallel_gloo_world2(tmp_path, compress):
     script = tmp_path / "ddp_check.py"
     script.write_text(_DDP_SCRIPT)
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    port = "29533" if compress is None else "29534"
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), ROOT],
+                        "--master-addr", "127.0.0.1", "--master-port", port, str(script), ROOT]
+                       + ([compress] if compress else []),
                        capture_output=True, text=True, env=env, timeout=280)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("ok") == 2
