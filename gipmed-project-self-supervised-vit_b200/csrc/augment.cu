@@ -24,6 +24,11 @@ namespace b200ssl {
 
 constexpr int AUG_TILE = 256;                          // source tile side (train.py:415)
 constexpr int AUG_TILE_BYTES = AUG_TILE * AUG_TILE * 3;
+// shared-memory row pitch: 768 B of pixels + 4 B of padding = 193 words, so that a COLUMN walk (crops rotated by 90 or
+// 270 degrees read the tile down its columns) steps through all 32 banks instead of hammering one (768 B = 192 words
+// = a multiple of 32 banks: 2.9e8 bank conflicts per launch in the first ncu capture, issue slots 48 % used)
+constexpr int AUG_ROW_PITCH = AUG_TILE * 3 + 4;
+constexpr int AUG_SMEM_BYTES = AUG_TILE * AUG_ROW_PITCH;
 constexpr int AUG_THREADS = 1024;
 constexpr int AUG_PARAM_WORDS = 16;
 
@@ -101,14 +106,17 @@ __device__ __forceinline__ void sample_rgb(const uint8_t* tile, const AugParams&
   const int y1 = min(y0 + 1, p.h - 1), x1 = min(x0 + 1, p.w - 1);
   const float ly = sy - static_cast<float>(y0), lx = sx - static_cast<float>(x0);
   const float hy = 1.f - ly, hx = 1.f - lx;
-  const uint8_t* p00 = tile + ((p.top + y0) * AUG_TILE + p.left + x0) * 3;
-  const uint8_t* p01 = tile + ((p.top + y0) * AUG_TILE + p.left + x1) * 3;
-  const uint8_t* p10 = tile + ((p.top + y1) * AUG_TILE + p.left + x0) * 3;
-  const uint8_t* p11 = tile + ((p.top + y1) * AUG_TILE + p.left + x1) * 3;
+  const uint8_t* p00 = tile + (p.top + y0) * AUG_ROW_PITCH + (p.left + x0) * 3;
+  const uint8_t* p01 = tile + (p.top + y0) * AUG_ROW_PITCH + (p.left + x1) * 3;
+  const uint8_t* p10 = tile + (p.top + y1) * AUG_ROW_PITCH + (p.left + x0) * 3;
+  const uint8_t* p11 = tile + (p.top + y1) * AUG_ROW_PITCH + (p.left + x1) * 3;
+  // uint8 -> float through the 2^23 trick on the ALU / FMA pipes (I2F runs on the quarter-rate XU pipe: with twelve
+  // taps per pixel it was the kernel's bound, 68 % XU utilisation in the first ncu capture)
+  auto f8 = [](uint8_t v) { return __uint_as_float(0x4B000000u | static_cast<unsigned>(v)) - 8388608.f; };
   const float k = 1.f / 255.f;
-  r = hy * (hx * (p00[0] * k) + lx * (p01[0] * k)) + ly * (hx * (p10[0] * k) + lx * (p11[0] * k));
-  g = hy * (hx * (p00[1] * k) + lx * (p01[1] * k)) + ly * (hx * (p10[1] * k) + lx * (p11[1] * k));
-  b = hy * (hx * (p00[2] * k) + lx * (p01[2] * k)) + ly * (hx * (p10[2] * k) + lx * (p11[2] * k));
+  r = (hy * (hx * f8(p00[0]) + lx * f8(p01[0])) + ly * (hx * f8(p10[0]) + lx * f8(p11[0]))) * k;
+  g = (hy * (hx * f8(p00[1]) + lx * f8(p01[1])) + ly * (hx * f8(p10[1]) + lx * f8(p11[1]))) * k;
+  b = (hy * (hx * f8(p00[2]) + lx * f8(p01[2])) + ly * (hx * f8(p10[2]) + lx * f8(p11[2]))) * k;
 }
 
 // colour ops [first, last) of the drawn order; `mean_gray` is what contrast blends with
@@ -153,9 +161,11 @@ multicrop_augment_kernel(const uint8_t* __restrict__ tiles, const AugParams* __r
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   {
-    const uint4* src = reinterpret_cast<const uint4*>(tiles + static_cast<long long>(b) * AUG_TILE_BYTES);
-    uint4* dst = reinterpret_cast<uint4*>(tile);
-    for (int i = tid; i < AUG_TILE_BYTES / 16; i += AUG_THREADS) dst[i] = __ldg(src + i);
+    constexpr int kRowWords = AUG_TILE * 3 / 4;  // 192
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tiles + static_cast<long long>(b) * AUG_TILE_BYTES);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(tile);
+    for (int i = tid; i < AUG_TILE * kRowWords; i += AUG_THREADS)
+      dst[(i / kRowWords) * (AUG_ROW_PITCH / 4) + i % kRowWords] = __ldg(src + i);
   }
   __syncthreads();
   const int ncrops = n_global + n_local;
@@ -176,11 +186,13 @@ multicrop_augment_kernel(const uint8_t* __restrict__ tiles, const AugParams* __r
       // pass A: mean grey level of the crop after the ops that precede contrast (the mean is invariant under the
       // flips and rotations, so the crop is walked in its own pixel order)
       float acc = 0.f;
-      for (int i = tid; i < S * S; i += AUG_THREADS) {
-        float r, g, bl;
-        sample_rgb(tile, p, sch, scw, i / S, i % S, r, g, bl);
-        colour_ops(p, 0, cpos, 0.f, r, g, bl);
-        acc += gray_of(r, g, bl);
+      for (int v = tid >> 5; v < S; v += AUG_THREADS / 32) {      // a warp per row: no per-pixel division by S
+        for (int u = tid & 31; u < S; u += 32) {
+          float r, g, bl;
+          sample_rgb(tile, p, sch, scw, v, u, r, g, bl);
+          colour_ops(p, 0, cpos, 0.f, r, g, bl);
+          acc += gray_of(r, g, bl);
+        }
       }
       acc = warp_sum(acc);
       if ((tid & 31) == 0) red[tid >> 5] = acc;
@@ -197,8 +209,9 @@ multicrop_augment_kernel(const uint8_t* __restrict__ tiles, const AugParams* __r
     __nv_bfloat16* out = is_g ? out_global + (static_cast<long long>(c) * B + b) * 3 * Sg * Sg
                               : out_local + (static_cast<long long>(c - n_global) * B + b) * 3 * Sl * Sl;
     const int half = S / 2;
-    for (int i = tid; i < S * half; i += AUG_THREADS) {
-      const int oy = i / half, ox = (i % half) * 2;
+    for (int oy = tid >> 5; oy < S; oy += AUG_THREADS / 32)
+    for (int ox2 = tid & 31; ox2 < half; ox2 += 32) {
+      const int ox = ox2 * 2;
       float px[2][3];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
@@ -256,10 +269,10 @@ extern "C" int b200ssl_multicrop_augment(const void* tiles, const void* params, 
                 "augment: output buffer missing");
   static bool cfg = false;
   if (!cfg) {
-    B200SSL_CUDA(cudaFuncSetAttribute(multicrop_augment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AUG_TILE_BYTES));
+    B200SSL_CUDA(cudaFuncSetAttribute(multicrop_augment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AUG_SMEM_BYTES));
     cfg = true;
   }
-  multicrop_augment_kernel<<<B, AUG_THREADS, AUG_TILE_BYTES, stream>>>(
+  multicrop_augment_kernel<<<B, AUG_THREADS, AUG_SMEM_BYTES, stream>>>(
       static_cast<const uint8_t*>(tiles), static_cast<const AugParams*>(params), static_cast<__nv_bfloat16*>(out_global),
       static_cast<__nv_bfloat16*>(out_local), B, n_global, n_local, size_global, size_local, mean[0], mean[1], mean[2],
       1.f / std[0], 1.f / std[1], 1.f / std[2]);
