@@ -251,6 +251,9 @@ def main():
     ap.add_argument("--embed-batch", type=int, default=512, help="5b: tiles per encoder forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-tiles", action="store_true", help="end-to-end leg fed with uint8 256x256 tiles from pinned "
+                    "host memory (H2D of the tiles + GPU multi-crop augmentation every step) instead of ready-made bf16 "
+                    "crops; training configs with 224/96 crops only")
     ap.add_argument("--no-teacher-stream", action="store_true",
                     help="teacher forward on the main stream instead of a second captured stream (A/B switch)")
     ap.add_argument("--no-merge-crops", action="store_true",
@@ -448,7 +451,52 @@ def main():
 
         # ---- end-to-end: pinned host crops -> H2D (prefetched on a copy stream) -> step -> D2H loss
         e2e = None
-        if not args.no_e2e:
+        if not args.no_e2e and args.e2e_tiles and graphed is not None:
+            # production input path: uint8 tiles + the per-crop parameter table travel host -> device (prefetched on a
+            # copy stream, two slots), MultiCropAugment writes the crops straight into the graph's static inputs
+            aug = b200ssl.MultiCropAugment("pcbnfrs", n_local=n_local)
+            gen = torch.Generator().manual_seed(4321 + rank)
+            tiles_host = torch.randint(0, 256, (B, 256, 256, 3), dtype=torch.uint8, generator=gen).pin_memory()
+            params_host = aug.sample_params(B, gen).pin_memory()
+            h2d_bytes = tiles_host.numel() + params_host.numel() * 4
+            copy_stream = torch.cuda.Stream()
+            t_bufs = [torch.empty_like(tiles_host, device=device) for _ in range(2)]
+            p_bufs = [torch.empty_like(params_host, device=device) for _ in range(2)]
+            ready = [torch.cuda.Event() for _ in range(2)]
+            consumed = [torch.cuda.Event() for _ in range(2)]
+            blocks = graphed.crop_blocks()
+            if n_local == 0:
+                blocks = (blocks[0], torch.empty(0, dtype=torch.bfloat16, device=device))
+
+            def prefetch(slot):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[slot])
+                    t_bufs[slot].copy_(tiles_host, non_blocking=True)
+                    p_bufs[slot].copy_(params_host, non_blocking=True)
+                    ready[slot].record(copy_stream)
+
+            losses = []
+
+            def e2e_step(i):
+                slot = i & 1
+                torch.cuda.current_stream().wait_event(ready[slot])
+                aug(t_bufs[slot], params=p_bufs[slot], out=blocks)
+                consumed[slot].record(torch.cuda.current_stream())
+                loss, _, _ = step(None, args.warmup + i)
+                prefetch(slot)
+                losses.append(loss.item())
+
+            for s_ in range(2):
+                consumed[s_].record(torch.cuda.current_stream())
+                prefetch(s_)
+            for i in range(2):
+                e2e_step(i)
+            ms_e2e = timed(e2e_step, args.steps) / args.steps
+            e2e = {"value": B * world / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
+                   "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e,
+                   "input": "uint8 256x256x3 tiles + per-crop parameter table; GPU multi-crop augmentation "
+                            "(b200ssl.MultiCropAugment 'pcbnfrs') inside the timed step"}
+        elif not args.no_e2e:
             host = make_crops(B, n_local, device, torch.bfloat16, 4321 + rank, pin=True)
             h2d_bytes = sum(c.numel() * c.element_size() for c in host)
             copy_stream = torch.cuda.Stream()

@@ -939,6 +939,22 @@ class GraphedDinoStep:
         self._pending_static = None
         torch.cuda.synchronize()
 
+    def crop_blocks(self):
+        """The static input buffers as one tensor per resolution group, ``[n_crops_of_that_size, B, 3, S, S]`` each
+        (the crops of a group lie back to back): ``MultiCropAugment(...)(tiles, out=step.crop_blocks())`` writes the
+        augmented crops straight into the graph's inputs, and ``step(None, ...)`` replays on them."""
+        blocks, i = [], 0
+        sc = self.static_crops
+        while i < len(sc):
+            j = i
+            while j + 1 < len(sc) and sc[j + 1].shape == sc[i].shape and \
+                    sc[j + 1].data_ptr() == sc[j].data_ptr() + sc[j].numel() * sc[j].element_size():
+                j += 1
+            blocks.append(torch.as_strided(sc[i], (j - i + 1,) + tuple(sc[i].shape), (sc[i].numel(),) + tuple(sc[i].stride()),
+                                           sc[i].storage_offset()))
+            i = j + 1
+        return tuple(blocks)
+
     def load(self, crops, non_blocking=True):
         """Copy a batch of crops into the graph's static input buffers (same stream as the replay)."""
         for dst, src in zip(self.static_crops, crops):

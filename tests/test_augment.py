@@ -134,6 +134,36 @@ def test_augment_feeds_the_training_step():
 
 
 @pytest.mark.gpu
+def test_augment_writes_into_the_graphed_step_inputs():
+    """GraphedDinoStep.crop_blocks() exposes the static inputs per resolution group; the augmentation kernel fills them
+    in place (no intermediate crops, no copy) and the replay consumes them."""
+    dev = torch.device("cuda")
+    B = 2
+    tiles = _tiles(B, seed=8).to(dev)
+    a = b200ssl.MultiCropAugment("pcbnfrs", n_local=2)
+    model = b200ssl.MultiCropWrapper(b200ssl.vit_tiny(), b200ssl.DINOHead(192, 512, hidden_dim=128, bottleneck_dim=64)).to(dev)
+    teacher = b200ssl.ModelEma(model)
+    loss_fn = b200ssl.DINOLoss(512, 4, 0.04, 0.04, 0, 10).to(dev)
+    opt = b200ssl.FusedAdamW(b200ssl.param_groups_wd(model, 0.04), lr=1e-4)
+    example = [torch.zeros(B, 3, 224, 224, device=dev, dtype=torch.bfloat16) for _ in range(2)] + \
+              [torch.zeros(B, 3, 96, 96, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    step = b200ssl.GraphedDinoStep(model, teacher, loss_fn, opt, example)
+    blocks = step.crop_blocks()
+    assert [tuple(b.shape) for b in blocks] == [(2, B, 3, 224, 224), (2, B, 3, 96, 96)]
+    assert blocks[0][1].data_ptr() == step.static_crops[1].data_ptr()
+    assert blocks[1][0].data_ptr() == step.static_crops[2].data_ptr()
+    p = a.sample_params(B, torch.Generator().manual_seed(9))
+    crops = a(tiles, params=p, out=blocks)
+    ref = a(tiles, params=p)
+    for c in range(4):
+        assert crops[c].data_ptr() == step.static_crops[c].data_ptr()
+        assert torch.equal(step.static_crops[c], ref[c])
+    loss = step(None, epoch=0, momentum=0.99)
+    assert torch.isfinite(loss).all()
+    step.release()
+
+
+@pytest.mark.gpu
 def test_augment_rejects_bad_input():
     a = b200ssl.MultiCropAugment()
     with pytest.raises(RuntimeError, match="CUDA|cuda"):
