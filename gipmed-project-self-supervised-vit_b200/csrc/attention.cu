@@ -2,7 +2,9 @@
 //
 // Replaces the materialised-score attention of the reference (VT.pyc@L119-131:
 // qkv.reshape.permute -> (q @ k^T) * scale -> softmax -> attn @ v -> transpose.reshape) for
-// head_dim 64 and sequences of up to 256 tokens (197 / 37 / 257->unsupported).
+// head_dim 64: sequences of up to 256 tokens in one fused launch (two-tile kernels below; 197 / 37 tokens for the
+// 224^2 / 96^2 crops), longer ones through the streaming forward kernel and a block-pair backward (257 tokens for the
+// reference's native 256^2 tiles, 785 / 1025 for ViT-S/8).
 //
 // Layout: qkv is the QKV-GEMM output as it lies in HBM, [B, N, 3, h, 64] bf16 (no permute copy);
 // out / d_out are [B, N, h, 64]; lse2 is [B, h, N] fp32 holding log2-sum-exp of the scaled scores.
