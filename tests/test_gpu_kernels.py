@@ -162,9 +162,10 @@ def test_attention(ops, B, N, H):
     _check_attention_grad(dqkv, qr.grad)
 
 
-@pytest.mark.parametrize("B,N,H", [(3, 257, 2), (2, 785, 3), (5, 325, 6)])
+@pytest.mark.parametrize("B,N,H", [(3, 257, 2), (2, 785, 3), (5, 325, 6), (1, 1025, 2), (3, 383, 2), (2, 512, 1)])
 def test_attention_long_sequences(ops, B, N, H):
-    """N > 256 (257 = the reference's native 256^2 tiles, 785 = ViT-S/8 at 224^2): block-decomposed path."""
+    """N > 256 (257 = the reference's native 256^2 tiles, 785 / 1025 = ViT-S/8 at 224^2 / 256^2): streaming forward
+    kernel, block-pair backward; block counts that are odd, even, and end in a one-key block."""
     g = torch.Generator(device="cuda").manual_seed(N)
     qkv = torch.randn(B * N, 3 * H * 64, device="cuda", generator=g).bfloat16()
     dout = torch.randn(B * N, H * 64, device="cuda", generator=g).bfloat16()
