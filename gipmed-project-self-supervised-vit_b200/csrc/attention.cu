@@ -25,6 +25,8 @@ struct AttnArgs {
   int Nk;            // key tokens handled by this launch (== N except for the block-decomposed long-sequence path)
   int Ns;            // tokens per sequence in memory (row stride of lse2 / out / dout); == N on the main path
   int acc_dq, acc_dkv;  // bwd, long-sequence path: add this launch's dQ / dK,dV to what is already there
+  int nblk;             // bwd, NT == 2: > 1 = ONE launch over all (query block, key block) pairs of 256 x 256 tokens of
+                        // every (sequence, head); N / Nk / keys_n are then per item and Ns is the sequence length
   int G;             // sequences packed per 128-row tile (NT == 1), else 1
   int rows;          // valid rows per tile group: G*N (NT == 1) or N (NT == 2)
   int keys_n;        // round_up(rows, 16): MMA N extent over keys
@@ -426,6 +428,29 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   const int n_my = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   auto item_of = [&](int k) { return static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x); };
   auto set_base = [&](int k) -> uint8_t* { return smem + (SETS == 2 ? (k & 1) : 0) * SET_BYTES; };
+  // what an item is: (packed group | sequence, head) -- or, in the paired long-sequence mode, additionally a (query block,
+  // key block) pair of up to 256 x 256 tokens of that sequence, addressed by row offsets into whole-sequence tensor maps
+  struct Item { int head, b0, q0, k0, nq, keys_n; };
+  auto decode = [&](int item) {
+    Item d;
+    if (NT == 2 && args.nblk > 1) {
+      const int npairs = args.nblk * args.nblk;
+      const int pair = item % npairs, bh = item / npairs;
+      d.head = bh % args.H;
+      d.b0 = bh / args.H;
+      d.q0 = (pair / args.nblk) * 256;
+      d.k0 = (pair % args.nblk) * 256;
+      d.nq = min(256, args.Ns - d.q0);
+      d.keys_n = (min(256, args.Ns - d.k0) + 15) & ~15;
+    } else {
+      d.head = item % args.H;
+      d.b0 = (item / args.H) * args.G;
+      d.q0 = d.k0 = 0;
+      d.nq = NT == 1 ? args.rows : args.N;
+      d.keys_n = args.keys_n;
+    }
+    return d;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -467,8 +492,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     // ------------------------------------------------------------------ control: TMA + MMA issue
     if (lane == 0 && n_my > 0) {
       auto issue_load = [&](int k) {
-        const int item = item_of(k);
-        const int head = item % args.H, b0 = (item / args.H) * args.G;
+        const Item it = decode(item_of(k));
+        const int head = it.head, b0 = it.b0;
         uint8_t* sQ = set_base(k);
         uint8_t* sdO = sQ + NT * TILE_BYTES;
         uint8_t* sK = sdO + NT * TILE_BYTES;
@@ -484,10 +509,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         } else {
           mbar_expect_tx(bar, 4 * NT * TILE_BYTES);
           for (int t = 0; t < NT; ++t) {
-            tma_load_3d(sQ + t * TILE_BYTES, &tmQKV, bar, cq, t * 128, b0);
-            tma_load_3d(sK + t * TILE_BYTES, &tmKV, bar, ck, t * 128, b0);
-            tma_load_3d(sV + t * TILE_BYTES, &tmKV, bar, cv, t * 128, b0);
-            tma_load_3d(sdO + t * TILE_BYTES, &tmDO, bar, cq, t * 128, b0);
+            tma_load_3d(sQ + t * TILE_BYTES, &tmQKV, bar, cq, it.q0 + t * 128, b0);
+            tma_load_3d(sK + t * TILE_BYTES, &tmKV, bar, ck, it.k0 + t * 128, b0);
+            tma_load_3d(sV + t * TILE_BYTES, &tmKV, bar, cv, it.k0 + t * 128, b0);
+            tma_load_3d(sdO + t * TILE_BYTES, &tmDO, bar, cq, it.q0 + t * 128, b0);
           }
         }
       };
@@ -500,8 +525,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       const uint32_t idesc_kv = make_idesc_bf16(128, 64, true, true);  // dK/dV: both MN-major
       auto issue_sdp = [&](int k, int p) {
         const int u = p / NT, t = p % NT;
-        const int ku = max(16, min(128, args.keys_n - u * 128));  // keys in this key tile (multiple of 16; an empty
-                                                                   // tile of a short key block still runs on zeros)
+        const int ku = max(16, min(128, decode(item_of(k)).keys_n - u * 128));  // keys in this key tile (multiple of 16;
+                                                                   // an empty tile of a short key block still runs on zeros)
         const uint32_t idesc_s = make_idesc_bf16(128, ku, false, false);
         const uint32_t base = smem_u32(set_base(k));
         const uint32_t q_t = base + t * TILE_BYTES, do_t = base + (NT + t) * TILE_BYTES;
@@ -518,7 +543,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       };
       auto issue_dqkv = [&](int k, int p) {
         const int u = p / NT, t = p % NT;
-        const int ku = max(16, min(128, args.keys_n - u * 128));
+        const Item it = decode(item_of(k));
+        const int ku = max(16, min(128, it.keys_n - u * 128));
         const uint32_t base = smem_u32(set_base(k));
         const uint32_t q_t = base + t * TILE_BYTES, do_t = base + (NT + t) * TILE_BYTES;
         const uint32_t k_u = base + (2 * NT + u) * TILE_BYTES;
@@ -529,7 +555,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                        make_smem_desc_sw128(k_u + j * 2048, 8192, 1024), idesc_q, (u > 0 || j > 0));
         // dV_u (+)= P^T[128 keys, 128 q] . dO_t[128 q, 64] ; dK_u (+)= dS^T . Q_t. The reduction runs over the query rows
         // of tile t: rows past the sequence end hold P = dS = 0 (lse2 = +inf), so only the live 16-row steps are issued
-        const int qsteps = (min(128, (NT == 1 ? args.rows : args.N) - t * 128) + 15) >> 4;
+        const int qsteps = (max(0, min(128, it.nq - t * 128)) + 15) >> 4;
         for (int j = 0; j < qsteps; ++j)
           umma_bf16_ss(T_DV, make_smem_desc_sw128(p0 + j * 2048, TILE_BYTES, 1024),
                        make_smem_desc_sw128(do_t + j * 2048, 8192, 1024), idesc_kv, (t > 0 || j > 0));
@@ -575,16 +601,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     // ------------------------------------------------------------------ row constants of item k (one ahead)
     const int ptid = threadIdx.x - 32;  // 0..95
     for (int k = 0; k < n_my; ++k) {
-      const int item = item_of(k);
-      const int head = item % args.H, b0 = (item / args.H) * args.G;
+      const Item it = decode(item_of(k));
+      const int head = it.head, b0 = it.b0;
       float* rc = rowc + (k & 1) * (NT * 128 * 2);
       mbar_wait(&bar_rowc_free[k & 1], ((k >> 1) & 1) ^ 1);
       for (int idx = ptid; idx < NT * 128; idx += BWD_ROWC_THREADS) {
         int lo_, hi_;
         bool row_valid;
         key_range(args, NT, idx, lo_, hi_, row_valid);
+        if (NT == 2) row_valid = idx < it.nq;
         const int b = b0 + (NT == 1 ? idx / args.N : 0);
-        const int n = NT == 1 ? idx % args.N : idx;
+        const int n = NT == 1 ? idx % args.N : it.q0 + idx;
         float delta = 0.f, l2 = INFINITY;  // invalid rows: lse2 = +inf so that P = 0
         if (row_valid && b < args.B) {
           const long long off = ((static_cast<long long>(b) * args.Ns + n) * args.H + head) * 64;
@@ -634,8 +661,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     };
 
     for (int k = 0; k < n_my; ++k) {
-      const int item = item_of(k);
-      const int head = item % args.H, b0 = (item / args.H) * args.G;
+      const Item it = decode(item_of(k));
+      const int head = it.head, b0 = it.b0;
       float delta[NT], lse2[NT];
       lap(7);
       {
@@ -679,7 +706,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 
 #pragma unroll
       for (int u = 0; u < NT; ++u) {
-        const int ku = max(16, min(128, args.keys_n - u * 128));
+        const int ku = max(16, min(128, it.keys_n - u * 128));
 #pragma unroll
         for (int t = 0; t < NT; ++t, ++gp) {
           mbar_wait(bar_sdp, gp & 1);
@@ -757,8 +784,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             mbar_wait(bar_mma, gp & 1);
             tcgen05_fence_after();
             lap(4);
-            store_tile(T_DK, sP, &tmDKV, args.acc_dkv != 0, (args.H + head) * 64, NT == 1 ? 0 : u * 128);
-            store_tile(T_DV, sP + TILE_BYTES, &tmDKV, args.acc_dkv != 0, (2 * args.H + head) * 64, NT == 1 ? 0 : u * 128);
+            store_tile(T_DK, sP, &tmDKV, args.acc_dkv != 0, (args.H + head) * 64, NT == 1 ? 0 : it.k0 + u * 128);
+            store_tile(T_DV, sP + TILE_BYTES, &tmDKV, args.acc_dkv != 0, (2 * args.H + head) * 64, NT == 1 ? 0 : it.k0 + u * 128);
             // the dK/dV accumulators are re-used by the next key tile: order these reads before its MMAs
             tcgen05_fence_before();
             lap(5);
@@ -768,7 +795,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       // dQ tiles (complete after the last pair; bar_mma already waited on above)
 #pragma unroll
       for (int t = 0; t < NT; ++t)
-        store_tile(T_DQ + t * 64, sdS + t * TILE_BYTES, &tmDQKV, args.acc_dq != 0, head * 64, NT == 1 ? 0 : t * 128);
+        store_tile(T_DQ + t * 64, sdS + t * TILE_BYTES, &tmDQKV, args.acc_dq != 0, head * 64, NT == 1 ? 0 : it.q0 + t * 128);
       tcgen05_fence_before();
       lap(6);
       if (prof_on) atomicAdd(args.prof + 8, 1ull);
@@ -1164,6 +1191,7 @@ static int setup_args(AttnArgs& a, int B, int Nq, int Nk, int Ns, int H, float s
                 Nq, Nk);
   a.B = B; a.N = Nq; a.Nk = Nk; a.Ns = Ns; a.H = H;
   a.acc_dq = 0; a.acc_dkv = 0;
+  a.nblk = 1;
   // blocks of a long sequence always take the two-tile kernels (no packing): their zero-padding rules cover any
   // Nq, Nk <= 256, including Nq != Nk
   nt = (!blocked && Nq <= 128) ? 1 : 2;
@@ -1288,6 +1316,39 @@ static int attention_bwd_block(const __nv_bfloat16* qkv, const __nv_bfloat16* ou
   return 0;
 }
 
+// backward for N > 256 in ONE launch: every (sequence, head, query block, key block) pair of 256 x 256 tokens is an item
+// of the persistent two-tile kernel; each pair is exact given the row's global lse and delta, dQ accumulates over key
+// blocks and dK / dV over query blocks through TMA reduce-add into a zeroed dqkv (sixteen launches per layer at 785
+// tokens before: each with its own ramp and a last, partly filled round of items)
+static int attention_bwd_paired(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse2,
+                                __nv_bfloat16* dqkv, int B, int N, int H, float scale, cudaStream_t stream) {
+  AttnArgs a{};
+  int nt, groups;
+  if (int rc = setup_args(a, B, 256, 256, N, H, scale, true, nt, groups)) return rc;
+  a.nblk = (N + 255) / 256;
+  a.acc_dq = 1; a.acc_dkv = 1;
+  a.lse2 = const_cast<float*>(lse2);
+  a.out = out;
+  a.dout = dout;
+  CUtensorMap tq, tdo, tdq;
+  if (int rc = make_bnd_map(&tq, qkv, 3 * H * 64, N, N, B, 2, 1)) return rc;
+  if (int rc = make_bnd_map(&tdo, dout, H * 64, N, N, B, 2, 1)) return rc;
+  if (int rc = make_bnd_map(&tdq, dqkv, 3 * H * 64, N, N, B, 2, 1)) return rc;
+  B200SSL_CUDA(cudaMemsetAsync(dqkv, 0, static_cast<size_t>(B) * N * 3 * H * 64 * sizeof(__nv_bfloat16), stream));
+  const long long items = static_cast<long long>(B) * H * a.nblk * a.nblk;
+  B200SSL_CHECK(items < (1LL << 30), -2, "attention: problem too large for the paired backward (%lld items)", items);
+  const int grid = items < sm_count() ? static_cast<int>(items) : sm_count();
+  const int smem = 12 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 2 * 256 * 2 * 4 + 256;
+  static bool cfg = false;
+  if (!cfg) {
+    B200SSL_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cfg = true;
+  }
+  B200SSL_CUDA(launch_pdl(attention_bwd_kernel<2>, dim3(grid), dim3(BWD_THREADS), smem, stream, 1, tq, tq, tdo, tdq, tdq, a,
+                          static_cast<int>(items)));
+  return 0;
+}
+
 // ---- long sequences (N > 256): key / query blocks of <= 256 tokens, partial softmax results merged by lse ----
 // out[b, n, h, :] = sum_j 2^(lse_j - L) O_j[b, n, h, :],  L = log2 sum_j 2^lse_j ; one warp per (b, n, h)
 __global__ void __launch_bounds__(256)
@@ -1407,6 +1468,11 @@ extern "C" int b200ssl_attention_bwd(const void* qkv_, const void* out_, const v
   __nv_bfloat16* dqkv = static_cast<__nv_bfloat16*>(dqkv_);
   if (N <= 256) return attention_bwd_block(qkv, out, dout, lse2, dqkv, B, N, H, 0, N, 0, N, scale, false, false, false, stream);
   B200SSL_CHECK(N <= 4096, -2, "attention: sequence length %d unsupported (1..4096)", N);
+  // three or more blocks per dimension: ONE launch over all block pairs (N = 785, B = 64: 723 -> 565 us). With two blocks
+  // the four launches of near-equal blocks stay ahead (N = 257, B = 256: 476 vs 610 us -- the second 256-token block
+  // would hold a single token, and the paired mode pays a memset plus reduce-adds where the first block stores)
+  if (g_attn_stream >= 0 && N > 512) return attention_bwd_paired(qkv, out, dout, lse2, dqkv, B, N, H, scale, stream);
+  // one launch per block pair (also the developer A/B path, b200ssl_set_attn_stream(-1))
   // every (query block, key block) pair is exact given the row's global lse and delta; dQ accumulates over key
   // blocks, dK / dV over query blocks (TMA reduce-add in bf16 after the first, plain store)
   const int nblk = num_blocks_for(N);

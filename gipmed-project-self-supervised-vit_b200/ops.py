@@ -415,7 +415,7 @@ def attention_bwd(qkv, out, dout, lse2, B, N, H, scale):
         r1 = r0 + b * n
         _call("b200ssl_attention_bwd", qkv[r0:r1].data_ptr(), out[r0:r1].data_ptr(), dout[r0:r1].data_ptr(),
               lse.data_ptr(), dqkv[r0:r1].data_ptr(), b, n, H, 64, float(scale), _stream(),
-              launches=((n + 255) // 256) ** 2)
+              launches=4 if 256 < n <= 512 else 1)   # 257..512 tokens: four block-pair launches; else one
     return dqkv
 
 

@@ -97,8 +97,9 @@ int b200ssl_attention_bwd(const void* qkv, const void* out, const void* dout, co
  * 785; up to 65536). b200ssl_set_attn_stream: 0 (default) = streaming kernel for N > 256, 1 = for every N > 128,
  * -1 = never (developer A/B: N > 256 then runs as blocks of <= 256 queries x <= 256 keys through the two-tile
  * kernel, partial results merged by their log-sum-exp in a caller-provided scratch buffer, N <= 4096).
- * Backward for N > 256 runs block pairs through the two-tile backward kernel (dQ accumulates over key blocks, dK/dV
- * over query blocks through TMA reduce-add; N <= 4096). b200ssl_attention_fwd == b200ssl_attention_fwd_ws with no
+ * Backward for N > 256 runs (query block, key block) pairs of <= 256 x 256 tokens through the two-tile backward kernel
+ * (dQ accumulates over key blocks, dK/dV over query blocks through TMA reduce-add; N <= 4096): four launches for
+ * 257..512 tokens, ONE launch over all pairs (into a zeroed dqkv) above. b200ssl_attention_fwd == b200ssl_attention_fwd_ws with no
  * workspace; b200ssl_attention_fwd_workspace_bytes returns 0 whenever none is needed. */
 int b200ssl_set_attn_stream(int mode);
 long long b200ssl_attention_fwd_workspace_bytes(int B, int N, int H);

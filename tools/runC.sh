@@ -1,3 +1,2 @@
 cd $GRAFT_REPO_ROOT
-echo "=== stream mode 1"; timeout 300 python tests/gpu_checks/attn_check.py --stream 1 --bench 2>&1 | grep -v Warn | tail -28
-timeout 200 python tests/gpu_checks/attn_stream_roles.py 2>&1 | grep -v Warn | tail
+for m in 0 -1; do echo "=== stream mode $m"; timeout 300 python tests/gpu_checks/attn_check.py --stream $m --bench 2>&1 | grep -v Warn | grep "N=257\|N=785\|N=325\|N=1025\|bench\|ALL\|FAIL" | tail -16; done
