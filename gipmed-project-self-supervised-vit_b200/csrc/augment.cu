@@ -170,7 +170,12 @@ multicrop_augment_kernel(const uint8_t* __restrict__ tiles, const AugParams* __r
   __syncthreads();
   const int ncrops = n_global + n_local;
   for (int c = 0; c < ncrops; ++c) {
-    const AugParams p = params[static_cast<long long>(b) * ncrops + c];
+    AugParams p = params[static_cast<long long>(b) * ncrops + c];
+    // the table is caller data: a box outside the tile must not become an out-of-bounds shared-memory read
+    p.top = min(max(p.top, 0), AUG_TILE - 1);
+    p.left = min(max(p.left, 0), AUG_TILE - 1);
+    p.h = min(max(p.h, 1), AUG_TILE - p.top);
+    p.w = min(max(p.w, 1), AUG_TILE - p.left);
     const bool is_g = c < n_global;
     const int S = is_g ? Sg : Sl;
     const float sch = static_cast<float>(p.h) / static_cast<float>(S), scw = static_cast<float>(p.w) / static_cast<float>(S);
