@@ -266,6 +266,8 @@ def main():
                     "bf16 (cast, all-reduce, cast back) instead of fp32")
     ap.add_argument("--ncu-step", action="store_true", help="profiling aid: after the warm-up run ONE steady-state eager "
                     "step between cudaProfilerStart/Stop and exit (use with ncu --profile-from-start off)")
+    ap.add_argument("--ln-tail", action="store_true", help="LayerNorm after each residual add in the tail of the proj / fc2 "
+                    "GEMM instead of its own kernel (A/B switch, measured slower; ViT-S only)")
     ap.add_argument("--pdl", action="store_true", help="enable programmatic dependent launch (A/B switch; off by default)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying "
                     "the captured CUDA graph of the step")
@@ -309,6 +311,8 @@ def main():
         b200ssl.dino.MERGE_CROP_GROUPS["on"] = False
     if args.no_nccl_graph:
         b200ssl.dino.NCCL_IN_GRAPH["on"] = False
+    if args.ln_tail:
+        ops._LN_TAIL["on"] = True
 
     def barrier():
         if world > 1:
@@ -335,14 +339,18 @@ def main():
     sampler = ClockSampler(local_rank)
     peak_burst, peak_sus, hbm_peak, peak_src = read_peaks()
     gemm_events = []
-    real_gemm = ops.gemm
+    real_gemm, real_gemm_res_ln = ops.gemm, ops.gemm_res_ln
 
-    def timed_gemm(*a, **kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        real_gemm(*a, **kw)
-        e1.record()
-        gemm_events.append((e0, e1))
+    def _timed(fn):
+        def wrapper(*a, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(*a, **kw)
+            e1.record()
+            gemm_events.append((e0, e1))
+        return wrapper
+
+    timed_gemm, timed_gemm_res_ln = _timed(real_gemm), _timed(real_gemm_res_ln)   # the latter: GEMM + LayerNorm tail
 
     if cfg["kind"] == "embed":
         # ------------------------------------------------------------------ 5b: frozen-encoder embedding
@@ -376,10 +384,10 @@ def main():
             ms_e2e = timed(slide_e2e, args.steps) / args.steps
             e2e = {"value": B * world / (ms_e2e / 1e3), "unit": "images/s",
                    "h2d_bytes_per_step": tiles_host.numel() * 2, "d2h_bytes_per_step": B * D * 4, "ms_per_step": ms_e2e}
-        ops.gemm = timed_gemm
+        ops.gemm, ops.gemm_res_ln = timed_gemm, timed_gemm_res_ln
         slide_resident(0)
         torch.cuda.synchronize()
-        ops.gemm = real_gemm
+        ops.gemm, ops.gemm_res_ln = real_gemm, real_gemm_res_ln
         step_api = "b200ssl.embed_tiles / VisionTransformer.forward under no_grad (eager launches)"
         host_ms = None
     else:
@@ -532,13 +540,13 @@ def main():
 
         # ---- roofline of the dominant kernel family (tcgen05 GEMM): one instrumented step on ONE stream (with the
         # teacher forward running concurrently the event-bracketed durations would include the other's share)
-        ops.gemm = timed_gemm
+        ops.gemm, ops.gemm_res_ln = timed_gemm, timed_gemm_res_ln
         teacher_branch = b200ssl.dino.TEACHER_STREAM["on"]
         b200ssl.dino.TEACHER_STREAM["on"] = False
         eager_step(crops, total_steps)
         torch.cuda.synchronize()
         b200ssl.dino.TEACHER_STREAM["on"] = teacher_branch
-        ops.gemm = real_gemm
+        ops.gemm, ops.gemm_res_ln = real_gemm, real_gemm_res_ln
         step_api = "b200ssl.GraphedDinoStep (CUDA graph replay)" if use_graph else "b200ssl.dino_step (eager)"
         if world > 1:
             step_api += "; " + (graphed.comm_mode if graphed is not None else

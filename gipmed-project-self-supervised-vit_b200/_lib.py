@@ -22,6 +22,7 @@ SIGNATURES = {
     "b200ssl_device_check": [],
     "b200ssl_gemm": [_P, _L, _I, _P, _L, _I, _P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P],
     "b200ssl_ln_gemm": [_P, _L, _P, _P, _F, _P, _P, _P, _P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _P],
+    "b200ssl_gemm_res_ln": [_P, _L, _P, _L, _P, _L, _P, _P, _P, _L, _I, _I, _I, _P, _P, _F, _P, _P, _P, _P],
     "b200ssl_set_gemm_cluster": [_I],
     "b200ssl_set_gemm_stationary": [_I],
     "b200ssl_set_gemm_prof": [_P],

@@ -157,6 +157,12 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& h, float& g) {
 // explicit shared-space accesses (32-bit shared addresses; generic pointers into dynamic smem lose their
 // address space after the alignment cast and would compile to generic LD/ST)
 // ----------------------------------------------------------------------------------------------
+// 16-byte global load that bypasses L1 (data another proxy / SM wrote moments ago: read it where it is coherent, in L2)
+__device__ __forceinline__ float4 ld_global_cg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");

@@ -74,7 +74,11 @@ constexpr int kMaxPanelKBlocks = 6;  // B-stationary mode: the whole K extent (<
 // MODE 0: A and B stream through the ring. MODE 1 (B-stationary): the B tile stays in a smem panel, the ring carries
 // A only. MODE 2 (LayerNorm-fused, A-stationary): the epilogue warps normalise 128 rows of the fp32 residual stream
 // straight into a bf16 A panel in the UMMA layout, every n block of those rows is computed from it, the ring
-// carries B only.
+// carries B only. MODE 3 (LayerNorm TAIL, fp32-residual epilogue, N = 384 as two 192-column n blocks): a cluster computes
+// BOTH n blocks of its m unit back to back, and one unit later two otherwise idle warps read the finished fp32 rows
+// back -- from L2, they were written microseconds ago -- and emit LayerNorm(rows) in bf16 plus the row statistics:
+// the LayerNorm that follows every residual add (Block.norm2 after attn.proj, the next Block.norm1 after mlp.fc2,
+// VT.pyc@L147-151) then costs its bf16 write only, not a second pass over the fp32 stream from HBM.
 template <int BN, int CL, int MODE = 0, bool WG = false>
 struct GemmCfg {
   static constexpr bool BS = MODE == 1;
@@ -113,8 +117,8 @@ struct TileIter {
       step = num_clusters / a.num_n_blocks + (n_blk < num_clusters % a.num_n_blocks ? 1 : 0);
       t = rank;
       total = num_m_units;
-    } else if (MODE == 2) {
-      // LayerNorm-fused: a cluster owns whole m units and walks all their n blocks from one A panel
+    } else if (MODE >= 2) {
+      // LayerNorm-fused (2: A panel, 3: LayerNorm tail): a cluster owns whole m units and walks all their n blocks
       n_blk = 0;
       t = cluster_id;
       step = num_clusters;
@@ -128,7 +132,7 @@ struct TileIter {
   template <int MODE>
   __device__ __forceinline__ bool valid(const GemmArgs& a, int num_m_units) {
     if (t >= total) return false;
-    if (MODE == 1 || MODE == 2) {
+    if (MODE >= 1) {
       m_unit = t;
       ks = 0;
     } else {
@@ -140,7 +144,7 @@ struct TileIter {
   }
   template <int MODE>
   __device__ __forceinline__ void next(const GemmArgs& a) {
-    if (MODE == 2) {
+    if (MODE >= 2) {
       if (++n_blk == a.num_n_blocks) { n_blk = 0; t += step; }
     } else {
       t += step;
@@ -165,6 +169,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   using Cfg = GemmCfg<BN, CL, MODE, is_wgrad_epi(EPI)>;
   constexpr bool BS = MODE == 1;
   constexpr bool LN = MODE == 2;
+  constexpr bool LNT = MODE == 3;
+  static_assert(!LNT || (EPI == EPI_BIAS_RES_F32 && CL == 2 && BN == 192), "the LayerNorm tail is built for the fp32-residual epilogue, 256 x 192 pair tiles");
   constexpr int kStages = Cfg::kStages;
   static_assert(kStages >= 2, "smem ring too shallow");
   static_assert(!LN || (CL == 2 && !is_wgrad_epi(EPI)), "the LayerNorm-fused mode is built for CTA pairs, fprop only");
@@ -187,7 +193,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* consumed_bar = tmem_empty + 2;   // [kStages] CTA-pair wgrad: "MMA is done reading this stage"
   uint64_t* panel_full = consumed_bar + kStages;  // [1] BS: the B panel has landed; LN: the A panel is written
   uint64_t* panel_empty = panel_full + 1;         // [1] LN: every MMA that reads the A panel has retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(panel_empty + 1);
+  uint64_t* ln_go = panel_empty + 1;              // [2] LayerNorm tail: this CTA's rows of an m unit have landed in memory
+  uint64_t* ln_done = ln_go + 2;                  // [2] ... and the helper warps have normalised them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_done + 2);
 
   const long long t_entry = args.prof ? clock64() : 0;
   const int warp = threadIdx.x >> 5;
@@ -214,6 +222,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     mbar_init(panel_full, LN ? CL * NUM_EPI_GROUPS * 4 : CL);  // LN: one arrive per transform warp of the pair
     mbar_init(panel_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ln_go[s], NUM_EPI_GROUPS * 4);  // one arrive per epilogue warp of THIS CTA
+      mbar_init(&ln_done[s], 2);                 // the two helper warps
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], CL * kEpiWarps);  // one arrive per epilogue warp of every CTA of the pair
@@ -813,8 +825,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           fence_proxy_async_smem();
           __syncwarp();
           lap(4);
-          if (lane == 0 && rows_ok) {
-            tma_store_2d_s(&tmD, slab, col0, row0);
+          if (lane == 0 && (rows_ok || LNT)) {   // LayerNorm tail: one group per chunk ALWAYS (its bookkeeping counts groups)
+            if (rows_ok) tma_store_2d_s(&tmD, slab, col0, row0);
             tma_store_commit();
           }
           ++ring;
@@ -880,9 +892,85 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           else mbar_arrive_leader(&tmem_empty[acc]);
         }
       }
+      if (LNT && n_blk == args.num_n_blocks - 1) {
+        // ---- LayerNorm tail, epilogue side: this warp has now ISSUED its stores of m unit `ln_unit` (six groups: empty
+        // groups are committed for row groups past M). Everything older has landed once at most those six are pending:
+        // tell the helper warps that the PREVIOUS unit's rows are in memory (a unit of slack: no stall here).
+        if (ln_unit > 0 && lane == 0) {
+          const int n = ln_unit - 1;
+          tma_store_wait_all<6>();
+          if (n >= 2) mbar_wait(&ln_done[n & 1], ((n - 2) >> 1) & 1);   // the helpers are done with this barrier's last use
+          mbar_arrive(&ln_go[n & 1]);
+        }
+        ++ln_unit;
+      }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait_all<0>();
+    if (LNT && ln_unit > 0 && lane == 0) {
+      const int n = ln_unit - 1;   // the last unit
+      if (n >= 2) mbar_wait(&ln_done[n & 1], ((n - 2) >> 1) & 1);
+      mbar_arrive(&ln_go[n & 1]);
+    }
+  } else if (LNT && warp >= 2) {
+    // ------------------------------------------------------------------ LayerNorm tail, helper warps 2 and 3
+    // One m unit behind the epilogue: normalise this CTA's 128 finished rows (64 per warp) of the fp32 stream -- read back
+    // from L2, where they were written a unit ago -- into bf16 LayerNorm rows + statistics. The epilogue warps, the
+    // bottleneck of these HBM-bound GEMMs, spend nothing on it.
+    constexpr int kK = 384;
+    int n = 0;
+    for (int t = cluster_id; t < num_m_units; t += num_clusters, ++n) {
+      const int r_base = (t * CL + cta_rank) * BLOCK_M + (warp - 2) * 64;
+      mbar_wait(&ln_go[n & 1], (n >> 1) & 1);
+#pragma unroll 1
+      for (int rr = 0; rr < 64; rr += 4) {
+        float4 xv[4][3];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int grow = r_base + rr + i;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            xv[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grow < args.M)
+              xv[i][j] = ld_global_cg_f4(args.out_f32 + static_cast<long long>(grow) * args.ldd + 128 * j + 4 * lane);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int grow = r_base + rr + i;
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) sum += (xv[i][j].x + xv[i][j].y) + (xv[i][j].z + xv[i][j].w);
+          const float mean = warp_sum(sum) * (1.f / kK);
+          float var = 0.f;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float a = xv[i][j].x - mean, b = xv[i][j].y - mean, c = xv[i][j].z - mean, d = xv[i][j].w - mean;
+            var += (a * a + b * b) + (c * c + d * d);
+          }
+          const float rstd = rsqrtf(warp_sum(var) * (1.f / kK) + args.ln_eps);
+          if (grow < args.M) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const float4 gv = __ldg(reinterpret_cast<const float4*>(args.ln_gamma + 128 * j) + lane);
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(args.ln_beta + 128 * j) + lane);
+              const float y0 = (xv[i][j].x - mean) * rstd * gv.x + bv.x;
+              const float y1 = (xv[i][j].y - mean) * rstd * gv.y + bv.y;
+              const float y2 = (xv[i][j].z - mean) * rstd * gv.z + bv.z;
+              const float y3 = (xv[i][j].w - mean) * rstd * gv.w + bv.w;
+              *reinterpret_cast<uint2*>(args.ln_out + static_cast<long long>(grow) * kK + 128 * j + 4 * lane) =
+                  make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+            }
+            if (lane == 0 && args.ln_mean != nullptr) {
+              args.ln_mean[grow] = mean;
+              args.ln_rstd[grow] = rstd;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ln_done[n & 1]);
+    }
   }
 
   tcgen05_fence_before();
@@ -1168,6 +1256,59 @@ extern "C" int b200ssl_ln_gemm(const float* x, long long ldx, const float* gamma
     case EPI_BIAS_GELU: return launch_gemm_cl<192, EPI_BIAS_GELU, 2, 2>(tmB, tmB, tmD, tmD2, args, stream);
     default: return launch_gemm_cl<192, EPI_BIAS_GELU_FWD, 2, 2>(tmB, tmB, tmD, tmD2, args, stream);
   }
+}
+
+// Residual GEMM with a LayerNorm tail (MODE 3):  D = rowscale * (A W^T + bias) + aux  on the fp32 residual stream, and
+// ln_out = LayerNorm(D; gamma, beta, eps) in bf16 (+ per-row mean / rstd, nullable) from the same kernel. For N = 384
+// (ViT-S): attn.proj + Block.norm2 and mlp.fc2 + the next Block.norm1 (VT.pyc@L147-151). A [M,K] bf16, W [384,K] bf16,
+// aux / D fp32 [M,384], ln_out bf16 [M,384] contiguous. rowscale (stochastic depth) and bias are nullable.
+extern "C" int b200ssl_gemm_res_ln(const void* A, long long lda, const void* W, long long ldw, float* D, long long ldd,
+                                   const float* rowscale, const float* bias, const float* aux, long long ldaux, int M,
+                                   int N, int K, const float* gamma, const float* beta, float eps, void* ln_out,
+                                   float* mean, float* rstd, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200SSL_CHECK(N == 384, -2, "gemm_res_ln: N=%d unsupported (the LayerNorm tail is built for D = 384)", N);
+  B200SSL_CHECK(M > BLOCK_M && K > 0 && g_gemm_cluster == 2, -2, "gemm_res_ln: needs more than 128 rows and the CTA-pair mode");
+  B200SSL_CHECK(lda % 8 == 0 && ldw % 8 == 0 && ldaux % 4 == 0 && ldd % 4 == 0, -2, "gemm_res_ln: lda/ldw %% 8, ldaux/ldd %% 4 must be 0");
+  B200SSL_CHECK(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(D) |
+                  reinterpret_cast<uintptr_t>(aux) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+                  reinterpret_cast<uintptr_t>(ln_out) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0,
+                -2, "gemm_res_ln: operands must be 16-byte aligned");
+  B200SSL_CHECK(aux != nullptr && gamma != nullptr && beta != nullptr && ln_out != nullptr, -2, "gemm_res_ln: aux, gamma, beta, ln_out are required");
+  B200SSL_CHECK((mean == nullptr) == (rstd == nullptr), -2, "gemm_res_ln: mean and rstd go together");
+  constexpr int bn = 192;
+  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  GemmArgs args;
+  args.M = M; args.N = N; args.K = K;
+  args.a_mn = 0; args.b_mn = 0;
+  args.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  args.num_n_blocks = N / bn;
+  args.k_splits = 1;
+  args.k_blocks_per_split = k_blocks;
+  args.k_blocks_total = k_blocks;
+  args.bias = bias;
+  args.aux = aux;
+  args.ldaux = ldaux;
+  args.out_f32 = D;
+  args.ldd = ldd;
+  args.prof = g_gemm_prof;
+  args.rowscale = rowscale;
+  args.ln_x = nullptr; args.ln_ldx = 0;
+  args.ln_gamma = gamma; args.ln_beta = beta; args.ln_eps = eps;
+  args.ln_out = static_cast<__nv_bfloat16*>(ln_out); args.ln_mean = mean; args.ln_rstd = rstd;
+  CUtensorMap tmA, tmB, tmD;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    uint64_t strides[2] = {2, static_cast<uint64_t>(lda) * 2};
+    uint32_t box[2] = {64, BLOCK_M};
+    if (int rc = make_tensor_map(&tmA, A, 2, 2, dims, strides, box, 128)) return rc;
+    dims[1] = N; strides[1] = static_cast<uint64_t>(ldw) * 2; box[1] = bn / 2;   // pair: each CTA loads half of the B tile
+    if (int rc = make_tensor_map(&tmB, W, 2, 2, dims, strides, box, 128)) return rc;
+    dims[0] = N; dims[1] = M; box[0] = 16; box[1] = 32;                          // per-warp slab: 32 rows x 64 B
+    strides[0] = 4; strides[1] = static_cast<uint64_t>(ldd) * 4;
+    if (int rc = make_tensor_map(&tmD, D, 4, 2, dims, strides, box, 64)) return rc;
+  }
+  return launch_gemm_cl<bn, EPI_BIAS_RES_F32, 2, 3>(tmA, tmB, tmD, tmD, args, stream);
 }
 
 // 1 = independent CTAs, 2 = clusters of two CTAs sharing the B tile through TMA multicast (default).

@@ -350,6 +350,42 @@ def ln_linear_fwd(x, ln_w, ln_b, eps, w16, bias=None, gelu=False, keep=True):
     return y, ln, mean, rstd
 
 
+# LayerNorm TAIL of the residual GEMMs (b200ssl_gemm_res_ln): attn.proj / mlp.fc2 write the fp32 stream AND the bf16
+# LayerNorm of it (Block.norm2 / the next Block.norm1) from one kernel; the standalone LayerNorm-forward launches of a
+# 384-wide encoder disappear. Correct (tests/test_gpu_kernels.py::test_residual_gemm_with_layernorm_tail, the model test
+# with the switch on) but measured SLOWER on the config-2 step, in both placements of the tail: inside the epilogue warps
+# (wait for the stores, re-read the rows from L2) 53.0 vs 52.7 ms per step; on the two idle warps one m unit behind the
+# epilogue 60.5 vs 54.3 ms (64 rows per warp with twelve 16-byte L2 loads in flight per lane is latency bound and
+# back-pressures the epilogue). The standalone LayerNorm kernel streams at 5.5 TB/s; the 300 MB of HBM reads the tail
+# saves per call are worth less than what it costs the warps these HBM-bound GEMMs are limited by. Off by default
+# (bench.py --ln-tail).
+_LN_TAIL = {"on": False}
+
+
+def ln_tail_ok(rows, n_out):
+    return _LN_TAIL["on"] and n_out == 384 and rows > 128
+
+
+def gemm_res_ln(x, w16, y, bias, residual, rowscale, ln_w, ln_b, eps, ln, mean, rstd):
+    M, K = x.shape
+    _call("b200ssl_gemm_res_ln", x.data_ptr(), x.stride(0), w16.data_ptr(), w16.stride(0), y.data_ptr(), y.stride(0),
+          _ptr(rowscale), _ptr(bias), residual.data_ptr(), residual.stride(0), M, w16.shape[0], K, ln_w.data_ptr(),
+          ln_b.data_ptr(), float(eps), ln.data_ptr(), _ptr(mean), _ptr(rstd), _stream())
+
+
+def linear_res_ln_fwd(x, w16, bias, residual, rowscale, ln_w, ln_b, eps, keep=True):
+    """y = residual + rowscale * (x @ w16^T + bias) on the fp32 stream, and LayerNorm(y) from the same kernel.
+    -> (y fp32, (ln bf16, mean, rstd)); mean / rstd are None with keep=False (no-grad forward)."""
+    M, N = x.shape[0], w16.shape[0]
+    dev = x.device
+    y = torch.empty(M, N, dtype=torch.float32, device=dev)
+    ln = torch.empty(M, N, dtype=_BF16, device=dev)
+    mean = torch.empty(M, dtype=torch.float32, device=dev) if keep else None
+    rstd = torch.empty(M, dtype=torch.float32, device=dev) if keep else None
+    gemm_res_ln(x, w16, y, bias, residual, rowscale, ln_w, ln_b, eps, ln, mean, rstd)
+    return y, (ln, mean, rstd)
+
+
 def layernorm_bwd(x, dy, w, mean, rstd, dres=None, weight=None, bias=None):
     """Gradients travel in bf16: dy, dres, dx are bf16 regardless of the stream dtype of x. dgamma / dbeta
     are accumulated into the parameters' gradient sinks when registered (then returned as None)."""
@@ -561,18 +597,30 @@ class AttentionCoreFn(torch.autograd.Function):
 
 
 # ---- residual half-blocks: plain functions shared by the per-block and whole-encoder autograd nodes ----
-def attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale, keep=True, rs=None):
-    """x + proj(attention(qkv(LN(x)))) (VT.pyc@L147,150). Returns (y, saved-for-backward)."""
+def attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale, keep=True, rs=None, pre=None,
+                  nxt=None):
+    """x + proj(attention(qkv(LN(x)))) (VT.pyc@L147,150). Returns (y, saved-for-backward, next LayerNorm state).
+    ``pre`` = (ln, mean, rstd) of THIS half's LayerNorm when the previous residual GEMM already produced it;
+    ``nxt`` = (ln_w, ln_b, eps) of the LayerNorm that follows (Block.norm2): produced by the proj GEMM's tail when the
+    shape allows, else the third return value is None."""
     wq16 = bf16_of(qkv_w)
     qb32 = _f32(qkv_b) if qkv_b is not None else None
-    if ln_gemm_ok(x, wq16):
+    if pre is not None:
+        ln, mean, rstd = pre
+        qkv = linear_fwd(ln, wq16, qb32)
+    elif ln_gemm_ok(x, wq16):
         qkv, ln, mean, rstd = ln_linear_fwd(x, _f32(ln_w), _f32(ln_b), eps, wq16, qb32, keep=keep)
     else:
         ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
         qkv = linear_fwd(ln, wq16, qb32)
     att, lse2 = attention_fwd(qkv, B, N, H, scale)
-    y = linear_fwd(att, bf16_of(proj_w), _f32(proj_b) if proj_b is not None else None, residual=x, rowscale=rs)
-    return y, (x, mean, rstd, ln, qkv, att, lse2, rs)
+    pb32 = _f32(proj_b) if proj_b is not None else None
+    nxt_state = None
+    if nxt is not None and ln_tail_ok(att.shape[0], proj_w.shape[0]):
+        y, nxt_state = linear_res_ln_fwd(att, bf16_of(proj_w), pb32, x, rs, _f32(nxt[0]), _f32(nxt[1]), nxt[2], keep=keep)
+    else:
+        y = linear_fwd(att, bf16_of(proj_w), pb32, residual=x, rowscale=rs)
+    return y, (x, mean, rstd, ln, qkv, att, lse2, rs), nxt_state
 
 
 def attn_half_bwd(dy, saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale, ln_b=None, qkv_b=None,
@@ -590,19 +638,29 @@ def attn_half_bwd(dy, saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale
     return dx, d_lw, d_lb, d_qw, d_qb, d_pw, d_pb
 
 
-def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, keep=True, rs=None, need_out=True):
+def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, keep=True, rs=None, need_out=True, pre=None, nxt=None):
     """x + fc2(gelu(fc1(LN(x)))) (VT.pyc@L151). keep=False (no-grad forward): gelu' is not produced.
-    need_out=False (activation recompute in backward): the fc2 GEMM is skipped, only the saved tensors are rebuilt."""
+    need_out=False (activation recompute in backward): the fc2 GEMM is skipped, only the saved tensors are rebuilt.
+    ``pre`` / ``nxt`` as in attn_half_fwd (``nxt`` = the next Block's norm1). Returns (y, saved, next LayerNorm state)."""
     w116 = bf16_of(w1)
     b132 = _f32(b1) if b1 is not None else None
-    if ln_gemm_ok(x, w116):
-        (pre, h), ln, mean, rstd = ln_linear_fwd(x, _f32(ln_w), _f32(ln_b), eps, w116, b132,
-                                                 gelu=True if keep else "fwd_only", keep=keep)
+    if pre is not None:
+        ln, mean, rstd = pre
+        pre_act, h = linear_fwd(ln, w116, b132, gelu=True if keep else "fwd_only")
+    elif ln_gemm_ok(x, w116):
+        (pre_act, h), ln, mean, rstd = ln_linear_fwd(x, _f32(ln_w), _f32(ln_b), eps, w116, b132,
+                                                     gelu=True if keep else "fwd_only", keep=keep)
     else:
         ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
-        pre, h = linear_fwd(ln, w116, b132, gelu=True if keep else "fwd_only")
-    y = linear_fwd(h, bf16_of(w2), _f32(b2) if b2 is not None else None, residual=x, rowscale=rs) if need_out else None
-    return y, (x, mean, rstd, ln, pre, h, rs)
+        pre_act, h = linear_fwd(ln, w116, b132, gelu=True if keep else "fwd_only")
+    b232 = _f32(b2) if b2 is not None else None
+    y, nxt_state = None, None
+    if need_out:
+        if nxt is not None and ln_tail_ok(h.shape[0], w2.shape[0]):
+            y, nxt_state = linear_res_ln_fwd(h, bf16_of(w2), b232, x, rs, _f32(nxt[0]), _f32(nxt[1]), nxt[2], keep=keep)
+        else:
+            y = linear_fwd(h, bf16_of(w2), b232, residual=x, rowscale=rs)
+    return y, (x, mean, rstd, ln, pre_act, h, rs), nxt_state
 
 
 def mlp_half_bwd(dy, saved, ln_w, w1, w2, has_b1, has_b2, ln_b=None, b1=None, b2=None):
@@ -621,7 +679,7 @@ class AttnHalfFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale, rs=None):
-        y, saved = attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale, rs=rs)
+        y, saved, _ = attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale, rs=rs)
         ctx.save_for_backward(*saved, ln_w, qkv_w, proj_w)
         ctx.meta = (B, N, H, scale, qkv_b is not None, proj_b is not None)
         return y
@@ -639,7 +697,7 @@ class MlpHalfFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, eps, rs=None):
-        y, saved = mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, rs=rs)
+        y, saved, _ = mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, rs=rs)
         ctx.save_for_backward(*saved, ln_w, w1, w2)
         ctx.meta = (b1 is not None, b2 is not None)
         return y
@@ -677,13 +735,22 @@ class EncoderFn(torch.autograd.Function):
         recompute = keep and len(meta) > 8 and bool(meta[8])
         saved = []
         x = tok
+        ln_state = None
         for i in range(depth):
             ln1w, ln1b, qw, qb, pw, pb, ln2w, ln2b, w1, b1, w2, b2 = params[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS]
             rs1, rs2 = rs_list[i] if rs_list is not None else (None, None)
             x_in = x
-            x, s1 = attn_half_fwd(x, ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale,
-                                  keep=keep and not recompute, rs=rs1)
-            x, s2 = mlp_half_fwd(x, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1], keep=keep and not recompute, rs=rs2)
+            # the LayerNorm after each residual add rides in the tail of the GEMM that produces the sum (when the shape
+            # allows): norm2 with attn.proj, the NEXT block's norm1 with mlp.fc2. Not under activation recompute.
+            nxt1 = None if recompute else (ln2w, ln2b, eps_list[i][1])
+            nxt2 = None
+            if not recompute and i + 1 < depth:
+                nb = params[(i + 1) * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS + 2]
+                nxt2 = (nb[0], nb[1], eps_list[i + 1][0])
+            x, s1, ln_state = attn_half_fwd(x, ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale,
+                                            keep=keep and not recompute, rs=rs1, pre=ln_state, nxt=nxt1)
+            x, s2, ln_state = mlp_half_fwd(x, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1], keep=keep and not recompute,
+                                           rs=rs2, pre=ln_state, nxt=nxt2)
             if recompute:
                 saved.append(x_in)
             elif keep:
@@ -725,8 +792,8 @@ class EncoderFn(torch.autograd.Function):
             ln1w, ln1b, qw, qb, pw, pb, ln2w, ln2b, w1, b1, w2, b2 = params[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS]
             if torch.is_tensor(ctx.saved[i]):   # activation recompute: rebuild this block's saved tensors from its input
                 rs1, rs2 = ctx.meta[6][i] if ctx.meta[6] is not None else (None, None)
-                x1, s1 = attn_half_fwd(ctx.saved[i], ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale, rs=rs1)
-                _, s2 = mlp_half_fwd(x1, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1], rs=rs2, need_out=False)
+                x1, s1, _ = attn_half_fwd(ctx.saved[i], ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale, rs=rs1)
+                _, s2, _ = mlp_half_fwd(x1, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1], rs=rs2, need_out=False)
             else:
                 s1, s2 = ctx.saved[i]
             dx, g_l2w, g_l2b, g_w1, g_b1, g_w2, g_b2 = mlp_half_bwd(dx, s2, ln2w, w1, w2, b1 is not None, b2 is not None,

@@ -55,6 +55,16 @@ int b200ssl_gemm(const void* A, long long lda, int a_mn_major, const void* B, lo
 int b200ssl_ln_gemm(const float* x, long long ldx, const float* gamma, const float* beta, float eps, void* ln_out,
                     float* mean, float* rstd, const void* W, long long ldw, void* D, long long ldd, void* D2,
                     const float* bias, int M, int N, int K, int epilogue, void* stream);
+/* Residual GEMM with a LayerNorm TAIL: D(fp32) = rowscale * (A W^T + bias) + aux, and in the same kernel
+ * ln_out(bf16) = LayerNorm(D; gamma, beta, eps) plus the row statistics (mean / rstd nullable, both or none). A cluster
+ * computes both 192-column halves of its 256 rows back to back and its epilogue warps normalise the finished rows out of
+ * L2: attn.proj + Block.norm2 and mlp.fc2 + the following Block.norm1 (VT.pyc@L147-151) without a second pass over the
+ * fp32 stream. N must be 384 (ViT-S), M > 128. rowscale / bias nullable. */
+int b200ssl_gemm_res_ln(const void* A, long long lda, const void* W, long long ldw, float* D, long long ldd,
+                        const float* rowscale, const float* bias, const float* aux, long long ldaux, int M, int N, int K,
+                        const float* gamma, const float* beta, float eps, void* ln_out, float* mean, float* rstd,
+                        void* stream);
+
 
 /* 1 = independent CTAs; 2 (default) = CTA pairs (tcgen05 cta_group::2: 256-row tiles, each CTA loads half of B). */
 int b200ssl_set_gemm_cluster(int ctas);

@@ -102,6 +102,38 @@ def test_layernorm(ops, D, dtype):
     assert rel(db, br.grad) < 1e-3
 
 
+@pytest.mark.parametrize("M,K,rowscale", [(300, 384, False), (1000, 1536, True), (4099, 384, False), (2048, 1536, False)])
+def test_residual_gemm_with_layernorm_tail(ops, M, K, rowscale):
+    """b200ssl_gemm_res_ln: y = res + rs * (x W^T + b) on the fp32 stream and LayerNorm(y) from the same kernel
+    (attn.proj + norm2, mlp.fc2 + the next norm1; VT.pyc@L147-151), against fp32 torch math; ragged row counts."""
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    D = 384
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(D, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(D, device="cuda", generator=g)
+    res = torch.randn(M, D, device="cuda", generator=g) * 3 + 0.5
+    rs = (torch.rand(M, device="cuda", generator=g) > 0.3).float() / 0.7 if rowscale else None
+    gamma = torch.randn(D, device="cuda", generator=g) * 0.3 + 1.0
+    beta = torch.randn(D, device="cuda", generator=g) * 0.2
+    y, (ln, mean, rstd) = ops.linear_res_ln_fwd(x, w, b, res, rs, gamma, beta, 1e-6)
+    torch.cuda.synchronize()
+    branch = x.float() @ w.float().t() + b
+    y_ref = res + (branch * rs[:, None] if rs is not None else branch)
+    assert rel(y, y_ref) < 2e-3
+    # the tail normalises the stream the kernel itself wrote: compare with LayerNorm of THAT (isolates the tail)
+    ln_ref = torch.nn.functional.layer_norm(y, (D,), gamma, beta, 1e-6)
+    assert rel(ln, ln_ref) < 4e-3                                           # bf16 output
+    assert rel(mean, y.mean(-1)) < 1e-5
+    assert rel(rstd, 1.0 / torch.sqrt(y.var(-1, unbiased=False) + 1e-6)) < 1e-5
+    # and it is the same function as the two separate kernels
+    y2 = ops.linear_fwd(x, w, b, residual=res, rowscale=rs)
+    ln2, mean2, rstd2 = ops.layernorm_fwd(y2, gamma, beta, 1e-6)
+    assert rel(y, y2) < 1e-6 and rel(ln, ln2) < 2.5e-3 and rel(mean, mean2) < 1e-5
+    # no-grad flavour: statistics not produced
+    y3, (ln3, m3, r3) = ops.linear_res_ln_fwd(x, w, b, res, rs, gamma, beta, 1e-6, keep=False)
+    assert m3 is None and r3 is None and torch.equal(ln3, ln) and torch.equal(y3, y)
+
+
 def _check_attention_grad(dqkv, ref):
     """Gradients are gated by COSINE in the north star (>= 0.999 per tensor); forward outputs by norm-wise relative
     error (<= 1e-2). dQ/dK/dV are required to reach cosine >= 0.9999 -- ten times closer to 1 than the gate. The

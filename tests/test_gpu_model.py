@@ -318,8 +318,36 @@ def test_merged_crop_groups_match_per_group_passes(libs, drop_path, patch):
     assert res[True][0].shape == (20, 1024)
     assert torch.equal(res[True][0], res[False][0]), rel(res[True][0], res[False][0])
     assert sorted(res[True][1]) == sorted(res[False][1])
+    # patch 8 (785 tokens): the one-launch paired attention backward reduce-adds its bf16 dQ / dK / dV partials in an
+    # order that varies from run to run, so the two passes differ at the bf16 rounding level of those sums
+    tol, cmin = (2e-3, 0.99999) if patch == 16 else (1e-2, 0.9999)
     for n, gm in res[True][1].items():
-        assert rel(gm, res[False][1][n]) < 2e-3 and cos(gm, res[False][1][n]) > 0.99999, (n, rel(gm, res[False][1][n]))
+        assert rel(gm, res[False][1][n]) < tol and cos(gm, res[False][1][n]) > cmin, (n, rel(gm, res[False][1][n]))
+
+
+def test_layernorm_tail_switch_gives_the_same_model(libs):
+    """ops._LN_TAIL (LayerNorm in the tail of the proj / fc2 GEMMs, off by default because it measured slower): same
+    features and gradients as the separate LayerNorm kernels, ViT-S (the 384-wide case the tail is built for)."""
+    b200ssl, ovt, _ = libs
+    from b200ssl import ops
+    torch.manual_seed(0)
+    model = b200ssl.vit_small(drop_path_rate=0.1).cuda().train()
+    x = torch.randn(6, 3, 224, 224, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)).bfloat16()
+    w = torch.randn(6, 384, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    res = {}
+    try:
+        for on in (False, True):
+            ops._LN_TAIL["on"] = on
+            model.zero_grad(set_to_none=True)
+            torch.manual_seed(99)
+            out = model(x)
+            (out.float() * w).sum().backward()
+            res[on] = (out.float().clone(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    finally:
+        ops._LN_TAIL["on"] = False
+    assert rel(res[True][0], res[False][0]) < 5e-3
+    for n, gm in res[True][1].items():
+        assert cos(gm, res[False][1][n]) > 0.9995, (n, cos(gm, res[False][1][n]))
 
 
 def test_grad_checkpointing_recomputes_the_same_gradients(libs):
