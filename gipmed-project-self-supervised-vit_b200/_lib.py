@@ -28,6 +28,7 @@ SIGNATURES = {
     "b200ssl_set_gemm_prof": [_P],
     "b200ssl_set_attn_prof": [_P],
     "b200ssl_set_attn_stream": [_I],
+    "b200ssl_set_attn_dephase": [_I],
     "b200ssl_set_gemm_wide": [_I],
     "b200ssl_set_pdl": [_I],
     "b200ssl_set_ln_bwd_staged": [_I],

@@ -28,6 +28,7 @@ struct AttnArgs {
   int nblk;             // bwd, NT == 2: > 1 = ONE launch over all (query block, key block) pairs of 256 x 256 tokens of
                         // every (sequence, head); N / Nk / keys_n are then per item and Ns is the sequence length
   int G;             // sequences packed per 128-row tile (NT == 1), else 1
+  int dephase;       // fwd two-tile kernel: event-driven MMA issue with the two slots half a period apart
   int rows;          // valid rows per tile group: G*N (NT == 1) or N (NT == 2)
   int keys_n;        // round_up(rows, 16): MMA N extent over keys
   float scale_log2;  // softmax scale * log2(e)
@@ -174,34 +175,87 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       const uint32_t idesc_s = make_idesc_bf16(128, args.keys_n, false, false);
       const uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
       const int ksteps = args.keys_n / 16;
-      int k = 0;
-      for (int round = blockIdx.x; round < num_rounds; round += gridDim.x, ++k) {
-        const int buf = k & 1;
-        const uint32_t par = k & 1;
-        mbar_wait(&load_full[buf], (k >> 1) & 1);
-        tcgen05_fence_after();
-        for (int slot = 0; slot < 2; ++slot) {
-          if (slot_item(round, slot) < 0) continue;
-          mbar_wait(&tmem_free[slot], par ^ 1);
-          tcgen05_fence_after();
-          const uint32_t a0 = smem_u32(q_tile(buf, slot)), bk = smem_u32(k_tile(buf, slot));
+      auto issue_s = [&](int buf, int slot) {
+        const uint32_t a0 = smem_u32(q_tile(buf, slot)), bk = smem_u32(k_tile(buf, slot));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_bf16_ss(tmem_base + slot * 256, make_smem_desc_sw128(a0 + kk * 32, 16, 1024),
-                         make_smem_desc_sw128(bk + kk * 32, 16, 1024), idesc_s, kk > 0);
-          umma_commit(&bar_s[slot]);
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ss(tmem_base + slot * 256, make_smem_desc_sw128(a0 + kk * 32, 16, 1024),
+                       make_smem_desc_sw128(bk + kk * 32, 16, 1024), idesc_s, kk > 0);
+        umma_commit(&bar_s[slot]);
+      };
+      auto issue_pv = [&](int buf, int slot) {
+        const uint32_t v0 = smem_u32(v_tile(buf, slot));
+        const int ch0 = (ksteps + 1) / 2;  // P column map of the softmax halves (see below)
+        for (int j = 0; j < ksteps; ++j)
+          umma_bf16_ts(tmem_base + slot * 256 + 192,
+                       tmem_base + slot * 256 + (j < ch0 ? 8 * j : 16 * ch0 + 8 * (j - ch0)),
+                       make_smem_desc_sw128(v0 + j * 2048, 8192, 1024), idesc_o, j > 0);
+        umma_commit(&bar_o[slot]);
+      };
+      if (args.dephase) {
+        // Event-driven issue: each slot walks S(k) -> P V(k) -> S(k+1) ... on its OWN barriers, whichever slot is ready
+        // goes next, and slot 1's first S is held back until slot 0 has finished its first exp2 pass. The two softmax
+        // groups then run half a period apart: one is in its (MUFU-bound) exp2 pass while the other waits for O, stores
+        // its output and takes the row maxima of its next tile -- instead of both queueing for the MUFU pipe together
+        // and both leaving it idle together (round-locked issue: exp2 pass 3,358 of 7,955 cycles per tile).
+        const int n_my = static_cast<int>(blockIdx.x) < num_rounds
+                             ? (num_rounds - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
+                             : 0;
+        int ks[2] = {0, 0}, kp[2] = {0, 0};   // next round (CTA-local index) whose S / whose P V is to be issued, per slot
+        long long spins = 0;
+        while (kp[0] < n_my || kp[1] < n_my) {
+          bool progress = false;
+#pragma unroll
+          for (int slot = 0; slot < 2; ++slot) {
+            if (kp[slot] >= n_my) continue;
+            if (ks[slot] == kp[slot]) {
+              const int k = ks[slot];
+              if (slot_item(static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x), slot) < 0) {  // empty tail slot
+                ++ks[slot]; ++kp[slot]; progress = true;
+                continue;
+              }
+              if (slot == 1 && k == 0 && kp[0] == 0) continue;   // the half-period offset
+              if (!mbar_test_wait(&load_full[k & 1], (k >> 1) & 1)) continue;
+              if (!mbar_test_wait(&tmem_free[slot], (k & 1) ^ 1)) continue;
+              tcgen05_fence_after();
+              issue_s(k & 1, slot);
+              ++ks[slot];
+              progress = true;
+            } else {
+              const int k = kp[slot];
+              if (!mbar_test_wait(&bar_p[slot], k & 1)) continue;
+              tcgen05_fence_after();
+              issue_pv(k & 1, slot);
+              ++kp[slot];
+              progress = true;
+            }
+          }
+          if (progress) {
+            spins = 0;
+          } else {
+            __nanosleep(args.dephase > 1 ? args.dephase : 0);   // keep the probe loop off the issue port of this warp's scheduler
+            if (++spins > (1ll << 26)) __trap();   // a dead pipeline must fail the launch, not hang the GPU
+          }
         }
-        for (int slot = 0; slot < 2; ++slot) {
-          if (slot_item(round, slot) < 0) continue;
-          mbar_wait(&bar_p[slot], par);
+      } else {
+        int k = 0;
+        for (int round = blockIdx.x; round < num_rounds; round += gridDim.x, ++k) {
+          const int buf = k & 1;
+          const uint32_t par = k & 1;
+          mbar_wait(&load_full[buf], (k >> 1) & 1);
           tcgen05_fence_after();
-          const uint32_t v0 = smem_u32(v_tile(buf, slot));
-          const int ch0 = (ksteps + 1) / 2;  // P column map of the softmax halves (see below)
-          for (int j = 0; j < ksteps; ++j)
-            umma_bf16_ts(tmem_base + slot * 256 + 192,
-                         tmem_base + slot * 256 + (j < ch0 ? 8 * j : 16 * ch0 + 8 * (j - ch0)),
-                         make_smem_desc_sw128(v0 + j * 2048, 8192, 1024), idesc_o, j > 0);
-          umma_commit(&bar_o[slot]);
+          for (int slot = 0; slot < 2; ++slot) {
+            if (slot_item(round, slot) < 0) continue;
+            mbar_wait(&tmem_free[slot], par ^ 1);
+            tcgen05_fence_after();
+            issue_s(buf, slot);
+          }
+          for (int slot = 0; slot < 2; ++slot) {
+            if (slot_item(round, slot) < 0) continue;
+            mbar_wait(&bar_p[slot], par);
+            tcgen05_fence_after();
+            issue_pv(buf, slot);
+          }
         }
       }
     }
@@ -1183,10 +1237,13 @@ static unsigned long long* g_attn_prof = nullptr;
 // forward kernel choice: 0 = streaming kernel for N > 256 only (two-tile kernel for 129..256), 1 = streaming kernel for
 // every N > 128, -1 = never (N > 256 falls back to the block decomposition with an lse merge; developer A/B)
 static int g_attn_stream = 0;
+static int g_attn_dephase = 0;  // two-tile forward: 1 = event-driven MMA issue, slots half a period apart (measured
+                                // slower: 107 vs 102 us at B = 512, N = 197); 0 = round-locked issue; > 1 = 1 with that many ns of back-off
 
 // Nq / Nk: query and key tokens of this launch (equal, and equal to the stride Ns, on the main path).
 static int setup_args(AttnArgs& a, int B, int Nq, int Nk, int Ns, int H, float scale, bool blocked, int& nt, int& groups) {
   a.prof = g_attn_prof;
+  a.dephase = g_attn_dephase;
   B200SSL_CHECK(Nq >= 1 && Nq <= 256 && Nk >= 1 && Nk <= 256, -2, "attention: block of %d x %d tokens unsupported (1..256)",
                 Nq, Nk);
   a.B = B; a.N = Nq; a.Nk = Nk; a.Ns = Ns; a.H = H;
@@ -1402,6 +1459,11 @@ extern "C" int b200ssl_set_attn_prof(void* counters) {
 }
 
 // bytes of scratch b200ssl_attention_fwd_ws needs (0 for N <= 256): per key block a partial output and lse
+extern "C" int b200ssl_set_attn_dephase(int on) {
+  b200ssl::g_attn_dephase = on;
+  return 0;
+}
+
 extern "C" int b200ssl_set_attn_stream(int mode) {
   B200SSL_CHECK(mode >= -1 && mode <= 1, -2, "attention stream mode must be -1, 0 or 1");
   b200ssl::g_attn_stream = mode;

@@ -283,6 +283,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (never parks the warp): for a thread that polls SEVERAL barriers and acts on whichever is ready
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // try_wait with an explicit suspend-time hint: the warp may be parked by the hardware for up to `ns` nanoseconds
 // waiting for the phase, instead of coming back to re-issue the probe (spinning warps steal issue slots from the
 // math warps: in the first profiles more than a third of all executed instructions were wait loops).

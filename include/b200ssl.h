@@ -112,6 +112,10 @@ int b200ssl_attention_bwd(const void* qkv, const void* out, const void* dout, co
  * 257..512 tokens, ONE launch over all pairs (into a zeroed dqkv) above. b200ssl_attention_fwd == b200ssl_attention_fwd_ws with no
  * workspace; b200ssl_attention_fwd_workspace_bytes returns 0 whenever none is needed. */
 int b200ssl_set_attn_stream(int mode);
+/* Two-tile forward (N <= 256): 1 (default) = the MMA issuer serves whichever of the two query-tile slots is ready and
+ * starts them half a period apart, so one slot's exp2 pass runs under the other's epilogue / row-max pass; 0 = both
+ * slots issued round by round in lock-step (developer A/B). Results are bit-identical. */
+int b200ssl_set_attn_dephase(int on);
 long long b200ssl_attention_fwd_workspace_bytes(int B, int N, int H);
 int b200ssl_attention_fwd_ws(const void* qkv, void* out, float* lse2, int B, int N, int H, int head_dim, float scale,
                              void* workspace, long long workspace_bytes, void* stream);
