@@ -13,6 +13,7 @@
 // rescaling), so logits are read once forward and once backward; gradients are written once.
 // Rows are crop-major: student row = v * B + b, teacher row = iq * B + b.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace b200ssl {
 
@@ -23,28 +24,67 @@ struct OnlineLSE {
   float m, z;  // running max and sum exp(x - m)
 };
 
-// exp(a - b) with the convention exp(-inf - anything) = 0 (an empty partial state)
-__device__ __forceinline__ float exp_diff(float a, float b) { return a == -INFINITY ? 0.f : __expf(a - b); }
+// 2^(a - b) with the convention 2^(-inf - anything) = 0 (an empty partial state)
+__device__ __forceinline__ float exp2_diff(float a, float b) { return a == -INFINITY ? 0.f : ex2_approx(a - b); }
 
-__device__ __forceinline__ void lse_merge(float& m, float& z, float m2, float z2) {
-  const float mn = fmaxf(m, m2);
-  z = z * exp_diff(m, mn) + z2 * exp_diff(m2, mn);
-  m = mn;
+// distributed shared memory: read a float of CTA `rank` of this cluster at the address `p` has in the caller's own smem
+__device__ __forceinline__ float ld_cluster_f32(const float* p, uint32_t rank) {
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
 }
 
+// Merge `n` partial online states for crop v. A part is [tm0, tz0, tm1, tz1, (sm, sz, u0, u1) x NC]; u0 / u1 of a part are
+// relative to that part's OWN teacher maxima, so they are rescaled to the merged maxima M0 / M1. All in the log2 domain.
+template <typename Get>
+__device__ __forceinline__ void merge_parts(Get get, int n, int v, float& M0, float& Z0, float& M1, float& Z1, float& M,
+                                            float& Z, float& U0, float& U1) {
+  M0 = -INFINITY; M1 = -INFINITY; M = -INFINITY;
+  for (int p = 0; p < n; ++p) {
+    M0 = fmaxf(M0, get(p, 0));
+    M1 = fmaxf(M1, get(p, 2));
+    M = fmaxf(M, get(p, 4 + 4 * v));
+  }
+  Z0 = 0.f; Z1 = 0.f; Z = 0.f; U0 = 0.f; U1 = 0.f;
+  for (int p = 0; p < n; ++p) {
+    const float r0 = exp2_diff(get(p, 0), M0), r1 = exp2_diff(get(p, 2), M1);
+    Z0 += get(p, 1) * r0;
+    Z1 += get(p, 3) * r1;
+    Z += get(p, 5 + 4 * v) * exp2_diff(get(p, 4 + 4 * v), M);
+    U0 += get(p, 6 + 4 * v) * r0;
+    U1 += get(p, 7 + 4 * v) * r1;
+  }
+}
+
+// One CTA per sample -- or, as a launch attribute, a CLUSTER of 2..8 CTAs per sample: CTA `rank` streams its slice of the K
+// prototypes of the sample's 2 + NC logit rows and the partial online states meet in CTA 0 through distributed shared
+// memory (measured slower, see the launcher). Arithmetic in the log2 domain (one FMUL less per ex2).
 template <int NC>
 __global__ void __launch_bounds__(LOSS_THREADS)
 dino_loss_fwd_kernel(const __nv_bfloat16* __restrict__ student, const __nv_bfloat16* __restrict__ teacher,
                      const float* __restrict__ center, float* __restrict__ loss, float* __restrict__ s_lse,
                      float* __restrict__ t_lse, int B, int K, float inv_ts, float inv_tt) {
-  const int b = blockIdx.x;
+  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+  pdl_wait();
+  const uint32_t cs = cluster_nctarank(), rank = cluster_ctarank();
+  const int b = blockIdx.x / cs;
   const int tid = threadIdx.x;
+  const int n8 = K / 8, per = (n8 + static_cast<int>(cs) - 1) / static_cast<int>(cs);
+  const int k_lo = static_cast<int>(rank) * per, k_hi = min(n8, k_lo + per);
+  const float ts2 = inv_ts * kLog2e, tt2 = inv_tt * kLog2e;
   float tm[2] = {-INFINITY, -INFINITY}, tz[2] = {0.f, 0.f};
   float sm[NC], sz[NC], u0[NC], u1[NC];
 #pragma unroll
   for (int v = 0; v < NC; ++v) { sm[v] = -INFINITY; sz[v] = 0.f; u0[v] = 0.f; u1[v] = 0.f; }
 
-  for (int k8 = tid; k8 < K / 8; k8 += LOSS_THREADS) {
+  for (int k8 = k_lo + tid; k8 < k_hi; k8 += LOSS_THREADS) {
     float w[2][8];
     const float4 c0 = __ldg(reinterpret_cast<const float4*>(center) + 2 * k8);
     const float4 c1 = __ldg(reinterpret_cast<const float4*>(center) + 2 * k8 + 1);
@@ -58,12 +98,12 @@ dino_loss_fwd_kernel(const __nv_bfloat16* __restrict__ student, const __nv_bfloa
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = unpack_bf16x2(tw[e]);
-        a[2 * e] = (f.x - cc[2 * e]) * inv_tt;
-        a[2 * e + 1] = (f.y - cc[2 * e + 1]) * inv_tt;
+        a[2 * e] = (f.x - cc[2 * e]) * tt2;
+        a[2 * e + 1] = (f.y - cc[2 * e + 1]) * tt2;
         mx = fmaxf(mx, fmaxf(a[2 * e], a[2 * e + 1]));
       }
       if (mx > tm[iq]) {  // rescale the running sums to the new max (rare after the first chunks)
-        const float r = __expf(tm[iq] - mx);
+        const float r = ex2_approx(tm[iq] - mx);
         tz[iq] *= r;
         if (iq == 0) {
 #pragma unroll
@@ -77,7 +117,7 @@ dino_loss_fwd_kernel(const __nv_bfloat16* __restrict__ student, const __nv_bfloa
       float zs = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        w[iq][e] = __expf(a[e] - tm[iq]);
+        w[iq][e] = ex2_approx(a[e] - tm[iq]);
         zs += w[iq][e];
       }
       tz[iq] += zs;
@@ -91,20 +131,20 @@ dino_loss_fwd_kernel(const __nv_bfloat16* __restrict__ student, const __nv_bfloa
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = unpack_bf16x2(sw[e]);
-        x[2 * e] = f.x * inv_ts;
-        x[2 * e + 1] = f.y * inv_ts;
+        x[2 * e] = f.x * ts2;
+        x[2 * e + 1] = f.y * ts2;
         mx = fmaxf(mx, fmaxf(x[2 * e], x[2 * e + 1]));
       }
       if (mx > sm[v]) {
-        sz[v] *= __expf(sm[v] - mx);
+        sz[v] *= ex2_approx(sm[v] - mx);
         sm[v] = mx;
       }
       float zs = 0.f, d0 = 0.f, d1 = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        zs += __expf(x[e] - sm[v]);
-        d0 += w[0][e] * x[e];
-        d1 += w[1][e] * x[e];
+        zs += ex2_approx(x[e] - sm[v]);
+        d0 = fmaf(w[0][e], x[e], d0);
+        d1 = fmaf(w[1][e], x[e], d1);
       }
       sz[v] += zs;
       u0[v] += d0;
@@ -112,8 +152,11 @@ dino_loss_fwd_kernel(const __nv_bfloat16* __restrict__ student, const __nv_bfloa
     }
   }
 
-  // ---- block reduction of the online states (warp shuffles, then one smem round) ----
-  __shared__ float red[LOSS_THREADS / 32][4 + 4 * NC];
+  // ---- reduction of the online states: warp shuffles, one smem round per CTA, one DSMEM round per cluster ----
+  constexpr int NW = LOSS_THREADS / 32;
+  constexpr int PART = 4 + 4 * NC;
+  __shared__ float red[NW][PART];
+  __shared__ float part[PART];
   const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -122,7 +165,7 @@ dino_loss_fwd_kernel(const __nv_bfloat16* __restrict__ student, const __nv_bfloa
       const float m2 = __shfl_xor_sync(0xffffffffu, tm[iq], o);
       const float z2 = __shfl_xor_sync(0xffffffffu, tz[iq], o);
       const float mn = fmaxf(tm[iq], m2);
-      const float r1 = exp_diff(tm[iq], mn), r2 = exp_diff(m2, mn);
+      const float r1 = exp2_diff(tm[iq], mn), r2 = exp2_diff(m2, mn);
       tz[iq] = tz[iq] * r1 + z2 * r2;
 #pragma unroll
       for (int v = 0; v < NC; ++v) {
@@ -136,7 +179,9 @@ dino_loss_fwd_kernel(const __nv_bfloat16* __restrict__ student, const __nv_bfloa
     for (int v = 0; v < NC; ++v) {
       const float m2 = __shfl_xor_sync(0xffffffffu, sm[v], o);
       const float z2 = __shfl_xor_sync(0xffffffffu, sz[v], o);
-      lse_merge(sm[v], sz[v], m2, z2);
+      const float mn = fmaxf(sm[v], m2);
+      sz[v] = sz[v] * exp2_diff(sm[v], mn) + z2 * exp2_diff(m2, mn);
+      sm[v] = mn;
     }
   }
   if (lane == 0) {
@@ -150,32 +195,38 @@ dino_loss_fwd_kernel(const __nv_bfloat16* __restrict__ student, const __nv_bfloa
     }
   }
   __syncthreads();
-  if (tid == 0) {
-    constexpr int NW = LOSS_THREADS / 32;
-    float M0 = -INFINITY, M1 = -INFINITY;
-    for (int w = 0; w < NW; ++w) { M0 = fmaxf(M0, red[w][0]); M1 = fmaxf(M1, red[w][2]); }
-    float Z0 = 0.f, Z1 = 0.f;
-    for (int w = 0; w < NW; ++w) { Z0 += red[w][1] * exp_diff(red[w][0], M0); Z1 += red[w][3] * exp_diff(red[w][2], M1); }
-    t_lse[b] = M0 + logf(Z0);
-    t_lse[B + b] = M1 + logf(Z1);
-    float total = 0.f;
-    for (int v = 0; v < NC; ++v) {
-      float M = -INFINITY;
-      for (int w = 0; w < NW; ++w) M = fmaxf(M, red[w][4 + 4 * v]);
-      float Z = 0.f, U0 = 0.f, U1 = 0.f;
-      for (int w = 0; w < NW; ++w) {
-        Z += red[w][5 + 4 * v] * exp_diff(red[w][4 + 4 * v], M);
-        U0 += red[w][6 + 4 * v] * exp_diff(red[w][0], M0);
-        U1 += red[w][7 + 4 * v] * exp_diff(red[w][2], M1);
-      }
-      const float lse = M + logf(Z);
-      s_lse[static_cast<long long>(v) * B + b] = lse;
-      if (v != 0) total += lse - U0 / Z0;
-      if (v != 1) total += lse - U1 / Z1;
+  float M0, Z0, M1, Z1, M, Z, U0, U1;
+  if (tid < NC) {  // thread v merges crop v over the warps of this CTA
+    merge_parts([&](int p, int i) { return red[p][i]; }, NW, tid, M0, Z0, M1, Z1, M, Z, U0, U1);
+    if (cs > 1) {
+      if (tid == 0) { part[0] = M0; part[1] = Z0; part[2] = M1; part[3] = Z1; }
+      part[4 + 4 * tid] = M; part[5 + 4 * tid] = Z; part[6 + 4 * tid] = U0; part[7 + 4 * tid] = U1;
     }
-    const int n_pairs = 2 * NC - 2;
-    atomicAdd(loss, total / (static_cast<float>(B) * n_pairs));
   }
+  if (cs > 1) {
+    cluster_sync_all();  // every CTA's `part` is written (release / acquire at cluster scope)
+    if (rank == 0 && tid < NC)
+      merge_parts([&](int p, int i) { return ld_cluster_f32(&part[i], static_cast<uint32_t>(p)); }, static_cast<int>(cs), tid,
+                  M0, Z0, M1, Z1, M, Z, U0, U1);
+  }
+  if (rank == 0 && tid < 32) {
+    float total = 0.f;
+    if (tid < NC) {
+      const float lse2 = M + log2f(Z);
+      s_lse[static_cast<long long>(tid) * B + b] = lse2 * kLn2;
+      // sum_k t_iq[k] * x[k] = U / Z_t (in log2 units, like lse2)
+      if (tid != 0) total += lse2 - U0 / Z0;
+      if (tid != 1) total += lse2 - U1 / Z1;
+      if (tid == 0) {
+        t_lse[b] = (M0 + log2f(Z0)) * kLn2;
+        t_lse[B + b] = (M1 + log2f(Z1)) * kLn2;
+      }
+    }
+    total = warp_sum(total);
+    const int n_pairs = 2 * NC - 2;
+    if (tid == 0) atomicAdd(loss, total * kLn2 / (static_cast<float>(B) * n_pairs));
+  }
+  if (cs > 1) cluster_sync_all();  // the other CTAs' shared memory must outlive CTA 0's reads
 }
 
 template <int NC>
@@ -260,11 +311,18 @@ extern "C" int b200ssl_dino_loss_fwd(const void* student, const void* teacher, c
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   B200SSL_CHECK(B > 0 && K > 0 && K % 8 == 0, -2, "dino_loss: B=%d K=%d (K must be a multiple of 8)", B, K);
   B200SSL_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+  // One CTA per sample by default. B200SSL_LOSS_CLUSTER=2|4|8 (developer A/B, read per call) spreads a sample over a
+  // cluster; measured at B = 256, 12 crops, K = 65,536: 142 us (1) / 150 (2) / 162 (4) / 190 (8) -- the kernel is bound by
+  // issue + MUFU (112 ex2 and ~900 instructions per thread and iteration), not by the 256-on-148 placement, and every
+  // extra CTA repeats the 52-value butterfly reduction.
+  const char* env_cs = getenv("B200SSL_LOSS_CLUSTER");
+  const int max_cs = env_cs ? atoi(env_cs) : 1;
+  int cs = 1;
+  while (cs < max_cs && cs < 8 && (K / 8) / (cs * 2) >= 2 * LOSS_THREADS) cs *= 2;
 #define CALL_F(NC)                                                                                          \
-  dino_loss_fwd_kernel<NC><<<B, LOSS_THREADS, 0, s>>>(static_cast<const __nv_bfloat16*>(student),           \
-                                                      static_cast<const __nv_bfloat16*>(teacher), center,  \
-                                                      loss, s_lse, t_lse, B, K, 1.f / student_temp,         \
-                                                      1.f / teacher_temp)
+  B200SSL_CUDA(launch_pdl(dino_loss_fwd_kernel<NC>, dim3(B * cs), dim3(LOSS_THREADS), 0, s, cs,             \
+                          static_cast<const __nv_bfloat16*>(student), static_cast<const __nv_bfloat16*>(teacher), \
+                          center, loss, s_lse, t_lse, B, K, 1.f / student_temp, 1.f / teacher_temp))
   NC_DISPATCH(ncrops, CALL_F)
 #undef CALL_F
   B200SSL_CUDA(cudaGetLastError());

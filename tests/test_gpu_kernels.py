@@ -247,8 +247,10 @@ def test_attention_forward_kernel_choices_agree(ops, mode):
     assert rel(lse, lse_ref) < 1e-5
 
 
-@pytest.mark.parametrize("ncrops,B,K", [(2, 8, 1024), (4, 5, 4096), (12, 3, 65536)])
-def test_dino_loss(ops, ncrops, B, K):
+@pytest.mark.parametrize("ncrops,B,K", [(2, 8, 1024), (4, 5, 4096), (12, 3, 65536), (3, 2, 8192), (5, 4, 8200), (12, 150, 65536)])
+@pytest.mark.parametrize("cluster", [1, 4])
+def test_dino_loss(ops, ncrops, B, K, cluster, monkeypatch):
+    monkeypatch.setenv("B200SSL_LOSS_CLUSTER", str(cluster))   # developer switch: a cluster of CTAs per sample
     from oracle.dino import DINOLoss as OracleLoss
     g = torch.Generator(device="cuda").manual_seed(6)
     s = (torch.randn(ncrops * B, K, device="cuda", generator=g)).bfloat16()
