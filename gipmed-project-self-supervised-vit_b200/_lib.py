@@ -11,7 +11,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200ssl.so")
+# B200SSL_LIB: another build of the same library (developer A/B of kernel versions); default = the in-tree build
+LIB_PATH = os.environ.get("B200SSL_LIB") or os.path.join(_HERE, "libb200ssl.so")
 
 _lib = None
 

@@ -36,6 +36,9 @@ struct AttnArgs {
   float* lse2;
   const __nv_bfloat16* out;   // bwd only
   const __nv_bfloat16* dout;  // bwd only
+  __nv_bfloat16* dq;          // bwd only: dqkv at the first query row of this launch's block ([B, Ns, 3, H, 64] layout)
+  __nv_bfloat16* dkv;         // bwd only: dqkv at the first key row of this launch's block
+  int dq_rows, dkv_rows;      // bwd only: query / key rows that exist behind dq / dkv (rows past them are not stored)
   unsigned long long* prof;   // developer instrumentation (null = off): per-phase cycle counters of one softmax thread
 };
 
@@ -136,13 +139,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for the compiler (MMA issuer)
   pdl_launch_dependents();  // set-up done: the next kernel may begin its own; then wait for the QKV producer
   pdl_wait();
 
   if (warp == 16) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int k = 0;
       for (int round = blockIdx.x; round < num_rounds; round += gridDim.x, ++k) {
         const int buf = k & 1;
@@ -171,25 +174,31 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     }
   } else if (warp == 17) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // One thread, chosen by elect.sync (the compiler then emits UTCHMMA straight, without a per-active-lane loop), and
+    // descriptors that are one add behind a base computed once (sw128_desc_at): the P.V MMAs are 32 cycles of tensor
+    // work each, the issue code around them used to take ~100.
+    if (elect_one_sync()) {
       const uint32_t idesc_s = make_idesc_bf16(128, args.keys_n, false, false);
       const uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
       const int ksteps = args.keys_n / 16;
+      const uint32_t lo0 = (smem_u32(smem) & 0x3FFFFu) >> 4;
+      auto tile_lo = [&](uint8_t* tile) -> uint32_t { return lo0 + (static_cast<uint32_t>(tile - smem) >> 4); };
       auto issue_s = [&](int buf, int slot) {
-        const uint32_t a0 = smem_u32(q_tile(buf, slot)), bk = smem_u32(k_tile(buf, slot));
+        const uint32_t a0 = tile_lo(q_tile(buf, slot)), bk = tile_lo(k_tile(buf, slot));
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_ss(tmem_base + slot * 256, make_smem_desc_sw128(a0 + kk * 32, 16, 1024),
-                       make_smem_desc_sw128(bk + kk * 32, 16, 1024), idesc_s, kk > 0);
+          umma_bf16_ss(tmem_base + slot * 256, sw128_desc_at(a0, kk * 32, 16, 1024), sw128_desc_at(bk, kk * 32, 16, 1024),
+                       idesc_s, kk > 0);
         umma_commit(&bar_s[slot]);
       };
       auto issue_pv = [&](int buf, int slot) {
-        const uint32_t v0 = smem_u32(v_tile(buf, slot));
+        const uint32_t v0 = tile_lo(v_tile(buf, slot));
         const int ch0 = (ksteps + 1) / 2;  // P column map of the softmax halves (see below)
-        for (int j = 0; j < ksteps; ++j)
-          umma_bf16_ts(tmem_base + slot * 256 + 192,
-                       tmem_base + slot * 256 + (j < ch0 ? 8 * j : 16 * ch0 + 8 * (j - ch0)),
-                       make_smem_desc_sw128(v0 + j * 2048, 8192, 1024), idesc_o, j > 0);
+        const uint32_t t_o = tmem_base + slot * 256 + 192, t_p0 = tmem_base + slot * 256, t_p1 = t_p0 + 8 * ch0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < ksteps)
+            umma_bf16_ts(t_o, (j < ch0 ? t_p0 : t_p1) + 8 * j, sw128_desc_at(v0, j * 2048, 8192, 1024), idesc_o, j > 0);
         umma_commit(&bar_o[slot]);
       };
       if (args.dephase) {
@@ -446,21 +455,24 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 // smem: operand sets [Q (NT) | dO (NT) | K (NT) | V (NT)] x SETS | P (2 chunks) | dS (2 chunks) | barriers |
 //       row constants (2 buffers). NT == 1 (N <= 128, packed local crops) has two operand sets, so the loads of
 //       item i+1 fly during the whole of item i; NT == 2 re-loads its single set as soon as the last MMA of the
-//       item has retired, under the store epilogue.
+//       item has retired.
 // TMEM: S [0,128) | dP [128,256) | dQ_t [256+64t) | dK [384,448) | dV [448,512), allocated once per CTA.
 // warps: 0      = control: TMA loads + every tcgen05.mma. S/dP of the NEXT pair is issued as soon as the math
 //                 warps hold the current S/dP in registers, i.e. before the dQ/dK/dV MMAs of the current pair.
-//        1..3   = row-constant producers: delta = sum_d dO*O and lse2 of item i+1 while item i computes.
-//        4..19  = math/epilogue, four threads per query row (32 key columns each).
+//        1..3, 20 = auxiliary group (one warp per TMEM lane quarter): row constants delta = sum_d dO*O and lse2 of
+//                 item i+1 while item i computes, AND the drain of the finished dK / dV / dQ accumulators: TMEM ->
+//                 bf16 -> global memory straight from registers (each thread owns one 128-byte output row; 256-bit
+//                 stores, vector red.add in the accumulating long-sequence mode). The math warps never wait for the
+//                 dK/dV MMAs and never store: they go from one pair's P/dS straight to the next pair's scores.
+//        4..19  = math, four threads per query row (32 key columns each).
 constexpr int BWD_MATH_THREADS = 512;
-constexpr int BWD_ROWC_THREADS = 96;
-constexpr int BWD_THREADS = 128 + BWD_MATH_THREADS;
+constexpr int BWD_AUX_THREADS = 128;
+constexpr int BWD_THREADS = 128 + BWD_MATH_THREADS + 32;
 
 template <int NT>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV,
-                     const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQKV,
-                     const __grid_constant__ CUtensorMap tmDKV, const AttnArgs args, const int num_items) {
+                     const __grid_constant__ CUtensorMap tmDO, const AttnArgs args, const int num_items) {
   constexpr int SETS = NT == 1 ? 2 : 1;
   constexpr int PPI = NT * NT;                    // (key tile, query tile) pairs per item
   constexpr int SET_BYTES = 4 * NT * TILE_BYTES;  // Q | dO | K | V
@@ -477,8 +489,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint64_t* bar_mma = bars + 5;       // dQ/dK/dV MMAs of the pair finished
   uint64_t* bar_rowc_full = bars + 6; // [2] row constants of an item written
   uint64_t* bar_rowc_free = bars + 8; // [2] ... and copied to registers by every math thread
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  float* rowc = reinterpret_cast<float*>(bars + 16);  // [2][NT*128][2]: delta, lse2
+  uint64_t* bar_dkv_ready = bars + 10; // every MMA up to the last pair of a key tile has retired: dK / dV complete
+  uint64_t* bar_dkv_free = bars + 11;  // the auxiliary group has read dK / dV out of TMEM
+  uint64_t* bar_dq_free = bars + 12;   // ... and the dQ tiles of the item
+  uint64_t* bar_grp = bars + 13;       // [4] NT == 2: operand groups {K0,V0} {Q0,dO0} {Q1,dO1} {K1,V1} of the single set
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  float* rowc = reinterpret_cast<float*>(bars + 24);  // [2][NT*128][2]: delta, lse2
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_my = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -512,8 +528,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmDO);
-    tma_prefetch_desc(&tmDQKV);
-    tma_prefetch_desc(&tmDKV);
     mbar_init(&bar_load[0], 1);
     mbar_init(&bar_load[1], 1);
     mbar_init(bar_sdp, 1);
@@ -522,9 +536,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     mbar_init(bar_pds, BWD_MATH_THREADS / 32);
     mbar_init(bar_mma, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_rowc_full[i], BWD_ROWC_THREADS / 32);
+      mbar_init(&bar_rowc_full[i], BWD_AUX_THREADS / 32);
       mbar_init(&bar_rowc_free[i], BWD_MATH_THREADS / 32);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_grp[i], 1);
+    mbar_init(bar_dkv_ready, 1);
+    mbar_init(bar_dkv_free, BWD_AUX_THREADS / 32);
+    mbar_init(bar_dq_free, BWD_AUX_THREADS / 32);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -539,7 +557,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for the compiler: the MMA issuer
+                                                                       // keeps it in a uniform register
   const uint32_t T_S = tmem_base, T_DP = tmem_base + 128, T_DQ = tmem_base + 256, T_DK = tmem_base + 384,
                  T_DV = tmem_base + 448;
   pdl_launch_dependents();
@@ -547,7 +566,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------------------------ control: TMA + MMA issue
-    if (lane == 0 && n_my > 0) {
+    // (elect.sync, not lane == 0: the compiler then knows a single thread runs this and issues the uniform-datapath
+    //  instructions -- UTCHMMA, UTMALDG -- straight, without a per-active-lane loop around each of them)
+    if (n_my > 0 && elect_one_sync()) {
       auto issue_load = [&](int k) {
         const Item it = decode(item_of(k));
         const int head = it.head, b0 = it.b0;
@@ -580,89 +601,173 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       };
       const uint32_t idesc_q = make_idesc_bf16(128, 64, false, true);  // dQ: A K-major, B MN-major
       const uint32_t idesc_kv = make_idesc_bf16(128, 64, true, true);  // dK/dV: both MN-major
-      auto issue_sdp = [&](int k, int p) {
+      // descriptors: every operand lies a compile-time number of bytes behind the 1024-aligned smem base (plus the set
+      // offset when there are two sets), so each one is a single add to `lo0` / `los` (common.cuh: sw128_desc_at)
+      const uint32_t lo0 = (smem_u32(smem) & 0x3FFFFu) >> 4;
+      constexpr uint32_t P_OFF = SETS * SET_BYTES, DS_OFF = P_OFF + 2 * TILE_BYTES;
+      auto set_lo = [&](int k) -> uint32_t { return lo0 + (SETS == 2 ? (k & 1) : 0) * (SET_BYTES >> 4); };
+      auto issue_sdp = [&](uint32_t los, int p, int keys_n) {
         const int u = p / NT, t = p % NT;
-        const int ku = max(16, min(128, decode(item_of(k)).keys_n - u * 128));  // keys in this key tile (multiple of 16;
-                                                                   // an empty tile of a short key block still runs on zeros)
+        const int ku = max(16, min(128, keys_n - u * 128));  // keys in this key tile (multiple of 16; an empty tile of a
+                                                             // short key block still runs on zeros)
         const uint32_t idesc_s = make_idesc_bf16(128, ku, false, false);
-        const uint32_t base = smem_u32(set_base(k));
-        const uint32_t q_t = base + t * TILE_BYTES, do_t = base + (NT + t) * TILE_BYTES;
-        const uint32_t k_u = base + (2 * NT + u) * TILE_BYTES, v_u = base + (3 * NT + u) * TILE_BYTES;
+        const uint32_t q_t = t * TILE_BYTES, do_t = (NT + t) * TILE_BYTES;
+        const uint32_t k_u = (2 * NT + u) * TILE_BYTES, v_u = (3 * NT + u) * TILE_BYTES;
+        // S and dP are independent accumulation chains: issued alternately, so an MMA never queues right behind the one
+        // it accumulates onto (back-to-back MMAs into ONE accumulator ran at ~100 cycles each whatever their N)
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_ss(T_S, make_smem_desc_sw128(q_t + kk * 32, 16, 1024), make_smem_desc_sw128(k_u + kk * 32, 16, 1024),
-                       idesc_s, kk > 0);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_ss(T_DP, make_smem_desc_sw128(do_t + kk * 32, 16, 1024),
-                       make_smem_desc_sw128(v_u + kk * 32, 16, 1024), idesc_s, kk > 0);
+        for (int kk = 0; kk < 4; ++kk) {
+          umma_bf16_ss(T_S, sw128_desc_at(los, q_t + kk * 32, 16, 1024), sw128_desc_at(los, k_u + kk * 32, 16, 1024), idesc_s,
+                       kk > 0);
+          umma_bf16_ss(T_DP, sw128_desc_at(los, do_t + kk * 32, 16, 1024), sw128_desc_at(los, v_u + kk * 32, 16, 1024), idesc_s,
+                       kk > 0);
+        }
         umma_commit(bar_sdp);
       };
-      auto issue_dqkv = [&](int k, int p) {
+      auto issue_dqkv = [&](uint32_t los, int p, int keys_n, int nq) {
         const int u = p / NT, t = p % NT;
-        const Item it = decode(item_of(k));
-        const int ku = max(16, min(128, it.keys_n - u * 128));
-        const uint32_t base = smem_u32(set_base(k));
-        const uint32_t q_t = base + t * TILE_BYTES, do_t = base + (NT + t) * TILE_BYTES;
-        const uint32_t k_u = base + (2 * NT + u) * TILE_BYTES;
-        const uint32_t p0 = smem_u32(sP), ds0 = smem_u32(sdS);
-        // dQ_t (+)= dS[128 q, ku keys] . K_u[ku keys, 64]
-        for (int j = 0; j < ku / 16; ++j)
-          umma_bf16_ss(T_DQ + t * 64, make_smem_desc_sw128(ds0 + (j >> 2) * TILE_BYTES + (j & 3) * 32, 16, 1024),
-                       make_smem_desc_sw128(k_u + j * 2048, 8192, 1024), idesc_q, (u > 0 || j > 0));
-        // dV_u (+)= P^T[128 keys, 128 q] . dO_t[128 q, 64] ; dK_u (+)= dS^T . Q_t. The reduction runs over the query rows
-        // of tile t: rows past the sequence end hold P = dS = 0 (lse2 = +inf), so only the live 16-row steps are issued
-        const int qsteps = (max(0, min(128, it.nq - t * 128)) + 15) >> 4;
-        for (int j = 0; j < qsteps; ++j)
-          umma_bf16_ss(T_DV, make_smem_desc_sw128(p0 + j * 2048, TILE_BYTES, 1024),
-                       make_smem_desc_sw128(do_t + j * 2048, 8192, 1024), idesc_kv, (t > 0 || j > 0));
-        for (int j = 0; j < qsteps; ++j)
-          umma_bf16_ss(T_DK, make_smem_desc_sw128(ds0 + j * 2048, TILE_BYTES, 1024),
-                       make_smem_desc_sw128(q_t + j * 2048, 8192, 1024), idesc_kv, (t > 0 || j > 0));
+        const int nk = max(16, min(128, keys_n - u * 128)) >> 4;
+        const uint32_t q_t = t * TILE_BYTES, do_t = (NT + t) * TILE_BYTES, k_u = (2 * NT + u) * TILE_BYTES;
+        // dQ_t (+)= dS[128 q, ku keys] . K_u[ku keys, 64] ; dV_u (+)= P^T[128 keys, 128 q] . dO_t[128 q, 64] ;
+        // dK_u (+)= dS^T . Q_t. The dK / dV reductions run over the query rows of tile t: rows past the sequence end hold
+        // P = dS = 0 (lse2 = +inf), so only the live 16-row steps are issued. Three independent accumulation chains,
+        // issued round-robin.
+        const int qsteps = (max(0, min(128, nq - t * 128)) + 15) >> 4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < nk)
+            umma_bf16_ss(T_DQ + t * 64, sw128_desc_at(lo0, DS_OFF + (j >> 2) * TILE_BYTES + (j & 3) * 32, 16, 1024),
+                         sw128_desc_at(los, k_u + j * 2048, 8192, 1024), idesc_q, (u > 0 || j > 0));
+          if (j < qsteps) {
+            umma_bf16_ss(T_DV, sw128_desc_at(lo0, P_OFF + j * 2048, TILE_BYTES, 1024),
+                         sw128_desc_at(los, do_t + j * 2048, 8192, 1024), idesc_kv, (t > 0 || j > 0));
+            umma_bf16_ss(T_DK, sw128_desc_at(lo0, DS_OFF + j * 2048, TILE_BYTES, 1024),
+                         sw128_desc_at(los, q_t + j * 2048, 8192, 1024), idesc_kv, (t > 0 || j > 0));
+          }
+        }
         umma_commit(bar_mma);
       };
 
-      issue_load(0);
-      if (SETS == 2 && n_my > 1) issue_load(1);
-      wait_load(0);
-      issue_sdp(0, 0);
+      // NT == 2 has ONE operand set (128 KB) and re-fills it group by group as the pairs of the item retire: pair order is
+      // (u,t) = (0,0) (0,1) (1,0) (1,1), so {K0,V0} is dead after pair 1 and {Q0,dO0} after pair 2 -- the next item's first
+      // scores are issued right behind the last dQ/dK/dV MMAs of this one, with no load latency in between.
+      auto issue_group = [&](int k, int g) {
+        const Item it = decode(item_of(k));
+        const int head = it.head, b0 = it.b0;
+        uint8_t* sQ = set_base(k);
+        uint8_t* sdO = sQ + NT * TILE_BYTES;
+        uint8_t* sK = sdO + NT * TILE_BYTES;
+        uint8_t* sV = sK + NT * TILE_BYTES;
+        const int cq = head * 64, ck = (args.H + head) * 64, cv = (2 * args.H + head) * 64;
+        uint64_t* bar = &bar_grp[g];
+        mbar_expect_tx(bar, 2 * TILE_BYTES);
+        const int t = (g == 0 || g == 1) ? 0 : 1;
+        if (g == 0 || g == 3) {
+          tma_load_3d(sK + t * TILE_BYTES, &tmKV, bar, ck, it.k0 + t * 128, b0);
+          tma_load_3d(sV + t * TILE_BYTES, &tmKV, bar, cv, it.k0 + t * 128, b0);
+        } else {
+          tma_load_3d(sQ + t * TILE_BYTES, &tmQKV, bar, cq, it.q0 + t * 128, b0);
+          tma_load_3d(sdO + t * TILE_BYTES, &tmDO, bar, cq, it.q0 + t * 128, b0);
+        }
+      };
+      auto wait_group = [&](int k, int g) { mbar_wait(&bar_grp[g], k & 1); };
+
+      if (NT == 2) {
+        for (int g = 0; g < 4; ++g) issue_group(0, g);
+        wait_group(0, 0);
+        wait_group(0, 1);
+      } else {
+        issue_load(0);
+        if (n_my > 1) issue_load(1);
+        wait_load(0);
+      }
+      Item cur = decode(item_of(0));
+      issue_sdp(set_lo(0), 0, cur.keys_n);
+      // developer instrumentation of the issuing thread (counters 9..15): cycles waiting for [9] the math warps to take
+      // S/dP, [10] operand loads, [11] P/dS in smem, [12] the accumulator drain, [14] the item's last MMAs; [13] / [15] =
+      // cycles inside the S/dP / dQ,dK,dV issue code (back-pressure of the MMA queue shows up here)
+      const bool cprof = args.prof != nullptr;
+      long long ct0 = cprof ? clock64() : 0;
+      auto clap = [&](int idx) {
+        if (cprof) {
+          const long long now = clock64();
+          atomicAdd(args.prof + idx, static_cast<unsigned long long>(now - ct0));
+          ct0 = now;
+        }
+      };
       int gp = 0;
       for (int k = 0; k < n_my; ++k) {
+        const Item nxt = k + 1 < n_my ? decode(item_of(k + 1)) : cur;
+        const uint32_t los = set_lo(k), los_n = set_lo(k + 1);
+#pragma unroll
         for (int p = 0; p < PPI; ++p, ++gp) {
           mbar_wait(bar_sdp_free, gp & 1);  // the math warps hold S/dP(gp) in registers
           tcgen05_fence_after();
+          clap(9);
           const bool last = p + 1 == PPI;
           if (!last) {
-            issue_sdp(k, p + 1);
-          } else if (SETS == 2 && k + 1 < n_my) {
+            if (NT == 2 && p == 0) wait_group(k, 2);  // pair 1 = (K0,V0,Q1,dO1)
+            if (NT == 2 && p == 1) wait_group(k, 3);  // pair 2 = (K1,V1,Q0,dO0)
+            clap(10);
+            issue_sdp(los, p + 1, cur.keys_n);
+            clap(13);
+          } else if (NT == 1 && k + 1 < n_my) {
             wait_load(k + 1);
-            issue_sdp(k + 1, 0);
+            clap(10);
+            issue_sdp(los_n, 0, nxt.keys_n);
+            clap(13);
           }
           mbar_wait(bar_pds, gp & 1);
+          clap(11);
+          if (p % NT == 0) {
+            // first pair of a key tile: its MMAs overwrite dK / dV (at p == 0 dQ as well) -- the auxiliary group must
+            // have read the previous contents out of TMEM
+            const int gk = k * NT + p / NT;
+            if (gk > 0) mbar_wait(bar_dkv_free, (gk - 1) & 1);
+            if (p == 0 && k > 0) mbar_wait(bar_dq_free, (k - 1) & 1);
+          }
           tcgen05_fence_after();
-          issue_dqkv(k, p);
+          clap(12);
+          issue_dqkv(los, p, cur.keys_n, cur.nq);
+          if (p % NT == NT - 1) umma_commit(bar_dkv_ready);
+          clap(15);
+          if (NT == 2 && k + 1 < n_my) {
+            // bar_pds(gp) implies bar_mma(gp - 1): every math warp waited for it before writing P / dS of this pair
+            if (p == 2) issue_group(k + 1, 0);
+            if (p == 3) {
+              issue_group(k + 1, 1);
+              wait_group(k + 1, 0);
+              wait_group(k + 1, 1);
+              clap(10);
+              issue_sdp(los_n, 0, nxt.keys_n);  // the math warps hold S/dP of pair 3 (bar_sdp_free above): T_S / T_DP are free
+              clap(13);
+            }
+          }
           if (last) {
             mbar_wait(bar_mma, gp & 1);  // every MMA of the item has retired: its operand set is free again
-            if (SETS == 2) {
+            clap(14);
+            if (NT == 1) {
               if (k + 2 < n_my) issue_load(k + 2);
             } else if (k + 1 < n_my) {
-              issue_load(k + 1);
-              wait_load(k + 1);
-              issue_sdp(k + 1, 0);
+              issue_group(k + 1, 2);
+              issue_group(k + 1, 3);
             }
           }
         }
+        cur = nxt;
       }
     }
-  } else if (warp < 4) {
-    // ------------------------------------------------------------------ row constants of item k (one ahead)
-    const int ptid = threadIdx.x - 32;  // 0..95
-    for (int k = 0; k < n_my; ++k) {
+  } else if (warp < 4 || warp == 20) {
+    // ------------------------------------------------------------------ auxiliary group: row constants + accumulator drain
+    const int aq = warp & 3;          // TMEM lane quarter (warp 20 takes quarter 0, the control warp's)
+    const int ar = aq * 32 + lane;    // the tile row this thread drains; also its index in the group
+    const uint32_t lane_off = static_cast<uint32_t>(aq * 32) << 16;
+    auto produce_rowc = [&](int k) {
       const Item it = decode(item_of(k));
       const int head = it.head, b0 = it.b0;
       float* rc = rowc + (k & 1) * (NT * 128 * 2);
       mbar_wait(&bar_rowc_free[k & 1], ((k >> 1) & 1) ^ 1);
-      for (int idx = ptid; idx < NT * 128; idx += BWD_ROWC_THREADS) {
+      for (int idx = ar; idx < NT * 128; idx += BWD_AUX_THREADS) {
         int lo_, hi_;
         bool row_valid;
         key_range(args, NT, idx, lo_, hi_, row_valid);
@@ -691,9 +796,82 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_rowc_full[k & 1]);
+    };
+    // 128x64 fp32 accumulator at TMEM column `tcol` -> bf16 -> row `row0 + ar` of `base` (a [B, Ns, 3, H, 64] tensor seen
+    // from its first row of this launch), 64 columns from `gcol`. One thread = one 128-byte output row: four 256-bit
+    // stores, or eight 128-bit bf16x2 vector reductions when the launch accumulates (long-sequence block pairs).
+    auto drain = [&](uint32_t tcol, __nv_bfloat16* base, int rows_behind, bool accumulate, int gcol, int row0, int b0) {
+      bool valid;
+      int b, n;
+      if (NT == 1) {
+        valid = ar < args.rows;
+        b = b0 + (valid ? ar / args.N : 0);
+        n = valid ? ar % args.N : 0;
+        valid = valid && b < args.B;
+      } else {
+        b = b0;
+        n = row0 + ar;
+        valid = n < rows_behind;
+      }
+      __nv_bfloat16* dst = base + (static_cast<long long>(b) * args.Ns + n) * (3LL * args.H * 64) + gcol;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tcol + lane_off + hf * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              pk[e] = pack_bf16x2(__uint_as_float(v[16 * j + 2 * e]), __uint_as_float(v[16 * j + 2 * e + 1]));
+            __nv_bfloat16* d16 = dst + hf * 32 + j * 16;
+            if (accumulate) {
+              asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(d16), "r"(pk[0]), "r"(pk[1]),
+                           "r"(pk[2]), "r"(pk[3])
+                           : "memory");
+              asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(d16 + 8), "r"(pk[4]), "r"(pk[5]),
+                           "r"(pk[6]), "r"(pk[7])
+                           : "memory");
+            } else {
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(d16), "r"(pk[0]), "r"(pk[1]),
+                           "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                           : "memory");
+            }
+          }
+        }
+      }
+    };
+
+    // the drain is what the MMA issuer waits for (TMEM re-use), the row constants have a whole item of slack: item k + 2's
+    // are produced after item k's accumulators are out (their buffer was released when the math warps started item k)
+    if (n_my > 0) produce_rowc(0);
+    if (n_my > 1) produce_rowc(1);
+    int gk = 0;
+    for (int k = 0; k < n_my; ++k) {
+      const Item it = decode(item_of(k));
+      for (int u = 0; u < NT; ++u, ++gk) {
+        mbar_wait(bar_dkv_ready, gk & 1);
+        tcgen05_fence_after();
+        const int row0 = NT == 1 ? 0 : it.k0 + u * 128;
+        drain(T_DK, args.dkv, args.dkv_rows, args.acc_dkv != 0, (args.H + it.head) * 64, row0, it.b0);
+        drain(T_DV, args.dkv, args.dkv_rows, args.acc_dkv != 0, (2 * args.H + it.head) * 64, row0, it.b0);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dkv_free);
+      }
+      // the last key tile's barrier covers every MMA of the item: dQ is complete as well
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+        drain(T_DQ + t * 64, args.dq, args.dq_rows, args.acc_dq != 0, it.head * 64, NT == 1 ? 0 : it.q0 + t * 128, it.b0);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_dq_free);
+      if (k + 2 < n_my) produce_rowc(k + 2);
     }
   } else {
-    // ------------------------------------------------------------------ math + epilogue
+    // ------------------------------------------------------------------ math: P and dS of every pair
     const int q = warp & 3;           // TMEM lane quarter
     const int qc = (warp - 4) >> 2;   // which 32 key columns of the 128-wide key tile
     const int r = q * 32 + lane;
@@ -706,7 +884,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       bool row_valid;
       key_range(args, NT, NT == 1 ? r : t * 128 + r, lo[t], hi[t], row_valid);
     }
-    bool stores_pending = false;
     int gp = 0;
     const bool prof_on = args.prof != nullptr && leader;
     long long tp0 = prof_on ? clock64() : 0;
@@ -720,7 +897,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 
     for (int k = 0; k < n_my; ++k) {
       const Item it = decode(item_of(k));
-      const int head = it.head, b0 = it.b0;
       float delta[NT], lse2[NT];
       lap(7);
       {
@@ -735,33 +911,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         if (lane == 0) mbar_arrive(&bar_rowc_free[k & 1]);
       }
       lap(0);
-
-      // 128x64 fp32 accumulator at TMEM column `tcol` -> bf16 -> staging tile `stage` -> TMA store at
-      // (col, row0, b0). Staging tiles are the P / dS chunk buffers, dead at the points of use, so several
-      // stores are in flight at once; `stores_pending` makes the next writer of those buffers wait.
-      auto store_tile = [&](uint32_t tcol, uint8_t* stage, const CUtensorMap* tm, bool accumulate, int gcol, int row0) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(tcol + lane_off + qc * 16, v);
-        tmem_ld_wait();
-        const uint32_t st = smem_u32(stage);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          uint4 pk;
-          pk.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-          pk.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-          pk.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-          pk.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-          sts128(st + sw128_offset(r, qc * 2 + j), pk);
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, BWD_MATH_THREADS);
-        if (leader) {
-          if (accumulate) tma_reduce_add_3d(tm, stage, gcol, row0, b0);
-          else tma_store_3d(tm, stage, gcol, row0, b0);
-          tma_store_commit();
-        }
-        stores_pending = true;
-      };
 
 #pragma unroll
       for (int u = 0; u < NT; ++u) {
@@ -820,11 +969,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           if (lane == 0) mbar_arrive(bar_sdp_free);
           lap(2);
           if (gp > 0) mbar_wait(bar_mma, (gp - 1) & 1);  // previous MMAs done with sP / sdS
-          if (stores_pending) {  // tiles staged in sP / sdS: let those TMA stores finish reading
-            if (leader) tma_store_wait_read<0>();
-            named_bar_sync(1, BWD_MATH_THREADS);
-            stores_pending = false;
-          }
           if (active) {
             const uint32_t pc = smem_u32(sP) + (qc >> 1) * TILE_BYTES;
             const uint32_t dc = smem_u32(sdS) + (qc >> 1) * TILE_BYTES;
@@ -840,28 +984,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           if (lane == 0) mbar_arrive(bar_pds);
           lap(3);
 
-          if (t == NT - 1) {
-            // dK_u and dV_u are complete once this pair's MMAs retire
-            mbar_wait(bar_mma, gp & 1);
-            tcgen05_fence_after();
-            lap(4);
-            store_tile(T_DK, sP, &tmDKV, args.acc_dkv != 0, (args.H + head) * 64, NT == 1 ? 0 : it.k0 + u * 128);
-            store_tile(T_DV, sP + TILE_BYTES, &tmDKV, args.acc_dkv != 0, (2 * args.H + head) * 64, NT == 1 ? 0 : it.k0 + u * 128);
-            // the dK/dV accumulators are re-used by the next key tile: order these reads before its MMAs
-            tcgen05_fence_before();
-            lap(5);
-          }
         }
       }
-      // dQ tiles (complete after the last pair; bar_mma already waited on above)
-#pragma unroll
-      for (int t = 0; t < NT; ++t)
-        store_tile(T_DQ + t * 64, sdS + t * TILE_BYTES, &tmDQKV, args.acc_dq != 0, head * 64, NT == 1 ? 0 : it.q0 + t * 128);
-      tcgen05_fence_before();
-      lap(6);
       if (prof_on) atomicAdd(args.prof + 8, 1ull);
     }
-    if (leader) tma_store_wait_all<0>();
   }
 
   tcgen05_fence_before();
@@ -948,13 +1074,13 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for the compiler (MMA issuer)
   pdl_launch_dependents();
   pdl_wait();
 
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int g = 0;
       for (int k = 0; k < n_my; ++k) {
         const int item = item_of(k);
@@ -975,9 +1101,12 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
       }
     }
   } else if (warp == 9) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (elect.sync + one-add descriptors,
+    // see the two-tile kernel: the issue code, not the tensor pipe, used to bound the N = 64 P.V MMAs)
+    if (elect_one_sync()) {
       const uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
+      const uint32_t lo0 = (smem_u32(smem) & 0x3FFFFu) >> 4;
+      auto tile_lo = [&](uint8_t* tile) -> uint32_t { return lo0 + (static_cast<uint32_t>(tile - smem) >> 4); };
       const int total = n_my * nkb;
       int gs = 0, gp = 0;        // blocks whose S / P.V have been issued
       int ks_item = 0, ks_j = 0; // (item, block) of gs
@@ -990,11 +1119,11 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
           mbar_wait(&k_full[ks], (gs / FS_KSTAGES) & 1);
           tcgen05_fence_after();
           const uint32_t idesc_s = make_idesc_bf16(128, keys_n_of(ks_j), false, false);
-          const uint32_t a0 = smem_u32(sQ + (ks_item & 1) * TILE_BYTES), b0 = smem_u32(sK + ks * TILE_BYTES);
+          const uint32_t a0 = tile_lo(sQ + (ks_item & 1) * TILE_BYTES), b0 = tile_lo(sK + ks * TILE_BYTES);
+          const uint32_t t_s = tmem_base + (gs % 3) * 128;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_bf16_ss(tmem_base + (gs % 3) * 128, make_smem_desc_sw128(a0 + kk * 32, 16, 1024),
-                         make_smem_desc_sw128(b0 + kk * 32, 16, 1024), idesc_s, kk > 0);
+            umma_bf16_ss(t_s, sw128_desc_at(a0, kk * 32, 16, 1024), sw128_desc_at(b0, kk * 32, 16, 1024), idesc_s, kk > 0);
           umma_commit(&k_free[ks]);
           umma_commit(&s_ready[gs % 3]);
           ++gs;
@@ -1004,11 +1133,12 @@ attention_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
         mbar_wait(&p_ready[gp % 3], (gp / 3) & 1);
         mbar_wait(&v_full[vs], (gp / FS_VSTAGES) & 1);
         tcgen05_fence_after();
-        const uint32_t v0 = smem_u32(sV + vs * TILE_BYTES);
+        const uint32_t v0 = tile_lo(sV + vs * TILE_BYTES);
         const int ksteps = keys_n_of(kp_j) / 16;
-        for (int s = 0; s < ksteps; ++s)
-          umma_bf16_ts(tmem_base + 384 + team * 64, tmem_base + (gp % 3) * 128 + 8 * s,
-                       make_smem_desc_sw128(v0 + s * 2048, 8192, 1024), idesc_o, s > 0);
+        const uint32_t t_o = tmem_base + 384 + team * 64, t_p = tmem_base + (gp % 3) * 128;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          if (s < ksteps) umma_bf16_ts(t_o, t_p + 8 * s, sw128_desc_at(v0, s * 2048, 8192, 1024), idesc_o, s > 0);
         umma_commit(&v_free[vs]);
         umma_commit(&o_ready[team]);
         ++gp;
@@ -1354,12 +1484,14 @@ static int attention_bwd_block(const __nv_bfloat16* qkv, const __nv_bfloat16* ou
   a.out = out + static_cast<long long>(q0) * H * 64;
   a.dout = dout + static_cast<long long>(q0) * H * 64;
   const long long row = 3LL * H * 64;
-  CUtensorMap tq, tkv, tdo, tdq, tdkv;
+  a.dq = dqkv + q0 * row;
+  a.dkv = dqkv + k0 * row;
+  a.dq_rows = Nq;
+  a.dkv_rows = Nk;
+  CUtensorMap tq, tkv, tdo;
   if (int rc = make_bnd_map(&tq, qkv + q0 * row, 3 * H * 64, Nq, Ns, B, nt, a.G)) return rc;
   if (int rc = make_bnd_map(&tkv, qkv + k0 * row, 3 * H * 64, Nk, Ns, B, nt, a.G)) return rc;
   if (int rc = make_bnd_map(&tdo, a.dout, H * 64, Nq, Ns, B, nt, a.G)) return rc;
-  if (int rc = make_bnd_map(&tdq, dqkv + q0 * row, 3 * H * 64, Nq, Ns, B, nt, a.G)) return rc;
-  if (int rc = make_bnd_map(&tdkv, dqkv + k0 * row, 3 * H * 64, Nk, Ns, B, nt, a.G)) return rc;
   const int num_items = groups * H;
   const int grid = num_items < sm_count() ? num_items : sm_count();
   if (nt == 1) {
@@ -1369,8 +1501,7 @@ static int attention_bwd_block(const __nv_bfloat16* qkv, const __nv_bfloat16* ou
       B200SSL_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       cfg = true;
     }
-    B200SSL_CUDA(launch_pdl(attention_bwd_kernel<1>, dim3(grid), dim3(BWD_THREADS), smem, stream, 1, tq, tkv, tdo, tdq, tdkv, a,
-                            num_items));
+    B200SSL_CUDA(launch_pdl(attention_bwd_kernel<1>, dim3(grid), dim3(BWD_THREADS), smem, stream, 1, tq, tkv, tdo, a, num_items));
   } else {
     const int smem = 12 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 2 * 256 * 2 * 4 + 256;
     static bool cfg = false;
@@ -1378,8 +1509,7 @@ static int attention_bwd_block(const __nv_bfloat16* qkv, const __nv_bfloat16* ou
       B200SSL_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       cfg = true;
     }
-    B200SSL_CUDA(launch_pdl(attention_bwd_kernel<2>, dim3(grid), dim3(BWD_THREADS), smem, stream, 1, tq, tkv, tdo, tdq, tdkv, a,
-                            num_items));
+    B200SSL_CUDA(launch_pdl(attention_bwd_kernel<2>, dim3(grid), dim3(BWD_THREADS), smem, stream, 1, tq, tkv, tdo, a, num_items));
   }
   return 0;
 }
@@ -1398,10 +1528,13 @@ static int attention_bwd_paired(const __nv_bfloat16* qkv, const __nv_bfloat16* o
   a.lse2 = const_cast<float*>(lse2);
   a.out = out;
   a.dout = dout;
-  CUtensorMap tq, tdo, tdq;
+  a.dq = dqkv;
+  a.dkv = dqkv;
+  a.dq_rows = N;
+  a.dkv_rows = N;
+  CUtensorMap tq, tdo;
   if (int rc = make_bnd_map(&tq, qkv, 3 * H * 64, N, N, B, 2, 1)) return rc;
   if (int rc = make_bnd_map(&tdo, dout, H * 64, N, N, B, 2, 1)) return rc;
-  if (int rc = make_bnd_map(&tdq, dqkv, 3 * H * 64, N, N, B, 2, 1)) return rc;
   B200SSL_CUDA(cudaMemsetAsync(dqkv, 0, static_cast<size_t>(B) * N * 3 * H * 64 * sizeof(__nv_bfloat16), stream));
   const long long items = static_cast<long long>(B) * H * a.nblk * a.nblk;
   B200SSL_CHECK(items < (1LL << 30), -2, "attention: problem too large for the paired backward (%lld items)", items);
@@ -1412,7 +1545,7 @@ static int attention_bwd_paired(const __nv_bfloat16* qkv, const __nv_bfloat16* o
     B200SSL_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cfg = true;
   }
-  B200SSL_CUDA(launch_pdl(attention_bwd_kernel<2>, dim3(grid), dim3(BWD_THREADS), smem, stream, 1, tq, tq, tdo, tdq, tdq, a,
+  B200SSL_CUDA(launch_pdl(attention_bwd_kernel<2>, dim3(grid), dim3(BWD_THREADS), smem, stream, 1, tq, tq, tdo, a,
                           static_cast<int>(items)));
   return 0;
 }
@@ -1462,8 +1595,8 @@ using namespace b200ssl;
 // Developer instrumentation: device buffer of 16 uint64 counters (2 slots x 8) the forward kernel's first softmax
 // thread of each slot adds to: cycles in [0] wait for S, [1] max pass, [2] barrier, [3] exp pass, [4] barrier + lse,
 // [5] wait for O, [6] epilogue + store, [7] tiles. NULL = off. The backward kernel's leader math thread adds:
-// [0] wait row constants, [1] wait S/dP, [2] P/dS math, [3] wait previous MMAs + smem writes, [4] wait dK/dV MMAs,
-// [5] dK/dV stores, [6] dQ stores, [7] item turnaround, [8] items.
+// [0] wait row constants, [1] wait S/dP, [2] P/dS math, [3] wait previous MMAs + smem writes, [7] item turnaround,
+// [8] items ([4..6] were the math warps' dK/dV waits and stores before the auxiliary group took the drain over).
 extern "C" int b200ssl_set_attn_prof(void* counters) {
   b200ssl::g_attn_prof = static_cast<unsigned long long*>(counters);
   return 0;

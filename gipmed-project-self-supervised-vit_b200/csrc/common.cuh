@@ -601,6 +601,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// The same descriptor for an operand `byte_off` bytes behind a base whose address field `lo_base` =
+// (smem address & 0x3FFFF) >> 4 the issuing thread computed once. With `byte_off` and the strides compile-time
+// constants this is ONE integer add per descriptor: the MMA-issuing thread runs alone on the uniform datapath, where
+// the mask / shift / or chain of make_smem_desc_sw128 costs ~8 dependent instructions per descriptor -- for MMAs
+// of N = 64 (32 cycles of tensor work) the issue loop, not the tensor pipe, was the bound (attention.cu).
+__device__ __forceinline__ uint64_t sw128_desc_at(uint32_t lo_base, uint32_t byte_off, uint32_t lbo_bytes,
+                                                  uint32_t sbo_bytes) {
+  const uint32_t lo = lo_base + ((byte_off >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16));
+  const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32.
 //   c_format [4,6)=1 (F32); a_format [7,10)=1 (BF16); b_format [10,13)=1; a_major bit 15;
 //   b_major bit 16 (0 = K-major, 1 = MN-major); n_dim [17,23) = N>>3; m_dim [24,29) = M>>4.

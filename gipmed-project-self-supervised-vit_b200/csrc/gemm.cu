@@ -240,7 +240,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for the compiler (MMA issuer)
   // everything above touched only this CTA's shared / tensor memory: let the next kernel in the stream start its
   // own set-up, then wait for the previous one's results before the first global access
   pdl_launch_dependents();
@@ -250,7 +250,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (elect.sync rather than lane == 0, here and in the MMA issuer: the compiler then knows ONE thread runs the block
+    //  and emits UTMALDG / UTCHMMA straight instead of wrapping each in a loop over the active lanes)
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       it.init<MODE>(args, cluster_id, num_clusters, num_m_units);
@@ -343,13 +345,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && cta_rank == 0) {  // CTA pair: only the leader issues MMAs
+    if (cta_rank == 0 && elect_one_sync()) {  // CTA pair: only the leader issues MMAs
       const uint32_t idesc = make_idesc_bf16(BLOCK_M * CL, BN == 384 ? 256 : BN, args.a_mn != 0, args.b_mn != 0);
       const uint32_t idesc2 = make_idesc_bf16(BLOCK_M * CL, 128, args.a_mn != 0, args.b_mn != 0);  // BN = 384 only
-      const uint32_t a_lbo = args.a_mn ? 8192u : 16u;
-      const uint32_t b_lbo = args.b_mn ? 8192u : 16u;
-      const uint32_t a_kstep = args.a_mn ? UMMA_K * 128u : UMMA_K * 2u;
-      const uint32_t b_kstep = args.b_mn ? UMMA_K * 128u : UMMA_K * 2u;
+      // Descriptors (SWIZZLE_128B, SBO 1024): high word constant; low word = address field | LBO field. Stepping an
+      // operand by `bytes` is ONE add of bytes >> 4 to the low word -- the issuing thread runs alone on the uniform
+      // datapath and the mask / shift / or chain of make_smem_desc_sw128 per operand per MMA took about as long as a
+      // 128 x 192 x 16 MMA itself.
+      const uint32_t desc_hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+      const uint32_t a_lbo_f = (((args.a_mn ? 8192u : 16u) >> 4) & 0x3FFFu) << 16;
+      const uint32_t b_lbo_f = (((args.b_mn ? 8192u : 16u) >> 4) & 0x3FFFu) << 16;
+      const uint32_t a_kstep = (args.a_mn ? UMMA_K * 128u : UMMA_K * 2u) >> 4;
+      const uint32_t b_kstep = (args.b_mn ? UMMA_K * 128u : UMMA_K * 2u) >> 4;
+      const uint32_t lo_smem = (smem_u32(smem) & 0x3FFFFu) >> 4, lo_panel = (smem_u32(panel) & 0x3FFFFu) >> 4;
+      auto mk_desc = [&](uint32_t lo) -> uint64_t {
+        uint64_t d;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(desc_hi));
+        return d;
+      };
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -383,18 +396,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&full_bar[stage], phase);
           w_full += clock64() - tw;
           tcgen05_fence_after();
-          const uint32_t sStage = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sA = LN ? smem_u32(panel + kb * A_STAGE_BYTES) : sStage;
-          const uint32_t sB = BS ? smem_u32(panel + kb * Cfg::kBStageBytes) : LN ? sStage : sStage + A_STAGE_BYTES;
+          const uint32_t loStage = lo_smem + static_cast<uint32_t>(stage) * (Cfg::kStageBytes >> 4);
+          const uint32_t loA = (LN ? lo_panel + static_cast<uint32_t>(kb) * (A_STAGE_BYTES >> 4) : loStage) + a_lbo_f;
+          const uint32_t loB = (BS ? lo_panel + static_cast<uint32_t>(kb) * (Cfg::kBStageBytes >> 4)
+                                   : LN ? loStage : loStage + (A_STAGE_BYTES >> 4)) + b_lbo_f;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(sA + k * a_kstep, a_lbo, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(sB + k * b_kstep, b_lbo, 1024);
+            const uint64_t adesc = mk_desc(loA + k * a_kstep);
+            const uint64_t bdesc = mk_desc(loB + k * b_kstep);
             if (CL == 1) umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else umma_bf16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             if (BN == 384) {
               // second MMA of the k step: output columns [256, 384) from the third 64-wide B piece of each CTA
-              const uint64_t bdesc2 = make_smem_desc_sw128(sB + 16384 + k * b_kstep, b_lbo, 1024);
+              const uint64_t bdesc2 = mk_desc(loB + (16384u >> 4) + k * b_kstep);
               umma_bf16_ss_2sm(d_tmem + 256, adesc, bdesc2, idesc2, (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }

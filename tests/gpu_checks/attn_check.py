@@ -6,7 +6,8 @@ import sys
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-h = ctypes.CDLL(os.path.join(ROOT, "gipmed-project-self-supervised-vit_b200", "libb200ssl.so"))
+# B200SSL_LIB: another build of the library (A/B against a previous kernel version)
+h = ctypes.CDLL(os.environ.get("B200SSL_LIB") or os.path.join(ROOT, "gipmed-project-self-supervised-vit_b200", "libb200ssl.so"))
 h.b200ssl_last_error.restype = ctypes.c_char_p
 P, I, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 h.b200ssl_attention_fwd.argtypes = [P, P, P, I, I, I, I, F, P]

@@ -30,7 +30,8 @@ for B, N, H in ((512, 197, 6), (2560, 37, 6)):
         tot = sum(p[s][:7])
         print(f"  slot {s}: {tot/n:7.0f} clk/tile  " + "  ".join(f"{nm} {p[s][i]/n:6.0f}" for i, nm in enumerate(names)))
 
-bnames = ["wait rowc", "wait S/dP", "math", "wait prev MMA + smem", "wait dK/dV MMA", "dK/dV stores", "dQ stores", "turnaround"]
+# [4..6] were the math warps' waits for the dK/dV MMAs and their dK/dV/dQ stores: the auxiliary group drains the accumulators now
+bnames = ["wait rowc", "wait S/dP", "math", "wait prev MMA + smem", "-", "-", "-", "turnaround"]
 for B, N, H in ((512, 197, 6), (2560, 37, 6)):
     qkv = torch.randn(B * N, 3 * H * 64, device="cuda").bfloat16()
     dout = torch.randn(B * N, H * 64, device="cuda").bfloat16()
@@ -45,4 +46,7 @@ for B, N, H in ((512, 197, 6), (2560, 37, 6)):
     lib.b200ssl_set_attn_prof(None)
     p = prof.tolist()
     n = max(p[8], 1)
-    print(f"bwd B={B} N={N} H={H}: {sum(p[:8])/n:7.0f} clk/item  " + "  ".join(f"{nm} {p[i]/n:6.0f}" for i, nm in enumerate(bnames)))
+    print(f"bwd B={B} N={N} H={H}: {sum(p[:8])/n:7.0f} clk/item  " + "  ".join(f"{nm} {p[i]/n:6.0f}" for i, nm in enumerate(bnames) if nm != "-"))
+    cn = ["wait S/dP taken", "wait loads", "wait P/dS", "wait drain", "issue S/dP", "wait last MMAs", "issue dQ/dK/dV"]
+    # the issuing thread of EVERY CTA adds to these (the math counters come from one thread per CTA as well): per item
+    print(f"    issuer: {sum(p[9:16])/n:7.0f} clk/item  " + "  ".join(f"{nm} {p[9+i]/n:6.0f}" for i, nm in enumerate(cn)))
