@@ -743,7 +743,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (EPI == EPI_BIAS_RES_F32 && has_bias) b4 = __ldg(reinterpret_cast<const float4*>(args.bias + col0) + (lane & 3));
         uint32_t slab = slab_base + (ring & 1) * SLAB_BYTES;
-        if (lane == 0) tma_store_wait_read<1>();  // the store that last read this slab has drained
+        if (!LNT || lane == 0) tma_store_wait_read<1>();  // the store that last read this slab has drained (every lane asks:
+                                                          // a no-op for lanes without bulk groups, and no assumption about WHICH lane
+                                                          // elect.sync picks for the stores below)
         __syncwarp();
         lap(0);
         // park this chunk's aux set in the slab (coalesced mapping) and refill the registers two chunks ahead
@@ -839,8 +841,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           fence_proxy_async_smem();
           __syncwarp();
           lap(4);
-          if (lane == 0 && (rows_ok || LNT)) {   // LayerNorm tail: one group per chunk ALWAYS (its bookkeeping counts groups)
-            if (rows_ok) tma_store_2d_s(&tmD, slab, col0, row0);
+          if (LNT) {
+            if (lane == 0) {   // LayerNorm tail: one group per chunk ALWAYS, on lane 0 (its bookkeeping counts groups)
+              if (rows_ok) tma_store_2d_s(&tmD, slab, col0, row0);
+              tma_store_commit();
+            }
+          } else if (rows_ok && elect_one_sync()) {   // elect.sync: the compiler emits UTMASTG straight (see the producer)
+            tma_store_2d_s(&tmD, slab, col0, row0);
             tma_store_commit();
           }
           ++ring;
@@ -873,7 +880,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         fence_proxy_async_smem();
         __syncwarp();
         lap(4);
-        if (lane == 0 && rows_ok) {
+        if (rows_ok && elect_one_sync()) {
           tma_store_2d_s(&tmD, slab, col0, row0);
           tma_store_commit();
         }
@@ -882,7 +889,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lap_on) atomicAdd(args.prof + 15, 1ull);
         if (EPI == EPI_BIAS_GELU) {
           slab = slab_base + (ring & 1) * SLAB_BYTES;
-          if (lane == 0) tma_store_wait_read<1>();
+          if (!LNT || lane == 0) tma_store_wait_read<1>();
           __syncwarp();
           constexpr int HM = EPI == EPI_BIAS_GELU ? W / 2 : 1;
 #pragma unroll
@@ -891,7 +898,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                    make_uint4(hpk[(4 * j) % HM], hpk[(4 * j + 1) % HM], hpk[(4 * j + 2) % HM], hpk[(4 * j + 3) % HM]));
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && rows_ok) {
+          if (rows_ok && elect_one_sync()) {
             tma_store_2d_s(&tmD2, slab, col0, row0);
             tma_store_commit();
           }
@@ -920,7 +927,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
-    if (lane == 0) tma_store_wait_all<0>();
+    if (!LNT || lane == 0) tma_store_wait_all<0>();
     if (LNT && ln_unit > 0 && lane == 0) {
       const int n = ln_unit - 1;   // the last unit
       if (n >= 2) mbar_wait(&ln_done[n & 1], ((n - 2) >> 1) & 1);
