@@ -36,6 +36,8 @@ struct AttnArgs {
   float* lse2;
   const __nv_bfloat16* out;   // bwd only
   const __nv_bfloat16* dout;  // bwd only
+  const __nv_bfloat16* qkv_q; // bwd only: qkv at the first query / key row of this launch's block (L2 prefetch of the next
+  const __nv_bfloat16* qkv_k; //           items' operand rows by the otherwise idle warps)
   __nv_bfloat16* dq;          // bwd only: dqkv at the first query row of this launch's block ([B, Ns, 3, H, 64] layout)
   __nv_bfloat16* dkv;         // bwd only: dqkv at the first key row of this launch's block
   int dq_rows, dkv_rows;      // bwd only: query / key rows that exist behind dq / dkv (rows past them are not stored)
@@ -459,15 +461,26 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 // TMEM: S [0,128) | dP [128,256) | dQ_t [256+64t) | dK [384,448) | dV [448,512), allocated once per CTA.
 // warps: 0      = control: TMA loads + every tcgen05.mma. S/dP of the NEXT pair is issued as soon as the math
 //                 warps hold the current S/dP in registers, i.e. before the dQ/dK/dV MMAs of the current pair.
-//        1..3, 20 = auxiliary group (one warp per TMEM lane quarter): row constants delta = sum_d dO*O and lse2 of
-//                 item i+1 while item i computes, AND the drain of the finished dK / dV / dQ accumulators: TMEM ->
-//                 bf16 -> global memory straight from registers (each thread owns one 128-byte output row; 256-bit
-//                 stores, vector red.add in the accumulating long-sequence mode). The math warps never wait for the
-//                 dK/dV MMAs and never store: they go from one pair's P/dS straight to the next pair's scores.
+//        1..3   = L2 prefetch (`prefetch.global.L2`, one 128-byte line per row and tensor) of the Q / K / V / dO / O rows of
+//                 the item two ahead of the one in work: the TMA loads can only be issued when the previous item's tiles
+//                 are dead, and the row-constant loads are latency-bound -- both should find their data in L2
+//        20..23 = auxiliary group (one warp per TMEM lane quarter): the finished dK / dV / dQ accumulators go TMEM -> bf16
+//                 -> global memory straight from registers (each thread owns one 128-byte output row; 256-bit stores,
+//                 vector red.add in the accumulating long-sequence mode), then the row constants delta = sum_d dO*O and
+//                 lse2 of item i+2. The math warps never wait for the dK/dV MMAs and never store: they go from one pair's
+//                 P/dS straight to the next pair's scores. (Measured alternative: row constants on warps 1..3, two items
+//                 ahead and off this group's chain -- slower, 134 -> 257 us on the packed crops: inside warpgroup 0's
+//                 64-register budget the producer spills, and every spill re-load is an L2 round trip.)
 //        4..19  = math, four threads per query row (32 key columns each).
+// Registers: 24 warps cap the kernel at 80 registers per thread, and at 80 the math warps spill a handful of loop
+// variables -- with 227 KB of shared memory carved out of L1 every spill re-load is an L2 round trip on the critical path
+// (ncu: a quarter of all stall samples). So warpgroup 0 (control + idle warps) and the auxiliary warpgroup shrink to 64
+// registers with setmaxnreg and the four math warpgroups grow to 88: 2 x 128 x 16 given back = 4 x 128 x 8 taken (only what
+// the CTA was launched with can be re-distributed; asking for more blocks forever). No spills anywhere then.
 constexpr int BWD_MATH_THREADS = 512;
 constexpr int BWD_AUX_THREADS = 128;
-constexpr int BWD_THREADS = 128 + BWD_MATH_THREADS + 32;
+constexpr int BWD_PF_THREADS = 96;
+constexpr int BWD_THREADS = 128 + BWD_MATH_THREADS + BWD_AUX_THREADS;
 
 template <int NT>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
@@ -494,7 +507,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint64_t* bar_dq_free = bars + 12;   // ... and the dQ tiles of the item
   uint64_t* bar_grp = bars + 13;       // [4] NT == 2: operand groups {K0,V0} {Q0,dO0} {Q1,dO1} {K1,V1} of the single set
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  volatile int* item_flag = reinterpret_cast<volatile int*>(bars + 18);  // the item (CTA-local index) the math warps work on
   float* rowc = reinterpret_cast<float*>(bars + 24);  // [2][NT*128][2]: delta, lse2
+  // NT == 1: tile row -> (sequence within the packed group) << 16 | token, -1 for rows past the group; filled once, so the
+  // per-item loops of the helper warps never divide (a division by a run-time N is ~40 dependent instructions, and a lone
+  // warp runs them at ~4 cycles each: index arithmetic, not memory, was what bounded the row constants)
+  int* rowtab = reinterpret_cast<int*>(rowc + 2 * NT * 128 * 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_my = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -540,12 +558,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       mbar_init(&bar_rowc_free[i], BWD_MATH_THREADS / 32);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&bar_grp[i], 1);
+    *item_flag = -1;
     mbar_init(bar_dkv_ready, 1);
     mbar_init(bar_dkv_free, BWD_AUX_THREADS / 32);
     mbar_init(bar_dq_free, BWD_AUX_THREADS / 32);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (NT == 1 && threadIdx.x < 128) {
+    const int idx = threadIdx.x;
+    rowtab[idx] = idx < args.rows ? ((idx / args.N) << 16) | (idx % args.N) : -1;
+  }
   if (NT == 1) {
     // rows never written by the TMA boxes: zero them once so 0 x garbage cannot become NaN
     const int first = args.rows * 128, last = 128 * 128;
@@ -564,6 +587,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   pdl_launch_dependents();
   pdl_wait();
 
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
+  else if (warp < 20) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;\n");
   if (warp == 0) {
     // ------------------------------------------------------------------ control: TMA + MMA issue
     // (elect.sync, not lane == 0: the compiler then knows a single thread runs this and issues the uniform-datapath
@@ -699,7 +724,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       for (int k = 0; k < n_my; ++k) {
         const Item nxt = k + 1 < n_my ? decode(item_of(k + 1)) : cur;
         const uint32_t los = set_lo(k), los_n = set_lo(k + 1);
-#pragma unroll
+#pragma unroll 1   // (unrolled, the compiler hoists every descriptor of every pair into registers and the issuer spills)
         for (int p = 0; p < PPI; ++p, ++gp) {
           mbar_wait(bar_sdp_free, gp & 1);  // the math warps hold S/dP(gp) in registers
           tcgen05_fence_after();
@@ -755,48 +780,47 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           }
         }
         cur = nxt;
+#ifndef B200SSL_ATTN_BWD_PROF
+        if (cprof) atomicAdd(args.prof + 8, 1ull);   // items (the math leader counts them when its own counters are compiled in)
+#endif
       }
     }
-  } else if (warp < 4 || warp == 20) {
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------ L2 prefetch, PF_AHEAD items ahead of the math warps
+    const int ptid = threadIdx.x - 32;  // 0..95
+    constexpr int PF_AHEAD = 2;
+    const long long row_qkv = 3LL * args.H * 64, row_o = static_cast<long long>(args.H) * 64;
+    for (int k = PF_AHEAD; k < n_my; ++k) {
+      while (*item_flag < k - PF_AHEAD) __nanosleep(256);
+      const Item it = decode(item_of(k));
+      for (int rr = ptid; rr < NT * 128; rr += BWD_PF_THREADS) {   // one row per thread and turn: five lines
+        int b = it.b0, nq_ = it.q0 + rr, nk_ = it.k0 + rr;
+        bool okq = nq_ < args.dq_rows, okk = nk_ < args.dkv_rows;
+        if (NT == 1) {
+          const int e = rowtab[rr];
+          b += e >> 16;
+          nq_ = nk_ = e & 0xffff;
+          okq = okk = e >= 0 && b < args.B;
+        }
+        if (okq) {
+          const long long bn = static_cast<long long>(b) * args.Ns + nq_;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(args.qkv_q + bn * row_qkv + it.head * 64));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(args.dout + bn * row_o + it.head * 64));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(args.out + bn * row_o + it.head * 64));
+        }
+        if (okk) {
+          const long long bn = static_cast<long long>(b) * args.Ns + nk_;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(args.qkv_k + bn * row_qkv + (args.H + it.head) * 64));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(args.qkv_k + bn * row_qkv + (2 * args.H + it.head) * 64));
+        }
+      }
+    }
+  } else if (warp >= 20) {
     // ------------------------------------------------------------------ auxiliary group: row constants + accumulator drain
-    const int aq = warp & 3;          // TMEM lane quarter (warp 20 takes quarter 0, the control warp's)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
+    const int aq = warp & 3;          // TMEM lane quarter
     const int ar = aq * 32 + lane;    // the tile row this thread drains; also its index in the group
     const uint32_t lane_off = static_cast<uint32_t>(aq * 32) << 16;
-    auto produce_rowc = [&](int k) {
-      const Item it = decode(item_of(k));
-      const int head = it.head, b0 = it.b0;
-      float* rc = rowc + (k & 1) * (NT * 128 * 2);
-      mbar_wait(&bar_rowc_free[k & 1], ((k >> 1) & 1) ^ 1);
-      for (int idx = ar; idx < NT * 128; idx += BWD_AUX_THREADS) {
-        int lo_, hi_;
-        bool row_valid;
-        key_range(args, NT, idx, lo_, hi_, row_valid);
-        if (NT == 2) row_valid = idx < it.nq;
-        const int b = b0 + (NT == 1 ? idx / args.N : 0);
-        const int n = NT == 1 ? idx % args.N : it.q0 + idx;
-        float delta = 0.f, l2 = INFINITY;  // invalid rows: lse2 = +inf so that P = 0
-        if (row_valid && b < args.B) {
-          const long long off = ((static_cast<long long>(b) * args.Ns + n) * args.H + head) * 64;
-          const uint4* po = reinterpret_cast<const uint4*>(args.out + off);
-          const uint4* pd = reinterpret_cast<const uint4*>(args.dout + off);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint4 a = __ldg(po + j), d = __ldg(pd + j);
-            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(dw[e]);
-              delta += x.x * y.x + x.y * y.y;
-            }
-          }
-          l2 = args.lse2[(static_cast<long long>(b) * args.H + head) * args.Ns + n];
-        }
-        rc[idx * 2] = delta;
-        rc[idx * 2 + 1] = l2;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_rowc_full[k & 1]);
-    };
     // 128x64 fp32 accumulator at TMEM column `tcol` -> bf16 -> row `row0 + ar` of `base` (a [B, Ns, 3, H, 64] tensor seen
     // from its first row of this launch), 64 columns from `gcol`. One thread = one 128-byte output row: four 256-bit
     // stores, or eight 128-bit bf16x2 vector reductions when the launch accumulates (long-sequence block pairs).
@@ -844,6 +868,47 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       }
     };
 
+    // row constants of item k: one thread per row (16 + 16 sixteen-byte loads of O and dO, one of lse2)
+    auto produce_rowc = [&](int k) {
+      const Item it = decode(item_of(k));
+      const int head = it.head, b0 = it.b0;
+      float* rc = rowc + (k & 1) * (NT * 128 * 2);
+      mbar_wait(&bar_rowc_free[k & 1], ((k >> 1) & 1) ^ 1);
+      for (int idx = ar; idx < NT * 128; idx += BWD_AUX_THREADS) {
+        bool row_valid;
+        int b = b0, n;
+        if (NT == 1) {
+          const int e = rowtab[idx];
+          row_valid = e >= 0;
+          b += e >> 16;
+          n = e & 0xffff;
+        } else {
+          row_valid = idx < it.nq;
+          n = it.q0 + idx;
+        }
+        float delta = 0.f, l2 = INFINITY;  // invalid rows: lse2 = +inf so that P = 0
+        if (row_valid && b < args.B) {
+          const long long off = ((static_cast<long long>(b) * args.Ns + n) * args.H + head) * 64;
+          const uint4* po = reinterpret_cast<const uint4*>(args.out + off);
+          const uint4* pd = reinterpret_cast<const uint4*>(args.dout + off);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 a = __ldg(po + j), d = __ldg(pd + j);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(dw[e]);
+              delta += x.x * y.x + x.y * y.y;
+            }
+          }
+          l2 = args.lse2[(static_cast<long long>(b) * args.H + head) * args.Ns + n];
+        }
+        rc[idx * 2] = delta;
+        rc[idx * 2 + 1] = l2;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_rowc_full[k & 1]);
+    };
     // the drain is what the MMA issuer waits for (TMEM re-use), the row constants have a whole item of slack: item k + 2's
     // are produced after item k's accumulators are out (their buffer was released when the math warps started item k)
     if (n_my > 0) produce_rowc(0);
@@ -885,19 +950,29 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       key_range(args, NT, NT == 1 ? r : t * 128 + r, lo[t], hi[t], row_valid);
     }
     int gp = 0;
+    // developer instrumentation: cycles of the leader math thread per phase. Compiled in only with -DB200SSL_ATTN_BWD_PROF:
+    // the clock and pointer registers it keeps alive are what tips the math warps (88 registers) into spilling their
+    // loop counters, and a spill re-load is an L2 round trip here. The issuer's counters (9..15) are always available.
+#ifdef B200SSL_ATTN_BWD_PROF
     const bool prof_on = args.prof != nullptr && leader;
     long long tp0 = prof_on ? clock64() : 0;
-    auto lap = [&](int idx) {  // developer instrumentation: cycles of the leader math thread per phase
+    auto lap = [&](int idx) {
       if (prof_on) {
         const long long now = clock64();
         atomicAdd(args.prof + idx, static_cast<unsigned long long>(now - tp0));
         tp0 = now;
       }
     };
+#else
+    constexpr bool prof_on = false;
+    auto lap = [](int) {};
+    (void)leader;
+#endif
 
     for (int k = 0; k < n_my; ++k) {
       const Item it = decode(item_of(k));
       float delta[NT], lse2[NT];
+      if (threadIdx.x == 128) *item_flag = k;   // paces the L2 prefetch warps
       lap(7);
       {
         const float* rc = rowc + (k & 1) * (NT * 128 * 2);
@@ -1484,6 +1559,8 @@ static int attention_bwd_block(const __nv_bfloat16* qkv, const __nv_bfloat16* ou
   a.out = out + static_cast<long long>(q0) * H * 64;
   a.dout = dout + static_cast<long long>(q0) * H * 64;
   const long long row = 3LL * H * 64;
+  a.qkv_q = qkv + q0 * row;
+  a.qkv_k = qkv + k0 * row;
   a.dq = dqkv + q0 * row;
   a.dkv = dqkv + k0 * row;
   a.dq_rows = Nq;
@@ -1495,7 +1572,7 @@ static int attention_bwd_block(const __nv_bfloat16* qkv, const __nv_bfloat16* ou
   const int num_items = groups * H;
   const int grid = num_items < sm_count() ? num_items : sm_count();
   if (nt == 1) {
-    const int smem = 12 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 2 * 128 * 2 * 4 + 256;
+    const int smem = 12 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 2 * 128 * 2 * 4 + 512 /*row table*/ + 256;
     static bool cfg = false;
     if (!cfg) {
       B200SSL_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1528,6 +1605,8 @@ static int attention_bwd_paired(const __nv_bfloat16* qkv, const __nv_bfloat16* o
   a.lse2 = const_cast<float*>(lse2);
   a.out = out;
   a.dout = dout;
+  a.qkv_q = qkv;
+  a.qkv_k = qkv;
   a.dq = dqkv;
   a.dkv = dqkv;
   a.dq_rows = N;

@@ -39,13 +39,14 @@ for B, N, H in ((512, 197, 6), (2560, 37, 6)):
     for _ in range(3):
         ops.attention_bwd(qkv, out, dout, lse2, B, N, H, 0.125)
     torch.cuda.synchronize()
-    prof = torch.zeros(16, dtype=torch.int64, device="cuda")
+    prof = torch.zeros(128, dtype=torch.int64, device="cuda")
     lib.b200ssl_set_attn_prof(prof.data_ptr())
     ops.attention_bwd(qkv, out, dout, lse2, B, N, H, 0.125)
     torch.cuda.synchronize()
     lib.b200ssl_set_attn_prof(None)
     p = prof.tolist()
     n = max(p[8], 1)
+    # math-side counters need a library built with -DB200SSL_ATTN_BWD_PROF (they cost the math warps registers); zeros otherwise
     print(f"bwd B={B} N={N} H={H}: {sum(p[:8])/n:7.0f} clk/item  " + "  ".join(f"{nm} {p[i]/n:6.0f}" for i, nm in enumerate(bnames) if nm != "-"))
     cn = ["wait S/dP taken", "wait loads", "wait P/dS", "wait drain", "issue S/dP", "wait last MMAs", "issue dQ/dK/dV"]
     # the issuing thread of EVERY CTA adds to these (the math counters come from one thread per CTA as well): per item
