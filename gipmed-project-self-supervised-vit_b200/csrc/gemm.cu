@@ -246,6 +246,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   pdl_launch_dependents();
   pdl_wait();
 
+  // Registers: 20 warps cap the kernel at 96 per thread, and at 96 the fused epilogues (GELU + GELU', x aux) spill a few
+  // values -- with 227 KB of shared memory carved out of L1 a spill re-load is an L2 round trip. Warpgroup 0 (producer,
+  // MMA issuer, TMEM owner, spare) needs far fewer: it shrinks to GEMM_WG0_REGS and the sixteen epilogue warps grow to
+  // GEMM_EPI_REGS (128 x 40 given back >= 512 x 8 taken). Not in the LayerNorm-fused modes, whose helper warps 2 / 3 do
+  // arithmetic of their own.
+  if constexpr (!LN && !LNT) {
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");   // the epilogue warps' inc sits at the top of their branch
+  }
+
   TileIter it;
 
   if (warp == 0) {
@@ -431,6 +440,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
+    if constexpr (!LN && !LNT) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n");
     // 16 fully independent warps. Warp (q, group) owns TMEM lane quarter q (rows 32q .. 32q+31 of the tile) and
     // the column chunks c with (c + tile_iter) % 4 == group (rotating, so uneven chunk counts even out). Its
     // private staging is a ring of two 2 KB slabs (32 rows x 64 B, 64B swizzle) from which lane 0 issues 32-row
