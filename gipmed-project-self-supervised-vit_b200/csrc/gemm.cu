@@ -109,6 +109,11 @@ struct GemmCfg {
 struct TileIter {
   int t, step, total;        // default mode: linear tile index; other modes: m unit index
   int n_blk, m_unit, ks;
+  // default mode: t = (ks * num_m_units + m_unit) * num_n_blocks + n_blk advances by `step` tiles; the three coordinates are
+  // carried along incrementally (step_n = step % num_n_blocks, step_m = step / num_n_blocks) -- a division by a run-time
+  // value is ~40 dependent instructions, and the producer / MMA-issuer threads run alone: dividing afresh for every tile
+  // (and, in the epilogue's aux prefetch, for every chunk) put hundreds of cycles between tiles
+  int step_n, step_m, nmu;
   template <int MODE>
   __device__ __forceinline__ void init(const GemmArgs& a, int cluster_id, int num_clusters, int num_m_units) {
     if (MODE == 1) {
@@ -127,6 +132,13 @@ struct TileIter {
       t = cluster_id;
       step = num_clusters;
       total = num_m_units * a.num_n_blocks * a.k_splits;
+      step_n = step % a.num_n_blocks;
+      step_m = step / a.num_n_blocks;
+      nmu = num_m_units;
+      n_blk = t % a.num_n_blocks;
+      const int m_lin = t / a.num_n_blocks;
+      ks = m_lin / num_m_units;
+      m_unit = m_lin - ks * num_m_units;
     }
   }
   template <int MODE>
@@ -135,10 +147,6 @@ struct TileIter {
     if (MODE >= 1) {
       m_unit = t;
       ks = 0;
-    } else {
-      n_blk = t % a.num_n_blocks;
-      m_unit = (t / a.num_n_blocks) % num_m_units;
-      ks = t / (num_m_units * a.num_n_blocks);
     }
     return true;
   }
@@ -146,8 +154,14 @@ struct TileIter {
   __device__ __forceinline__ void next(const GemmArgs& a) {
     if (MODE >= 2) {
       if (++n_blk == a.num_n_blocks) { n_blk = 0; t += step; }
+    } else if (MODE == 1) {
+      t += step;
     } else {
       t += step;
+      n_blk += step_n;
+      m_unit += step_m;
+      if (n_blk >= a.num_n_blocks) { n_blk -= a.num_n_blocks; ++m_unit; }
+      while (m_unit >= nmu) { m_unit -= nmu; ++ks; }
     }
   }
 };
