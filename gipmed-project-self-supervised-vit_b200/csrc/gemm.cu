@@ -261,7 +261,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   pdl_wait();
 
   // Registers: 20 warps cap the kernel at 96 per thread, and at 96 the fused epilogues (GELU + GELU', x aux) spill a few
-  // values -- with 227 KB of shared memory carved out of L1 a spill re-load is an L2 round trip. Warpgroup 0 (producer,
+  // values inside their chunk loops (here the re-loads still hit what is left of L1 -- ncu: 100 % -- in the attention
+  // backward, with less L1 to spare, they were L2 round trips). Warpgroup 0 (producer,
   // MMA issuer, TMEM owner, spare) needs far fewer: it shrinks to GEMM_WG0_REGS and the sixteen epilogue warps grow to
   // GEMM_EPI_REGS (128 x 40 given back >= 512 x 8 taken). Not in the LayerNorm-fused modes, whose helper warps 2 / 3 do
   // arithmetic of their own.
