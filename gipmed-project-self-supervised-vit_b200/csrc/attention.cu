@@ -1751,6 +1751,8 @@ extern "C" int b200ssl_attention_bwd(const void* qkv_, const void* out_, const v
   const __nv_bfloat16* out = static_cast<const __nv_bfloat16*>(out_);
   const __nv_bfloat16* dout = static_cast<const __nv_bfloat16*>(dout_);
   __nv_bfloat16* dqkv = static_cast<__nv_bfloat16*>(dqkv_);
+  // the drain warps write whole 128-byte rows with 256-bit stores
+  B200SSL_CHECK((reinterpret_cast<uintptr_t>(dqkv) & 31) == 0, -2, "attention_bwd: dqkv must be 32-byte aligned");
   if (N <= 256) return attention_bwd_block(qkv, out, dout, lse2, dqkv, B, N, H, 0, N, 0, N, scale, false, false, false, stream);
   B200SSL_CHECK(N <= 4096, -2, "attention: sequence length %d unsupported (1..4096)", N);
   // three or more blocks per dimension: ONE launch over all block pairs (N = 785, B = 64: 723 -> 565 us). With two blocks

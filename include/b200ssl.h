@@ -96,7 +96,8 @@ int b200ssl_layernorm_bwd(const void* x, int x_f32, const void* dy, const float*
 
 /* ---- K4: fused attention (Attention.forward VT.pyc@L119-131) --------------------------------------
  * qkv [B,N,3,H,64] bf16 (the QKV GEMM output as is), out/dout [B,N,H,64] bf16, lse2 [B,H,N] fp32
- * (log2-sum-exp of the scaled scores), dqkv like qkv. head_dim must be 64. */
+ * (log2-sum-exp of the scaled scores), dqkv like qkv (32-byte aligned: the backward writes whole 128-byte rows with
+ * 256-bit stores). head_dim must be 64. */
 int b200ssl_attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, int head_dim,
                           float scale, void* stream);
 int b200ssl_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv,
