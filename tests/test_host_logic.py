@@ -44,6 +44,25 @@ def test_library_holds_blackwell_kernels():
         assert mnemonic in sass, mnemonic
 
 
+def test_mma_issue_code_is_straight_line():
+    """Regression guard for the round-2 issue-path finding (profiles/README.md item 10): every tcgen05.mma must be issued
+    straight -- by a thread chosen with elect.sync, with uniform operands -- not inside the per-active-lane
+    ELECT / R2UR.BROADCAST / BRA.U.ANY loop the compiler wraps around uniform-datapath instructions under `lane == 0`."""
+    import b200ssl
+    r = subprocess.run(["cuobjdump", "-sass", b200ssl._lib.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "R2UR.BROADCAST" not in r.stdout
+    looped = {}
+    for fn in re.split(r"\n\s*Function : ", r.stdout)[1:]:
+        lines = fn.splitlines()
+        n = sum(1 for i, l in enumerate(lines) if "UTCHMMA" in l
+                and any("BRA.U.ANY" in w or "ELECT" in w for w in lines[max(0, i - 6):i + 6]))
+        if n:
+            looped[lines[0][:80]] = n
+    assert not looped, f"tcgen05.mma issued inside per-lane loops: {looped}"
+
+
 def test_ops_refuse_cpu_tensors():
     import b200ssl
     with pytest.raises(RuntimeError, match="no CPU fallback"):
