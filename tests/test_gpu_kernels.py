@@ -214,6 +214,27 @@ def test_attention_long_sequences(ops, B, N, H):
     _check_attention_grad(dqkv, qr.grad)
 
 
+@pytest.mark.parametrize("B,N,H", [(2, 197, 2), (7, 37, 3), (3, 64, 2), (1, 128, 1), (5, 100, 1), (3, 257, 2), (2, 600, 1), (1, 1, 1)])
+def test_attention_bwd_writes_exactly_its_output(ops, B, N, H):
+    """The backward's drain warps write dq / dk / dv from registers with computed addresses (no TMA clipping): every
+    element of dqkv must be written (NaN canary inside) and nothing around it touched (sentinel canaries outside)."""
+    g = torch.Generator(device="cuda").manual_seed(17 + N)
+    qkv = torch.randn(B * N, 3 * H * 64, device="cuda", generator=g).bfloat16()
+    dout = torch.randn(B * N, H * 64, device="cuda", generator=g).bfloat16()
+    out, lse2 = ops.attention_fwd(qkv, B, N, H, 0.125)
+    pad = 1 << 16                                    # elements (128 KB) on either side, 32-byte aligned
+    n = qkv.numel()
+    buf = torch.full((pad + n + pad,), 12288.0, device="cuda", dtype=torch.bfloat16)
+    dqkv = buf[pad:pad + n].view_as(qkv)
+    dqkv.fill_(float("nan"))
+    ops._call("b200ssl_attention_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse2.data_ptr(), dqkv.data_ptr(),
+              B, N, H, 64, 0.125, ops._stream(), launches=1)
+    torch.cuda.synchronize()
+    assert not torch.isnan(dqkv.float()).any(), "rows of dqkv left unwritten"
+    assert bool((buf[:pad] == 12288.0).all()) and bool((buf[pad + n:] == 12288.0).all()), "write outside dqkv"
+    assert torch.equal(dqkv, ops.attention_bwd(qkv, out, dout, lse2, B, N, H, 0.125)) or N > 512   # reduce-add order above 512
+
+
 def test_attention_rejects_unsupported_lengths(ops):
     """The streaming forward takes up to 65,536 tokens; the block-pair backward up to 4,096. Beyond: a loud error."""
     qkv = torch.zeros(70000, 192, device="cuda", dtype=torch.bfloat16)
