@@ -788,7 +788,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   } else if (warp < 4) {
     // ------------------------------------------------------------------ L2 prefetch, PF_AHEAD items ahead of the math warps
     const int ptid = threadIdx.x - 32;  // 0..95
-    constexpr int PF_AHEAD = 2;
+    // how far ahead: far enough for an HBM round trip before the TMA loads are issued, near enough that the lines are still
+    // in L2 when they are -- the whole GPU streams ~3 MB per microsecond through a 126 MB L2. Two-tile items last ~10 us
+    // and load their operands during the previous item: one item ahead; packed items last ~3.5 us and load two items
+    // ahead: two.
+    constexpr int PF_AHEAD = NT == 2 ? 1 : 2;
     const long long row_qkv = 3LL * args.H * 64, row_o = static_cast<long long>(args.H) * 64;
     for (int k = PF_AHEAD; k < n_my; ++k) {
       while (*item_flag < k - PF_AHEAD) __nanosleep(256);
