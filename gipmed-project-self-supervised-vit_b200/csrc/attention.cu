@@ -290,9 +290,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     constexpr int O_COL = 192;
 
     int k = 0;
+    int store_buf = -1;   // gtid 0: the smem buffer whose output store is committed but not yet known to have been read
+    // The group's store thread hands a buffer back one step late: it commits the TMA store of round k, goes on, and only
+    // after the NEXT round's max pass does it wait for the store to have read the staging tile (long done by then) and
+    // release the buffer -- the read-completion latency (~500 cycles) is off the group's per-tile chain, and the producer
+    // still has most of a round to re-fill the buffer for round k + 2.
+    auto release_store_buf = [&]() {
+      if (gtid == 0 && store_buf >= 0) {
+        tma_store_wait_read<0>();
+        mbar_arrive(&buf_free[store_buf]);
+        store_buf = -1;
+      }
+    };
     for (int round = blockIdx.x; round < num_rounds; round += gridDim.x, ++k) {
       const int item = slot_item(round, slot);
       if (item < 0) {  // empty tail slot: still hand the smem buffer back
+        release_store_buf();
         if (gtid == 0) mbar_arrive(&buf_free[k & 1]);
         continue;
       }
@@ -353,6 +366,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         }
       }
       xchg[hf * 128 + r] = mx;
+      release_store_buf();   // the previous round's output store has had the whole max pass to read its staging tile
       lap(1);
       named_bar_sync(1 + slot, 256);  // also: every thread of the group is done with pass 1
       lap(2);
@@ -437,12 +451,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       if (gtid == 0) {
         tma_store_3d(&tmO, stg, head * 64, NT == 1 ? 0 : t * 128, b0);
         tma_store_commit();
-        tma_store_wait_read<0>();      // staging (and with it the whole buffer, for this group) is reusable
-        mbar_arrive(&buf_free[buf]);
+        store_buf = buf;               // released in release_store_buf(): staging (the dead Q tile) is part of the buffer
       }
       lap(6);
       if (prof_on) atomicAdd(args.prof + slot * 8 + 7, 1ull);
     }
+    release_store_buf();
     if (gtid == 0) tma_store_wait_all<0>();
   }
 
