@@ -318,6 +318,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       bool row_valid;
       key_range(args, NT, NT == 1 ? r : t * 128 + r, lo, hi, row_valid);
       if (!row_valid) hi = lo;  // no valid keys: the row is all padding
+      // A warp whose 32 rows ALL lie past the last query row skips both passes (N = 197: rows 224..255 of the second
+      // tile, two of the sixteen softmax warps -- an eighth of the exp2 work of a MUFU-bound pass). Its P columns keep
+      // whatever bits S left there: the P.V MMA is row-wise, and output rows past the sequence are clipped by the store.
+      const bool warp_live = (NT == 1 ? 0 : t * 128) + q * 32 < (NT == 1 ? args.rows : args.N);
+      const int c_end_w = warp_live ? c_end : c_begin;
       // NT == 2: no masking. Key rows >= N are zero-filled by TMA, so their scores are exactly 0 (harmless
       // in the max), their V rows are 0 (no contribution to O) and their exp2(-m) terms are subtracted
       // from the row sum below. NT == 1 (packed sequences): whole 16-key chunks are classified as
@@ -344,7 +349,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       // ---- pass 1: row max of the raw scores over this thread's column range
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
+      for (int c = c_begin; c < c_end_w; ++c) {
         // tcgen05.ld/st are warp-collective (.sync.aligned): every lane issues them for every chunk; only the
         // arithmetic in between may diverge on the per-row chunk class
         const int cls = chunk_class(c);
@@ -375,7 +380,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       // ---- pass 2: p = 2^(s*c - m) -> bf16 pairs -> written over the already-consumed S columns
       float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
+      for (int c = c_begin; c < c_end_w; ++c) {
         const int cls = chunk_class(c);
         uint32_t pk[8];
         uint32_t v[16];
@@ -1014,7 +1019,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           tcgen05_fence_after();
           lap(1);
           const int col0 = qc * 32;             // first key column (within the tile) of this thread
-          const bool active = col0 < ku;
+          // warp-uniform: this warp's 32 key columns lie inside the key tile, and at least one of its 32 query rows exists.
+          // A warp of padding rows only (N = 197: rows 224..255, the last quarter of query tile 1) skips the pair: the
+          // dK / dV MMAs read the live 16-row steps only (qsteps), and the dQ rows it would feed are never stored.
+          const bool active = col0 < ku && (NT == 1 ? 0 : t * 128) + q * 32 < (NT == 1 ? args.rows : it.nq);
           uint32_t pp[16], dd[16];              // 32 columns of P and dS, packed bf16 pairs
           if (active) {                         // warp-uniform: col0 depends on the warp only
 #pragma unroll
