@@ -613,6 +613,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     // (elect.sync, not lane == 0: the compiler then knows a single thread runs this and issues the uniform-datapath
     //  instructions -- UTCHMMA, UTMALDG -- straight, without a per-active-lane loop around each of them)
     if (n_my > 0 && elect_one_sync()) {
+      // NT == 1: a whole operand set (Q, K, V, dO of one packed group) per barrier, two sets in flight
       auto issue_load = [&](int k) {
         const Item it = decode(item_of(k));
         const int head = it.head, b0 = it.b0;
@@ -620,27 +621,16 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         uint8_t* sdO = sQ + NT * TILE_BYTES;
         uint8_t* sK = sdO + NT * TILE_BYTES;
         uint8_t* sV = sK + NT * TILE_BYTES;
-        uint64_t* bar = &bar_load[SETS == 2 ? (k & 1) : 0];
+        uint64_t* bar = &bar_load[k & 1];
         const int cq = head * 64, ck = (args.H + head) * 64, cv = (2 * args.H + head) * 64;
-        if (NT == 1) {
-          mbar_expect_tx(bar, 4 * args.rows * 128);
-          tma_load_3d(sQ, &tmQKV, bar, cq, 0, b0);
-          tma_load_3d(sK, &tmQKV, bar, ck, 0, b0);
-          tma_load_3d(sV, &tmQKV, bar, cv, 0, b0);
-          tma_load_3d(sdO, &tmDO, bar, cq, 0, b0);
-        } else {
-          mbar_expect_tx(bar, 4 * NT * TILE_BYTES);
-          for (int t = 0; t < NT; ++t) {
-            tma_load_3d(sQ + t * TILE_BYTES, &tmQKV, bar, cq, it.q0 + t * 128, b0);
-            tma_load_3d(sK + t * TILE_BYTES, &tmKV, bar, ck, it.k0 + t * 128, b0);
-            tma_load_3d(sV + t * TILE_BYTES, &tmKV, bar, cv, it.k0 + t * 128, b0);
-            tma_load_3d(sdO + t * TILE_BYTES, &tmDO, bar, cq, it.q0 + t * 128, b0);
-          }
-        }
+        mbar_expect_tx(bar, 4 * args.rows * 128);
+        tma_load_3d(sQ, &tmQKV, bar, cq, 0, b0);
+        tma_load_3d(sK, &tmQKV, bar, ck, 0, b0);
+        tma_load_3d(sV, &tmQKV, bar, cv, 0, b0);
+        tma_load_3d(sdO, &tmDO, bar, cq, 0, b0);
       };
       auto wait_load = [&](int k) {
-        const int uses = SETS == 2 ? (k >> 1) : k;  // completed phases of this set's barrier before item k
-        mbar_wait(&bar_load[SETS == 2 ? (k & 1) : 0], uses & 1);
+        mbar_wait(&bar_load[k & 1], (k >> 1) & 1);  // k >> 1 completed phases of this set's barrier before item k
         tcgen05_fence_after();
       };
       const uint32_t idesc_q = make_idesc_bf16(128, 64, false, true);  // dQ: A K-major, B MN-major
