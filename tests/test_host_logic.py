@@ -63,6 +63,33 @@ def test_mma_issue_code_is_straight_line():
     assert not looped, f"tcgen05.mma issued inside per-lane loops: {looped}"
 
 
+def test_gemm_tile_coordinates_carried_incrementally_match_the_closed_form():
+    """csrc/gemm.cu TileIter (default mode) carries (n_blk, m_unit, ks) along with additions instead of dividing the
+    linear tile index for every tile; this is the same update in Python against t % n, (t / n) % m, t / (m * n)."""
+    import itertools
+    for step, nnb, nmu, ksplits in itertools.product((1, 2, 37, 74, 148), (1, 2, 3, 6, 8), (1, 3, 37, 394, 764), (1, 4, 13)):
+        total = nmu * nnb * ksplits
+        for start in {0, 1, step - 1}:
+            t = start
+            if t >= total:
+                continue
+            step_n, step_m = step % nnb, step // nnb
+            n_blk, m_lin = t % nnb, t // nnb
+            ks = m_lin // nmu
+            m_unit = m_lin - ks * nmu
+            while t < total:
+                assert (n_blk, m_unit, ks) == (t % nnb, (t // nnb) % nmu, t // (nmu * nnb)), (step, nnb, nmu, ksplits, t)
+                t += step
+                n_blk += step_n
+                m_unit += step_m
+                if n_blk >= nnb:
+                    n_blk -= nnb
+                    m_unit += 1
+                while m_unit >= nmu:
+                    m_unit -= nmu
+                    ks += 1
+
+
 def test_ops_refuse_cpu_tensors():
     import b200ssl
     with pytest.raises(RuntimeError, match="no CPU fallback"):
