@@ -39,6 +39,19 @@ _TYPES = {
     "cbnfr": "cbnfr", "cbnfrs": "cbnfrs", "cbnfrsc": "cbnfrs",
     "pcbnfrs": "pcbnfrs", "pcbnfrsc": "pcbnfrs", "bnfrs": "bnfrs", "bnfrsc": "bnfrs",
 }
+# the types define_transformations appends Cutout(n_holes=1, length=100) to, behind Normalize (transformations.py:206-207;
+# 'c_0_05_bnfrsc' of that list never gets there: it leaves through the "custom transform" return at :201-202)
+_CUTOUT_TYPES = ("cbnfrsc", "bnfrsc", "pcbnfrsc")
+CUTOUT_LENGTH = 100      # pixels of the reference's 256 x 256 output frame (transformations.py:207)
+
+
+def cutout_box(y, x, length, size):
+    """The hole of the reference's ``Cutout.__call__`` (transformations.py:35-40) for a centre draw (y, x) on a
+    ``size`` x ``size`` image: ``[y1, y2) x [x1, x2)`` with ``clip(c -+ length // 2, 0, size)``. Tensors or ints."""
+    half = length // 2
+    lo = lambda c: torch.clamp(torch.as_tensor(c) - half, 0, size)    # noqa: E731
+    hi = lambda c: torch.clamp(torch.as_tensor(c) + half, 0, size)    # noqa: E731
+    return lo(y), hi(y), lo(x), hi(x)
 
 
 class MultiCropAugment:
@@ -53,14 +66,24 @@ class MultiCropAugment:
     hue=(-0.1,0.1)); 'pc' ColorJitter(color_param, 2*color_param, color_param, color_param); 'b' GaussianBlur(3,
     sigma<=0.1) (the identity to 2e-22: skipped); 'n' Gaussian noise sigma ~ U(0, 0.05); 'f' vertical flip p=0.5 (and
     horizontal flip p=0.5 for 'flip'); 'r' rotation by a uniform multiple of 90 degrees; 's' zoom 1..1.2 about the
-    centre (folded into the crop box). Random-resized crops: area fraction ~ U(scale), log-uniform aspect ratio in
-    (3/4, 4/3), torchvision's ``RandomResizedCrop.get_params`` procedure."""
+    centre (folded into the crop box); trailing 'c' (``cbnfrsc``, ``bnfrsc``, ``pcbnfrsc``) Cutout(n_holes=1): one
+    square hole, centre uniform over the output frame, clipped at the borders, set to 0 AFTER Normalize like the
+    reference does. The reference cuts 100 pixels out of its 256 x 256 output; a crop of side S gets
+    ``cutout_length * S // 256`` (the same fraction of the frame), ``cutout_length`` defaulting to 100.
+    Random-resized crops: area fraction ~ U(scale), log-uniform aspect ratio in (3/4, 4/3), torchvision's
+    ``RandomResizedCrop.get_params`` procedure."""
 
     def __init__(self, transform_type="pcbnfrs", color_param=0.1, norm_type="Ron", global_size=224, local_size=96,
-                 n_global=2, n_local=10, global_scale=(0.4, 1.0), local_scale=(0.05, 0.4), train=True):
+                 n_global=2, n_local=10, global_scale=(0.4, 1.0), local_scale=(0.05, 0.4), train=True,
+                 cutout_length=CUTOUT_LENGTH):
         if transform_type not in _TYPES:
             raise ValueError(f"unknown transform_type {transform_type!r}")
         self.ops = _TYPES[transform_type] if train else ""
+        # define_transformations appends the Cutout outside its `train` branch (transformations.py:206-207)
+        self.cutout = transform_type in _CUTOUT_TYPES
+        self.cutout_length = int(cutout_length)
+        if self.cutout and not 0 <= self.cutout_length < 65536:
+            raise ValueError(f"cutout_length {cutout_length!r} out of range")
         self.transform_type, self.color_param, self.norm_type = transform_type, color_param, norm_type
         self.global_size, self.local_size, self.n_global, self.n_local = global_size, local_size, n_global, n_local
         self.global_scale, self.local_scale = global_scale, local_scale
@@ -129,6 +152,15 @@ class MultiCropAugment:
             fp[..., 9] = u(0.0, 0.05)
         p[..., 4] = flags.int()
         p[..., 10] = torch.randint(0, 2 ** 31 - 1, (B, ncrops), generator=g).int()
+        if self.cutout:
+            # words 11 / 12: the hole in OUTPUT-frame pixels, y1 | y2 << 16 and x1 | x2 << 16 (0 = no hole)
+            for lo, hi, S in ((0, self.n_global, self.global_size), (self.n_global, ncrops, self.local_size)):
+                if hi > lo:
+                    y = torch.randint(0, S, (B, hi - lo), generator=g)
+                    x = torch.randint(0, S, (B, hi - lo), generator=g)
+                    y1, y2, x1, x2 = cutout_box(y, x, self.cutout_length * S // TILE, S)
+                    p[:, lo:hi, 11] = (y1 | (y2 << 16)).int()
+                    p[:, lo:hi, 12] = (x1 | (x2 << 16)).int()
         return p
 
     # ------------------------------------------------------------------ launch

@@ -15,7 +15,9 @@
 //              with the mean grey level of the image AT THAT POINT of the pipeline: a first pass over the crop computes it);
 //   noise    : x + sigma * n, n ~ N(0,1) from a counter-based generator (PCG hash of (seed, element pair), Box-Muller),
 //              clamped to [0,1] (skimage.util.random_noise(mode='gaussian', clip=True));
-//   output   : (x - mean[c]) / std[c] -> bf16, CHW.
+//   output   : (x - mean[c]) / std[c] -> bf16, CHW;
+//   cutout   : the reference's Cutout (transformations.py:10-45, appended behind Normalize at :206-207) multiplies the
+//              NORMALISED image by a mask that is 0 inside one square hole: the hole's pixels are written as 0.
 // GaussianBlur(3, sigma in (1e-7, 0.1)) is the identity to 2e-22 (off-centre tap weight exp(-1 / (2 * 0.1^2))) and is
 // skipped; intermediate uint8 re-quantisation of the PIL pipeline is not reproduced (float pipeline, documented).
 #include "common.cuh"
@@ -39,7 +41,8 @@ struct AugParams {
   float brightness, contrast, saturation, hue;
   float sigma;           // noise standard deviation (0 = none)
   unsigned seed;
-  unsigned pad[5];
+  unsigned cut_y, cut_x;  // Cutout hole in output-frame pixels: y1 | y2 << 16, x1 | x2 << 16 (empty when y2 <= y1 or x2 <= x1)
+  unsigned pad[3];
 };
 static_assert(sizeof(AugParams) == AUG_PARAM_WORDS * 4, "parameter row is 16 words");
 
@@ -214,6 +217,7 @@ multicrop_augment_kernel(const uint8_t* __restrict__ tiles, const AugParams* __r
     __nv_bfloat16* out = is_g ? out_global + (static_cast<long long>(c) * B + b) * 3 * Sg * Sg
                               : out_local + (static_cast<long long>(c - n_global) * B + b) * 3 * Sl * Sl;
     const int half = S / 2;
+    const int cut_y1 = p.cut_y & 0xFFFFu, cut_y2 = p.cut_y >> 16, cut_x1 = p.cut_x & 0xFFFFu, cut_x2 = p.cut_x >> 16;
     for (int oy = tid >> 5; oy < S; oy += AUG_THREADS / 32)
     for (int ox2 = tid & 31; ox2 < half; ox2 += 32) {
       const int ox = ox2 * 2;
@@ -241,6 +245,11 @@ multicrop_augment_kernel(const uint8_t* __restrict__ tiles, const AugParams* __r
         px[e][0] = (px[e][0] - mean0) * istd0;
         px[e][1] = (px[e][1] - mean1) * istd1;
         px[e][2] = (px[e][2] - mean2) * istd2;
+      }
+      if (oy >= cut_y1 && oy < cut_y2) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (ox + e >= cut_x1 && ox + e < cut_x2) px[e][0] = px[e][1] = px[e][2] = 0.f;
       }
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch)

@@ -5,7 +5,8 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import 
 
 What it follows: the reference's per-tile transform pipeline, transformations.py:103-208 (``define_transformations``:
 ColorJitter :142-143/:153-154, GaussianBlur :144, MyGaussianNoiseTransform :71-87, RandomVerticalFlip :146,
-MyRotation :47-55, RandomAffine(scale) :148, ToTensor + Normalize with the MEAN / STD tables :104-128), applied per
+MyRotation :47-55, RandomAffine(scale) :148, ToTensor + Normalize with the MEAN / STD tables :104-128, Cutout :10-45
+appended behind Normalize :206-207), applied per
 tile at datasets.py:498-502 -- with torchvision's own TENSOR implementations of the operators
 (torchvision.transforms.functional.adjust_brightness / adjust_contrast / adjust_saturation / adjust_hue on float
 images, torch.rot90, flips, F.interpolate bilinear) -- plus the DINO multi-crop random-resized crops the training step
@@ -70,7 +71,17 @@ def augment_one(tile_u8: torch.Tensor, row: torch.Tensor, size: int, mean, std) 
         img = (img + sigma * normal_of(seed, idx)).clamp(0.0, 1.0)
     m = torch.tensor(mean, dtype=torch.float32, device=img.device).view(3, 1, 1)
     s_ = torch.tensor(std, dtype=torch.float32, device=img.device).view(3, 1, 1)
-    return (img - m) / s_
+    return cutout((img - m) / s_, int(row[11]), int(row[12]))
+
+
+def cutout(img: torch.Tensor, word_y: int, word_x: int) -> torch.Tensor:
+    """Cutout.__call__ of the reference (transformations.py:21-45) for a hole already drawn: ``img * mask`` with the
+    mask 0 on ``[y1, y2) x [x1, x2)`` and 1 elsewhere, applied to the NORMALISED image (define_transformations appends it
+    behind Normalize, :206-207). The words hold ``y1 | y2 << 16`` / ``x1 | x2 << 16`` (0 = no hole)."""
+    y1, y2, x1, x2 = word_y & 0xFFFF, (word_y >> 16) & 0xFFFF, word_x & 0xFFFF, (word_x >> 16) & 0xFFFF
+    mask = torch.ones(img.shape[-2:], dtype=img.dtype, device=img.device)
+    mask[y1:y2, x1:x2] = 0.0
+    return img * mask.expand_as(img)
 
 
 def multicrop_augment(tiles_u8: torch.Tensor, params: torch.Tensor, n_global: int, n_local: int, size_global: int,
@@ -105,4 +116,4 @@ def reference_style_pipeline(tile_u8: torch.Tensor, row: torch.Tensor, size: int
     k = (flags >> 2) & 3
     if k:
         img = TF.rotate(img, 90.0 * k)     # MyRotation: transforms.functional.rotate(x, angle), counter-clockwise
-    return TF.normalize(img, list(mean), list(std))
+    return cutout(TF.normalize(img, list(mean), list(std)), int(row[11]), int(row[12]))
