@@ -128,7 +128,9 @@ int b200ssl_attention_fwd_ws(const void* qkv, void* out, float* lse2, int B, int
  *        {top, left, h, w (int32 crop box), flags (bit 0 hflip, bit 1 vflip, bits 2-3 rot90 k, bits 4-11 the order of
  *         brightness(0) / contrast(1) / saturation(2) / hue(3) as 4 x 2 bits, bit 12 colour jitter on),
  *         brightness, contrast, saturation, hue (float factors, torchvision semantics), noise sigma (float),
- *         noise seed (uint32), 5 reserved};
+ *         noise seed (uint32), Cutout hole in output-frame pixels as y1 | y2 << 16 and x1 | x2 << 16 (two uint32; the
+ *         hole [y1,y2) x [x1,x2) is written as 0 AFTER Normalize like Cutout at transformations.py:10-45 / :206-207;
+ *         0 = no hole), 3 reserved};
  *      out_global bf16 [n_global,B,3,Sg,Sg], out_local bf16 [n_local,B,3,Sl,Sl] (crop-major); mean / std: HOST
  *      pointers to the 3 channel statistics of Normalize (transformations.py:104-116). Bilinear resize with
  *      align_corners = false and no antialiasing; GaussianBlur(3, sigma <= 0.1) is the identity to 2e-22 and skipped. */
