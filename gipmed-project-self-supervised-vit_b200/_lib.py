@@ -47,6 +47,8 @@ SIGNATURES = {
     "b200ssl_cast_f32_to_bf16": [_P, _P, _L, _P],
     "b200ssl_cast_bf16_to_f32": [_P, _P, _L, _P],
     "b200ssl_scale_rows": [_P, _P, _P, _L, _I, _P],
+    "b200ssl_dropout": [_P, _P, _P, _L, _I, _F, _P, ctypes.c_uint, _P],
+    "b200ssl_dropout_residual": [_P, _P, _P, _P, _L, _I, _F, _P, ctypes.c_uint, _P],
     "b200ssl_l2norm_fwd": [_P, _P, _P, _L, _I, _F, _P],
     "b200ssl_l2norm_bwd": [_P, _P, _P, _P, _L, _I, _F, _P],
     "b200ssl_weightnorm_fwd": [_P, _P, _P, _P, _L, _I, _P],

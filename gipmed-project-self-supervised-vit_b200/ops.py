@@ -224,6 +224,29 @@ def scale_rows(x, rs):
     return y
 
 
+def dropout(x, drop, site, second=None, out=None):
+    """nn.Dropout on the encoder path: ``out = x * mask / (1 - p)`` (bf16 or fp32, contiguous; ``out=x`` for in place,
+    default a new tensor). ``drop`` = (p, seed): seed an int64 CUDA tensor of one element; the mask is a pure function
+    of (seed, site, flat element index), so backward calls this again instead of saving it. ``second`` (bf16, optional)
+    receives the same mask in place."""
+    p, seed = drop
+    out = torch.empty_like(x) if out is None else out
+    if not x.is_contiguous() or not out.is_contiguous():
+        raise RuntimeError("dropout: contiguous tensors only")
+    _call("b200ssl_dropout", x.data_ptr(), out.data_ptr(), _ptr(second), x.numel(), int(x.dtype == torch.float32),
+          float(p), seed.data_ptr(), int(site), _stream())
+    return out
+
+
+def dropout_residual(branch, residual, rowscale, drop, site):
+    """``residual + rowscale[row] * dropout(branch)`` on the fp32 stream (x + drop_path(drop(branch)), VT.pyc@L150-151)."""
+    p, seed = drop
+    y = torch.empty_like(residual)
+    _call("b200ssl_dropout_residual", branch.data_ptr(), residual.data_ptr(), _ptr(rowscale), y.data_ptr(),
+          branch.shape[0], branch.shape[1], float(p), seed.data_ptr(), int(site), _stream())
+    return y
+
+
 def linear_fwd(x, w16, bias=None, residual=None, gelu=False, rowscale=None):
     """y = x @ w16^T (+bias) (+residual); with gelu=True returns (gelu'(pre), gelu(pre)) — the derivative is
     what backward needs, so it is saved instead of the pre-activation (one erf evaluation serves both).
@@ -509,6 +532,19 @@ class LayerNormFn(torch.autograd.Function):
         return dx.to(x.dtype), dw.to(weight.dtype), db.to(weight.dtype), None
 
 
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout as its own autograd node (standalone prepare_tokens / get_intermediate_layers: pos_drop)."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed, site):
+        ctx.drop, ctx.site = (p, seed), site
+        return dropout(x.contiguous(), ctx.drop, site)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dropout(dy.contiguous(), ctx.drop, ctx.site), None, None, None
+
+
 class LinearFn(torch.autograd.Function):
     """y = x W^T + b (+ residual)."""
 
@@ -598,11 +634,13 @@ class AttentionCoreFn(torch.autograd.Function):
 
 # ---- residual half-blocks: plain functions shared by the per-block and whole-encoder autograd nodes ----
 def attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale, keep=True, rs=None, pre=None,
-                  nxt=None):
+                  nxt=None, drop=None, site=0):
     """x + proj(attention(qkv(LN(x)))) (VT.pyc@L147,150). Returns (y, saved-for-backward, next LayerNorm state).
     ``pre`` = (ln, mean, rstd) of THIS half's LayerNorm when the previous residual GEMM already produced it;
     ``nxt`` = (ln_w, ln_b, eps) of the LayerNorm that follows (Block.norm2): produced by the proj GEMM's tail when the
-    shape allows, else the third return value is None."""
+    shape allows, else the third return value is None. ``drop`` = (p, seed) turns on Attention.proj_drop
+    (VT.pyc@L130) with the mask of ``site``: the branch leaves the proj GEMM in bf16 and a second kernel masks it and
+    adds it to the stream."""
     wq16 = bf16_of(qkv_w)
     qb32 = _f32(qkv_b) if qkv_b is not None else None
     if pre is not None:
@@ -616,7 +654,9 @@ def attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, sca
     att, lse2 = attention_fwd(qkv, B, N, H, scale)
     pb32 = _f32(proj_b) if proj_b is not None else None
     nxt_state = None
-    if nxt is not None and ln_tail_ok(att.shape[0], proj_w.shape[0]):
+    if drop is not None:
+        y = dropout_residual(linear_fwd(att, bf16_of(proj_w), pb32), x, rs, drop, site)
+    elif nxt is not None and ln_tail_ok(att.shape[0], proj_w.shape[0]):
         y, nxt_state = linear_res_ln_fwd(att, bf16_of(proj_w), pb32, x, rs, _f32(nxt[0]), _f32(nxt[1]), nxt[2], keep=keep)
     else:
         y = linear_fwd(att, bf16_of(proj_w), pb32, residual=x, rowscale=rs)
@@ -624,11 +664,13 @@ def attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, sca
 
 
 def attn_half_bwd(dy, saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale, ln_b=None, qkv_b=None,
-                  proj_b=None):
+                  proj_b=None, drop=None, site=0):
     """dy: bf16 gradient of the half-block output. Returns (dx bf16, d_ln_w, d_ln_b, d_qkv_w, d_qkv_b,
     d_proj_w, d_proj_b); the residual gradient is added inside the LayerNorm-backward kernel."""
     x, mean, rstd, ln, qkv, att, lse2, rs = saved
     dyb = dy if rs is None else scale_rows(dy, rs)   # stochastic depth: the branch sees the scaled gradient
+    if drop is not None:
+        dyb = dropout(dyb, drop, site)   # proj_drop: forward's mask, regenerated; dy itself stays whole for the residual
     d_att = linear_dgrad(dyb, bf16_of(proj_w))
     d_pw, d_pb = linear_wgrad(dyb, att, has_pb, proj_w, proj_b)
     d_qkv = attention_bwd(qkv, att, d_att, lse2, B, N, H, scale)
@@ -638,10 +680,14 @@ def attn_half_bwd(dy, saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale
     return dx, d_lw, d_lb, d_qw, d_qb, d_pw, d_pb
 
 
-def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, keep=True, rs=None, need_out=True, pre=None, nxt=None):
+def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, keep=True, rs=None, need_out=True, pre=None, nxt=None, drop=None,
+                 site=0):
     """x + fc2(gelu(fc1(LN(x)))) (VT.pyc@L151). keep=False (no-grad forward): gelu' is not produced.
     need_out=False (activation recompute in backward): the fc2 GEMM is skipped, only the saved tensors are rebuilt.
-    ``pre`` / ``nxt`` as in attn_half_fwd (``nxt`` = the next Block's norm1). Returns (y, saved, next LayerNorm state)."""
+    ``pre`` / ``nxt`` as in attn_half_fwd (``nxt`` = the next Block's norm1). Returns (y, saved, next LayerNorm state).
+    ``drop`` = (p, seed): Mlp.drop behind the activation (mask ``site``: gelu(pre) and the saved gelu'(pre) are masked in
+    place together, so fc2's wgrad and the fused gelu' dgrad epilogue see the dropped activation without knowing) and
+    behind fc2 (mask ``site + 1``, applied with the residual add)."""
     w116 = bf16_of(w1)
     b132 = _f32(b1) if b1 is not None else None
     if pre is not None:
@@ -653,19 +699,25 @@ def mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, keep=True, rs=None, need_ou
     else:
         ln, mean, rstd = layernorm_fwd(x, _f32(ln_w), _f32(ln_b), eps)
         pre_act, h = linear_fwd(ln, w116, b132, gelu=True if keep else "fwd_only")
+    if drop is not None:
+        dropout(h, drop, site, second=pre_act, out=h)
     b232 = _f32(b2) if b2 is not None else None
     y, nxt_state = None, None
     if need_out:
-        if nxt is not None and ln_tail_ok(h.shape[0], w2.shape[0]):
+        if drop is not None:
+            y = dropout_residual(linear_fwd(h, bf16_of(w2), b232), x, rs, drop, site + 1)
+        elif nxt is not None and ln_tail_ok(h.shape[0], w2.shape[0]):
             y, nxt_state = linear_res_ln_fwd(h, bf16_of(w2), b232, x, rs, _f32(nxt[0]), _f32(nxt[1]), nxt[2], keep=keep)
         else:
             y = linear_fwd(h, bf16_of(w2), b232, residual=x, rowscale=rs)
     return y, (x, mean, rstd, ln, pre_act, h, rs), nxt_state
 
 
-def mlp_half_bwd(dy, saved, ln_w, w1, w2, has_b1, has_b2, ln_b=None, b1=None, b2=None):
+def mlp_half_bwd(dy, saved, ln_w, w1, w2, has_b1, has_b2, ln_b=None, b1=None, b2=None, drop=None, site=0):
     x, mean, rstd, ln, pre, h, rs = saved
     dyb = dy if rs is None else scale_rows(dy, rs)
+    if drop is not None:
+        dyb = dropout(dyb, drop, site + 1)           # Mlp.drop behind fc2; the one behind the activation lives in pre / h
     d_pre = linear_dgrad(dyb, bf16_of(w2), dgelu_of=pre)
     d_w2, d_b2 = linear_wgrad(dyb, h, has_b2, w2, b2)
     d_ln = linear_dgrad(d_pre, bf16_of(w1))
@@ -678,36 +730,40 @@ class AttnHalfFn(torch.autograd.Function):
     """First residual branch of a Block as one autograd node (standalone Block.forward path)."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale, rs=None):
-        y, saved, _ = attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale, rs=rs)
+    def forward(ctx, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale, rs=None, drop=None, site=0):
+        y, saved, _ = attn_half_fwd(x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b, eps, B, N, H, scale, rs=rs, drop=drop,
+                                    site=site)
         ctx.save_for_backward(*saved, ln_w, qkv_w, proj_w)
         ctx.meta = (B, N, H, scale, qkv_b is not None, proj_b is not None)
+        ctx.drop = (drop, site)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         *saved, ln_w, qkv_w, proj_w = ctx.saved_tensors
         B, N, H, scale, has_qb, has_pb = ctx.meta
-        dx, *g = attn_half_bwd(_g16(dy), saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale)
-        return (dx.to(dy.dtype), *g, None, None, None, None, None, None)
+        dx, *g = attn_half_bwd(_g16(dy), saved, ln_w, qkv_w, proj_w, has_qb, has_pb, B, N, H, scale, drop=ctx.drop[0],
+                               site=ctx.drop[1])
+        return (dx.to(dy.dtype), *g, None, None, None, None, None, None, None, None)
 
 
 class MlpHalfFn(torch.autograd.Function):
     """Second residual branch of a Block as one autograd node (standalone Block.forward path)."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, eps, rs=None):
-        y, saved, _ = mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, rs=rs)
+    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, eps, rs=None, drop=None, site=0):
+        y, saved, _ = mlp_half_fwd(x, ln_w, ln_b, w1, b1, w2, b2, eps, rs=rs, drop=drop, site=site)
         ctx.save_for_backward(*saved, ln_w, w1, w2)
         ctx.meta = (b1 is not None, b2 is not None)
+        ctx.drop = (drop, site)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         *saved, ln_w, w1, w2 = ctx.saved_tensors
         has_b1, has_b2 = ctx.meta
-        dx, *g = mlp_half_bwd(_g16(dy), saved, ln_w, w1, w2, has_b1, has_b2)
-        return (dx.to(dy.dtype), *g, None, None)
+        dx, *g = mlp_half_bwd(_g16(dy), saved, ln_w, w1, w2, has_b1, has_b2, drop=ctx.drop[0], site=ctx.drop[1])
+        return (dx.to(dy.dtype), *g, None, None, None, None)
 
 
 BLOCK_PARAMS = 12  # ln1 w,b | qkv w,b | proj w,b | ln2 w,b | fc1 w,b | fc2 w,b
@@ -733,8 +789,13 @@ class EncoderFn(torch.autograd.Function):
         # activation recompute (the reference's --grad-checkpointing, train.py:146,509-510): keep only every block's
         # input (the fp32 stream) and rebuild the block's activations in backward
         recompute = keep and len(meta) > 8 and bool(meta[8])
+        # element dropout (drop_rate > 0 in training mode): (p, seed) or None. Sites: 0 = pos_drop, block i:
+        # 1 + 3 i = attn.proj_drop, 2 + 3 i / 3 + 3 i = mlp.drop behind the activation / behind fc2
+        drop = meta[9] if len(meta) > 9 else None
         saved = []
         x = tok
+        if drop is not None:
+            dropout(tok, drop, 0, out=tok)   # pos_drop (VT.pyc@L245), in place: nothing else reads the token stream
         ln_state = None
         for i in range(depth):
             ln1w, ln1b, qw, qb, pw, pb, ln2w, ln2b, w1, b1, w2, b2 = params[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS]
@@ -748,9 +809,10 @@ class EncoderFn(torch.autograd.Function):
                 nb = params[(i + 1) * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS + 2]
                 nxt2 = (nb[0], nb[1], eps_list[i + 1][0])
             x, s1, ln_state = attn_half_fwd(x, ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale,
-                                            keep=keep and not recompute, rs=rs1, pre=ln_state, nxt=nxt1)
+                                            keep=keep and not recompute, rs=rs1, pre=ln_state, nxt=nxt1, drop=drop,
+                                            site=1 + 3 * i)
             x, s2, ln_state = mlp_half_fwd(x, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1], keep=keep and not recompute,
-                                           rs=rs2, pre=ln_state, nxt=nxt2)
+                                           rs=rs2, pre=ln_state, nxt=nxt2, drop=drop, site=2 + 3 * i)
             if recompute:
                 saved.append(x_in)
             elif keep:
@@ -777,6 +839,7 @@ class EncoderFn(torch.autograd.Function):
         B, N, H, scale, eps_list, norm_eps = ctx.meta[:6]
         params = ctx.params
         depth = (len(params) - 2) // BLOCK_PARAMS
+        drop = ctx.meta[9] if len(ctx.meta) > 9 else None
         cls, mean, rstd = ctx.final
         d_cls, d_nw, d_nb = layernorm_bwd(cls, _g16(dout), _f32(params[-2]), mean, rstd, weight=params[-2],
                                           bias=params[-1])
@@ -792,18 +855,23 @@ class EncoderFn(torch.autograd.Function):
             ln1w, ln1b, qw, qb, pw, pb, ln2w, ln2b, w1, b1, w2, b2 = params[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS]
             if torch.is_tensor(ctx.saved[i]):   # activation recompute: rebuild this block's saved tensors from its input
                 rs1, rs2 = ctx.meta[6][i] if ctx.meta[6] is not None else (None, None)
-                x1, s1, _ = attn_half_fwd(ctx.saved[i], ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale, rs=rs1)
-                _, s2, _ = mlp_half_fwd(x1, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1], rs=rs2, need_out=False)
+                x1, s1, _ = attn_half_fwd(ctx.saved[i], ln1w, ln1b, qw, qb, pw, pb, eps_list[i][0], B, N, H, scale, rs=rs1,
+                                          drop=drop, site=1 + 3 * i)
+                _, s2, _ = mlp_half_fwd(x1, ln2w, ln2b, w1, b1, w2, b2, eps_list[i][1], rs=rs2, need_out=False, drop=drop,
+                                        site=2 + 3 * i)
             else:
                 s1, s2 = ctx.saved[i]
             dx, g_l2w, g_l2b, g_w1, g_b1, g_w2, g_b2 = mlp_half_bwd(dx, s2, ln2w, w1, w2, b1 is not None, b2 is not None,
-                                                                    ln2b, b1, b2)
+                                                                    ln2b, b1, b2, drop=drop, site=2 + 3 * i)
             dx, g_l1w, g_l1b, g_qw, g_qb, g_pw, g_pb = attn_half_bwd(dx, s1, ln1w, qw, pw, qb is not None,
-                                                                      pb is not None, B, N, H, scale, ln1b, qb, pb)
+                                                                      pb is not None, B, N, H, scale, ln1b, qb, pb,
+                                                                      drop=drop, site=1 + 3 * i)
             grads[i * BLOCK_PARAMS:(i + 1) * BLOCK_PARAMS] = [g_l1w, g_l1b, g_qw, g_qb, g_pw, g_pb, g_l2w, g_l2b,
                                                               g_w1, g_b1, g_w2, g_b2]
             ctx.saved[i] = None  # free this block's activations as soon as they are consumed
         grads[-2], grads[-1] = d_nw, d_nb
+        if drop is not None and ctx.needs_input_grad[0]:
+            dropout(dx, drop, 0, out=dx)     # pos_drop backward: the token gradient through the same mask
         relay = ctx.meta[7] if len(ctx.meta) > 7 else None
         if not ctx.needs_input_grad[0]:
             d_tok = None

@@ -64,6 +64,13 @@ def _layer_norm(mod: nn.LayerNorm, x2d: torch.Tensor) -> torch.Tensor:
     return ops.LayerNormFn.apply(x2d, mod.weight, mod.bias, mod.eps)
 
 
+def draw_dropout_seed(device):
+    """One 64-bit seed for the dropout masks of a model call, drawn ON the device from torch's CUDA generator: seeded
+    runs reproduce, and a captured CUDA graph draws a fresh one on every replay (the generator's offset is a graph
+    input). The kernels derive every mask from (seed, site, element index) -- ops.dropout."""
+    return torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=device)
+
+
 class Mlp(nn.Module):
     """fc1 -> GELU(erf) -> drop -> fc2 -> drop (VT.pyc@L88-104)."""
 
@@ -77,13 +84,17 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def _fusable(self):
-        return isinstance(self.act, nn.GELU) and getattr(self.act, "approximate", "none") == "none" and \
-            (self.drop.p == 0.0 or not self.training)
+        return isinstance(self.act, nn.GELU) and getattr(self.act, "approximate", "none") == "none"
 
     def forward(self, x):
         ops.require_cuda(x, "Mlp")
         if not self._fusable():
-            raise NotImplementedError("b200ssl Mlp supports exact-erf GELU and drop=0 (reference defaults)")
+            raise NotImplementedError("b200ssl Mlp supports the exact-erf GELU (reference default)")
+        if self.training and self.drop.p > 0:
+            # dropout lives on the fused Block / VisionTransformer path (ops.mlp_half_fwd); a bare Mlp call has no
+            # residual stream to fuse it with
+            raise NotImplementedError("b200ssl Mlp.forward on its own: drop > 0 is supported through Block / "
+                                      "VisionTransformer (drop_rate), not on the standalone module")
         shape, dtype = x.shape, x.dtype
         y = ops.MlpChainFn.apply(ops.to_bf16_2d(x), None, self.fc1.weight, self.fc1.bias, self.fc2.weight,
                                  self.fc2.bias)
@@ -105,16 +116,24 @@ class Attention(nn.Module):
         self.proj = nn.Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
 
-    def _check(self, C):
+    def _check(self, C, standalone=False):
         if C // self.num_heads != 64 or C % self.num_heads:
             raise NotImplementedError("b200ssl attention kernels are built for head_dim 64 (vit_tiny/small/base)")
-        if self.training and (self.attn_drop.p > 0 or self.proj_drop.p > 0):
-            raise NotImplementedError("attention / projection dropout is not on the b200ssl hot path (reference default 0)")
+        if self.training and self.attn_drop.p > 0:
+            raise NotImplementedError("dropout on the attention probabilities (attn_drop_rate > 0) is not on the b200ssl "
+                                      "hot path: the fused kernel never forms them (reference default 0; train.py has "
+                                      "no flag for it)")
+        if standalone and self.training and self.proj_drop.p > 0:
+            raise NotImplementedError("b200ssl Attention.forward on its own: proj_drop > 0 is supported through Block / "
+                                      "VisionTransformer (drop_rate), not on the standalone module")
 
     def forward(self, x):
+        return self._forward(x)
+
+    def _forward(self, x, map_only=False):
         ops.require_cuda(x, "Attention")
         B, N, C = x.shape
-        self._check(C)
+        self._check(C, standalone=not map_only)   # map_only: Block(return_attention=True) discards the projection
         dtype = x.dtype
         x2 = ops.to_bf16_2d(x)
         qkv = ops.LinearFn.apply(x2, self.qkv.weight, self.qkv.bias, None)
@@ -162,25 +181,32 @@ class Block(nn.Module):
         return [self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
                 self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias]
 
-    def forward_tokens(self, x2, B, N):
-        """Fused path on the packed fp32 token stream [B*N, C]: two autograd nodes per block."""
+    def forward_tokens(self, x2, B, N, seed=None, index=0):
+        """Fused path on the packed fp32 token stream [B*N, C]: two autograd nodes per block. ``seed`` / ``index``:
+        the dropout seed of the enclosing model call and this block's position in it (mask sites 1 + 3 index ...);
+        a Block called on its own draws a seed per call."""
         a = self.attn
         a._check(x2.shape[1])
         if not self._fused_ok():
             raise NotImplementedError("b200ssl Block: custom norm or activation layers are not on the accelerated "
                                       "path (SURVEY.md §8f)")
         rs1, rs2 = self._drop_path_scales(B, N, x2.device)
+        drop_a = drop_m = None
+        if self.training and (a.proj_drop.p > 0 or self.mlp.drop.p > 0):
+            seed = draw_dropout_seed(x2.device) if seed is None else seed
+            drop_a = (a.proj_drop.p, seed) if a.proj_drop.p > 0 else None
+            drop_m = (self.mlp.drop.p, seed) if self.mlp.drop.p > 0 else None
         x2 = ops.AttnHalfFn.apply(x2, self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.proj.weight,
-                                  a.proj.bias, self.norm1.eps, B, N, a.num_heads, a.scale, rs1)
+                                  a.proj.bias, self.norm1.eps, B, N, a.num_heads, a.scale, rs1, drop_a, 1 + 3 * index)
         m = self.mlp
         return ops.MlpHalfFn.apply(x2, self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight,
-                                   m.fc2.bias, self.norm2.eps, rs2)
+                                   m.fc2.bias, self.norm2.eps, rs2, drop_m, 2 + 3 * index)
 
     def forward(self, x, return_attention=False):
         ops.require_cuda(x, "Block")
         B, N, C = x.shape
         if return_attention:
-            y, attn = self.attn(_layer_norm(self.norm1, ops.to_stream_2d(x)).view(B, N, C))
+            y, attn = self.attn._forward(_layer_norm(self.norm1, ops.to_stream_2d(x)).view(B, N, C), map_only=True)
             return attn.to(x.dtype)
         dtype = x.dtype
         return self.forward_tokens(ops.to_stream_2d(x), B, N).view(B, N, C).to(dtype)
@@ -291,8 +317,6 @@ class VisionTransformer(nn.Module):
     def _tokens(self, x, relay=None):
         """prepare_tokens on the packed layout: returns ([B*N, D] fp32 stream, B, N)."""
         ops.require_cuda(x, "VisionTransformer")
-        if self.training and self.pos_drop.p > 0:
-            raise NotImplementedError("drop_rate > 0 is not on the b200ssl hot path (reference default 0)")
         B, nc, w, h = x.shape
         P = self.patch_embed.patch_size
         tok = ops.TokensFn.apply(x.to(torch.bfloat16).contiguous(), self.patch_embed.proj.weight,
@@ -300,8 +324,27 @@ class VisionTransformer(nn.Module):
                                  self._pos_matrix(w, h))
         return tok, B, (w // P) * (h // P) + 1
 
+    def _dropout(self, device):
+        """(p, seed) for this call when element dropout is on (training mode, drop_rate > 0), else None. The whole
+        encoder runs as one node with one rate: every block must carry the rate of ``pos_drop`` (the constructor's
+        ``drop_rate``, VT.pyc@L196-200)."""
+        p = self.pos_drop.p
+        rates = {p} | {b.attn.proj_drop.p for b in self.blocks} | {b.mlp.drop.p for b in self.blocks}
+        if not self.training or rates == {0.0}:
+            return None
+        if len(rates) != 1:
+            raise NotImplementedError(f"b200ssl VisionTransformer: one dropout rate for pos_drop / proj_drop / mlp.drop "
+                                      f"(the constructor's drop_rate), got {sorted(rates)}")
+        self._last_dropout_seed = draw_dropout_seed(device)
+        return (p, self._last_dropout_seed)
+
+    def _pos_drop(self, tok, drop):
+        """pos_drop as its own autograd node, for the callers that walk the blocks themselves."""
+        return tok if drop is None else ops.DropoutFn.apply(tok, drop[0], drop[1], 0)
+
     def prepare_tokens(self, x):
         tok, B, N = self._tokens(x)
+        tok = self._pos_drop(tok, self._dropout(tok.device))
         return tok.view(B, N, -1).to(x.dtype)
 
     def set_grad_checkpointing(self, enable=True):
@@ -310,7 +353,7 @@ class VisionTransformer(nn.Module):
         activation memory drops from ~23 to 4 bytes per token feature)."""
         self.grad_checkpointing = bool(enable)
 
-    def _encode(self, tok, B, N, rs_list, relay=None):
+    def _encode(self, tok, B, N, rs_list, relay=None, drop=None):
         """All blocks + the final norm on the CLS rows as one autograd node. ``B`` / ``N`` are ints, or tuples when
         ``tok`` packs several crop groups (``forward_multi``)."""
         blk0 = self.blocks[0]
@@ -325,7 +368,7 @@ class VisionTransformer(nn.Module):
         if all(r[0] is None for r in rs_list):
             rs_list = None
         meta = (B, N, blk0.attn.num_heads, blk0.attn.scale, [(b.norm1.eps, b.norm2.eps) for b in self.blocks],
-                self.norm.eps, rs_list, relay, getattr(self, "grad_checkpointing", False))
+                self.norm.eps, rs_list, relay, getattr(self, "grad_checkpointing", False), drop)
         # the reference normalises every token then keeps row 0 (@L252-253); only CLS rows are normalised here
         return ops.EncoderFn.apply(tok, meta, *params)
 
@@ -333,7 +376,7 @@ class VisionTransformer(nn.Module):
         relay = ops.GradRelay()   # the token stream is private to this call: its gradient travels in bf16
         tok, B, N = self._tokens(x, relay)
         rs_list = [b._drop_path_scales(B, N, tok.device) for b in self.blocks]
-        return self._encode(tok, B, N, rs_list, relay).to(x.dtype)
+        return self._encode(tok, B, N, rs_list, relay, self._dropout(tok.device)).to(x.dtype)
 
     def forward_multi(self, xs):
         """``torch.cat([self(x) for x in xs])`` for image batches of DIFFERENT resolution (the multi-crop student:
@@ -348,8 +391,6 @@ class VisionTransformer(nn.Module):
             return self.forward(xs[0])
         for x in xs:
             ops.require_cuda(x, "VisionTransformer")
-        if self.training and self.pos_drop.p > 0:
-            raise NotImplementedError("drop_rate > 0 is not on the b200ssl hot path (reference default 0)")
         P = self.patch_embed.patch_size
         mats = tuple(self._pos_matrix(x.shape[2], x.shape[3]) for x in xs)
         relay = ops.GradRelay()
@@ -364,21 +405,27 @@ class VisionTransformer(nn.Module):
             pair = tuple(None if per_group[0][i][j] is None else torch.cat([g[i][j] for g in per_group])
                          for j in range(2))
             rs_list.append(pair)
-        return self._encode(tok, Bs, Ns, rs_list, relay).to(xs[0].dtype)
+        return self._encode(tok, Bs, Ns, rs_list, relay, self._dropout(tok.device)).to(xs[0].dtype)
 
     def get_last_selfattention(self, x):
         tok, B, N = self._tokens(x)
+        drop = self._dropout(tok.device)
+        seed = drop[1] if drop is not None else None
+        tok = self._pos_drop(tok, drop)
         for i, blk in enumerate(self.blocks):
             if i < len(self.blocks) - 1:
-                tok = blk.forward_tokens(tok, B, N)
+                tok = blk.forward_tokens(tok, B, N, seed, i)
             else:
                 return blk(tok.view(B, N, -1), return_attention=True).to(x.dtype)
 
     def get_intermediate_layers(self, x, n=1):
         tok, B, N = self._tokens(x)
+        drop = self._dropout(tok.device)
+        seed = drop[1] if drop is not None else None
+        tok = self._pos_drop(tok, drop)
         output = []
         for i, blk in enumerate(self.blocks):
-            tok = blk.forward_tokens(tok, B, N)
+            tok = blk.forward_tokens(tok, B, N, seed, i)
             if len(self.blocks) - i <= n:
                 output.append(_layer_norm(self.norm, tok).view(B, N, -1).to(x.dtype))
         return output

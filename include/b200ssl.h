@@ -138,6 +138,20 @@ int b200ssl_multicrop_augment(const void* tiles, const void* params, void* out_g
                               int n_global, int n_local, int size_global, int size_local, const float* mean,
                               const float* std, void* stream);
 
+/* ---- Element dropout on the encoder path: nn.Dropout(drop_rate) of the reference's VisionTransformer -- pos_drop
+ *      (VT.pyc@L196,245), Attention.proj_drop (@L117,130), Mlp.drop behind the activation and behind fc2 (@L96,101-104);
+ *      train.py --drop (train.py:283,487). The keep mask is a pure function of (seed, site, element index) -- one
+ *      splitmix64 word per four consecutive elements, 16 bits each, dropped when below round(p * 65536), kept elements
+ *      scaled by 1 / (1 - p) -- so backward regenerates it (nothing is stored). seed: DEVICE pointer to one 64-bit word.
+ *      b200ssl_dropout: dst = src * mask (bf16, or fp32 with is_f32; src == dst allowed; n % 8 == 0); `second` (bf16,
+ *      optional) is masked in place with the same mask (the saved gelu' next to gelu).
+ *      b200ssl_dropout_residual: y = residual + rowscale[row] * dropout(branch) (branch bf16 [rows, D]; residual, y fp32;
+ *      rowscale optional, the stochastic-depth row scale): x + drop_path(drop(branch)) of Block.forward @L150-151. */
+int b200ssl_dropout(const void* src, void* dst, void* second, long long n, int is_f32, float p, const void* seed,
+                    unsigned site, void* stream);
+int b200ssl_dropout_residual(const void* branch, const float* residual, const float* rowscale, float* y, long long rows,
+                             int D, float p, const void* seed, unsigned site, void* stream);
+
 /* ---- K1 helpers: patch gathering and token assembly (PatchEmbed.forward VT.pyc@L167-170,
  *      prepare_tokens @L235-246). img [B,C,H,W] bf16 -> cols [B*Np, C*P*P] bf16 (then b200ssl_gemm);
  *      x(fp32)[b,0]=cls+pos[0], x[b,1+p]=y[b*Np+p]+pos[1+p]; bwd: dy=dx[:,1:], dpos=sum_b dx, dcls=dpos[0]. */
