@@ -175,3 +175,42 @@ def test_dropout_on_the_other_entry_points(cuda_device):
     assert torch.isfinite(blk.mlp(tok).float()).all()                 # eval mode: nn.Dropout is the identity
     with pytest.raises(NotImplementedError):
         b200ssl.vit_tiny(attn_drop_rate=0.1).cuda().train()(xg)
+
+
+@pytest.mark.gpu
+def test_graphed_step_draws_a_fresh_mask_on_every_replay(cuda_device):
+    """The whole DINO step with drop_rate > 0 as a CUDA-graph replay: the seed is drawn on the device inside the
+    captured graph (torch's CUDA generator is a graph input), so every replay sees a new mask; the teacher (eval mode)
+    is mask free. Eager and graphed steps from the same generator state agree."""
+    import b200ssl
+    out_dim, ncrops, B = 1024, 4, 4
+    g = torch.Generator(device="cuda").manual_seed(5)
+    crops = [torch.randn(B, 3, 224, 224, device="cuda", generator=g).bfloat16() for _ in range(2)] + \
+            [torch.randn(B, 3, 96, 96, device="cuda", generator=g).bfloat16() for _ in range(ncrops - 2)]
+
+    def build():
+        torch.manual_seed(0)
+        mod = b200ssl.MultiCropWrapper(b200ssl.vit_tiny(drop_rate=0.1, drop_path_rate=0.1),
+                                       b200ssl.DINOHead(192, out_dim, hidden_dim=256, bottleneck_dim=64)).cuda()
+        teacher = b200ssl.ModelEma(mod)
+        loss_fn = b200ssl.DINOLoss(out_dim, ncrops, 0.04, 0.04, 0, 10).cuda()
+        opt = b200ssl.FusedAdamW(b200ssl.param_groups_wd(mod, 0.04), lr=1e-3)
+        return mod, teacher, loss_fn, opt
+
+    mod, teacher, loss_fn, opt = build()
+    step = b200ssl.GraphedDinoStep(b200ssl.GradBucketDataParallel(mod), teacher, loss_fn, opt, crops)
+    seeds, losses = [], []
+    for i in range(4):
+        loss = step(crops if i == 0 else None, momentum=0.99)
+        torch.cuda.synchronize()
+        seeds.append(int(mod.backbone._last_dropout_seed.item()))
+        losses.append(float(loss))
+    assert len(set(seeds)) == 4, seeds
+    assert all(torch.isfinite(torch.tensor(losses))), losses
+    assert all(torch.isfinite(q).all() for q in mod.parameters())
+    step.release()
+    # eager step 0 from the same generator state as the graph's step 0: same masks, same loss (to bf16 / atomics noise)
+    mod2, teacher2, loss_fn2, opt2 = build()
+    l2, _, _ = b200ssl.dino_step(mod2, teacher2, loss_fn2, opt2, crops, momentum=0.99)
+    assert int(mod2.backbone._last_dropout_seed.item()) == seeds[0]
+    assert abs(float(l2) - losses[0]) / abs(losses[0]) < 2e-3, (float(l2), losses[0])
