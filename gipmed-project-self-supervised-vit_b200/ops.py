@@ -615,6 +615,36 @@ class MlpChainFn(torch.autograd.Function):
         return (d, dres, *grads)
 
 
+class MlpDropFn(torch.autograd.Function):
+    """The bare Mlp module with dropout (VT.pyc@L98-104: fc1 -> GELU -> drop -> fc2 -> drop) as one autograd node;
+    mask sites 0 (behind the activation) and 1 (behind fc2) of ``seed``. The Block / VisionTransformer paths do not
+    come through here (mlp_half_fwd fuses the second dropout with the residual add)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, p, seed):
+        drop = (p, seed)
+        keep = any(ctx.needs_input_grad)
+        pre, h = linear_fwd(x, bf16_of(w1), _f32(b1) if b1 is not None else None, gelu=True if keep else "fwd_only")
+        dropout(h, drop, 0, second=pre, out=h)
+        y = linear_fwd(h, bf16_of(w2), _f32(b2) if b2 is not None else None)
+        dropout(y, drop, 1, out=y)
+        ctx.drop, ctx.biases = drop, (b1, b2)
+        if keep:
+            ctx.save_for_backward(x, pre, h, w1, w2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, pre, h, w1, w2 = ctx.saved_tensors
+        b1, b2 = ctx.biases
+        dyb = dropout(_g16(dy).contiguous(), ctx.drop, 1)
+        d_w2, d_b2 = linear_wgrad(dyb, h, b2 is not None, w2, b2)
+        d_pre = linear_dgrad(dyb, bf16_of(w2), dgelu_of=pre)
+        d_w1, d_b1 = linear_wgrad(d_pre, x, b1 is not None, w1, b1)
+        dx = linear_dgrad(d_pre, bf16_of(w1)) if ctx.needs_input_grad[0] else None
+        return dx, d_w1, d_b1, d_w2, d_b2, None, None
+
+
 class AttentionCoreFn(torch.autograd.Function):
     """softmax(q k^T * scale) v on the packed QKV-GEMM output [B*N, 3*H*64] -> [B*N, H*64]."""
 

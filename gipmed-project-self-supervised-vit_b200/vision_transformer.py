@@ -91,10 +91,12 @@ class Mlp(nn.Module):
         if not self._fusable():
             raise NotImplementedError("b200ssl Mlp supports the exact-erf GELU (reference default)")
         if self.training and self.drop.p > 0:
-            # dropout lives on the fused Block / VisionTransformer path (ops.mlp_half_fwd); a bare Mlp call has no
-            # residual stream to fuse it with
-            raise NotImplementedError("b200ssl Mlp.forward on its own: drop > 0 is supported through Block / "
-                                      "VisionTransformer (drop_rate), not on the standalone module")
+            # the bare module (Block / VisionTransformer fuse their dropouts into the residual path instead)
+            shape, dtype = x.shape, x.dtype
+            self._last_dropout_seed = draw_dropout_seed(x.device)
+            y = ops.MlpDropFn.apply(ops.to_bf16_2d(x), self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
+                                    self.drop.p, self._last_dropout_seed)
+            return y.view(*shape[:-1], -1).to(dtype)
         shape, dtype = x.shape, x.dtype
         y = ops.MlpChainFn.apply(ops.to_bf16_2d(x), None, self.fc1.weight, self.fc1.bias, self.fc2.weight,
                                  self.fc2.bias)
@@ -116,16 +118,13 @@ class Attention(nn.Module):
         self.proj = nn.Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
 
-    def _check(self, C, standalone=False):
+    def _check(self, C):
         if C // self.num_heads != 64 or C % self.num_heads:
             raise NotImplementedError("b200ssl attention kernels are built for head_dim 64 (vit_tiny/small/base)")
         if self.training and self.attn_drop.p > 0:
             raise NotImplementedError("dropout on the attention probabilities (attn_drop_rate > 0) is not on the b200ssl "
                                       "hot path: the fused kernel never forms them (reference default 0; train.py has "
                                       "no flag for it)")
-        if standalone and self.training and self.proj_drop.p > 0:
-            raise NotImplementedError("b200ssl Attention.forward on its own: proj_drop > 0 is supported through Block / "
-                                      "VisionTransformer (drop_rate), not on the standalone module")
 
     def forward(self, x):
         return self._forward(x)
@@ -133,12 +132,15 @@ class Attention(nn.Module):
     def _forward(self, x, map_only=False):
         ops.require_cuda(x, "Attention")
         B, N, C = x.shape
-        self._check(C, standalone=not map_only)   # map_only: Block(return_attention=True) discards the projection
+        self._check(C)
         dtype = x.dtype
         x2 = ops.to_bf16_2d(x)
         qkv = ops.LinearFn.apply(x2, self.qkv.weight, self.qkv.bias, None)
         out = ops.AttentionCoreFn.apply(qkv, B, N, self.num_heads, self.scale)
         y = ops.LinearFn.apply(out, self.proj.weight, self.proj.bias, None)
+        if self.training and self.proj_drop.p > 0 and not map_only:   # the bare module: proj_drop as its own node
+            self._last_dropout_seed = draw_dropout_seed(x.device)
+            y = ops.DropoutFn.apply(y, self.proj_drop.p, self._last_dropout_seed, 0)
         with torch.no_grad():  # probability map for callers that ask for it (not the training path)
             q, k = qkv.view(B, N, 3, self.num_heads, 64)[:, :, :2].permute(2, 0, 3, 1, 4).float()
             attn = ((q @ k.transpose(-2, -1)) * self.scale).softmax(dim=-1).to(dtype)

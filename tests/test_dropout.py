@@ -140,7 +140,7 @@ def test_vit_with_drop_rate_matches_oracle_replaying_the_mask(cuda_device, drop_
 @pytest.mark.gpu
 def test_dropout_on_the_other_entry_points(cuda_device):
     """forward_multi (the packed multi-crop pass), get_intermediate_layers / prepare_tokens (pos_drop as its own node,
-    blocks one by one), Block.forward on its own, and what still refuses: attn_drop, the bare Mlp / Attention modules."""
+    blocks one by one), Block.forward on its own, and what still refuses: attn_drop."""
     import b200ssl
     torch.manual_seed(0)
     m = b200ssl.vit_tiny(drop_rate=0.2).cuda().train()
@@ -167,12 +167,9 @@ def test_dropout_on_the_other_entry_points(cuda_device):
     assert y.shape == tok.shape and torch.isfinite(y.float()).all()
     attn = m.get_last_selfattention(xg)                               # inspection path: works in training mode too
     assert attn.shape == (2, 3, 197, 197)
-    with pytest.raises(NotImplementedError):
-        blk.mlp(tok)
-    with pytest.raises(NotImplementedError):
-        blk.attn(tok)
     m.eval()
     assert torch.isfinite(blk.mlp(tok).float()).all()                 # eval mode: nn.Dropout is the identity
+    m.train()
     with pytest.raises(NotImplementedError):
         b200ssl.vit_tiny(attn_drop_rate=0.1).cuda().train()(xg)
 
@@ -214,3 +211,47 @@ def test_graphed_step_draws_a_fresh_mask_on_every_replay(cuda_device):
     l2, _, _ = b200ssl.dino_step(mod2, teacher2, loss_fn2, opt2, crops, momentum=0.99)
     assert int(mod2.backbone._last_dropout_seed.item()) == seeds[0]
     assert abs(float(l2) - losses[0]) / abs(losses[0]) < 2e-3, (float(l2), losses[0])
+
+
+@pytest.mark.gpu
+def test_bare_mlp_and_attention_modules_with_dropout(cuda_device):
+    """Mlp(drop=p) and Attention(proj_drop=p) called on their own in training mode (VT.pyc@L98-104, @L119-131): against
+    the oracle modules replaying the mask (Mlp.drop: sites 0 and 1; proj_drop: site 0)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    import b200ssl
+    from oracle import vision_transformer as ovt
+    p = 0.25
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.randn(5, 37, 192, device="cuda", generator=g)
+    w = torch.randn(5, 37, 192, device="cuda", generator=g)
+    for kind in ("mlp", "attn"):
+        torch.manual_seed(0)
+        if kind == "mlp":
+            ref, mine = ovt.Mlp(192, 768, drop=p).cuda().train(), b200ssl.Mlp(192, 768, drop=p).cuda().train()
+        else:
+            ref = ovt.Attention(192, num_heads=3, qkv_bias=True, proj_drop=p).cuda().train()
+            mine = b200ssl.Attention(192, num_heads=3, qkv_bias=True, proj_drop=p).cuda().train()
+        with torch.no_grad():
+            for q in ref.parameters():
+                if q.ndim == 1:
+                    q.add_(torch.randn_like(q) * 0.1)
+        mine.load_state_dict(ref.state_dict())
+        xm = x.clone().requires_grad_(True)
+        xr = x.clone().requires_grad_(True)
+        out = mine(xm)
+        out = out[0] if kind == "attn" else out
+        (out.float() * w).sum().backward()
+        seed = int(mine._last_dropout_seed.item())
+        if kind == "mlp":
+            ref.drop = odrop.ReplayDropout(p, seed, [0, 1])
+        else:
+            ref.proj_drop = odrop.ReplayDropout(p, seed, [0])
+        out_ref = ref(xr)
+        out_ref = out_ref[0] if kind == "attn" else out_ref
+        (out_ref * w).sum().backward()
+        assert 0.2 < float((out == 0).float().mean()) < 0.3, kind              # a quarter of the output is masked
+        assert rel(out, out_ref) < 1e-2, (kind, rel(out, out_ref))
+        assert cos(xm.grad, xr.grad) > 0.999, (kind, cos(xm.grad, xr.grad))
+        bad = [(n, cos(q.grad, r.grad)) for (n, r), (_, q) in zip(ref.named_parameters(), mine.named_parameters())
+               if cos(q.grad, r.grad) < 0.999]
+        assert not bad, (kind, bad)
