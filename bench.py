@@ -182,8 +182,9 @@ def workload_text(cfg, args):
     if cfg["kind"] == "embed":
         return (f"{m}/{p} frozen-encoder embedding (train.py --extract_features flow), {args.batch} tiles of 3x224x224 per "
                 f"slide, forward only, bf16 ({cfg['label']})")
+    extra = f", NON-DEFAULT drop_rate {args.drop_rate}" if getattr(args, "drop_rate", 0.0) > 0 else ""
     return (f"{m}/{p} DINO multi-crop 2x224+{args.local_crops}x96, batch {args.batch}/GPU, head out_dim "
-            f"{args.out_dim}, bf16 ({cfg['label']})")
+            f"{args.out_dim}, bf16 ({cfg['label']}){extra}")
 
 
 def make_config(cfg, args, world, total_f):
@@ -269,6 +270,9 @@ def main():
     ap.add_argument("--ln-tail", action="store_true", help="LayerNorm after each residual add in the tail of the proj / fc2 "
                     "GEMM instead of its own kernel (A/B switch, measured slower; ViT-S only)")
     ap.add_argument("--pdl", action="store_true", help="enable programmatic dependent launch (A/B switch; off by default)")
+    ap.add_argument("--drop-rate", type=float, default=0.0, help="developer switch: element dropout in the student "
+                    "(the reference's --drop; default 0 = BASELINE.json's configuration). A non-zero value is recorded in "
+                    "config.workload: such a line is not the headline metric")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying "
                     "the captured CUDA graph of the step")
     args = ap.parse_args()
@@ -392,7 +396,8 @@ def main():
         host_ms = None
     else:
         # ------------------------------------------------------------------ training step
-        student = b200ssl.MultiCropWrapper(getattr(b200ssl, args.model)(patch_size=args.patch),
+        vit_kw = {"drop_rate": args.drop_rate} if args.drop_rate > 0 else {}
+        student = b200ssl.MultiCropWrapper(getattr(b200ssl, args.model)(patch_size=args.patch, **vit_kw),
                                            b200ssl.DINOHead(D, args.out_dim)).to(device)
         teacher = b200ssl.ModelEma(student)
         ddp_kw = {}
