@@ -274,3 +274,51 @@ def test_grad_bucket_data_parallel_gloo_world2(tmp_path, compress):
                        capture_output=True, text=True, env=env, timeout=280)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_c_abi_rejects_bad_arguments_before_touching_the_device():
+    """Every entry point validates shapes / alignment / ranges BEFORE its first CUDA call and reports through the
+    return code + b200ssl_last_error() (never throws across the C boundary; SURVEY.md §8b "Errors"): checked here,
+    without a GPU, by calling the real library with arguments that must be refused."""
+    import ctypes
+    from b200ssl import _lib
+    h = _lib.lib()
+    buf = (ctypes.c_char * 4096)()
+    p = ctypes.addressof(buf)
+    p = (p + 255) & ~255                     # a 256-byte aligned host address: never dereferenced by the checks
+    f3 = (ctypes.c_float * 3)(0.5, 0.5, 0.5)
+    bad_std = (ctypes.c_float * 3)(0.5, 0.0, 0.5)
+    cases = [
+        ("b200ssl_gemm", (p, 64, 0, p, 64, 0, p, 64, None, None, None, 0, 128, 100, 64, 0, 1, 0, None), "multiple of 64"),
+        ("b200ssl_gemm", (p, 64, 0, p, 64, 0, p, 64, None, None, None, 0, 0, 64, 64, 0, 1, 0, None), "empty problem"),
+        ("b200ssl_gemm", (p + 2, 64, 0, p, 64, 0, p, 64, None, None, None, 0, 128, 64, 64, 0, 1, 0, None), "16-byte aligned"),
+        ("b200ssl_gemm", (p, 64, 0, p, 64, 0, p, 64, None, None, None, 0, 128, 64, 64, 9, 1, 0, None), "unknown epilogue"),
+        ("b200ssl_gemm", (p, 64, 0, p, 64, 0, p, 64, None, None, None, 0, 128, 64, 64, 1, 1, 0, None), "needs D2"),
+        ("b200ssl_attention_fwd", (p, p, p, 2, 197, 6, 32, 0.125, None), "head_dim 32 unsupported"),
+        ("b200ssl_attention_bwd", (p, p, p, p, p, 2, 197, 6, 128, 0.125, None), "head_dim 128 unsupported"),
+        ("b200ssl_layernorm_fwd", (p, 1, p, p, p, p, p, 0, 384, 1e-6, None), "no rows"),
+        ("b200ssl_patchify", (p, p, 2, 3, 224, 224, 12, None), "must divide"),
+        ("b200ssl_assemble_tokens", (p, p, p, p, 2, 196, 100, None), "multiple of 8"),
+        ("b200ssl_scale_rows", (p, p, p, 16, 100, None), "multiple of 8"),
+        ("b200ssl_colsum", (p, 100, p, 16, 100, 0, None), "multiples of 8"),
+        ("b200ssl_center_update", (p, p, 1024, 0, 0.9, None), "total_rows"),
+        ("b200ssl_dino_loss_fwd", (p, p, p, p, p, p, 4, 4, 1001, 0.1, 0.04, None), "multiple of 8"),
+        ("b200ssl_multicrop_augment", (p, p, p, p, 2, 2, 10, 223, 96, f3, f3, None), "must be even"),
+        ("b200ssl_multicrop_augment", (p, p, p, p, 0, 2, 10, 224, 96, f3, f3, None), "empty problem"),
+        ("b200ssl_multicrop_augment", (p, p, p, p, 2, 2, 10, 224, 96, f3, bad_std, None), "std > 0"),
+        ("b200ssl_dropout", (p, p, None, 1001, 0, 0.1, p, 0, None), "multiple of 8"),
+        ("b200ssl_dropout", (p, p, None, 1024, 0, 1.5, p, 0, None), "outside [0, 1]"),
+        ("b200ssl_dropout", (p, p, None, 1024, 0, 0.1, None, 0, None), "seed"),
+        ("b200ssl_dropout", (p, p, p, 1024, 1, 0.1, p, 0, None), "second"),
+        ("b200ssl_dropout_residual", (p, p, None, p, 16, 100, 0.1, p, 0, None), "multiple of 8"),
+        ("b200ssl_set_attn_stream", (7,), "stream mode"),
+        ("b200ssl_set_gemm_cluster", (3,), "cluster size"),
+    ]
+    for name, args, needle in cases:
+        args = tuple(ctypes.cast(a, ctypes.c_void_p) if isinstance(a, ctypes.Array) else a for a in args)
+        rc = getattr(h, name)(*args)
+        assert rc == -2, (name, rc)
+        assert needle in _lib.last_error(), (name, needle, _lib.last_error())
+    # a no-op size is accepted without a device, too (nothing to launch)
+    assert h.b200ssl_dropout(p, p, None, 0, 0, 0.1, p, 0, None) == 0
+    assert h.b200ssl_zero_bytes(p, 0, None) == 0 and h.b200ssl_copy_rows(p, 16, p, 16, 0, 16, None) == 0
