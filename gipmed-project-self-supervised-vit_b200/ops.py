@@ -233,6 +233,10 @@ def dropout(x, drop, site, second=None, out=None):
     out = torch.empty_like(x) if out is None else out
     if not x.is_contiguous() or not out.is_contiguous():
         raise RuntimeError("dropout: contiguous tensors only")
+    if x.dtype not in (torch.float32, _BF16) or out.dtype != x.dtype or out.numel() != x.numel():
+        raise RuntimeError(f"dropout: fp32 or bf16 in, the same out (got {x.dtype} -> {out.dtype})")
+    if second is not None and (second.dtype != _BF16 or second.numel() != x.numel() or not second.is_contiguous()):
+        raise RuntimeError("dropout: the second tensor must be contiguous bf16 of the same size")
     _call("b200ssl_dropout", x.data_ptr(), out.data_ptr(), _ptr(second), x.numel(), int(x.dtype == torch.float32),
           float(p), seed.data_ptr(), int(site), _stream())
     return out
@@ -241,6 +245,9 @@ def dropout(x, drop, site, second=None, out=None):
 def dropout_residual(branch, residual, rowscale, drop, site):
     """``residual + rowscale[row] * dropout(branch)`` on the fp32 stream (x + drop_path(drop(branch)), VT.pyc@L150-151)."""
     p, seed = drop
+    if branch.dtype != _BF16 or residual.dtype != torch.float32 or branch.shape != residual.shape or \
+            not (branch.is_contiguous() and residual.is_contiguous()):
+        raise RuntimeError("dropout_residual: contiguous bf16 branch and fp32 stream of the same shape")
     y = torch.empty_like(residual)
     _call("b200ssl_dropout_residual", branch.data_ptr(), residual.data_ptr(), _ptr(rowscale), y.data_ptr(),
           branch.shape[0], branch.shape[1], float(p), seed.data_ptr(), int(site), _stream())
