@@ -75,6 +75,50 @@ def test_oracle_matches_torchvision_pipeline_in_the_reference_operator_order():
             assert float((x - y).abs().max()) < 1e-4, (b, c, float((x - y).abs().max()))
 
 
+def test_float_pipeline_stays_within_quantisation_of_the_pil_pipeline():
+    """The reference applies its operators to PIL images (uint8 between operators, hue rotated in 8-bit HSV); the
+    oracle / kernel keep floats throughout -- a stated difference (oracle/augment.py). This bounds it: the same draw
+    through torchvision's PIL implementations (what transformations.py:131-160 runs per tile) against augment_one, in
+    grey levels of 255. Per operator the two differ by PIL's truncation to uint8 (< 1 level; hue <= 7); the four colour
+    operators in sequence: mean < 2, 99th percentile < 7, maximum < 16 levels. Flips and rotations are exact."""
+    from PIL import Image
+    import torchvision.transforms.functional as TF
+    tiles = _tiles(3, seed=11)
+    ft = tiles[0].permute(2, 0, 1).float() / 255
+    pil = Image.fromarray(tiles[0].numpy())
+    for fn, factors, bound in ((TF.adjust_brightness, (0.9, 1.1), 1.0), (TF.adjust_contrast, (0.8, 1.2), 1.5),
+                               (TF.adjust_saturation, (0.9, 1.1), 1.0), (TF.adjust_hue, (-0.1, 0.05, 0.1), 8.0)):
+        for f in factors:
+            d = (fn(ft, f) - TF.to_tensor(fn(pil, f))).abs() * 255
+            assert float(d.max()) < bound and float(d.mean()) < 0.8, (fn.__name__, f, float(d.max()), float(d.mean()))
+    for k in (1, 2, 3):
+        assert torch.equal(torch.rot90(ft, k, dims=(-2, -1)), TF.to_tensor(TF.rotate(pil, 90 * k)))
+    assert torch.equal(ft.flip(-2), TF.to_tensor(TF.vflip(pil)))
+    a = b200ssl.MultiCropAugment("pcbnfrs", color_param=0.1, global_size=256, local_size=256, n_global=1, n_local=1)
+    p = a.sample_params(3, torch.Generator().manual_seed(3))
+    p[..., 0:2] = 0
+    p[..., 2:4] = 256                              # whole tile at its own size: no resampling in this comparison
+    p.view(torch.float32)[..., 9] = 0.0            # no noise (the generators differ by construction)
+    mean, std = aug.MEAN["Ron"], aug.STD["Ron"]
+    s = torch.tensor(std).view(3, 1, 1)
+    for b in range(3):
+        for c in range(2):
+            row = p[b, c]
+            flags, fp = int(row[4]), row.view(torch.float32)
+            img = Image.fromarray(tiles[b].numpy())
+            for k in range(4):                       # ColorJitter: the drawn order, PIL implementations
+                op = (flags >> (4 + 2 * k)) & 3
+                img = (TF.adjust_brightness, TF.adjust_contrast, TF.adjust_saturation, TF.adjust_hue)[op](img, float(fp[5 + op]))
+            if flags & 2:
+                img = TF.vflip(img)
+            if (flags >> 2) & 3:
+                img = TF.rotate(img, 90 * ((flags >> 2) & 3))
+            ref = TF.normalize(TF.to_tensor(img), mean, std)
+            d = ((oaug.augment_one(tiles[b], row, 256, mean, std) - ref) * s).abs().flatten() * 255
+            p99 = float(d.kthvalue(int(0.99 * d.numel())).values)
+            assert float(d.mean()) < 2.0 and p99 < 7.0 and float(d.max()) < 16.0, (b, c, float(d.mean()), p99, float(d.max()))
+
+
 def _gold():
     import json
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "transform_goldens.json")) as fh:
