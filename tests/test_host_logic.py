@@ -322,3 +322,40 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_device():
     # a no-op size is accepted without a device, too (nothing to launch)
     assert h.b200ssl_dropout(p, p, None, 0, 0, 0.1, p, 0, None) == 0
     assert h.b200ssl_zero_bytes(p, 0, None) == 0 and h.b200ssl_copy_rows(p, 16, p, 16, 0, 16, None) == 0
+
+
+def test_header_is_plain_c_and_the_integration_example_type_checks(tmp_path):
+    """include/b200ssl.h must be consumable from C (the drop-in boundary is a C ABI: no C++ / torch types), and the C
+    calls INTEGRATION.md shows must match the declared prototypes: the ```c block of INTEGRATION.md is wrapped in a
+    function and compiled with gcc -std=c99 -pedantic -Werror (syntax + types only, nothing is linked or run)."""
+    import re
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    with open(os.path.join(ROOT, "INTEGRATION.md"), encoding="utf-8") as fh:
+        blocks = re.findall(r"```c\n(.*?)```", fh.read(), flags=re.S)
+    assert blocks, "INTEGRATION.md lost its C example"
+    body = "\n".join(line for line in blocks[0].splitlines() if not line.startswith("#include"))
+    src = ('#include <stdio.h>\n#include "b200ssl.h"\n'
+           "int example(const void* tiles_u8, const void* params, void* crops224, void* crops96, const void* x,\n"
+           "            const void* W1, const void* W2, void* dact, void* h, const float* b1, const float* b2,\n"
+           "            float* x1_f32, const float* x0_f32, const void* qkv, void* out, float* lse2, int rows, int B,\n"
+           "            int N, int H, void* stream) {\n" + body + "\nreturn 0;\n}\n")
+    path = tmp_path / "example.c"
+    path.write_text(src)
+    r = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter",
+                        "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # and a C translation unit that names every declared entry point (their addresses type-check against `int (*)()` etc.)
+    with open(os.path.join(ROOT, "include", "b200ssl.h")) as fh:
+        names = sorted(set(re.findall(r"\b(b200ssl_[a-z0-9_]+)\s*\(", fh.read())))
+    from b200ssl import _lib
+    assert set(names) == set(_lib.exported_symbols())
+    tu = '#include "b200ssl.h"\nconst void* table[] = {\n' + "".join(f"  (const void*)&{n},\n" for n in names) + "};\n"
+    path2 = tmp_path / "table.c"
+    path2.write_text(tu)
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                        str(path2)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
